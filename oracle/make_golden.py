@@ -1,0 +1,165 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from
+/root/reference via oracle/ref_shim.py) on seeded synthetic inputs.
+
+Run in the dev container (the reference tree does not exist on the GPU box):
+    python -m oracle.make_golden
+Weights are regenerated from zeggs_b200.synth.make_params(seed) on both sides, so only
+inputs' seeds and the reference OUTPUTS are stored.
+"""
+import os
+import types
+
+import numpy as np
+import torch
+
+from oracle import ref_shim
+from zeggs_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def tt(d):
+    return {k: torch.from_numpy(np.asarray(v)) for k, v in d.items()}
+
+
+def build_ref_nets(P, H, S=64, Z=64, style_hidden=512, use_vae=True):
+    m = ref_shim.ref_modules()
+    se = m.SpeechEncoder(synth.N_AUDIO, S, S)
+    de = m.Decoder(synth.P_IN, synth.P_OUT, S, Z, H, 2)
+    st = m.StyleEncoder(synth.P_IN, style_hidden, Z, type="attn", use_vae=use_vae)
+    Pt = tt(P)
+    se.load_state_dict({k[len("speech_encoder."):]: v for k, v in Pt.items() if k.startswith("speech_encoder.")})
+    de.load_state_dict({k[len("decoder."):]: v for k, v in Pt.items() if k.startswith("decoder.")})
+    st.load_state_dict({k[len("style_encoder."):]: v for k, v in Pt.items() if k.startswith("style_encoder.")})
+    return se, st, de
+
+
+def audio_params(hop=200, n_fft=800):
+    return types.SimpleNamespace(
+        sampling_rate=16000, filter_length=n_fft, hop_length=hop, n_mel_channels=80, mel_fmin=20, mel_fmax=7600,
+        min_clipping=1e-5, pre_emphasis=False, pre_emph_coeff=0.97, real_amplitude=True, centered=True,
+        normalize_mel_bins=True, normalize_range=True, resample_method="linear", normalize_loudness=False)
+
+
+def ref_train_losses(ns):
+    """Execute the reference's own loss lines (train.py:277-421) where they lie, in namespace `ns`
+    (expects O_*/W_* tensors, parents, dt, mu, logvar, iteration); returns the namespace."""
+    ref_shim.install()
+    path = os.path.join(ref_shim.REF_ZEGGS, "train.py")
+    lines = open(path).read().split("\n")[275:421]       # train.py:276-421
+    import textwrap
+    src = textwrap.dedent("\n".join(lines))
+    import anim.tquat as tq
+    import anim.txform as tx
+    import modules as m
+    env = dict(torch=torch)
+    for mod in (tq, tx):
+        env.update({k: getattr(mod, k) for k in dir(mod) if not k.startswith("_")})
+    env.update(compute_KL_div=m.compute_KL_div, normalize=m.normalize)
+    env.update(ns)
+    exec(compile(src, path, "exec"), env)
+    return env
+
+
+def stats_t():
+    st = synth.load_stats()
+    f = lambda k: torch.as_tensor(st[k], dtype=torch.float32)
+    return (f("audio_input_mean"), f("audio_input_std"), f("anim_input_mean"), f("anim_input_std"),
+            f("anim_output_mean"), f("anim_output_std"), torch.as_tensor(st["parents"]), float(st["dt"]))
+
+
+def ref_forward_train(se, st, de, win, audio, style_ex, eps, iteration):
+    """The reference's train-step forward in eval mode (no dropout) with injected VAE eps."""
+    a_mu, a_sd, i_mu, i_sd, o_mu, o_sd, parents, dt = stats_t()
+    W = tt(win)
+    speech = se((torch.from_numpy(audio) - a_mu) / a_sd)
+    # StyleEncoder.forward with eps injected (modules.py:289-304): replicate randn_like via manual formula
+    enc = st.encoder((torch.from_numpy(style_ex) - i_mu) / i_sd)
+    Z = st.style_embedding_size
+    mu, logvar = enc[:, :Z], enc[:, Z:]
+    z = mu + torch.from_numpy(eps) * torch.exp(0.5 * logvar)
+    T = speech.shape[1]
+    O = de(W["root_pos"][:, 0], W["root_rot"][:, 0], W["root_vel"][:, 0], W["root_vrt"][:, 0], W["lpos"][:, 0],
+           W["ltxy"][:, 0], W["lvel"][:, 0], W["lvrt"][:, 0], W["gaze_pos"], speech, z.unsqueeze(1).repeat((1, T, 1)),
+           parents, i_mu, i_sd, o_mu, o_sd, dt)
+    names = ["root_pos", "root_rot", "root_vel", "root_vrt", "lpos", "ltxy", "lvel", "lvrt"]
+    ns = {"O_" + n: o for n, o in zip(names, O)}
+    ns.update({"W_" + n: W[n] for n in names})
+    ns.update(W_gaze_pos=W["gaze_pos"], parents=parents, dt=dt, mu=mu, logvar=logvar, iteration=iteration)
+    env = ref_train_losses(ns)
+    return speech, (z, mu, logvar), O, env
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    torch.manual_seed(0)
+    # ---- mel / preprocess_audio (hop 200 reference-actual, hop 160 BASELINE.json-stated)
+    pa = ref_shim.ref_preprocess_audio()
+    from audio.spectrograms import extract_mel_spectrogram_for_tts
+    wav = synth.make_waveforms(2, 16000, seed=7)
+    wav[1, 4000:9000] = 0.0          # a silent stretch: exercises the 1.25e-8 clip floor
+    out = {"wav": wav}
+    for hop in (200, 160):
+        p = audio_params(hop)
+        n60 = int(round(60.0 * wav.shape[1] / 16000))
+        feats, mels = [], []
+        for i in range(wav.shape[0]):
+            feats.append(pa(wav[i], 60, n60, p, ["mel_spec", "energy"]))
+            mels.append(extract_mel_spectrogram_for_tts(
+                wav_signal=wav[i], fs=16000, n_fft=800, step_size=hop, n_mels=80, mel_fmin=20, mel_fmax=7600,
+                min_amplitude=1e-5, pre_emphasis=False, real_amplitude=True, centered=True,
+                normalize_mel_bins=True, normalize_range=True)[0])
+        out[f"feat_hop{hop}"] = np.stack(feats)
+        out[f"mel_hop{hop}"] = np.stack(mels)
+    np.savez_compressed(os.path.join(GOLD, "mel_small.npz"), **out)
+
+    # ---- networks, small hidden (H=64) and a wider one (H=128), eval mode
+    for tag, H, B, T, T_ex in (("h64", 64, 2, 6, 16), ("h128", 128, 4, 9, 24)):
+        P = synth.make_params(H=H, seed=11)
+        se, st, de = build_ref_nets(P, H)
+        se.eval(); st.eval(); de.eval()
+        win = synth.make_pose_windows(B, T, seed=5)
+        audio = synth.make_audio_features(B, T, seed=5)
+        style_ex = synth.make_style_example(B, T_ex, seed=5)
+        eps = np.random.RandomState(3).randn(B, 64).astype(np.float32)
+        speech, (z, mu, logvar), O, env = ref_forward_train(se, st, de, win, audio, style_ex, eps, iteration=9000)
+        loss = env["loss"]
+        params = list(se.parameters()) + list(de.parameters()) + list(st.parameters())
+        names = (["speech_encoder." + n for n, _ in se.named_parameters()] +
+                 ["decoder." + n for n, _ in de.named_parameters()] +
+                 ["style_encoder." + n for n, _ in st.named_parameters()])
+        grads = torch.autograd.grad(loss, params)
+        g = {"grad." + n: x.detach().numpy() for n, x in zip(names, grads) if x.numel() <= 4096}
+        gn = {"gradnorm." + n: np.float64(x.double().norm().item()) for n, x in zip(names, grads)}
+        d = dict(H=H, B=B, T=T, T_ex=T_ex, param_seed=11, input_seed=5, eps=eps, iteration=9000,
+                 speech=speech.detach().numpy(), z=z.detach().numpy(), mu=mu.detach().numpy(),
+                 logvar=logvar.detach().numpy(), loss=np.float64(loss.item()))
+        for n, o in zip(["root_pos", "root_rot", "root_vel", "root_vrt", "lpos", "ltxy", "lvel", "lvrt"], O):
+            d["O_" + n] = o.detach().numpy()
+        for k in ["loss_root_pos", "loss_root_rot", "loss_root_vel", "loss_root_vrt", "loss_lpos", "loss_lrot",
+                  "loss_lvel", "loss_lvrt", "loss_cpos", "loss_crot", "loss_cvel", "loss_cvrt", "loss_ldvl",
+                  "loss_ldvt", "loss_cdvl", "loss_cdvt", "loss_gaze", "loss_kl_div"]:
+            d[k] = np.float64(float(env[k]))
+        d.update(g); d.update(gn)
+        np.savez_compressed(os.path.join(GOLD, f"train_{tag}.npz"), **d)
+        print(tag, "loss", loss.item())
+
+    # ---- RAdam trajectory (optimizers.py), 8 steps crossing the N_sma>=5 switch (step 6)
+    ref_shim.install()
+    from optimizers import RAdam
+    rs = np.random.RandomState(2)
+    p0 = rs.randn(257).astype(np.float32)
+    gs = rs.randn(8, 257).astype(np.float32)
+    p = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+    opt = RAdam([p], lr=1e-4, eps=1e-5)
+    traj = []
+    for i in range(8):
+        p.grad = torch.from_numpy(gs[i].copy())
+        opt.step()
+        traj.append(p.detach().numpy().copy())
+    np.savez_compressed(os.path.join(GOLD, "radam.npz"), p0=p0, grads=gs, traj=np.stack(traj))
+    print("golden written to", GOLD)
+
+
+if __name__ == "__main__":
+    main()
