@@ -1,0 +1,132 @@
+/* zeggs_b200 -- C ABI of the B200-native ZeroEGGS audio->gesture hot path (libzeggs_b200.so).
+ *
+ * The reference (ubisoft/ubisoft-laforge-ZeroEGGS) is pure Python/PyTorch and has no FFI today; its
+ * "plugin API" for this path is the Python call surface of ZEGGS/modules.py, ZEGGS/audio/spectrograms.py,
+ * ZEGGS/data_pipeline.py:33 and the train step body of ZEGGS/train.py.  Each entry point below names the
+ * reference function it replaces (file:line relative to /root/reference).  INTEGRATION.md shows the
+ * ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, <0 = error (ZEGGS_ERR_*); text via zeggs_last_error().
+ *   - the CALLER owns every buffer; the library allocates nothing persistent.  Workspace sizes come
+ *     from the *_workspace_bytes() functions.  All pointers are DEVICE pointers unless named h_*.
+ *   - every call is asynchronous on the given cudaStream_t (passed as void*), re-entrant per stream.
+ *   - tensors are dense row-major float32 unless stated; quaternions are w-first (anim/tquat.py:8-15);
+ *     pose vector order is [root_vel 3 | root_vrt 3 | lpos 225 | ltxy 450 | lvel 225 | lvrt 225 | gaze 3]
+ *     (modules.py:699-710) and the output order of modules.py:731-736.
+ */
+#ifndef ZEGGS_B200_H
+#define ZEGGS_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZEGGS_OK 0
+#define ZEGGS_ERR_ARG (-1)
+#define ZEGGS_ERR_CUDA (-2)
+#define ZEGGS_ERR_UNSUPPORTED (-3)
+#define ZEGGS_ERR_TIMEOUT (-4)
+
+#define ZEGGS_NJ 75
+#define ZEGGS_P_OUT 1131 /* modules.py:731-736 */
+#define ZEGGS_P_IN 1134  /* modules.py:699-710 */
+
+const char* zeggs_last_error(void);
+int zeggs_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches claim) */
+long long zeggs_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Mel front end.  Replaces audio/spectrograms.py:8-54 (extract_mel_spectrogram_for_tts, pre-emphasis
+ * off), :216-269 (extract_spectrogram), :161-183 + :386-503 (Slaney filterbank), :57-131 (clip/dB/[0,1])
+ * and, for `feat`, data_pipeline.py:62-82 (ln(10^(s/20)), 80->60 fps linear resample, energy channel).
+ *   wav      [n_clips, n_samples] f32
+ *   mel_out  [n_clips, n_mels, L] f32 or NULL   (the reference's (n_mels, L) layout, values in [0,1])
+ *   feat_out [n_clips, anim_length, n_mels+1] f32 or NULL
+ * L = zeggs_mel_num_frames(n_samples, n_fft, hop) (spectrograms.py:242-245, centered).
+ * fb_* describe the sparse filterbank built on the host by zeggs_b200.audio (same closed form as the
+ * reference): band i covers FFT bins [fb_start[i], fb_start[i]+fb_len[i]) with weights fb_w[fb_off[i]..].
+ */
+typedef struct {
+  int n_clips, n_samples, n_fft, hop, n_mels;
+  int anim_length;        /* rows of feat_out per clip (60 fps frames) */
+  float min_amp;          /* min_clipping / n_fft, spectrograms.py:86-88 */
+  double frames_per_anim; /* (fs/hop)/anim_fs, data_pipeline.py:68 (kept in double: floor() must match the f64 reference) */
+  const float* wav;
+  const float* window;   /* [n_fft] symmetric Hann, spectrograms.py:230 */
+  const float* twiddle;  /* (cos,-sin) pairs: [n_fft/2] of exp(-2*pi*i*k/(n_fft/2)) then [n_fft/2+1] of exp(-2*pi*i*k/n_fft) */
+  const int* fb_start;
+  const int* fb_len;
+  const int* fb_off;
+  const float* fb_w;
+  float* mel_out;
+  float* feat_out;
+} zeggs_mel_args;
+int zeggs_mel_num_frames(int n_samples, int n_fft, int hop);
+int zeggs_mel_forward(const zeggs_mel_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decoder (modules.py:11-243, 677-742): CellStateEncoder + T-1 autoregressive steps of
+ * vectorize_input -> Linear+ELU -> 2-layer GRU -> Linear -> devectorize_output, one persistent kernel.
+ */
+typedef struct {
+  int B, T, H, S, Z; /* batch, frames, hidden (modules.py:18), speech / style encoding sizes */
+  float dt;
+  /* reference state-dict tensors, fp32 row-major */
+  const float *W0, *b0;                 /* recurrent_decoder.layer0  [H, 1134+S+Z] */
+  const float *W_ih0, *b_ih0;           /* layer1.weight_ih_l0 [3H, H+1134+S+Z] */
+  const float *W_hh0, *b_hh0;           /* layer1.weight_hh_l0 [3H, H] */
+  const float *W_ih1, *b_ih1, *W_hh1, *b_hh1;
+  const float *W2, *b2;                 /* layer2 [1131, H] */
+  const float *Wc0, *bc0, *Wc1, *bc1, *Wc2, *bc2; /* cell_state_encoder.layer{0,1,2} */
+  const float* packed;                  /* zeggs_decoder_pack_weights output */
+  const float *in_mean, *in_std, *out_mean, *out_std; /* [1134],[1134],[1131],[1131] */
+  /* inputs */
+  const float* root_pos0; /* [B,3] */
+  const float* root_rot0; /* [B,4] */
+  const float* pose0;     /* [B,1131] first frame: vel|vrt|lpos|ltxy|lvel|lvrt (un-normalised) */
+  const float* gaze_pos;  /* [B,T,3] */
+  const float* speech;    /* [B,T,S] */
+  const float* style;     /* [B,T,Z] */
+  /* outputs (frame 0 = the given pose, modules.py:72-79) */
+  float* Y;        /* [B,T,1131] de-normalised pose vector per frame */
+  float* root_pos; /* [B,T,3] */
+  float* root_rot; /* [B,T,4] */
+  void* workspace;
+  size_t workspace_bytes;
+  int save_for_backward; /* 1: keep every step's activations in the workspace for zeggs_decoder_window_bwd */
+} zeggs_decoder_fwd_args;
+
+size_t zeggs_decoder_packed_bytes(int H, int S, int Z);
+/* one-off re-layout of the decoder weights into per-CTA k-major slices (re-run after each optimizer step) */
+int zeggs_decoder_pack_weights(const zeggs_decoder_fwd_args* a, float* packed, void* stream);
+size_t zeggs_decoder_workspace_bytes(int B, int T, int H, int S, int Z, int save_for_backward);
+int zeggs_decoder_window_fwd(const zeggs_decoder_fwd_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Generic fp32 GEMM used for the batched (non-recurrent) linear layers:
+ *   C[M,N] = act(A[M,K] * B[N,K]^T + bias[N])            (trans_a = 0;  nn.Linear)
+ *   C[M,N] = A[K,M]^T * B[K,N] (+ C if accumulate)        (trans_a = 1;  weight gradients)
+ * act: 0 none, 1 ELU, 2 ReLU.
+ */
+int zeggs_sgemm(int trans_a, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                const float* bias, float* C, int ldc, int act, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * tcgen05 / TMEM / TMA GEMM (bf16 operands, f32 accumulate in tensor memory):
+ *   C[M,N] = act(A[M,K] * B[N,K]^T + bias) (+ C)   A, B row-major bf16 (K contiguous), lda/ldb in elements (%8==0)
+ * With A_lo/B_lo non-NULL the product is evaluated as A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (split-bf16, ~fp32
+ * product accuracy); zeggs_split_bf16 produces hi = bf16(x), lo = bf16(x - hi) with rows zero-padded to ld_out.
+ */
+int zeggs_tc_gemm_bf16(int M, int N, int K, const void* A_hi, const void* A_lo, int lda, const void* B_hi,
+                       const void* B_lo, int ldb, const float* bias, float* C, int ldc, int act, int accumulate,
+                       void* stream);
+int zeggs_split_bf16(const float* x, int rows, int cols, int ld_in, void* hi, void* lo, int ld_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZEGGS_B200_H */

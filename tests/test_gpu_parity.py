@@ -1,0 +1,151 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the committed reference goldens.
+
+Tolerances (stated per SURVEY.md 8d):
+  mel features            abs <= 2e-4 on the ln-domain 80-mel + energy features (fp32 FFT vs the f64 reference)
+  sgemm (fp32 SIMT)       rel <= 2e-5 of max|C|
+  tc_gemm bf16            equals fp32 matmul of the bf16-rounded operands to 1e-5 rel; split-bf16 (x3) <= 2e-5 rel
+  decoder fp32 path       per-pose-channel max-abs <= 2e-4 * max(1, max|ref|) (de-normalised units), free-running
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests._util import NAMES, ensure_built, make_decoder, report, stats_tensors, tt
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    ensure_built()
+    return torch.device("cuda:0")
+
+
+# ---------------------------------------------------------------------------------------------- GEMMs
+@pytest.mark.parametrize("M,N,K", [(7, 5, 3), (64, 64, 16), (130, 257, 1198), (32, 2048, 1024)])
+def test_sgemm(dev, M, N, K):
+    from zeggs_b200 import ops
+    g = torch.Generator().manual_seed(M * 1000 + N)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    bias = torch.randn(N, generator=g)
+    ref = torch.nn.functional.elu(A.double() @ B.double().T + bias.double())
+    got = ops.sgemm(A.to(dev), B.to(dev), bias.to(dev), act=1)
+    err, sc = report(f"sgemm nt {M}x{N}x{K}", got, ref)
+    assert err <= 2e-5 * max(sc, 1.0)
+    At = torch.randn(K, M, generator=g)
+    Bt = torch.randn(K, N, generator=g)
+    got = ops.sgemm(At.to(dev), Bt.to(dev), trans_a=True)
+    err, sc = report(f"sgemm tn {M}x{N}x{K}", got, At.double().T @ Bt.double())
+    assert err <= 2e-5 * max(sc, 1.0)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 256), (256, 384, 512), (200, 300, 1136), (3072, 2286, 1024)])
+def test_tc_gemm_bf16(dev, M, N, K):
+    from zeggs_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(dev)
+    B = torch.randn(N, K, generator=g).to(dev)
+    Ah, Al = ops.split_bf16(A)
+    Bh, Bl = ops.split_bf16(B)
+    assert torch.equal(Ah[:, :K], A.to(torch.bfloat16))
+    got1 = ops.tc_gemm(Ah, Bh, K=K)
+    ref1 = Ah[:, :K].double() @ Bh[:, :K].double().T
+    err, sc = report(f"tc_gemm bf16 {M}x{N}x{K}", got1, ref1)
+    assert err <= 1e-5 * sc
+    got3 = ops.tc_gemm(Ah, Bh, Al, Bl, K=K)
+    ref3 = A.double() @ B.double().T
+    err, sc = report(f"tc_gemm bf16x3 {M}x{N}x{K}", got3, ref3)
+    assert err <= 2e-5 * sc
+
+
+# ---------------------------------------------------------------------------------------------- mel
+@pytest.mark.parametrize("hop", [200, 160])
+def test_mel_against_reference_golden(dev, golden_dir, hop):
+    from zeggs_b200 import audio
+    g = np.load(os.path.join(golden_dir, "mel_small.npz"))
+    wav = torch.from_numpy(g["wav"]).to(dev)
+    fe = audio.MelFrontEnd(dev, hop_length=hop)
+    n60 = g[f"feat_hop{hop}"].shape[1]
+    mel, feat = fe.forward(wav, 60, n60, want_mel=True, want_feat=True)
+    err, _ = report(f"mel[0,1] hop{hop}", mel, torch.from_numpy(g[f"mel_hop{hop}"]))
+    assert err <= 1e-4
+    err, _ = report(f"feat hop{hop}", feat, torch.from_numpy(g[f"feat_hop{hop}"]))
+    assert err <= 2e-4
+
+
+def test_mel_long_clips_against_oracle(dev):
+    from oracle import mel_oracle
+    from zeggs_b200 import audio, synth
+    wav = synth.make_waveforms(3, 160000, seed=5)
+    wav[2, 50000:90000] = 0.0
+    fe = audio.MelFrontEnd(dev)
+    _, feat = fe.forward(torch.from_numpy(wav).to(dev), 60, 600)
+    for i in range(3):
+        ref = mel_oracle.preprocess_audio(wav[i], 60, 600)
+        err, _ = report(f"feat clip{i}", feat[i], torch.from_numpy(ref))
+        assert err <= 2e-4
+    # drop-in surface (numpy in -> numpy out), ragged length
+    from oracle.make_golden import audio_params
+    x = wav[0, :12345]
+    n60 = int(round(60.0 * len(x) / 16000))
+    got = audio.preprocess_audio(x, 60, n60, audio_params(200), ["mel_spec", "energy"])
+    ref = mel_oracle.preprocess_audio(x, 60, n60)
+    assert got.dtype == np.float32 and got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 2e-4
+
+
+# ---------------------------------------------------------------------------------------------- decoder
+def _decoder_case(dev, H, B, T, seed, P=None, speech=None, style=None):
+    from oracle import model_oracle as mo
+    from zeggs_b200 import synth
+    st = stats_tensors()
+    P = P or synth.make_params(H=H, seed=seed, with_style=False)
+    win = tt(synth.make_pose_windows(B, T, seed=seed))
+    rs = np.random.RandomState(seed)
+    if speech is None:
+        speech = torch.from_numpy((rs.randn(B, T, 64) * 0.5).astype(np.float32))
+        style = torch.from_numpy(rs.randn(B, 1, 64).astype(np.float32)).repeat(1, T, 1)
+    with torch.no_grad():
+        ref = mo.decoder_forward(tt(P), *[win[n][:, 0] for n in NAMES], win["gaze_pos"], speech, style,
+                                 st["anim_input_mean"], st["anim_input_std"], st["anim_output_mean"], st["anim_output_std"], st["dt"])
+        dec = make_decoder(P, H, device=dev)
+        out = dec(*[win[n][:, 0].to(dev) for n in NAMES], win["gaze_pos"].to(dev), speech.to(dev), style.to(dev),
+                  st["parents"], st["anim_input_mean"].to(dev), st["anim_input_std"].to(dev),
+                  st["anim_output_mean"].to(dev), st["anim_output_std"].to(dev), st["dt"])
+    torch.cuda.synchronize()
+    return out, ref
+
+
+@pytest.mark.parametrize("H,B,T", [(64, 2, 6), (128, 4, 9), (128, 40, 5), (512, 16, 12), (1024, 32, 8), (1024, 1, 40)])
+def test_decoder_forward_vs_oracle(dev, H, B, T):
+    out, ref = _decoder_case(dev, H, B, T, seed=100 + H + B)
+    assert len(out) == 8
+    for n, o, r in zip(NAMES, out, ref):
+        assert tuple(o.shape) == tuple(r.shape), n
+        err, sc = report(f"decoder H{H} B{B} T{T} {n}", o, r)
+        assert err <= 2e-4 * max(1.0, sc), n
+
+
+@pytest.mark.parametrize("tag", ["h64", "h128"])
+def test_decoder_forward_vs_reference_golden(dev, golden_dir, tag):
+    from zeggs_b200 import synth
+    g = np.load(os.path.join(golden_dir, f"train_{tag}.npz"))
+    H, B, T = int(g["H"]), int(g["B"]), int(g["T"])
+    P = synth.make_params(H=H, seed=int(g["param_seed"]))
+    st = stats_tensors(dev)
+    win = tt(synth.make_pose_windows(B, T, seed=int(g["input_seed"])), dev)
+    dec = make_decoder(P, H, device=dev)
+    speech = torch.from_numpy(g["speech"]).to(dev)
+    style = torch.from_numpy(g["z"]).to(dev).unsqueeze(1).repeat(1, T, 1)
+    with torch.no_grad():
+        out = dec(*[win[n][:, 0] for n in NAMES], win["gaze_pos"], speech, style, st["parents"], st["anim_input_mean"],
+                  st["anim_input_std"], st["anim_output_mean"], st["anim_output_std"], st["dt"])
+    for n, o in zip(NAMES, out):
+        ref = torch.from_numpy(g["O_" + n])
+        err, sc = report(f"decoder golden {tag} {n}", o, ref)
+        assert err <= 2e-4 * max(1.0, sc), n

@@ -1,0 +1,93 @@
+"""ctypes binding of libzeggs_b200.so (include/zeggs_b200.h).  Fails loudly when the library is
+missing: there is no CPU or PyTorch fallback for the compute path."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzeggs_b200.so")
+
+c_float_p = C.c_void_p  # raw device pointers are passed as integers (tensor.data_ptr())
+
+
+class MelArgs(C.Structure):
+    _fields_ = [("n_clips", C.c_int), ("n_samples", C.c_int), ("n_fft", C.c_int), ("hop", C.c_int),
+                ("n_mels", C.c_int), ("anim_length", C.c_int), ("min_amp", C.c_float),
+                ("frames_per_anim", C.c_double),
+                ("wav", C.c_void_p), ("window", C.c_void_p), ("twiddle", C.c_void_p),
+                ("fb_start", C.c_void_p), ("fb_len", C.c_void_p), ("fb_off", C.c_void_p), ("fb_w", C.c_void_p),
+                ("mel_out", C.c_void_p), ("feat_out", C.c_void_p)]
+
+
+class DecoderFwdArgs(C.Structure):
+    _fields_ = ([("B", C.c_int), ("T", C.c_int), ("H", C.c_int), ("S", C.c_int), ("Z", C.c_int), ("dt", C.c_float)] +
+                [(n, C.c_void_p) for n in (
+                    "W0", "b0", "W_ih0", "b_ih0", "W_hh0", "b_hh0", "W_ih1", "b_ih1", "W_hh1", "b_hh1", "W2", "b2",
+                    "Wc0", "bc0", "Wc1", "bc1", "Wc2", "bc2", "packed",
+                    "in_mean", "in_std", "out_mean", "out_std",
+                    "root_pos0", "root_rot0", "pose0", "gaze_pos", "speech", "style",
+                    "Y", "root_pos", "root_rot", "workspace")] +
+                [("workspace_bytes", C.c_size_t), ("save_for_backward", C.c_int)])
+
+
+# every symbol include/zeggs_b200.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("zeggs_last_error", C.c_char_p, []),
+    ("zeggs_version", C.c_int, []),
+    ("zeggs_launch_count", C.c_longlong, []),
+    ("zeggs_mel_num_frames", C.c_int, [C.c_int, C.c_int, C.c_int]),
+    ("zeggs_mel_forward", C.c_int, [C.POINTER(MelArgs), C.c_void_p]),
+    ("zeggs_decoder_packed_bytes", C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    ("zeggs_decoder_pack_weights", C.c_int, [C.POINTER(DecoderFwdArgs), C.c_void_p, C.c_void_p]),
+    ("zeggs_decoder_workspace_bytes", C.c_size_t, [C.c_int] * 6),
+    ("zeggs_decoder_window_fwd", C.c_int, [C.POINTER(DecoderFwdArgs), C.c_void_p]),
+    ("zeggs_sgemm", C.c_int, [C.c_int] * 4 + [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("zeggs_tc_gemm_bf16", C.c_int, [C.c_int] * 3 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("zeggs_split_bf16", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+]
+
+_lib = None
+
+
+class ZeggsError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ZeggsError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "zeggs_b200 has no CPU fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(l, name)  # AttributeError if the ABI and the header drift apart
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().zeggs_last_error()
+        raise ZeggsError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a contiguous float32/int32 CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ZeggsError("zeggs_b200 kernels take CUDA tensors (no CPU path)")
+    if not t.is_contiguous():
+        raise ZeggsError("tensor must be contiguous")
+    return t.data_ptr()

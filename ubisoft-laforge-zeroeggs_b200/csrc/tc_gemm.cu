@@ -1,0 +1,182 @@
+// tcgen05 / TMEM / TMA GEMM for the batched (non-recurrent) contractions on the path:
+//   C[M,N] (f32) = sum over passes p of  A_p[M,K] (bf16, K-major) * B_p[N,K]^T (bf16, K-major)  (+bias, act)
+// One 128x128 output tile per CTA; BLOCK_K = 64 bf16 (one 128-byte swizzle atom row).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane issues
+// tcgen05.mma, accumulator in TMEM), warps 2..5 = epilogue (tcgen05.ld -> registers -> global).
+// `passes` > 1 implements the split-bf16 ("bf16x3") scheme: x = hi + lo with hi = bf16(x),
+// lo = bf16(x - hi); passes (A_hi,B_hi), (A_lo,B_hi), (A_hi,B_lo) accumulate into the same TMEM tile,
+// recovering ~fp32 product accuracy at 3x the tensor work.
+#include <cuda.h>
+#include "decoder_common.cuh"
+#include "tc_common.cuh"
+
+namespace zeggs {
+
+constexpr int TG_BM = 128, TG_BN = 128, TG_BK = 64, TG_STAGES = 4;
+constexpr int TG_A_BYTES = TG_BM * TG_BK * 2, TG_B_BYTES = TG_BN * TG_BK * 2;
+
+struct TcGemmMaps {
+  CUtensorMap a[2];
+  CUtensorMap b[2];
+};
+
+__global__ void __launch_bounds__(192, 1)
+tc_gemm_kernel(const __grid_constant__ TcGemmMaps maps, int M, int N, int K, int passes,
+               const float* __restrict__ bias, float* __restrict__ C, int ldc, int act, int accumulate) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + TG_STAGES * TG_A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + TG_STAGES * TG_B_BYTES);
+  uint64_t* empty = full + TG_STAGES;
+  uint64_t* tmem_full = empty + TG_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TG_BM, n0 = blockIdx.x * TG_BN;
+  const int kblocks = ceil_div(K, TG_BK);
+  // pass order: (A0,B0), (A1,B0), (A0,B1)
+  const int total = kblocks * (passes == 1 ? 1 : 3);
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < (passes == 1 ? 1 : 2); ++i) { tma_prefetch_desc(&maps.a[i]); tma_prefetch_desc(&maps.b[i]); }
+    for (int s = 0; s < TG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, TG_BN); tmem_relinquish(); }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < total; ++it) {
+        const int s = it % TG_STAGES, ph = (it / TG_STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        const int p = it / kblocks, kb = it - p * kblocks;
+        const CUtensorMap* ma = &maps.a[p == 1 ? 1 : 0];
+        const CUtensorMap* mb = &maps.b[p == 2 ? 1 : 0];
+        mbar_arrive_expect_tx(&full[s], TG_A_BYTES + TG_B_BYTES);
+        tma_load_2d(sA + s * TG_A_BYTES, ma, &full[s], kb * TG_BK, m0);
+        tma_load_2d(sB + s * TG_B_BYTES, mb, &full[s], kb * TG_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_bf16_f32(TG_BM, TG_BN);
+    for (int it = 0; it < total; ++it) {
+      const int s = it % TG_STAGES, ph = (it / TG_STAGES) & 1;
+      mbar_wait(&full[s], ph);
+      tc_fence_after_sync();
+      if (lane == 0) {
+        const uint64_t da = make_smem_desc_sw128(sA + s * TG_A_BYTES);
+        const uint64_t db = make_smem_desc_sw128(sB + s * TG_B_BYTES);
+#pragma unroll
+        for (int k = 0; k < TG_BK / 16; ++k)
+          umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
+        umma_commit(&empty[s]);
+        if (it == total - 1) umma_commit(tmem_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // epilogue: warp w reads TMEM lanes [32*(w%4), +32)
+    const int q = warp & 3;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after_sync();
+    const int m = m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < TG_BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (m < M) {
+        float* crow = C + (size_t)m * ldc + n0 + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + c0 + j;
+          if (n < N) {
+            float x = __uint_as_float(v[j]);
+            if (bias) x += bias[n];
+            if (act == 1) x = elu_f(x); else if (act == 2) x = fmaxf(x, 0.f);
+            if (accumulate) x += crow[j];
+            crow[j] = x;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem_base, TG_BN); }
+}
+
+// fp32 -> (hi, lo) bf16 split, row-major, optional zero padding of the row to ld_out
+__global__ void split_bf16_kernel(const float* __restrict__ x, int rows, int cols, int ld_in,
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ld_out) {
+  const size_t total = (size_t)rows * ld_out;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ld_out), c = (int)(i % ld_out);
+    float v = c < cols ? x[(size_t)r * ld_in + c] : 0.f;
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rows, int K, int ld_elems, int box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  ZCHECK_ARG(fn != nullptr, "tc_gemm: cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TG_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ZCHECK_ARG(r == CUDA_SUCCESS, "tc_gemm: cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%d", (int)r, rows, K, ld_elems);
+  return ZEGGS_OK;
+}
+
+int tc_gemm_launch(int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, int lda,
+                   const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, const float* bias,
+                   float* C, int ldc, int act, int accumulate, cudaStream_t stream) {
+  ZCHECK_ARG(M > 0 && N > 0 && K > 0 && A_hi && B_hi && C, "tc_gemm: bad arguments");
+  ZCHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "tc_gemm: leading dimensions must be multiples of 8 bf16 (16 B)");
+  ZCHECK_ARG(((uintptr_t)A_hi & 15) == 0 && ((uintptr_t)B_hi & 15) == 0, "tc_gemm: operands must be 16-byte aligned");
+  const int passes = (A_lo && B_lo) ? 3 : 1;
+  TcGemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc;
+  if ((rc = encode_map(&maps.a[0], A_hi, M, K, lda, TG_BM))) return rc;
+  if ((rc = encode_map(&maps.b[0], B_hi, N, K, ldb, TG_BN))) return rc;
+  if (passes == 3) {
+    if ((rc = encode_map(&maps.a[1], A_lo, M, K, lda, TG_BM))) return rc;
+    if ((rc = encode_map(&maps.b[1], B_lo, N, K, ldb, TG_BN))) return rc;
+  }
+  const size_t smem = 1024 + TG_STAGES * (TG_A_BYTES + TG_B_BYTES) + (2 * TG_STAGES + 1) * 8 + 16;
+  ZCHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div(N, TG_BN), ceil_div(M, TG_BM));
+  tc_gemm_kernel<<<grid, 192, smem, stream>>>(maps, M, N, K, passes, bias, C, ldc, act, accumulate);
+  count_launch();
+  ZCHECK_LAUNCH();
+  return ZEGGS_OK;
+}
+
+extern "C" int zeggs_tc_gemm_bf16(int M, int N, int K, const void* A_hi, const void* A_lo, int lda, const void* B_hi,
+                                  const void* B_lo, int ldb, const float* bias, float* C, int ldc, int act,
+                                  int accumulate, void* stream) {
+  return tc_gemm_launch(M, N, K, (const __nv_bfloat16*)A_hi, (const __nv_bfloat16*)A_lo, lda, (const __nv_bfloat16*)B_hi,
+                        (const __nv_bfloat16*)B_lo, ldb, bias, C, ldc, act, accumulate, (cudaStream_t)stream);
+}
+
+extern "C" int zeggs_split_bf16(const float* x, int rows, int cols, int ld_in, void* hi, void* lo, int ld_out, void* stream) {
+  ZCHECK_ARG(x && hi && rows > 0 && cols > 0 && ld_out >= cols, "split_bf16: bad arguments");
+  split_bf16_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld_in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld_out);
+  count_launch();
+  ZCHECK_LAUNCH();
+  return ZEGGS_OK;
+}
+
+}  // namespace zeggs

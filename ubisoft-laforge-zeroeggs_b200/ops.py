@@ -1,0 +1,161 @@
+"""Launchers: torch tensors -> C-ABI calls (libzeggs_b200.so).  Plumbing only (buffers, streams,
+autograd wiring); all arithmetic is in csrc/*.cu."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+NJ, P_IN, P_OUT = 75, 1134, 1131
+
+
+def _f32c(t, device=None):
+    t = t.detach() if t.requires_grad else t
+    if device is not None and t.device != device:
+        t = t.to(device)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class _Workspace:
+    """Grow-only per-device scratch buffers owned by the caller side (the library allocates nothing)."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def get(self, key, nbytes, device):
+        b = self.bufs.get((key, str(device)))
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+            self.bufs[(key, str(device))] = b
+        return b
+
+
+WS = _Workspace()
+
+
+def split_pose(Y, root_pos, root_rot):
+    """[B,T,1131] pose vectors -> the reference's 8-tuple (modules.py:153-162, 731-736)."""
+    B, T = Y.shape[0], Y.shape[1]
+    o = 6
+    return (root_pos, root_rot, Y[..., 0:3], Y[..., 3:6],
+            Y[..., o:o + NJ * 3].reshape(B, T, NJ, 3),
+            Y[..., o + NJ * 3:o + NJ * 9].reshape(B, T, NJ, 2, 3),
+            Y[..., o + NJ * 9:o + NJ * 12].reshape(B, T, NJ, 3),
+            Y[..., o + NJ * 12:o + NJ * 15].reshape(B, T, NJ, 3))
+
+
+def _decoder_args(dec, B, T, dev, tensors, stats, dt, save):
+    """Fill a DecoderFwdArgs; returns (args, keepalive list)."""
+    H, S, Z = dec.hidden_size, dec.speech_encoding_size, dec.style_encoding_size
+    l = _lib.lib()
+    w = [_f32c(p, dev) for p in dec._weights()]
+    names = ["W0", "b0", "W_ih0", "b_ih0", "W_hh0", "b_hh0", "W_ih1", "b_ih1", "W_hh1", "b_hh1", "W2", "b2",
+             "Wc0", "bc0", "Wc1", "bc1", "Wc2", "bc2"]
+    a = _lib.DecoderFwdArgs(B=B, T=T, H=H, S=S, Z=Z, dt=dt)
+    for n, t in zip(names, w):
+        setattr(a, n, _lib.ptr(t))
+    keep = list(w)
+    st = [_f32c(s, dev).reshape(-1) for s in stats]
+    for n, t in zip(["in_mean", "in_std", "out_mean", "out_std"], st):
+        setattr(a, n, _lib.ptr(t))
+    keep += st
+    for n, t in tensors.items():
+        setattr(a, n, _lib.ptr(t))
+        keep.append(t)
+    # packed weights: re-packed whenever any parameter's version counter moved
+    ver = tuple(p._version for p in dec._weights()) + tuple(p.data_ptr() for p in dec._weights())
+    cache = getattr(dec, "_zeggs_packed", None)
+    if cache is None or cache[0] != ver or cache[1].device != dev:
+        nbytes = l.zeggs_decoder_packed_bytes(H, S, Z)
+        if nbytes == 0:
+            raise _lib.ZeggsError(f"decoder hidden size {H} unsupported")
+        packed = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+        _lib.check(l.zeggs_decoder_pack_weights(a, packed.data_ptr(), _lib.stream_ptr()), "zeggs_decoder_pack_weights")
+        dec.__dict__["_zeggs_packed"] = (ver, packed)
+        cache = dec.__dict__["_zeggs_packed"]
+    a.packed = cache[1].data_ptr()
+    keep.append(cache[1])
+    wsb = l.zeggs_decoder_workspace_bytes(B, T, H, S, Z, int(save))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if save else WS.get("dec_fwd", wsb, dev)
+    a.workspace = ws.data_ptr()
+    a.workspace_bytes = wsb
+    a.save_for_backward = int(save)
+    keep.append(ws)
+    return a, keep, ws
+
+
+def decoder_window_forward(dec, root_pos0, root_rot0, pose0, gaze_pos, speech, style, stats, dt, save=False):
+    dev = speech.device
+    if dev.type != "cuda":
+        raise _lib.ZeggsError("zeggs_b200.Decoder runs on CUDA tensors only (no CPU fallback)")
+    B, T = speech.shape[0], speech.shape[1]
+    tensors = dict(root_pos0=_f32c(root_pos0, dev).reshape(B, 3), root_rot0=_f32c(root_rot0, dev).reshape(B, 4),
+                   pose0=_f32c(pose0, dev).reshape(B, P_OUT), gaze_pos=_f32c(gaze_pos, dev).reshape(B, T, 3),
+                   speech=_f32c(speech, dev), style=_f32c(style, dev))
+    if tensors["style"].shape[:2] != (B, T):
+        raise _lib.ZeggsError("style_encoding must be [B,T,Z] (modules.py:119)")
+    Y = torch.empty((B, T, P_OUT), dtype=torch.float32, device=dev)
+    rp = torch.empty((B, T, 3), dtype=torch.float32, device=dev)
+    rq = torch.empty((B, T, 4), dtype=torch.float32, device=dev)
+    tensors.update(Y=Y, root_pos=rp, root_rot=rq)
+    a, keep, ws = _decoder_args(dec, B, T, dev, tensors, stats, dt, save)
+    _lib.check(_lib.lib().zeggs_decoder_window_fwd(a, _lib.stream_ptr()), "zeggs_decoder_window_fwd")
+    return Y, rp, rq, (a, keep, ws)
+
+
+def decoder_window(dec, root_pos0, root_rot0, pose0, gaze_pos, speech, style,
+                   in_mean, in_std, out_mean, out_std, dt):
+    if speech.device.type != "cuda":
+        raise _lib.ZeggsError("zeggs_b200.Decoder runs on CUDA tensors only (no CPU fallback)")
+    needs_grad = torch.is_grad_enabled() and (
+        any(p.requires_grad for p in dec.parameters()) or speech.requires_grad or style.requires_grad)
+    if needs_grad:
+        from .autograd import DecoderWindowFn
+        return DecoderWindowFn.apply(dec, root_pos0, root_rot0, pose0, gaze_pos, speech, style,
+                                     in_mean, in_std, out_mean, out_std, dt, *dec._weights())
+    Y, rp, rq, _ = decoder_window_forward(dec, root_pos0, root_rot0, pose0, gaze_pos, speech, style,
+                                          (in_mean, in_std, out_mean, out_std), dt, save=False)
+    return Y, rp, rq
+
+
+def sgemm(A, B, bias=None, act=0, trans_a=False, out=None, accumulate=False):
+    """trans_a False: act(A[M,K] @ B[N,K]^T + bias);  True: A[K,M]^T @ B[K,N]."""
+    if trans_a:
+        K, M = A.shape
+        N = B.shape[1]
+    else:
+        M, K = A.shape
+        N = B.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    _lib.check(_lib.lib().zeggs_sgemm(int(trans_a), M, N, K, _lib.ptr(A), A.stride(0), _lib.ptr(B), B.stride(0),
+                                     _lib.ptr(bias) if bias is not None else None, _lib.ptr(out), out.stride(0),
+                                     act, int(accumulate), _lib.stream_ptr()), "zeggs_sgemm")
+    return out
+
+
+def split_bf16(x, want_lo=True, pad_to=8):
+    """fp32 [rows, cols] -> (hi, lo) bf16 [rows, ld] with ld = cols rounded up to `pad_to` (zero padded)."""
+    rows, cols = x.shape
+    ld = (cols + pad_to - 1) // pad_to * pad_to
+    hi = torch.empty((rows, ld), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty((rows, ld), dtype=torch.bfloat16, device=x.device) if want_lo else None
+    _lib.check(_lib.lib().zeggs_split_bf16(_lib.ptr(x), rows, cols, x.stride(0), hi.data_ptr(),
+                                          lo.data_ptr() if want_lo else None, ld, _lib.stream_ptr()), "zeggs_split_bf16")
+    return hi, lo
+
+
+def tc_gemm(A_hi, B_hi, A_lo=None, B_lo=None, K=None, bias=None, act=0, out=None, accumulate=False):
+    """tcgen05 GEMM: act(A[M,K] @ B[N,K]^T + bias); bf16 operands (optionally split hi/lo), fp32 result."""
+    M, N = A_hi.shape[0], B_hi.shape[0]
+    K = K or A_hi.shape[1]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A_hi.device)
+    _lib.check(_lib.lib().zeggs_tc_gemm_bf16(
+        M, N, K, A_hi.data_ptr(), A_lo.data_ptr() if A_lo is not None else None, A_hi.stride(0),
+        B_hi.data_ptr(), B_lo.data_ptr() if B_lo is not None else None, B_hi.stride(0),
+        _lib.ptr(bias) if bias is not None else None, _lib.ptr(out), out.stride(0), act, int(accumulate),
+        _lib.stream_ptr()), "zeggs_tc_gemm_bf16")
+    return out
