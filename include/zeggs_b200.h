@@ -106,10 +106,32 @@ int zeggs_decoder_pack_weights(const zeggs_decoder_fwd_args* a, float* packed, v
 size_t zeggs_decoder_workspace_bytes(int B, int T, int H, int S, int Z, int save_for_backward);
 int zeggs_decoder_window_fwd(const zeggs_decoder_fwd_args* a, void* stream);
 
+/* Backward of zeggs_decoder_window_fwd (the autograd of modules.py:47-162: full BPTT through the GRU stack,
+ * the pose feedback, the gaze transform and the root integration).  Needs the forward's workspace
+ * (save_for_backward = 1) and outputs (Y, root_pos, root_rot) untouched.  Gradient buffers have the shapes
+ * of the corresponding weights and are overwritten. */
+typedef struct {
+  const float* dY;       /* [B,T,1131] upstream gradient of the pose vectors (NULL = 0) */
+  const float* dRootPos; /* [B,T,3] (NULL = 0) */
+  const float* dRootRot; /* [B,T,4] (NULL = 0) */
+  const float* packed_bwd; /* zeggs_decoder_pack_weights_bwd output */
+  float *dW0, *db0, *dW_ih0, *db_ih0, *dW_hh0, *db_hh0, *dW_ih1, *db_ih1, *dW_hh1, *db_hh1, *dW2, *db2;
+  float *dWc0, *dbc0, *dWc1, *dbc1, *dWc2, *dbc2;
+  float* dSpeech; /* [B,T,S] or NULL */
+  float* dStyle;  /* [B,T,Z] or NULL */
+  void* workspace;
+  size_t workspace_bytes;
+} zeggs_decoder_bwd_args;
+size_t zeggs_decoder_packed_bwd_bytes(int H, int S, int Z);
+int zeggs_decoder_pack_weights_bwd(const zeggs_decoder_fwd_args* a, float* packed, void* stream);
+size_t zeggs_decoder_bwd_workspace_bytes(int B, int T, int H, int S, int Z);
+int zeggs_decoder_window_bwd(const zeggs_decoder_fwd_args* f, const zeggs_decoder_bwd_args* b, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Generic fp32 GEMM used for the batched (non-recurrent) linear layers:
  *   C[M,N] = act(A[M,K] * B[N,K]^T + bias[N])            (trans_a = 0;  nn.Linear)
  *   C[M,N] = A[K,M]^T * B[K,N] (+ C if accumulate)        (trans_a = 1;  weight gradients)
+ *   C[M,N] = A[M,K] * B[K,N]                              (trans_a = 2;  input gradients)
  * act: 0 none, 1 ELU, 2 ReLU.
  */
 int zeggs_sgemm(int trans_a, int M, int N, int K, const float* A, int lda, const float* B, int ldb,

@@ -149,3 +149,43 @@ def test_decoder_forward_vs_reference_golden(dev, golden_dir, tag):
         ref = torch.from_numpy(g["O_" + n])
         err, sc = report(f"decoder golden {tag} {n}", o, ref)
         assert err <= 2e-4 * max(1.0, sc), n
+
+
+# ---------------------------------------------------------------------------------------------- decoder backward (BPTT)
+@pytest.mark.parametrize("H,B,T", [(64, 2, 6), (128, 4, 9), (128, 40, 4), (512, 16, 6), (1024, 32, 5)])
+def test_decoder_backward_vs_oracle_autograd(dev, H, B, T):
+    from oracle import model_oracle as mo
+    from zeggs_b200 import synth
+    seed = 300 + H + B
+    st = stats_tensors()
+    P = synth.make_params(H=H, seed=seed, with_style=False)
+    win = tt(synth.make_pose_windows(B, T, seed=seed))
+    rs = np.random.RandomState(seed)
+    speech = torch.from_numpy((rs.randn(B, T, 64) * 0.5).astype(np.float32))
+    style = torch.from_numpy(rs.randn(B, T, 64).astype(np.float32))
+    cot = [torch.from_numpy(rs.randn(*win[n].shape).astype(np.float32)) for n in NAMES]
+    # oracle (CPU autograd)
+    Pt = {k: v.clone().requires_grad_(True) for k, v in tt(P).items() if k.startswith("decoder.")}
+    sp_o, sy_o = speech.clone().requires_grad_(True), style.clone().requires_grad_(True)
+    ref = mo.decoder_forward(Pt, *[win[n][:, 0] for n in NAMES], win["gaze_pos"], sp_o, sy_o, st["anim_input_mean"],
+                             st["anim_input_std"], st["anim_output_mean"], st["anim_output_std"], st["dt"])
+    loss_o = sum((o * c).sum() for o, c in zip(ref, cot))
+    keys = sorted(Pt.keys())
+    g_ref = torch.autograd.grad(loss_o, [Pt[k] for k in keys] + [sp_o, sy_o])
+    # CUDA path
+    dec = make_decoder(P, H, device=dev).train()
+    sp_g, sy_g = speech.to(dev).requires_grad_(True), style.to(dev).requires_grad_(True)
+    out = dec(*[win[n][:, 0].to(dev) for n in NAMES], win["gaze_pos"].to(dev), sp_g, sy_g, st["parents"],
+              st["anim_input_mean"].to(dev), st["anim_input_std"].to(dev), st["anim_output_mean"].to(dev),
+              st["anim_output_std"].to(dev), st["dt"])
+    loss_g = sum((o * c.to(dev)).sum() for o, c in zip(out, cot))
+    named = dict(dec.named_parameters())
+    g_got = torch.autograd.grad(loss_g, [named[k[len("decoder."):]] for k in keys] + [sp_g, sy_g])
+    torch.cuda.synchronize()
+    assert abs(loss_g.item() - loss_o.item()) <= 1e-4 * max(1.0, abs(loss_o.item()))
+    bad = []
+    for k, a, b in zip(keys + ["speech", "style"], g_got, g_ref):
+        err, sc = report(f"bwd H{H} B{B} T{T} {k}", a, b)
+        if not err <= 3e-4 * max(sc, 1e-6):
+            bad.append((k, err, sc))
+    assert not bad, bad

@@ -29,6 +29,14 @@ class DecoderFwdArgs(C.Structure):
                 [("workspace_bytes", C.c_size_t), ("save_for_backward", C.c_int)])
 
 
+class DecoderBwdArgs(C.Structure):
+    _fields_ = ([(n, C.c_void_p) for n in (
+        "dY", "dRootPos", "dRootRot", "packed_bwd",
+        "dW0", "db0", "dW_ih0", "db_ih0", "dW_hh0", "db_hh0", "dW_ih1", "db_ih1", "dW_hh1", "db_hh1", "dW2", "db2",
+        "dWc0", "dbc0", "dWc1", "dbc1", "dWc2", "dbc2", "dSpeech", "dStyle", "workspace")] +
+        [("workspace_bytes", C.c_size_t)])
+
+
 # every symbol include/zeggs_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("zeggs_last_error", C.c_char_p, []),
@@ -40,6 +48,10 @@ SYMBOLS = [
     ("zeggs_decoder_pack_weights", C.c_int, [C.POINTER(DecoderFwdArgs), C.c_void_p, C.c_void_p]),
     ("zeggs_decoder_workspace_bytes", C.c_size_t, [C.c_int] * 6),
     ("zeggs_decoder_window_fwd", C.c_int, [C.POINTER(DecoderFwdArgs), C.c_void_p]),
+    ("zeggs_decoder_packed_bwd_bytes", C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    ("zeggs_decoder_pack_weights_bwd", C.c_int, [C.POINTER(DecoderFwdArgs), C.c_void_p, C.c_void_p]),
+    ("zeggs_decoder_bwd_workspace_bytes", C.c_size_t, [C.c_int] * 5),
+    ("zeggs_decoder_window_bwd", C.c_int, [C.POINTER(DecoderFwdArgs), C.POINTER(DecoderBwdArgs), C.c_void_p]),
     ("zeggs_sgemm", C.c_int, [C.c_int] * 4 + [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("zeggs_tc_gemm_bf16", C.c_int, [C.c_int] * 3 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,

@@ -94,6 +94,49 @@ __host__ __device__ inline Q4 quat_from_helical(V3 h) {
   return r;
 }
 
+// ---- backward helpers (BPTT through the root integration, modules.py:696, 739-740)
+// f = quat_mul_vec(q, v); given df returns dq, dv
+__host__ __device__ inline void quat_mul_vec_bwd(Q4 q, V3 v, V3 df, Q4& dq, V3& dv) {
+  V3 u = v3(q.x, q.y, q.z);
+  V3 t = 2.0f * cross(u, v);
+  V3 dt = q.w * df + cross(df, u);
+  V3 du = cross(t, df) + 2.0f * cross(v, dt);
+  dv = df + 2.0f * cross(dt, u);
+  dq.w = dot(df, t); dq.x = du.x; dq.y = du.y; dq.z = du.z;
+}
+// r = quat_mul(x, y); given dr returns dx, dy
+__host__ __device__ inline void quat_mul_bwd(Q4 x, Q4 y, Q4 d, Q4& dx, Q4& dy) {
+  dx.w = d.w * y.w + d.x * y.x + d.y * y.y + d.z * y.z;
+  dx.x = -d.w * y.x + d.x * y.w - d.y * y.z + d.z * y.y;
+  dx.y = -d.w * y.y + d.x * y.z + d.y * y.w - d.z * y.x;
+  dx.z = -d.w * y.z - d.x * y.y + d.y * y.x + d.z * y.w;
+  dy.w = d.w * x.w + d.x * x.x + d.y * x.y + d.z * x.z;
+  dy.x = -d.w * x.x + d.x * x.w + d.y * x.z - d.z * x.y;
+  dy.y = -d.w * x.y - d.x * x.z + d.y * x.w + d.z * x.x;
+  dy.z = -d.w * x.z + d.x * x.y - d.y * x.x + d.z * x.w;
+}
+// E = quat_from_helical(h) = quat_exp(h/2); given dE returns dh
+__host__ __device__ inline V3 quat_from_helical_bwd(V3 h, Q4 dE) {
+  V3 x = 0.5f * h;
+  float a2 = dot(x, x);
+  float a = sqrtf(a2);
+  V3 dEv = v3(dE.x, dE.y, dE.z);
+  V3 dx;
+  if (a < 1e-5f) {
+    float rn = sqrtf(1.0f + a2);
+    float n = rn + 1e-5f;
+    float proj = dE.w + dot(dEv, x);            // dE . [1, x]
+    dx = (1.0f / n) * dEv - (proj / (n * n * rn)) * x;
+  } else {
+    float sn = sinf(a), cs = cosf(a);
+    float s = sn / a;
+    float dsda = (a * cs - sn) / a2;
+    float coef = (-dE.w * sn + dot(dEv, x) * dsda) / a;
+    dx = s * dEv + coef * x;
+  }
+  return 0.5f * dx;
+}
+
 __device__ __forceinline__ float elu_f(float x) { return x > 0.0f ? x : expm1f(x); }
 __device__ __forceinline__ float elu_grad_from_pre(float pre) { return pre > 0.0f ? 1.0f : expf(pre); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }

@@ -11,6 +11,9 @@ constexpr int K1P = 1136;  // P_IN (1134) rounded up to the 16-row k-chunk
 void count_launch();
 int sgemm_launch(int trans_a, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                  const float* bias, float* C, int ldc, int act, int accumulate, cudaStream_t stream);
+int sgemm_batched_launch(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                         const float* bias, float* C, int ldc, int act, int accumulate, int batch,
+                         long long sA, long long sB, long long sC, cudaStream_t stream);
 
 // units per CTA: the grid G = H/U must fit one CTA per SM (148)
 inline int pick_U(int H) {

@@ -1,15 +1,19 @@
 // Generic fp32 SIMT GEMM for the batched (non-recurrent) linear layers and weight gradients.
 //   trans_a = 0:  C[M,N] = act(A[M,K] * B[N,K]^T + bias)     (nn.Linear forward / input gradients)
 //   trans_a = 1:  C[M,N] = A[K,M]^T * B[K,N] (+ C)           (weight gradients, contraction over rows)
+//   trans_a = 2:  C[M,N] = A[M,K]   * B[K,N]                 (input gradients)
 // 64x64x16 tiles, 256 threads, 4x4 register tile per thread.
 #include "decoder_common.cuh"
 
 namespace zeggs {
 
-template <bool TA>
+// MODE 0: A[M,K] B[N,K] (NT)   1: A[K,M] B[K,N] (TN)   2: A[M,K] B[K,N] (NN); blockIdx.z = batch
+template <int MODE>
 __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
                                                     const float* __restrict__ B, int ldb, const float* __restrict__ bias,
-                                                    float* __restrict__ C, int ldc, int act, int accumulate) {
+                                                    float* __restrict__ C, int ldc, int act, int accumulate,
+                                                    long long sA, long long sB, long long sC) {
+  A += blockIdx.z * sA; B += blockIdx.z * sB; C += blockIdx.z * sC;
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -20,13 +24,20 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (int k0 = 0; k0 < K; k0 += 16) {
-    if (TA) {
+    if (MODE == 1) {
       // A[k][m], B[k][n]: 16 x 64 each, 4 elements per thread, coalesced along m / n
       for (int i = tid; i < 16 * 64; i += 256) {
         int kk = i >> 6, mm = i & 63;
         int k = k0 + kk;
         As[kk][mm] = (k < K && m0 + mm < M) ? A[(size_t)k * lda + m0 + mm] : 0.f;
         Bs[kk][mm] = (k < K && n0 + mm < N) ? B[(size_t)k * ldb + n0 + mm] : 0.f;
+      }
+    } else if (MODE == 2) {
+      for (int i = tid; i < 16 * 64; i += 256) {
+        int mm = i >> 4, kk = i & 15;
+        As[kk][mm] = (k0 + kk < K && m0 + mm < M) ? A[(size_t)(m0 + mm) * lda + k0 + kk] : 0.f;
+        int kb = i >> 6, nn = i & 63;
+        Bs[kb][nn] = (k0 + kb < K && n0 + nn < N) ? B[(size_t)(k0 + kb) * ldb + n0 + nn] : 0.f;
       }
     } else {
       for (int i = tid; i < 16 * 64; i += 256) {
@@ -66,15 +77,22 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
   }
 }
 
-int sgemm_launch(int trans_a, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-                 const float* bias, float* C, int ldc, int act, int accumulate, cudaStream_t stream) {
-  ZCHECK_ARG(M > 0 && N > 0 && K > 0 && A && B && C, "sgemm: bad arguments M=%d N=%d K=%d", M, N, K);
-  dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
-  if (trans_a) sgemm_kernel<true><<<grid, 256, 0, stream>>>(M, N, K, A, lda, B, ldb, bias, C, ldc, act, accumulate);
-  else sgemm_kernel<false><<<grid, 256, 0, stream>>>(M, N, K, A, lda, B, ldb, bias, C, ldc, act, accumulate);
+int sgemm_batched_launch(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                         const float* bias, float* C, int ldc, int act, int accumulate, int batch,
+                         long long sA, long long sB, long long sC, cudaStream_t stream) {
+  ZCHECK_ARG(M > 0 && N > 0 && K > 0 && A && B && C && batch >= 1 && batch <= 65535, "sgemm: bad arguments M=%d N=%d K=%d batch=%d", M, N, K, batch);
+  dim3 grid(ceil_div(N, 64), ceil_div(M, 64), batch);
+  if (mode == 1) sgemm_kernel<1><<<grid, 256, 0, stream>>>(M, N, K, A, lda, B, ldb, bias, C, ldc, act, accumulate, sA, sB, sC);
+  else if (mode == 2) sgemm_kernel<2><<<grid, 256, 0, stream>>>(M, N, K, A, lda, B, ldb, bias, C, ldc, act, accumulate, sA, sB, sC);
+  else sgemm_kernel<0><<<grid, 256, 0, stream>>>(M, N, K, A, lda, B, ldb, bias, C, ldc, act, accumulate, sA, sB, sC);
   count_launch();
   ZCHECK_LAUNCH();
   return ZEGGS_OK;
+}
+
+int sgemm_launch(int trans_a, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                 const float* bias, float* C, int ldc, int act, int accumulate, cudaStream_t stream) {
+  return sgemm_batched_launch(trans_a, M, N, K, A, lda, B, ldb, bias, C, ldc, act, accumulate, 1, 0, 0, 0, stream);
 }
 
 extern "C" int zeggs_sgemm(int trans_a, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
