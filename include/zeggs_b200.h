@@ -128,6 +128,60 @@ size_t zeggs_decoder_bwd_workspace_bytes(int B, int T, int H, int S, int Z);
 int zeggs_decoder_window_bwd(const zeggs_decoder_fwd_args* f, const zeggs_decoder_bwd_args* b, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * SpeechEncoder (modules.py:249-272): conv k1 + ELU + drop -> conv k31 (replicate 'same') + ELU + drop -> Linear + ELU.
+ * x is the already normalised feature tensor (train.py:232-234).  mask0/mask1 are dropout multipliers
+ * (0 or 1/(1-p), p = 0.2) in [B,T,C] layout, NULL in eval mode.  The workspace keeps the activations for _bwd.
+ */
+typedef struct {
+  int B, T, C_in, H, O;
+  const float *W0, *b0; /* layer0.weight [H, C_in, 1] */
+  const float *W1, *b1; /* layer1.weight [O, H, 31]  */
+  const float *W2, *b2; /* layer2.weight [O, O]      */
+  const float* x;       /* [B,T,C_in] */
+  const float* mask0;   /* [B,T,H] or NULL */
+  const float* mask1;   /* [B,T,O] or NULL */
+  float* y;             /* [B,T,O] */
+  void* workspace;
+  size_t workspace_bytes;
+} zeggs_speech_enc_args;
+typedef struct {
+  const float* dy; /* [B,T,O] */
+  float *dW0, *db0, *dW1, *db1, *dW2, *db2;
+} zeggs_speech_enc_grads;
+size_t zeggs_speech_enc_workspace_bytes(int B, int T, int C_in, int H, int O);
+int zeggs_speech_enc_fwd(const zeggs_speech_enc_args* a, void* stream);
+int zeggs_speech_enc_bwd(const zeggs_speech_enc_args* a, const zeggs_speech_enc_grads* g, void* stream);
+
+/* StyleEncoder, type "attn", use_vae (modules.py:278-304, 346-420, 484-651): two conv k3 + ReLU + LayerNorm + drop,
+ * + sinusoidal positions, one FFT block (4-head self-attention + residual LN, 2x conv k3 feed-forward + residual LN),
+ * mean over time, mu/logvar split, z = mu + eps * exp(logvar/2) / temperature.
+ * x is the normalised style example [B,T,C_in]; eps [B,E/2] is the N(0,1) sample (NULL = 0); pe [T,E] the
+ * positional table; masks are dropout multipliers (NULL = eval): c1 [B,T,H], c2/ao/ff [B,T,E], attn [B,nheads,T,T].
+ */
+typedef struct {
+  int B, T, C_in, H, E, nheads;
+  float temperature;
+  const float *Wc1, *bc1, *ln1_g, *ln1_b; /* encoder.convs.0.conv, encoder.convs.2 */
+  const float *Wc2, *bc2, *ln2_g, *ln2_b; /* encoder.convs.4.conv, encoder.convs.6 */
+  const float *Win, *bin, *Wout, *bout, *ln3_g, *ln3_b; /* blocks.0.attention.* */
+  const float *Wf1, *bf1, *Wf2, *bf2, *ln4_g, *ln4_b;   /* blocks.0.feed_forward.* */
+  const float *x, *eps, *pe;
+  const float *mask_c1, *mask_c2, *mask_attn, *mask_ao, *mask_ff;
+  float *z, *mu, *logvar; /* [B, E/2] each */
+  void* workspace;
+  size_t workspace_bytes;
+} zeggs_style_enc_args;
+typedef struct {
+  const float *dz, *dmu, *dlogvar; /* [B,E/2], any may be NULL */
+  float *dWc1, *dbc1, *dln1_g, *dln1_b, *dWc2, *dbc2, *dln2_g, *dln2_b;
+  float *dWin, *dbin, *dWout, *dbout, *dln3_g, *dln3_b;
+  float *dWf1, *dbf1, *dWf2, *dbf2, *dln4_g, *dln4_b;
+} zeggs_style_enc_grads;
+size_t zeggs_style_enc_workspace_bytes(int B, int T, int C_in, int H, int E, int nheads);
+int zeggs_style_enc_fwd(const zeggs_style_enc_args* a, void* stream);
+int zeggs_style_enc_bwd(const zeggs_style_enc_args* a, const zeggs_style_enc_grads* g, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Generic fp32 GEMM used for the batched (non-recurrent) linear layers:
  *   C[M,N] = act(A[M,K] * B[N,K]^T + bias[N])            (trans_a = 0;  nn.Linear)
  *   C[M,N] = A[K,M]^T * B[K,N] (+ C if accumulate)        (trans_a = 1;  weight gradients)

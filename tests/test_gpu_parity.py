@@ -189,3 +189,74 @@ def test_decoder_backward_vs_oracle_autograd(dev, H, B, T):
         if not err <= 3e-4 * max(sc, 1e-6):
             bad.append((k, err, sc))
     assert not bad, bad
+
+
+# ---------------------------------------------------------------------------------------------- encoders
+def _load(mod, P, prefix, dev):
+    mod.load_state_dict({k[len(prefix):]: torch.from_numpy(v) for k, v in P.items() if k.startswith(prefix)})
+    return mod.to(dev)
+
+
+@pytest.mark.parametrize("B,T,train", [(2, 6, False), (3, 40, True), (4, 97, True)])
+def test_speech_encoder_fwd_bwd(dev, B, T, train):
+    """abs <= 1e-5 forward, rel 2e-4 gradients vs oracle autograd (same injected dropout masks)."""
+    from oracle import model_oracle as mo
+    from zeggs_b200 import modules, synth
+    P = synth.make_params(H=64, seed=21)
+    rs = np.random.RandomState(B * 100 + T)
+    x = torch.from_numpy(rs.randn(B, T, 81).astype(np.float32))
+    masks = None
+    if train:
+        masks = [torch.from_numpy(((rs.rand(B, T, 64) >= 0.2) / 0.8).astype(np.float32)) for _ in range(2)]
+    cot = torch.from_numpy(rs.randn(B, T, 64).astype(np.float32))
+    Pt = {k: v.clone().requires_grad_(True) for k, v in tt(P).items() if k.startswith("speech_encoder.")}
+    ref = mo.speech_encoder(Pt, x, None if masks is None else [m.transpose(1, 2) for m in masks])
+    keys = sorted(Pt)
+    g_ref = torch.autograd.grad((ref * cot).sum(), [Pt[k] for k in keys])
+    enc = _load(modules.SpeechEncoder(81, 64, 64), P, "speech_encoder.", dev)
+    enc.train(train)
+    out = enc(x.to(dev), None if masks is None else [m.to(dev) for m in masks])
+    named = dict(enc.named_parameters())
+    g_got = torch.autograd.grad((out * cot.to(dev)).sum(), [named[k[len("speech_encoder."):]] for k in keys])
+    err, sc = report(f"speech fwd B{B} T{T}", out, ref)
+    assert err <= 1e-5 * max(1.0, sc)
+    for k, a, b in zip(keys, g_got, g_ref):
+        err, sc = report(f"speech bwd {k}", a, b)
+        assert err <= 2e-4 * max(sc, 1e-6), k
+
+
+@pytest.mark.parametrize("B,T,train", [(2, 16, False), (3, 33, True), (2, 130, True)])
+def test_style_encoder_fwd_bwd(dev, B, T, train):
+    """abs <= 2e-5 on (z, mu, logvar); rel 3e-4 gradients vs oracle autograd (injected eps and dropout masks)."""
+    from oracle import model_oracle as mo
+    from zeggs_b200 import modules, synth
+    P = synth.make_params(H=64, seed=22)
+    st = stats_tensors()
+    rs = np.random.RandomState(B * 100 + T)
+    x = (torch.from_numpy(synth.make_style_example(B, T, seed=B + T)) - st["anim_input_mean"]) / st["anim_input_std"]
+    eps = torch.from_numpy(rs.randn(B, 64).astype(np.float32))
+    masks = None
+    if train:
+        mk = lambda shape, p: torch.from_numpy(((rs.rand(*shape) >= p) / (1 - p)).astype(np.float32))
+        masks = dict(c1=mk((B, T, 512), 0.2), c2=mk((B, T, 128), 0.2), attn=mk((B, 4, T, T), 0.1), ao=mk((B, T, 128), 0.1),
+                     ff=mk((B, T, 128), 0.1))
+    cots = [torch.from_numpy(rs.randn(B, 64).astype(np.float32)) for _ in range(3)]
+    Pt = {k: v.clone().requires_grad_(True) for k, v in tt(P).items() if k.startswith("style_encoder.")}
+    ref = mo.style_encoder(Pt, x, eps=eps, temperature=1.3, masks=masks)
+    keys = sorted(Pt)
+    g_ref = torch.autograd.grad(sum((r * c).sum() for r, c in zip(ref, cots)), [Pt[k] for k in keys])
+    enc = _load(modules.StyleEncoder(1134, 512, 64, type="attn", use_vae=True), P, "style_encoder.", dev)
+    enc.train(train)
+    out = enc(x.to(dev), 1.3, eps=eps.to(dev), masks=None if masks is None else {k: v.to(dev) for k, v in masks.items()})
+    named = dict(enc.named_parameters())
+    g_got = torch.autograd.grad(sum((o * c.to(dev)).sum() for o, c in zip(out, cots)),
+                                [named[k[len("style_encoder."):]] for k in keys])
+    for n, o, r in zip(("z", "mu", "logvar"), out, ref):
+        err, sc = report(f"style fwd B{B} T{T} {n}", o, r)
+        assert err <= 2e-5 * max(1.0, sc), n
+    bad = []
+    for k, a, b in zip(keys, g_got, g_ref):
+        err, sc = report(f"style bwd {k}", a, b)
+        if not err <= 3e-4 * max(sc, 1e-6):
+            bad.append((k, err, sc))
+    assert not bad, bad

@@ -37,6 +37,24 @@ class DecoderBwdArgs(C.Structure):
         [("workspace_bytes", C.c_size_t)])
 
 
+def _struct(name, ints=(), floats=(), ptrs=(), tail=()):
+    fields = [(n, C.c_int) for n in ints] + [(n, C.c_float) for n in floats] + [(n, C.c_void_p) for n in ptrs] + list(tail)
+    return type(name, (C.Structure,), {"_fields_": fields})
+
+
+SpeechEncArgs = _struct("SpeechEncArgs", ints=("B", "T", "C_in", "H", "O"),
+                        ptrs=("W0", "b0", "W1", "b1", "W2", "b2", "x", "mask0", "mask1", "y", "workspace"),
+                        tail=[("workspace_bytes", C.c_size_t)])
+SpeechEncGrads = _struct("SpeechEncGrads", ptrs=("dy", "dW0", "db0", "dW1", "db1", "dW2", "db2"))
+STYLE_W = ("Wc1", "bc1", "ln1_g", "ln1_b", "Wc2", "bc2", "ln2_g", "ln2_b", "Win", "bin", "Wout", "bout", "ln3_g", "ln3_b",
+           "Wf1", "bf1", "Wf2", "bf2", "ln4_g", "ln4_b")
+StyleEncArgs = _struct("StyleEncArgs", ints=("B", "T", "C_in", "H", "E", "nheads"), floats=("temperature",),
+                       ptrs=STYLE_W + ("x", "eps", "pe", "mask_c1", "mask_c2", "mask_attn", "mask_ao", "mask_ff",
+                                       "z", "mu", "logvar", "workspace"),
+                       tail=[("workspace_bytes", C.c_size_t)])
+StyleEncGrads = _struct("StyleEncGrads", ptrs=("dz", "dmu", "dlogvar") + tuple("d" + n for n in STYLE_W))
+
+
 # every symbol include/zeggs_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("zeggs_last_error", C.c_char_p, []),
@@ -52,6 +70,12 @@ SYMBOLS = [
     ("zeggs_decoder_pack_weights_bwd", C.c_int, [C.POINTER(DecoderFwdArgs), C.c_void_p, C.c_void_p]),
     ("zeggs_decoder_bwd_workspace_bytes", C.c_size_t, [C.c_int] * 5),
     ("zeggs_decoder_window_bwd", C.c_int, [C.POINTER(DecoderFwdArgs), C.POINTER(DecoderBwdArgs), C.c_void_p]),
+    ("zeggs_speech_enc_workspace_bytes", C.c_size_t, [C.c_int] * 5),
+    ("zeggs_speech_enc_fwd", C.c_int, [C.POINTER(SpeechEncArgs), C.c_void_p]),
+    ("zeggs_speech_enc_bwd", C.c_int, [C.POINTER(SpeechEncArgs), C.POINTER(SpeechEncGrads), C.c_void_p]),
+    ("zeggs_style_enc_workspace_bytes", C.c_size_t, [C.c_int] * 6),
+    ("zeggs_style_enc_fwd", C.c_int, [C.POINTER(StyleEncArgs), C.c_void_p]),
+    ("zeggs_style_enc_bwd", C.c_int, [C.POINTER(StyleEncArgs), C.POINTER(StyleEncGrads), C.c_void_p]),
     ("zeggs_sgemm", C.c_int, [C.c_int] * 4 + [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("zeggs_tc_gemm_bf16", C.c_int, [C.c_int] * 3 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,

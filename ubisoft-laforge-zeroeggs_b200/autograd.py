@@ -60,3 +60,66 @@ class DecoderWindowFn(torch.autograd.Function):
         ctx.state = None
         return (None, None, None, None, None, dSpeech if ctx.need_cond[0] else None, dStyle if ctx.need_cond[1] else None,
                 None, None, None, None, None) + tuple(grads)
+
+
+class SpeechEncoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, enc, x, masks, *weights):
+        l = _lib.lib()
+        x = ops._f32c(x)
+        B, T = x.shape[0], x.shape[1]
+        Cin, H, O = weights[0].shape[1], weights[0].shape[0], weights[2].shape[0]
+        y = torch.empty((B, T, O), dtype=torch.float32, device=x.device)
+        ws = torch.empty(l.zeggs_speech_enc_workspace_bytes(B, T, Cin, H, O), dtype=torch.uint8, device=x.device)
+        a, keep = ops.speech_enc_args(enc, x, masks, y, ws)
+        _lib.check(l.zeggs_speech_enc_fwd(a, _lib.stream_ptr()), "zeggs_speech_enc_fwd")
+        ctx.state = (a, keep, x, masks, y, ws)
+        ctx.wshapes = [w.shape for w in weights]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, keep, x, masks, y, ws = ctx.state
+        dy = dy.contiguous().float()
+        grads = [torch.empty(s, dtype=torch.float32, device=dy.device) for s in ctx.wshapes]
+        g = _lib.SpeechEncGrads(dy=dy.data_ptr())
+        for n, t in zip(("dW0", "db0", "dW1", "db1", "dW2", "db2"), grads):
+            setattr(g, n, t.data_ptr())
+        _lib.check(_lib.lib().zeggs_speech_enc_bwd(a, g, _lib.stream_ptr()), "zeggs_speech_enc_bwd")
+        ctx.state = None
+        return (None, None, None) + tuple(grads)
+
+
+class StyleEncoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, enc, x, eps, masks, temperature, *weights):
+        l = _lib.lib()
+        x = ops._f32c(x)
+        B, T, Cin = x.shape
+        Hs, E = weights[0].shape[0], weights[4].shape[0]
+        nh = enc.encoder.blocks[0].attention.multi_head_attention.num_heads
+        outs = [torch.empty((B, E // 2), dtype=torch.float32, device=x.device) for _ in range(3)]
+        ws = torch.empty(l.zeggs_style_enc_workspace_bytes(B, T, Cin, Hs, E, nh), dtype=torch.uint8, device=x.device)
+        a, keep = ops.style_enc_args(enc, x, eps, masks, temperature, outs, ws)
+        _lib.check(l.zeggs_style_enc_fwd(a, _lib.stream_ptr()), "zeggs_style_enc_fwd")
+        ctx.state = (a, keep, x, eps, masks, outs, ws)
+        ctx.wshapes = [w.shape for w in weights]
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, dz, dmu, dlv):
+        a, keep, x, eps, masks, outs, ws = ctx.state
+        dev = x.device
+        g = _lib.StyleEncGrads()
+        hold = []
+        for n, t in (("dz", dz), ("dmu", dmu), ("dlogvar", dlv)):
+            if t is not None:
+                t = t.contiguous().float()
+                hold.append(t)
+                setattr(g, n, t.data_ptr())
+        grads = [torch.empty(s, dtype=torch.float32, device=dev) for s in ctx.wshapes]
+        for n, t in zip(_lib.STYLE_W, grads):
+            setattr(g, "d" + n, t.data_ptr())
+        _lib.check(_lib.lib().zeggs_style_enc_bwd(a, g, _lib.stream_ptr()), "zeggs_style_enc_bwd")
+        ctx.state = None
+        return (None, None, None, None, None) + tuple(grads)

@@ -14,6 +14,10 @@ int sgemm_launch(int trans_a, int M, int N, int K, const float* A, int lda, cons
 int sgemm_batched_launch(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                          const float* bias, float* C, int ldc, int act, int accumulate, int batch,
                          long long sA, long long sB, long long sC, cudaStream_t stream);
+int sgemm_batched2_launch(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                          const float* bias, float* C, int ldc, int act, int accumulate, int batch,
+                          long long sA, long long sB, long long sC, int inner, long long iA, long long iB, long long iC,
+                          float alpha, cudaStream_t stream);
 
 // units per CTA: the grid G = H/U must fit one CTA per SM (148)
 inline int pick_U(int H) {

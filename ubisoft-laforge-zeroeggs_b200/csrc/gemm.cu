@@ -12,8 +12,10 @@ template <int MODE>
 __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
                                                     const float* __restrict__ B, int ldb, const float* __restrict__ bias,
                                                     float* __restrict__ C, int ldc, int act, int accumulate,
-                                                    long long sA, long long sB, long long sC) {
-  A += blockIdx.z * sA; B += blockIdx.z * sB; C += blockIdx.z * sC;
+                                                    long long sA, long long sB, long long sC, int inner,
+                                                    long long iA, long long iB, long long iC, float alpha) {
+  { const int zo = blockIdx.z / inner, zi = blockIdx.z - zo * inner;
+    A += zo * sA + zi * iA; B += zo * sB + zi * iB; C += zo * sC + zi * iC; }
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
     for (int j = 0; j < 4; ++j) {
       int n = n0 + tx * 4 + j;
       if (n >= N) continue;
-      float v = acc[i][j];
+      float v = acc[i][j] * alpha;
       if (bias) v += bias[n];
       if (act == 1) v = elu_f(v); else if (act == 2) v = fmaxf(v, 0.f);
       if (accumulate) v += C[(size_t)m * ldc + n];
@@ -77,17 +79,25 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
   }
 }
 
-int sgemm_batched_launch(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-                         const float* bias, float* C, int ldc, int act, int accumulate, int batch,
-                         long long sA, long long sB, long long sC, cudaStream_t stream) {
-  ZCHECK_ARG(M > 0 && N > 0 && K > 0 && A && B && C && batch >= 1 && batch <= 65535, "sgemm: bad arguments M=%d N=%d K=%d batch=%d", M, N, K, batch);
+// batch index z = zo*inner + zi; operand X is offset by zo*sX + zi*iX (e.g. zo = sample, zi = attention head)
+int sgemm_batched2_launch(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                          const float* bias, float* C, int ldc, int act, int accumulate, int batch,
+                          long long sA, long long sB, long long sC, int inner, long long iA, long long iB, long long iC,
+                          float alpha, cudaStream_t stream) {
+  ZCHECK_ARG(M > 0 && N > 0 && K > 0 && A && B && C && batch >= 1 && batch <= 65535 && inner >= 1, "sgemm: bad arguments M=%d N=%d K=%d batch=%d", M, N, K, batch);
   dim3 grid(ceil_div(N, 64), ceil_div(M, 64), batch);
-  if (mode == 1) sgemm_kernel<1><<<grid, 256, 0, stream>>>(M, N, K, A, lda, B, ldb, bias, C, ldc, act, accumulate, sA, sB, sC);
-  else if (mode == 2) sgemm_kernel<2><<<grid, 256, 0, stream>>>(M, N, K, A, lda, B, ldb, bias, C, ldc, act, accumulate, sA, sB, sC);
-  else sgemm_kernel<0><<<grid, 256, 0, stream>>>(M, N, K, A, lda, B, ldb, bias, C, ldc, act, accumulate, sA, sB, sC);
+  if (mode == 1) sgemm_kernel<1><<<grid, 256, 0, stream>>>(M, N, K, A, lda, B, ldb, bias, C, ldc, act, accumulate, sA, sB, sC, inner, iA, iB, iC, alpha);
+  else if (mode == 2) sgemm_kernel<2><<<grid, 256, 0, stream>>>(M, N, K, A, lda, B, ldb, bias, C, ldc, act, accumulate, sA, sB, sC, inner, iA, iB, iC, alpha);
+  else sgemm_kernel<0><<<grid, 256, 0, stream>>>(M, N, K, A, lda, B, ldb, bias, C, ldc, act, accumulate, sA, sB, sC, inner, iA, iB, iC, alpha);
   count_launch();
   ZCHECK_LAUNCH();
   return ZEGGS_OK;
+}
+
+int sgemm_batched_launch(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                         const float* bias, float* C, int ldc, int act, int accumulate, int batch,
+                         long long sA, long long sB, long long sC, cudaStream_t stream) {
+  return sgemm_batched2_launch(mode, M, N, K, A, lda, B, ldb, bias, C, ldc, act, accumulate, batch, sA, sB, sC, 1, 0, 0, 0, 1.0f, stream);
 }
 
 int sgemm_launch(int trans_a, int M, int N, int K, const float* A, int lda, const float* B, int ldb,

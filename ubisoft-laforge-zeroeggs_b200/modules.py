@@ -101,3 +101,132 @@ def compute_KL_div(mu, logvar, iteration):  # modules.py:764-789
     kl_div = torch.mean(-0.5 * torch.mean(1 + logvar - mu.pow(2) - logvar.exp(), dim=1))
     w = min(generalized_logistic_function(iteration, center=7500, B=0.005), 2e-1)
     return kl_div, w
+
+
+# ===============================================================================================
+#                                        Speech Encoder
+# ===============================================================================================
+class SpeechEncoder(nn.Module):
+    """modules.py:249-272.  x[B,T,81] (normalised) -> [B,T,64] via zeggs_speech_enc_fwd/_bwd."""
+
+    def __init__(self, input_size, hidden_size, output_size):
+        super().__init__()
+        self.layer0 = nn.Conv1d(input_size, hidden_size, kernel_size=1, padding="same", padding_mode="replicate")
+        self.drop0 = nn.Dropout(p=0.2)
+        self.layer1 = nn.Conv1d(hidden_size, output_size, kernel_size=31, padding="same", padding_mode="replicate")
+        self.drop1 = nn.Dropout(p=0.2)
+        self.layer2 = nn.Linear(output_size, output_size)
+
+    def _weights(self):
+        return [self.layer0.weight, self.layer0.bias, self.layer1.weight, self.layer1.bias,
+                self.layer2.weight, self.layer2.bias]
+
+    def forward(self, x, masks=None):
+        """masks (testing hook): (m0[B,T,H], m1[B,T,O]) dropout multipliers; default: sampled in train mode."""
+        return ops.speech_encoder(self, x, masks)
+
+
+# ===============================================================================================
+#                                        Style Encoder
+# ===============================================================================================
+class ConvNorm1D(nn.Module):
+    """Parameter container of modules.py:615-651 (key `conv.*`)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=1, stride=1, padding=None, dilation=1, bias=True,
+                 w_init_gain="linear"):
+        super().__init__()
+        self.conv = nn.Conv1d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=padding,
+                              dilation=dilation, bias=bias)
+        nn.init.xavier_uniform_(self.conv.weight, gain=nn.init.calculate_gain(w_init_gain))
+
+
+class LinearNorm(nn.Module):
+    def __init__(self, in_dim, out_dim, bias=True, w_init_gain="linear"):
+        super().__init__()
+        self.linear_layer = nn.Linear(in_dim, out_dim, bias=bias)
+        nn.init.xavier_uniform_(self.linear_layer.weight, gain=nn.init.calculate_gain(w_init_gain))
+
+
+class PositionalEncoding(nn.Module):
+    """modules.py:445-481; only the table rows 0..T-1 are ever used (all lengths are equal, :399-403)."""
+
+    def __init__(self, embed_dim, max_len=20000, timestep=10000.0):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.timestep = timestep
+
+    def table(self, T):
+        pos = torch.arange(0, T, dtype=torch.float).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, self.embed_dim, 2).float() * (-np.log(self.timestep) / self.embed_dim))
+        pe = torch.zeros(T, self.embed_dim)
+        pe[:, 0::2] = torch.sin(pos * div_term)
+        pe[:, 1::2] = torch.cos(pos * div_term)
+        return pe
+
+
+class MultiHeadAttention(nn.Module):
+    def __init__(self, hidden_size):
+        super().__init__()
+        self.multi_head_attention = nn.MultiheadAttention(hidden_size, 4, 0.1)
+        self.dropout = nn.Dropout(0.1)
+        self.layer_norm = nn.LayerNorm(hidden_size)
+
+
+class PositionWiseConvFF(nn.Module):
+    def __init__(self, hidden_size):
+        super().__init__()
+        self.convs = nn.Sequential(
+            ConvNorm1D(hidden_size, hidden_size, kernel_size=3, stride=1, padding=1, dilation=1, w_init_gain="relu"),
+            nn.ReLU(),
+            ConvNorm1D(hidden_size, hidden_size, kernel_size=3, stride=1, padding=1, dilation=1, w_init_gain="linear"),
+            nn.Dropout(0.1))
+        self.layer_norm = nn.LayerNorm(hidden_size)
+
+
+class FFTBlock(nn.Module):
+    def __init__(self, hidden_size):
+        super().__init__()
+        self.attention = MultiHeadAttention(hidden_size)
+        self.feed_forward = PositionWiseConvFF(hidden_size)
+
+
+class StyleEncoderAttn(nn.Module):
+    """Parameter container of modules.py:346-389."""
+
+    def __init__(self, input_size, hidden_size, style_embedding_size):
+        super().__init__()
+        self.pos_enc = PositionalEncoding(style_embedding_size)
+        self.convs = nn.Sequential(
+            ConvNorm1D(input_size, hidden_size, kernel_size=3, stride=1, padding=1, dilation=1, w_init_gain="relu"),
+            nn.ReLU(), nn.LayerNorm(hidden_size), nn.Dropout(0.2),
+            ConvNorm1D(hidden_size, style_embedding_size, kernel_size=3, stride=1, padding=1, dilation=1, w_init_gain="relu"),
+            nn.ReLU(), nn.LayerNorm(style_embedding_size), nn.Dropout(0.2))
+        self.blocks = nn.ModuleList([FFTBlock(style_embedding_size)])
+
+
+class StyleEncoder(nn.Module):
+    """modules.py:278-304 (type 'attn').  forward(input[B,T_ex,1134], temprature) -> (z, mu, logvar)."""
+
+    def __init__(self, input_size, hidden_size, style_embedding_size, type="attn", use_vae=False):
+        super().__init__()
+        if type != "attn":
+            raise _lib.ZeggsError("only the 'attn' style encoder (the shipped configs) is on the accelerated path")
+        if not use_vae:
+            raise _lib.ZeggsError("use_vae=False is not on the accelerated path (the shipped configs use the VAE)")
+        self.use_vae = use_vae
+        self.style_embedding_size = style_embedding_size
+        self.encoder = StyleEncoderAttn(input_size, hidden_size, 2 * style_embedding_size)
+
+    def _weights(self):
+        e = self.encoder
+        a, f = e.blocks[0].attention, e.blocks[0].feed_forward
+        m = a.multi_head_attention
+        return [e.convs[0].conv.weight, e.convs[0].conv.bias, e.convs[2].weight, e.convs[2].bias,
+                e.convs[4].conv.weight, e.convs[4].conv.bias, e.convs[6].weight, e.convs[6].bias,
+                m.in_proj_weight, m.in_proj_bias, m.out_proj.weight, m.out_proj.bias, a.layer_norm.weight, a.layer_norm.bias,
+                f.convs[0].conv.weight, f.convs[0].conv.bias, f.convs[2].conv.weight, f.convs[2].conv.bias,
+                f.layer_norm.weight, f.layer_norm.bias]
+
+    def forward(self, input, temprature: float = 1.0, eps=None, masks=None):
+        """eps / masks are testing hooks (injected N(0,1) sample and dropout multipliers)."""
+        return ops.style_encoder(self, input, float(temprature), eps, masks)

@@ -159,3 +159,83 @@ def tc_gemm(A_hi, B_hi, A_lo=None, B_lo=None, K=None, bias=None, act=0, out=None
         _lib.ptr(bias) if bias is not None else None, _lib.ptr(out), out.stride(0), act, int(accumulate),
         _lib.stream_ptr()), "zeggs_tc_gemm_bf16")
     return out
+
+
+# ---------------------------------------------------------------------------------------------- encoders
+def _drop_mask(shape, p, device):
+    return (torch.rand(shape, device=device) >= p).float().mul_(1.0 / (1.0 - p))
+
+
+def speech_enc_args(enc, x, masks, y, ws):
+    w = [_f32c(p, x.device) for p in enc._weights()]
+    H, Cin = w[0].shape[0], w[0].shape[1]
+    O = w[2].shape[0]
+    B, T = x.shape[0], x.shape[1]
+    a = _lib.SpeechEncArgs(B=B, T=T, C_in=Cin, H=H, O=O)
+    for n, t in zip(("W0", "b0", "W1", "b1", "W2", "b2"), w):
+        setattr(a, n, t.data_ptr())
+    a.x, a.y = x.data_ptr(), y.data_ptr()
+    if masks is not None:
+        a.mask0, a.mask1 = masks[0].data_ptr(), masks[1].data_ptr()
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    return a, w
+
+
+def speech_encoder(enc, x, masks=None):
+    if x.device.type != "cuda":
+        raise _lib.ZeggsError("zeggs_b200.SpeechEncoder runs on CUDA tensors only (no CPU fallback)")
+    from .autograd import SpeechEncoderFn
+    B, T = x.shape[0], x.shape[1]
+    H, O = enc.layer0.weight.shape[0], enc.layer1.weight.shape[0]
+    if masks is None and enc.training:
+        masks = (_drop_mask((B, T, H), 0.2, x.device), _drop_mask((B, T, O), 0.2, x.device))
+    if masks is not None:
+        masks = tuple(_f32c(m, x.device) for m in masks)
+    return SpeechEncoderFn.apply(enc, x, masks, *enc._weights())
+
+
+_pe_cache = {}
+
+
+def style_enc_args(enc, x, eps, masks, temperature, outs, ws):
+    dev = x.device
+    w = [_f32c(p, dev) for p in enc._weights()]
+    B, T, Cin = x.shape
+    Hs, E = w[0].shape[0], w[4].shape[0]
+    nh = enc.encoder.blocks[0].attention.multi_head_attention.num_heads
+    a = _lib.StyleEncArgs(B=B, T=T, C_in=Cin, H=Hs, E=E, nheads=nh, temperature=temperature)
+    for n, t in zip(_lib.STYLE_W, w):
+        setattr(a, n, t.data_ptr())
+    key = (T, E, str(dev))
+    if key not in _pe_cache:
+        _pe_cache[key] = enc.encoder.pos_enc.table(T).to(dev).contiguous()
+    pe = _pe_cache[key]
+    a.x, a.pe = x.data_ptr(), pe.data_ptr()
+    if eps is not None:
+        a.eps = eps.data_ptr()
+    if masks is not None:
+        for n in ("c1", "c2", "attn", "ao", "ff"):
+            setattr(a, "mask_" + n, masks[n].data_ptr())
+    a.z, a.mu, a.logvar = (o.data_ptr() for o in outs)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    return a, w + [pe]
+
+
+def style_encoder(enc, x, temperature=1.0, eps=None, masks=None):
+    if x.device.type != "cuda":
+        raise _lib.ZeggsError("zeggs_b200.StyleEncoder runs on CUDA tensors only (no CPU fallback)")
+    from .autograd import StyleEncoderFn
+    dev = x.device
+    B, T = x.shape[0], x.shape[1]
+    Hs = enc.encoder.convs[0].conv.weight.shape[0]
+    E = enc.encoder.convs[4].conv.weight.shape[0]
+    nh = enc.encoder.blocks[0].attention.multi_head_attention.num_heads
+    if eps is None:
+        eps = torch.randn((B, E // 2), device=dev)          # modules.py:299
+    if masks is None and enc.training:
+        masks = dict(c1=_drop_mask((B, T, Hs), 0.2, dev), c2=_drop_mask((B, T, E), 0.2, dev),
+                     attn=_drop_mask((B, nh, T, T), 0.1, dev), ao=_drop_mask((B, T, E), 0.1, dev),
+                     ff=_drop_mask((B, T, E), 0.1, dev))
+    if masks is not None:
+        masks = {k: _f32c(v, dev) for k, v in masks.items()}
+    return StyleEncoderFn.apply(enc, x, _f32c(eps, dev), masks, temperature, *enc._weights())
