@@ -182,6 +182,36 @@ int zeggs_style_enc_fwd(const zeggs_style_enc_args* a, void* stream);
 int zeggs_style_enc_bwd(const zeggs_style_enc_args* a, const zeggs_style_enc_grads* g, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Training loss, forward and backward in one call (train.py:277-421): world-space transforms, 75-joint FK with
+ * velocities for the output and the ground truth, 17 weighted L1 means + kl_weight * KL(mu, logvar), divided by 18.
+ * (Y, root_pos, root_rot) are the decoder outputs; (WY, W_root_pos, W_root_rot) the ground-truth window in the
+ * same packed layout.  losses[0] = total, losses[1..17] = loss_root_pos .. loss_gaze in train.py:397-416 order,
+ * losses[18] = weighted KL term.  If dY != NULL the gradient of `total` w.r.t. Y / root_pos / root_rot (and mu /
+ * logvar) is written too.  torch.cross is taken over the LAST dim (the reference's dim-less calls at
+ * train.py:301,315 / txform.py:25-26 only differ when B or T == 3).
+ */
+typedef struct {
+  int B, T, Z;
+  float dt, kl_weight;
+  const float *Y, *root_pos, *root_rot;
+  const float *WY, *W_root_pos, *W_root_rot;
+  const float* gaze_pos; /* [B,T,3] */
+  const int* parents;    /* int32 [75] */
+  const float *mu, *logvar; /* [B,Z] or NULL */
+  float* losses;         /* [19] */
+  float *dY, *dRootPos, *dRootRot, *dmu, *dlogvar;
+  void* workspace;
+  size_t workspace_bytes;
+} zeggs_loss_args;
+size_t zeggs_loss_workspace_bytes(int B, int T);
+int zeggs_loss_fwd_bwd(const zeggs_loss_args* a, void* stream);
+
+/* Fused RAdam step over a flat fp32 parameter buffer (optimizers.py:31-99; weight_decay 0,
+ * degenerated_to_sgd).  `step` is the 1-based step count; gradients are multiplied by grad_scale first. */
+int zeggs_radam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
+                     float eps, int step, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Generic fp32 GEMM used for the batched (non-recurrent) linear layers:
  *   C[M,N] = act(A[M,K] * B[N,K]^T + bias[N])            (trans_a = 0;  nn.Linear)
  *   C[M,N] = A[K,M]^T * B[K,N] (+ C if accumulate)        (trans_a = 1;  weight gradients)

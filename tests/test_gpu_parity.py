@@ -260,3 +260,98 @@ def test_style_encoder_fwd_bwd(dev, B, T, train):
         if not err <= 3e-4 * max(sc, 1e-6):
             bad.append((k, err, sc))
     assert not bad, bad
+
+
+# ---------------------------------------------------------------------------------------------- loss / optimizer / train step
+def _make_step(dev, H, param_seed):
+    from zeggs_b200 import modules, synth
+    from zeggs_b200.train import TrainStep
+    P = synth.make_params(H=H, seed=param_seed)
+    se = _load(modules.SpeechEncoder(81, 64, 64), P, "speech_encoder.", dev)
+    st = _load(modules.StyleEncoder(1134, 512, 64, type="attn", use_vae=True), P, "style_encoder.", dev)
+    de = _load(modules.Decoder(1134, 1131, 64, 64, H, 2), P, "decoder.", dev)
+    stats = synth.load_stats()
+    return TrainStep(se, de, st, stats, stats["parents"], float(stats["dt"])), P
+
+
+def _batch(dev, B, T, T_ex, seed):
+    from zeggs_b200 import synth
+    b = tt(synth.make_pose_windows(B, T, seed=seed), dev)
+    b["audio"] = torch.from_numpy(synth.make_audio_features(B, T, seed=seed)).to(dev)
+    b["style"] = torch.from_numpy(synth.make_style_example(B, T_ex, seed=seed)).to(dev)
+    return b
+
+
+@pytest.mark.parametrize("tag", ["h64", "h128"])
+def test_train_step_loss_and_gradients_vs_reference_golden(dev, golden_dir, tag):
+    """Whole step body (encoders -> decoder -> FK loss -> backward) against the reference's own loss / gradients
+    (golden written by oracle/make_golden.py from the unmodified reference, eval-mode dropout, injected VAE eps)."""
+    g = np.load(os.path.join(golden_dir, f"train_{tag}.npz"))
+    H, B, T, T_ex = int(g["H"]), int(g["B"]), int(g["T"]), int(g["T_ex"])
+    step, P = _make_step(dev, H, int(g["param_seed"]))
+    step.iteration = int(g["iteration"])
+    batch = _batch(dev, B, T, T_ex, int(g["input_seed"]))
+    step.optimizer.zero_grad()
+    loss = step.forward_backward(batch, eps=torch.from_numpy(g["eps"]).to(dev), train_mode=False)
+    torch.cuda.synchronize()
+    terms = step.terms.cpu().numpy()
+    print(f"  loss {loss.item():.6f} vs golden {float(g['loss']):.6f}")
+    assert abs(loss.item() - float(g["loss"])) <= 2e-5 * abs(float(g["loss"]))
+    names = ["root_pos", "root_rot", "root_vel", "root_vrt", "lpos", "lrot", "lvel", "lvrt", "cpos", "crot", "cvel", "cvrt",
+             "ldvl", "ldvt", "cdvl", "cdvt", "gaze", "kl_div"]
+    for i, n in enumerate(names):
+        ref = float(g["loss_" + n])
+        assert abs(terms[1 + i] - ref) <= 3e-5 * max(1e-3, abs(ref)), (n, terms[1 + i], ref)
+    bad = []
+    for prefix, net in (("speech_encoder.", step.se), ("decoder.", step.dec), ("style_encoder.", step.st)):
+        for k, p in net.named_parameters():
+            ref_n = float(g["gradnorm." + prefix + k])
+            got_n = float(p.grad.double().norm())
+            if not abs(got_n - ref_n) <= 5e-4 * max(ref_n, 1e-7):
+                bad.append((prefix + k, got_n, ref_n))
+            if "grad." + prefix + k in g.files:
+                ref = g["grad." + prefix + k]
+                err = float(np.abs(p.grad.cpu().numpy() - ref).max())
+                if not err <= 5e-4 * max(float(np.abs(ref).max()), 1e-7):
+                    bad.append((prefix + k, "elementwise", err))
+    assert not bad, bad
+
+
+def test_loss_kernel_vs_oracle_autograd(dev):
+    from oracle import model_oracle as mo
+    from zeggs_b200 import synth
+    from zeggs_b200.autograd import TrainLossFn
+    from zeggs_b200.train import pack_pose
+    B, T = 5, 33
+    st = synth.load_stats()
+    O = tt(synth.make_pose_windows(B, T, seed=41)); W = tt(synth.make_pose_windows(B, T, seed=42))
+    rs = np.random.RandomState(0)
+    mu = torch.from_numpy(rs.randn(B, 64).astype(np.float32)); lv = torch.from_numpy((rs.randn(B, 64) * 0.3).astype(np.float32))
+    Ot = [O[k].clone().requires_grad_(True) for k in NAMES]
+    mu_o, lv_o = mu.clone().requires_grad_(True), lv.clone().requires_grad_(True)
+    loss_o, L = mo.train_losses(Ot, [W[k] for k in NAMES], W["gaze_pos"], st["parents"], float(st["dt"]), mu_o, lv_o, 9000)
+    g_ref = torch.autograd.grad(loss_o, Ot + [mu_o, lv_o])
+    Og = [O[k].to(dev).requires_grad_(True) for k in NAMES]
+    mu_g, lv_g = mu.to(dev).requires_grad_(True), lv.to(dev).requires_grad_(True)
+    Y = pack_pose(*Og[2:]); WY = pack_pose(*[W[k].to(dev) for k in NAMES[2:]])
+    terms = torch.zeros(19, device=dev)
+    loss_g = TrainLossFn.apply(Y, Og[0], Og[1], WY, W["root_pos"].to(dev), W["root_rot"].to(dev), W["gaze_pos"].to(dev),
+                               torch.as_tensor(st["parents"], dtype=torch.int32, device=dev), float(st["dt"]), mu_g, lv_g,
+                               mo.kl_weight(9000), terms)
+    g_got = torch.autograd.grad(loss_g, Og + [mu_g, lv_g])
+    assert abs(loss_g.item() - loss_o.item()) <= 2e-5 * abs(loss_o.item())
+    for n, a, b in zip(NAMES + ["mu", "logvar"], g_got, g_ref):
+        err, sc = report(f"loss grad {n}", a, b)
+        assert err <= 3e-4 * max(sc, 1e-9), n
+
+
+def test_fused_radam_vs_reference_golden(dev, golden_dir):
+    from zeggs_b200.optimizers import RAdam
+    g = np.load(os.path.join(golden_dir, "radam.npz"))
+    p = torch.nn.Parameter(torch.from_numpy(g["p0"].copy()).to(dev))
+    opt = RAdam([p], lr=1e-4, eps=1e-5)
+    for i in range(g["grads"].shape[0]):
+        opt.zero_grad()
+        p.grad.copy_(torch.from_numpy(g["grads"][i]).to(dev))
+        opt.step()
+        assert np.abs(p.detach().cpu().numpy() - g["traj"][i]).max() <= 2e-7, i

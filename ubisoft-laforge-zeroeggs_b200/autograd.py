@@ -38,7 +38,7 @@ class DecoderWindowFn(torch.autograd.Function):
                 hold.append(g)
                 setattr(b, name, g.data_ptr())
         # transposed weight slices for the backward recurrence (cached on the module like the forward pack)
-        ver = tuple(p._version for p in dec._weights()) + tuple(p.data_ptr() for p in dec._weights())
+        ver = ops.weights_key(dec._weights())
         cache = dec.__dict__.get("_zeggs_packed_bwd")
         if cache is None or cache[0] != ver or cache[1].device != dev:
             nb = l.zeggs_decoder_packed_bwd_bytes(H, S, Z)
@@ -123,3 +123,40 @@ class StyleEncoderFn(torch.autograd.Function):
         _lib.check(_lib.lib().zeggs_style_enc_bwd(a, g, _lib.stream_ptr()), "zeggs_style_enc_bwd")
         ctx.state = None
         return (None, None, None, None, None) + tuple(grads)
+
+
+class TrainLossFn(torch.autograd.Function):
+    """loss = train.py:277-421 evaluated (and differentiated) by zeggs_loss_fwd_bwd in the forward call."""
+
+    @staticmethod
+    def forward(ctx, Y, rp, rq, WY, Wrp, Wrq, gaze, parents_i32, dt, mu, logvar, kl_weight, terms_out):
+        l = _lib.lib()
+        dev = Y.device
+        B, T = Y.shape[0], Y.shape[1]
+        f = ops._f32c
+        Y, rp, rq, WY, Wrp, Wrq, gaze = f(Y), f(rp), f(rq), f(WY), f(Wrp), f(Wrq), f(gaze)
+        losses = terms_out if terms_out is not None else torch.empty(19, dtype=torch.float32, device=dev)
+        dY, dRp, dRq = torch.empty_like(Y), torch.empty_like(rp), torch.empty_like(rq)
+        a = _lib.LossArgs(B=B, T=T, Z=(mu.shape[1] if mu is not None else 0), dt=dt, kl_weight=kl_weight)
+        a.Y, a.root_pos, a.root_rot = Y.data_ptr(), rp.data_ptr(), rq.data_ptr()
+        a.WY, a.W_root_pos, a.W_root_rot = WY.data_ptr(), Wrp.data_ptr(), Wrq.data_ptr()
+        a.gaze_pos, a.parents, a.losses = gaze.data_ptr(), parents_i32.data_ptr(), losses.data_ptr()
+        a.dY, a.dRootPos, a.dRootRot = dY.data_ptr(), dRp.data_ptr(), dRq.data_ptr()
+        dmu = dlv = None
+        if mu is not None:
+            mu, logvar = f(mu), f(logvar)
+            dmu, dlv = torch.empty_like(mu), torch.empty_like(logvar)
+            a.mu, a.logvar, a.dmu, a.dlogvar = mu.data_ptr(), logvar.data_ptr(), dmu.data_ptr(), dlv.data_ptr()
+        wsb = l.zeggs_loss_workspace_bytes(B, T)
+        ws = ops.WS.get("loss", wsb, dev)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), wsb
+        _lib.check(l.zeggs_loss_fwd_bwd(a, _lib.stream_ptr()), "zeggs_loss_fwd_bwd")
+        ctx.grads = (dY, dRp, dRq, dmu, dlv)
+        return losses[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        dY, dRp, dRq, dmu, dlv = ctx.grads
+        ctx.grads = None
+        s = lambda t: None if t is None else t * g
+        return (s(dY), s(dRp), s(dRq), None, None, None, None, None, None, s(dmu), s(dlv), None, None)

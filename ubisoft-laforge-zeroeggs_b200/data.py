@@ -1,0 +1,73 @@
+"""Window supplier with the reference's processed_data.npz schema (ZEGGS/data_pipeline.py:650-684,
+ZEGGS/dataset.py:9-204): sliding training windows + the style-example window around each of them.
+Whole arrays are kept pinned on the host and every batch is gathered with fancy indexing and copied with one
+non-blocking H2D per tensor (the reference does 11 synchronous copies per step, train.py:215-225)."""
+import json
+
+import numpy as np
+import torch
+
+KEYS = ["root_pos", "root_rot", "root_vel", "root_vrt", "lpos", "ltxy", "lvel", "lvrt", "gaze_pos"]
+
+
+class WindowDataset:
+    def __init__(self, path_data_definition, path_processed_data, window, style_encoding_type, example_window_length, seed=0):
+        with open(path_data_definition, "r") as f:
+            self.details = json.load(f)
+        d = np.load(path_processed_data)
+        self.window = window
+        self.style_encoding_type = style_encoding_type
+        self.example_window_length = example_window_length
+        self.nlabels = len(self.details["label_names"])
+        self.ranges = d["ranges_train"]
+        self.labels = d["ranges_train_labels"]
+        self.X = torch.as_tensor(d["X_audio_features"], dtype=torch.float32)
+        self.Y = {k: torch.as_tensor(d["Y_" + k], dtype=torch.float32) for k in KEYS}
+        self.stats = {k: d[k] for k in ("audio_input_mean", "audio_input_std", "anim_input_mean", "anim_input_std",
+                                        "anim_output_mean", "anim_output_std")}
+        starts, rng_idx = [], []
+        for i, (s, e) in enumerate(self.ranges):                       # dataset.py:82-93
+            n = max(0, int(e) - window - int(s))
+            starts.append(np.arange(int(s), int(s) + n))
+            rng_idx.append(np.full(n, i))
+        self.starts = np.concatenate(starts) if starts else np.zeros(0, np.int64)
+        self.rng_idx = np.concatenate(rng_idx) if rng_idx else np.zeros(0, np.int64)
+        self.rs = np.random.RandomState(seed)
+
+    def __len__(self):
+        return len(self.starts)
+
+    def get_shapes(self):
+        return dict(num_audio_features=self.X.shape[1], pose_input_size=len(self.stats["anim_input_std"]),
+                    pose_output_size=len(self.stats["anim_output_std"]))
+
+    def _example(self, start, ri):
+        """dataset.py:176-204."""
+        L, W = self.example_window_length, self.window
+        s0, e0 = int(self.ranges[ri][0]), int(self.ranges[ri][1])
+        first, last = start, start + W - 1
+        ext = (L - W) // 2
+        ws, we = min(ext, first - s0), min(ext, e0 - last)
+        s_ext, w_ext = ws + ext - we, we + ext - ws
+        a = max(first - s_ext, s0)
+        b = min(min(last + w_ext, e0) + 1, len(self.Y["root_vel"]))
+        n = b - a
+        parts = [self.Y[k][a:b].reshape(n, -1) for k in ("root_vel", "root_vrt", "lpos", "ltxy", "lvel", "lvrt")]
+        vec = torch.cat(parts + [torch.zeros(n, 3)], dim=1)
+        if n < L:
+            vec = torch.cat([vec, vec[-L + n:]], dim=0)
+        return vec
+
+    def sample_batch(self, batchsize, device):
+        idx = self.rs.randint(0, len(self.starts), size=batchsize)
+        rows = torch.as_tensor(self.starts[idx][:, None] + np.arange(self.window)[None, :])
+        out = {"audio": self.X[rows]}
+        for k in KEYS:
+            out[k] = self.Y[k][rows]
+        if self.style_encoding_type == "label":
+            lab = torch.zeros(batchsize, self.nlabels)
+            lab[torch.arange(batchsize), torch.as_tensor(self.labels[self.rng_idx[idx]]).long()] = 1.0
+            out["style"] = lab
+        else:
+            out["style"] = torch.stack([self._example(int(self.starts[i]), int(self.rng_idx[i])) for i in idx])
+        return {k: v.pin_memory().to(device, non_blocking=True) for k, v in out.items()}

@@ -34,6 +34,18 @@ class _Workspace:
 
 WS = _Workspace()
 
+_weights_epoch = 0
+
+
+def bump_weights_epoch():
+    """Called by anything that rewrites parameters without going through torch (the fused optimizer)."""
+    global _weights_epoch
+    _weights_epoch += 1
+
+
+def weights_key(params):
+    return (_weights_epoch,) + tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)
+
 
 def split_pose(Y, root_pos, root_rot):
     """[B,T,1131] pose vectors -> the reference's 8-tuple (modules.py:153-162, 731-736)."""
@@ -65,7 +77,7 @@ def _decoder_args(dec, B, T, dev, tensors, stats, dt, save):
         setattr(a, n, _lib.ptr(t))
         keep.append(t)
     # packed weights: re-packed whenever any parameter's version counter moved
-    ver = tuple(p._version for p in dec._weights()) + tuple(p.data_ptr() for p in dec._weights())
+    ver = weights_key(dec._weights())
     cache = getattr(dec, "_zeggs_packed", None)
     if cache is None or cache[0] != ver or cache[1].device != dev:
         nbytes = l.zeggs_decoder_packed_bytes(H, S, Z)

@@ -1,0 +1,166 @@
+"""Training on the B200 path.  `train()` keeps the reference's call surface (ZEGGS/train.py:29-36, called from
+main.py:64-71); `TrainStep` is the step body (train.py:196-432) with every stage running in libzeggs_b200.so:
+speech encoder, style encoder (VAE), persistent decoder window (fwd + BPTT), fused FK/L1 loss, fused RAdam,
+and -- when torch.distributed is initialised -- ONE NCCL all-reduce of the flat gradient per step.
+"""
+import datetime
+import json
+import math
+import os
+import random
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import _lib, modules, ops
+from .autograd import TrainLossFn
+from .optimizers import RAdam
+
+POSE_KEYS = ["root_pos", "root_rot", "root_vel", "root_vrt", "lpos", "ltxy", "lvel", "lvrt"]
+
+
+def kl_weight(iteration, center=7500, rate=0.005, threshold=0.2):
+    """modules.py:745-761, 784-788: logistic annealing clipped at 0.2."""
+    return min(1.0 / (1.0 + math.exp(-rate * (iteration - center))), threshold)
+
+
+def pack_pose(root_vel, root_vrt, lpos, ltxy, lvel, lvrt):
+    B, T = root_vel.shape[0], root_vel.shape[1]
+    return torch.cat([root_vel.reshape(B, T, -1), root_vrt.reshape(B, T, -1), lpos.reshape(B, T, -1),
+                      ltxy.reshape(B, T, -1), lvel.reshape(B, T, -1), lvrt.reshape(B, T, -1)], dim=2)
+
+
+class TrainStep:
+    """One optimisation step on one GPU (one rank).  Networks are zeggs_b200.modules.* instances."""
+
+    def __init__(self, speech_encoder, decoder, style_encoder, stats, parents, dt, lr=1e-4, eps=1e-5,
+                 world_size=1, process_group=None):
+        self.se, self.dec, self.st = speech_encoder, decoder, style_encoder
+        self.dev = next(decoder.parameters()).device
+        f = lambda k: torch.as_tensor(stats[k], dtype=torch.float32, device=self.dev)
+        self.audio_mean, self.audio_std = f("audio_input_mean"), f("audio_input_std")
+        self.in_mean, self.in_std = f("anim_input_mean"), f("anim_input_std")
+        self.out_mean, self.out_std = f("anim_output_mean"), f("anim_output_std")
+        self.parents = torch.as_tensor(np.asarray(parents), dtype=torch.int32, device=self.dev)
+        self.dt = float(dt)
+        params = list(self.se.parameters()) + list(self.dec.parameters()) + \
+            (list(self.st.parameters()) if self.st is not None else [])
+        self.optimizer = RAdam(params, lr=lr, eps=eps)
+        self.world_size = world_size
+        self.pg = process_group
+        self.optimizer.grad_scale = 1.0 / world_size
+        self.iteration = 0
+        self.terms = torch.zeros(19, dtype=torch.float32, device=self.dev)
+
+    def forward_backward(self, batch, eps=None, masks=None, train_mode=True):
+        """batch: dict of DEVICE tensors: audio[B,T,81], the 8 pose tensors [B,T,...], gaze_pos[B,T,3], style (example
+        [B,T_ex,1134] raw, or label [B,Z]).  Returns the loss tensor (device scalar); gradients land in optimizer.flat_grad."""
+        self.se.train(train_mode); self.dec.train(train_mode)
+        speech = self.se((batch["audio"] - self.audio_mean) / self.audio_std, masks=None if masks is None else masks.get("speech"))
+        mu = logvar = None
+        if self.st is not None:
+            self.st.train(train_mode)
+            z, mu, logvar = self.st((batch["style"] - self.in_mean) / self.in_std, 1.0, eps=eps,
+                                    masks=None if masks is None else masks.get("style"))
+        else:
+            z = batch["style"]
+        T = speech.shape[1]
+        W = [batch[k] for k in POSE_KEYS]
+        out = self.dec(*[w[:, 0] for w in W], batch["gaze_pos"], speech, z.unsqueeze(1).repeat((1, T, 1)),
+                       None, self.in_mean, self.in_std, self.out_mean, self.out_std, self.dt)
+        Y = pack_pose(*out[2:])
+        WY = pack_pose(*W[2:])
+        loss = TrainLossFn.apply(Y, out[0], out[1], WY, W[0], W[1], batch["gaze_pos"], self.parents, self.dt, mu, logvar,
+                                 kl_weight(self.iteration) if mu is not None else 0.0, self.terms)
+        loss.backward()
+        return loss
+
+    def step(self, batch, eps=None, masks=None):
+        self.optimizer.zero_grad()
+        loss = self.forward_backward(batch, eps, masks)
+        if self.world_size > 1:
+            torch.distributed.all_reduce(self.optimizer.flat_grad, group=self.pg)   # the one collective of the step
+        self.optimizer.step()
+        self.iteration += 1
+        return loss
+
+
+def build_networks(network_options, dimensions, style_encoding_type, nlabels, device):
+    """train.py:96-139."""
+    se_o, st_o, de_o = network_options["speech_encoder"], network_options["style_encoder"], network_options["decoder"]
+    Z = nlabels if style_encoding_type == "label" else st_o["style_encoding_size"]
+    se = modules.SpeechEncoder(dimensions["num_audio_features"], se_o["nhidden"], se_o["speech_encoding_size"]).to(device)
+    de = modules.Decoder(pose_input_size=dimensions["pose_input_size"], pose_output_size=dimensions["pose_output_size"],
+                         speech_encoding_size=se_o["speech_encoding_size"], style_encoding_size=Z,
+                         hidden_size=de_o["nhidden"], num_rnn_layers=2).to(device)
+    st = None
+    if style_encoding_type == "example":
+        st = modules.StyleEncoder(dimensions["pose_input_size"], st_o["nhidden"], Z, type=st_o["type"],
+                                  use_vae=st_o["use_vae"]).to(device)
+    return se, de, st
+
+
+def train(models_dir, logs_dir, path_processed_data, path_data_definition, train_options, network_options):
+    """Drop-in for ZEGGS/train.py:29 (same arguments, same artefacts in models_dir).  Data-parallel when launched under
+    torchrun (RANK/WORLD_SIZE set): each rank draws its own windows, one gradient all-reduce per step."""
+    from .data import WindowDataset
+    np.random.seed(train_options["seed"])
+    torch.manual_seed(train_options["seed"])
+    if not (train_options["use_gpu"] and torch.cuda.is_available()):
+        raise _lib.ZeggsError("zeggs_b200.train needs a CUDA device (no CPU fallback)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1 and not torch.distributed.is_initialized():
+        torch.distributed.init_process_group("nccl")
+    models_dir, logs_dir = Path(models_dir), Path(logs_dir)
+    with open(path_data_definition, "r") as f:
+        details = json.load(f)
+    style_encoding_type = train_options["style_encoding_type"]
+    ds = WindowDataset(path_data_definition, path_processed_data, train_options["window"], style_encoding_type,
+                       network_options["style_encoder"]["example_length"], seed=train_options["seed"] + rank)
+    se, de, st = build_networks(network_options, ds.get_shapes(), style_encoding_type, len(details["label_names"]), device)
+    if train_options["resume"] and (models_dir / "checkpoints.pt").exists():
+        for net, name in ((se, "speech_encoder"), (de, "decoder"), (st, "style_encoder")):
+            if net is not None:
+                net.load_state_dict(torch.load(models_dir / f"{name}.pt", weights_only=False).state_dict())
+    stepper = TrainStep(se, de, st, ds.stats, details["parents"], details["dt"], lr=train_options["learning_rate"],
+                        eps=train_options["eps"], world_size=world)
+    if train_options["resume"] and (models_dir / "checkpoints.pt").exists():
+        ck = torch.load(models_dir / "checkpoints.pt", weights_only=False)
+        stepper.iteration = ck["iteration"]
+        stepper.optimizer.load_state_dict(ck["optimizer_state_dict"])
+    decay = train_options["learning_rate_decay"]
+    total = 1000 * train_options["niterations"]
+    batchsize = train_options["batchsize"]
+    ex_len = network_options["style_encoder"]["example_length"]
+    start = datetime.datetime.now()
+    while stepper.iteration < total:
+        batch = ds.sample_batch(batchsize, device)
+        ds.example_window_length = 2 * random.randint(ex_len // 2, ex_len)          # train.py:228-229
+        loss = stepper.step(batch)
+        it = stepper.iteration
+        if it % 1000 == 0:
+            for g in stepper.optimizer.param_groups:
+                g["lr"] *= decay                                                     # ExponentialLR every 1000 its (:431-432)
+        if rank == 0 and (it % 100 == 0 or it == 1):
+            print(f"iteration {it}/{total} loss {loss.item():.5f} elapsed {datetime.datetime.now() - start}", flush=True)
+        if rank == 0 and it % train_options["generate_samples_step"] == 0:
+            save_checkpoint(models_dir, se, de, st, stepper, float(loss.item()))
+    if rank == 0:
+        save_checkpoint(models_dir, se, de, st, stepper, float(loss.item()))
+
+
+def save_checkpoint(models_dir, se, de, st, stepper, loss):
+    """train.py:477-509: whole-module pickles + optimizer state."""
+    models_dir = Path(models_dir)
+    models_dir.mkdir(parents=True, exist_ok=True)
+    torch.save(se, models_dir / "speech_encoder.pt")
+    torch.save(de, models_dir / "decoder.pt")
+    if st is not None:
+        torch.save(st, models_dir / "style_encoder.pt")
+    torch.save({"iteration": stepper.iteration, "epoch": 0, "loss": loss,
+                "optimizer_state_dict": stepper.optimizer.state_dict()}, models_dir / "checkpoints.pt")
