@@ -38,6 +38,11 @@ const char* zeggs_last_error(void);
 int zeggs_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches claim) */
 long long zeggs_launch_count(void);
+/* Live device timing of the main kernel groups ("decoder_fwd", "decoder_bwd", "decoder_wgrad", "mel", "loss",
+ * "encoders_fwd", "encoders_bwd"): CUDA events recorded on the launching stream around each group; read after a sync. */
+void zeggs_timing_enable(int on);
+void zeggs_timing_reset(void);
+int zeggs_timing_read(const char* name, double* total_ms, int* count);
 
 /* ------------------------------------------------------------------------------------------------
  * Mel front end.  Replaces audio/spectrograms.py:8-54 (extract_mel_spectrogram_for_tts, pre-emphasis

@@ -66,6 +66,9 @@ SYMBOLS = [
     ("zeggs_last_error", C.c_char_p, []),
     ("zeggs_version", C.c_int, []),
     ("zeggs_launch_count", C.c_longlong, []),
+    ("zeggs_timing_enable", None, [C.c_int]),
+    ("zeggs_timing_reset", None, []),
+    ("zeggs_timing_read", C.c_int, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     ("zeggs_mel_num_frames", C.c_int, [C.c_int, C.c_int, C.c_int]),
     ("zeggs_mel_forward", C.c_int, [C.POINTER(MelArgs), C.c_void_p]),
     ("zeggs_decoder_packed_bytes", C.c_size_t, [C.c_int, C.c_int, C.c_int]),

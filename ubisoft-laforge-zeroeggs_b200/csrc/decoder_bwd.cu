@@ -537,8 +537,11 @@ extern "C" int zeggs_decoder_window_bwd(const zeggs_decoder_fwd_args* ap, const 
   ZCHECK_CUDA(cudaMemsetAsync(bw.bar, 0, 256, stream));
   ZCHECK_CUDA(cudaMemsetAsync(bw.DY, 0, (size_t)T * nbt * K1P * 32 * sizeof(float), stream));
   BwdArgsDev d; d.dY = b.dY; d.dRootPos = b.dRootPos; d.dRootRot = b.dRootRot; d.packed = b.packed_bwd;
-  int rc = (g.U == 4) ? launch_bwd<4>(a, g, bg, w, bw, d, stream) : launch_bwd<8>(a, g, bg, w, bw, d, stream);
+  int rc;
+  { ScopedTimer tm("decoder_bwd", stream);
+    rc = (g.U == 4) ? launch_bwd<4>(a, g, bg, w, bw, d, stream) : launch_bwd<8>(a, g, bg, w, bw, d, stream); }
   if (rc) return rc;
+  ScopedTimer tmw("decoder_wgrad", stream);
   cond_kmajor_kernel<<<592, 256, 0, stream>>>(a, g, bw.COND);
   count_launch();
   ZCHECK_LAUNCH();

@@ -9,6 +9,14 @@ namespace zeggs {
 constexpr int K1P = 1136;  // P_IN (1134) rounded up to the 16-row k-chunk
 
 void count_launch();
+int timer_id(const char* name);
+void* timer_begin(int id, cudaStream_t s);
+void timer_end(void* h, cudaStream_t s);
+struct ScopedTimer {
+  void* h; cudaStream_t s;
+  ScopedTimer(const char* name, cudaStream_t st) : h(timer_begin(timer_id(name), st)), s(st) {}
+  ~ScopedTimer() { timer_end(h, s); }
+};
 int sgemm_launch(int trans_a, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                  const float* bias, float* C, int ldc, int act, int accumulate, cudaStream_t stream);
 int sgemm_batched_launch(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,

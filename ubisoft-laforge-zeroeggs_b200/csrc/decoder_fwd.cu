@@ -372,7 +372,8 @@ extern "C" int zeggs_decoder_window_fwd(const zeggs_decoder_fwd_args* ap, void* 
     cond_precompute_kernel<<<dim3(a.T, g.nbt, ceil_div(4 * a.H, 64)), 256, sm, stream>>>(a, g, w.S01);
     count_launch();
     ZCHECK_LAUNCH();
-    if (g.U == 4) rc = launch_fwd<4>(a, g, w, stream); else rc = launch_fwd<8>(a, g, w, stream);
+    { ScopedTimer tm("decoder_fwd", stream);
+      if (g.U == 4) rc = launch_fwd<4>(a, g, w, stream); else rc = launch_fwd<8>(a, g, w, stream); }
     if (rc) return rc;
   }
   return ZEGGS_OK;

@@ -260,6 +260,7 @@ extern "C" int zeggs_speech_enc_fwd(const zeggs_speech_enc_args* ap, void* strea
   ZCHECK_ARG(B >= 1 && T >= 1 && Cin >= 1 && H >= 1 && O >= 1 && a.x && a.y, "speech_enc: bad arguments");
   SpeechWs w = speech_ws(a.workspace, B, T, Cin, H, O, k);
   ZCHECK_ARG(a.workspace && a.workspace_bytes >= w.bytes, "speech_enc: workspace too small");
+  ScopedTimer tm("encoders_fwd", s);
   RC(lin_fwd(a.x, a.W0, a.b0, w.h0, M, H, Cin, 1, s));                              // conv k=1 + ELU   (:267)
   RC(ew_mul(w.h0d, w.h0, a.mask0, nullptr, 0, (size_t)M * H, s));                   // drop0
   RC(im2col(w.h0d, B, T, H, k, k / 2, 1, w.col1, s));                               // replicate 'same' padding
@@ -273,6 +274,7 @@ extern "C" int zeggs_speech_enc_bwd(const zeggs_speech_enc_args* ap, const zeggs
   const zeggs_speech_enc_args& a = *ap; const zeggs_speech_enc_grads& g = *gp; cudaStream_t s = (cudaStream_t)stream_;
   const int B = a.B, T = a.T, Cin = a.C_in, H = a.H, O = a.O, k = 31, M = B * T;
   SpeechWs w = speech_ws(a.workspace, B, T, Cin, H, O, k);
+  ScopedTimer tm("encoders_bwd", s);
   RC(ew_mul(w.t0, g.dy, nullptr, a.y, 1, (size_t)M * O, s));                        // dpre2 = dy * ELU'(y)
   RC(lin_bwd(w.t0, w.h1d, a.W2, g.dW2, g.db2, w.t1, M, O, O, s));                   // t1 = d h1d
   RC(ew_mul(w.t0, w.t1, a.mask1, w.h1, 1, (size_t)M * O, s));                       // dpre1
@@ -318,6 +320,7 @@ extern "C" int zeggs_style_enc_fwd(const zeggs_style_enc_args* ap, void* stream_
   ZCHECK_ARG((long long)B * nh <= 65535, "style_enc: B*nheads too large for one launch");
   StyleWs w = style_ws(a.workspace, B, T, Cin, Hs, E, nh);
   ZCHECK_ARG(a.workspace && a.workspace_bytes >= w.bytes, "style_enc: workspace too small");
+  ScopedTimer tm("encoders_fwd", s);
   // conv stack (modules.py:359-384): conv k3 zero-pad -> ReLU -> LayerNorm -> Dropout, twice
   RC(im2col(a.x, B, T, Cin, 3, 1, 0, w.col0, s));
   RC(lin_fwd(w.col0, a.Wc1, a.bc1, w.c1, M, Hs, Cin * 3, 2, s));
@@ -359,6 +362,7 @@ extern "C" int zeggs_style_enc_bwd(const zeggs_style_enc_args* ap, const zeggs_s
   StyleWs w = style_ws(a.workspace, B, T, Cin, Hs, E, nh);
   const long long TT = (long long)T * T;
   const size_t nE = (size_t)M * E;
+  ScopedTimer tm("encoders_bwd", s);
   // VAE sample + mean pool
   vae_sample_bwd_kernel<<<ceil_div(B * (E / 2), 256), 256, 0, s>>>(g.dz, g.dmu, g.dlogvar, a.eps, a.logvar, B, E / 2, 1.0f / a.temperature, w.pooled); LAUNCH_OK();
   meanpool_bwd_kernel<<<GRID1(nE), 256, 0, s>>>(w.pooled, B, T, E, w.g0); LAUNCH_OK();               // g0 = d x2

@@ -211,6 +211,7 @@ extern "C" int zeggs_loss_fwd_bwd(const zeggs_loss_args* ap, void* stream_) {
   ZCHECK_ARG(a.workspace && a.workspace_bytes >= w.bytes, "loss: workspace too small");
   const int BT = a.B * a.T;
   ZCHECK_ARG((long long)a.B * a.T < (1ll << 31), "loss: too many frames");
+  ScopedTimer tm("loss", s);
   dim3 tb(32, 8);
   transpose_kernel<<<dim3(ceil_div(P_OUT, 32), ceil_div(BT, 32)), tb, 0, s>>>(a.Y, BT, P_OUT, P_OUT, w.Ys[0], (int)w.stride); count_launch();
   transpose_kernel<<<dim3(ceil_div(P_OUT, 32), ceil_div(BT, 32)), tb, 0, s>>>(a.WY, BT, P_OUT, P_OUT, w.Ys[1], (int)w.stride); count_launch();

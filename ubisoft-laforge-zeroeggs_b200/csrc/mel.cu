@@ -202,6 +202,7 @@ extern "C" int zeggs_mel_forward(const zeggs_mel_args* ap, void* stream_) {
               + (size_t)MEL_WARPS * 2 * MEL_N2 * sizeof(C2);
   ZCHECK_CUDA(cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(L, MEL_FT), a.n_clips);
+  ScopedTimer tm("mel", stream);
   mel_kernel<<<grid, MEL_WARPS * 32, smem, stream>>>(a, L, a.frames_per_anim);
   count_launch();
   ZCHECK_LAUNCH();
