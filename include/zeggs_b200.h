@@ -235,6 +235,13 @@ int zeggs_sgemm(int trans_a, int M, int N, int K, const float* A, int lda, const
 int zeggs_tc_gemm_bf16(int M, int N, int K, const void* A_hi, const void* A_lo, int lda, const void* B_hi,
                        const void* B_lo, int ldb, const float* bias, float* C, int ldc, int act, int accumulate,
                        void* stream);
+/* fp32 GEMM front end used by the encoders: mode 0 NT / 1 TN / 2 NN as zeggs_sgemm.  Large products run on tcgen05
+ * with operands split to bf16 (hi, lo) in the caller-provided scratch buffer (zeggs_set_scratch); small ones on the
+ * fp32 SIMT kernel.  zeggs_set_gemm_mode: 0 = fp32 SIMT only, 1 = tcgen05 split-bf16 x3 (default), 2 = tcgen05 bf16. */
+int zeggs_set_scratch(void* device_ptr, size_t bytes);
+int zeggs_set_gemm_mode(int mode);
+int zeggs_gemm_f32(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* bias,
+                   float* C, int ldc, int act, int accumulate, void* stream);
 int zeggs_split_bf16(const float* x, int rows, int cols, int ld_in, void* hi, void* lo, int ld_out, void* stream);
 
 #ifdef __cplusplus

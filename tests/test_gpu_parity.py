@@ -355,3 +355,23 @@ def test_fused_radam_vs_reference_golden(dev, golden_dir):
         p.grad.copy_(torch.from_numpy(g["grads"][i]).to(dev))
         opt.step()
         assert np.abs(p.detach().cpu().numpy() - g["traj"][i]).max() <= 2e-7, i
+
+
+@pytest.mark.parametrize("mode,M,N,K", [(0, 300, 200, 1000), (1, 512, 3402, 1536), (2, 700, 260, 129), (0, 12288 // 8, 512, 3402)])
+def test_gemm_f32_front_end_tcgen05(dev, mode, M, N, K):
+    """fp32 in/out GEMM through tcgen05 split-bf16 (default mode 1): <= 2e-5 relative to max|C| vs float64."""
+    from zeggs_b200 import _lib, ops
+    ops.ensure_scratch(dev)
+    g = torch.Generator().manual_seed(mode * 7 + M)
+    if mode == 0:
+        A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g); ref = A.double() @ B.double().T
+    elif mode == 1:
+        A, B = torch.randn(K, M, generator=g), torch.randn(K, N, generator=g); ref = A.double().T @ B.double()
+    else:
+        A, B = torch.randn(M, K, generator=g), torch.randn(K, N, generator=g); ref = A.double() @ B.double()
+    Ad, Bd = A.to(dev), B.to(dev)
+    out = torch.empty(M, N, device=dev)
+    _lib.check(_lib.lib().zeggs_gemm_f32(mode, M, N, K, Ad.data_ptr(), Ad.stride(0), Bd.data_ptr(), Bd.stride(0), None,
+                                         out.data_ptr(), N, 0, 0, _lib.stream_ptr()), "zeggs_gemm_f32")
+    err, sc = report(f"gemm_f32 mode{mode} {M}x{N}x{K}", out, ref)
+    assert err <= 2e-5 * sc

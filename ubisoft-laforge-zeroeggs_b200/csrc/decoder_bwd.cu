@@ -545,10 +545,53 @@ extern "C" int zeggs_decoder_window_bwd(const zeggs_decoder_fwd_args* ap, const 
   cond_kmajor_kernel<<<592, 256, 0, stream>>>(a, g, bw.COND);
   count_launch();
   ZCHECK_LAUNCH();
-  // ---- weight gradients (slots t = 1..T-1); strides in floats
   const long long sH = (long long)nbt * H * 32, s3 = (long long)nbt * 3 * H * 32, sX = (long long)nbt * K1P * 32, sC = (long long)nbt * C * 32;
   const int nT = T - 1;
-#define WG(...) do { rc = wgrad(__VA_ARGS__); if (rc) return rc; } while (0)
+  // ---- weight gradients (slots t = 1..T-1).  tcgen05 path: every history is re-laid out once as bf16 (hi, lo)
+  // [rows][(T*nbt)*32] (contraction index contiguous) in the scratch buffer, then each dW is one NT GEMM with
+  // K = (T-1)*nbt*32; "previous step" operands are the same buffer shifted by one slot (32*nbt columns).
+  bool tc_done = false;
+  if (gemm_mode() != 0 && scratch_base() != nullptr) {
+    const bool want_lo = gemm_mode() == 1;
+    const int S = T * nbt;                       // slots per history
+    const size_t ld = (size_t)S * 32;
+    char* p = scratch_base();
+    struct Hist { const float* src; long long stride; int rows; __nv_bfloat16 *hi, *lo; };
+    Hist hs[11] = {
+      {bw.DY, sX, P_OUT, nullptr, nullptr}, {bw.DGI1, s3, 3 * H, nullptr, nullptr}, {bw.DGH1, s3, 3 * H, nullptr, nullptr},
+      {bw.DGI0, s3, 3 * H, nullptr, nullptr}, {bw.DGH0, s3, 3 * H, nullptr, nullptr}, {bw.DPA, sH, H, nullptr, nullptr},
+      {w.H0, sH, H, nullptr, nullptr}, {w.H1, sH, H, nullptr, nullptr}, {w.A, sH, H, nullptr, nullptr},
+      {w.XP, sX, P_IN, nullptr, nullptr}, {bw.COND, sC, C, nullptr, nullptr}};
+    size_t need = 0;
+    for (auto& h : hs) need += (((size_t)h.rows * ld * 2 + 255) / 256) * 256 * (want_lo ? 2 : 1);
+    if (need <= scratch_bytes()) {
+      for (auto& h : hs) {
+        h.hi = (__nv_bfloat16*)p; p += (((size_t)h.rows * ld * 2 + 255) / 256) * 256;
+        if (want_lo) { h.lo = (__nv_bfloat16*)p; p += (((size_t)h.rows * ld * 2 + 255) / 256) * 256; }
+        // per-slot stride of the fp32 history is (stride / nbt) floats: slots (t,bt) are contiguous
+        rc = split_hist_launch(h.src, h.stride / nbt, S, h.rows, h.hi, h.lo, stream); if (rc) return rc;
+      }
+      const int Kc = nT * nbt * 32;
+      const int cur = nbt * 32;                  // column offset of slot t = 1
+      auto G = [&](const Hist& ga, int ga_off, int N, const Hist& xb, int xb_off, int K, float* dW, int ldw) {
+        return tc_gemm_launch(N, K, Kc, ga.hi + ga_off, want_lo ? ga.lo + ga_off : nullptr, (int)ld,
+                              xb.hi + xb_off, want_lo ? xb.lo + xb_off : nullptr, (int)ld, nullptr, dW, ldw, 0, 0, stream);
+      };
+      const Hist &hDY = hs[0], &hGI1 = hs[1], &hGH1 = hs[2], &hGI0 = hs[3], &hGH0 = hs[4], &hPA = hs[5], &hH0 = hs[6], &hH1 = hs[7],
+                 &hA = hs[8], &hXP = hs[9], &hCO = hs[10];
+      if ((rc = G(hDY, cur, P_OUT, hH1, cur, H, b.dW2, H))) return rc;
+      if ((rc = G(hGI1, cur, 3 * H, hH0, cur, H, b.dW_ih1, H))) return rc;
+      if ((rc = G(hGH1, cur, 3 * H, hH1, 0, H, b.dW_hh1, H))) return rc;
+      if ((rc = G(hGI0, cur, 3 * H, hA, cur, H, b.dW_ih0, A + H))) return rc;
+      if ((rc = G(hGI0, cur, 3 * H, hXP, cur, P_IN, b.dW_ih0 + H, A + H))) return rc;
+      if ((rc = G(hGI0, cur, 3 * H, hCO, cur, C, b.dW_ih0 + H + P_IN, A + H))) return rc;
+      if ((rc = G(hGH0, cur, 3 * H, hH0, 0, H, b.dW_hh0, H))) return rc;
+      if ((rc = G(hPA, cur, H, hXP, cur, P_IN, b.dW0, A))) return rc;
+      if ((rc = G(hPA, cur, H, hCO, cur, C, b.dW0 + P_IN, A))) return rc;
+      tc_done = true;
+    }
+  }
+#define WG(...) do { if (!tc_done) { rc = wgrad(__VA_ARGS__); if (rc) return rc; } } while (0)
 #define RS(...) do { rc = rowsum(__VA_ARGS__); if (rc) return rc; } while (0)
   // layer2: dW2 = DY . H1[t]^T
   WG(bw.DY + sX, sX, (long long)K1P * 32, P_OUT, w.H1 + sH, sH, (long long)H * 32, H, nT, nbt, b.dW2, H, stream);

@@ -22,6 +22,15 @@ int sgemm_launch(int trans_a, int M, int N, int K, const float* A, int lda, cons
 int sgemm_batched_launch(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                          const float* bias, float* C, int ldc, int act, int accumulate, int batch,
                          long long sA, long long sB, long long sC, cudaStream_t stream);
+int gemm_f32_auto(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* bias,
+                  float* C, int ldc, int act, int accumulate, cudaStream_t stream);
+int gemm_mode();
+char* scratch_base();
+size_t scratch_bytes();
+int split_hist_launch(const float* x, long long slot_stride, int S, int R, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t stream);
+int tc_gemm_launch(int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, int lda,
+                   const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, const float* bias,
+                   float* C, int ldc, int act, int accumulate, cudaStream_t stream);
 int sgemm_batched2_launch(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                           const float* bias, float* C, int ldc, int act, int accumulate, int batch,
                           long long sA, long long sB, long long sC, int inner, long long iA, long long iB, long long iC,

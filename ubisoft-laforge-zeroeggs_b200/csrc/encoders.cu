@@ -231,12 +231,12 @@ static int colsum(const float* x, int rows, int cols, float* out, cudaStream_t s
   colsum2_kernel<<<ceil_div(cols, 32), dim3(32, 8), 0, s>>>(x, rows, cols, out); LAUNCH_OK(); return 0; }
 // Linear / conv-as-GEMM forward: y[M,N] = act(x[M,K] W[N,K]^T + b)
 static int lin_fwd(const float* x, const float* W, const float* b, float* y, int M, int N, int K, int act, cudaStream_t s) {
-  return sgemm_launch(0, M, N, K, x, K, W, K, b, y, N, act, 0, s); }
+  return gemm_f32_auto(0, M, N, K, x, K, W, K, b, y, N, act, 0, s); }
 // backward of y = x W^T + b given dpre[M,N]:  dW[N,K] = dpre^T x ; db ; dx[M,K] = dpre W (optional)
 static int lin_bwd(const float* dpre, const float* x, const float* W, float* dW, float* db, float* dx, int M, int N, int K, cudaStream_t s) {
-  RC(sgemm_launch(1, N, K, M, dpre, N, x, K, nullptr, dW, K, 0, 0, s));
+  RC(gemm_f32_auto(1, N, K, M, dpre, N, x, K, nullptr, dW, K, 0, 0, s));
   if (db) RC(colsum(dpre, M, N, db, s));
-  if (dx) RC(sgemm_launch(2, M, K, N, dpre, N, W, K, nullptr, dx, K, 0, 0, s));
+  if (dx) RC(gemm_f32_auto(2, M, K, N, dpre, N, W, K, nullptr, dx, K, 0, 0, s));
   return 0;
 }
 

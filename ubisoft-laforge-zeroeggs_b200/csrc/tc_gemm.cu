@@ -125,6 +125,43 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, int rows, int col
   }
 }
 
+// transposing split: x[rows][cols] (ld_in) -> hi/lo [cols][ld_out] (ld_out >= rows, zero padded); 32x32 tiles
+__global__ void split_bf16_t_kernel(const float* __restrict__ x, int rows, int cols, int ld_in,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ld_out) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? x[(size_t)r * ld_in + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;     // output row c, output column r
+    if (c < cols && r < ld_out) {
+      const float v = tile[threadIdx.x][i];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      hi[(size_t)c * ld_out + r] = h;
+      if (lo) lo[(size_t)c * ld_out + r] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+// k-major history [S][R_src][32] (slot stride given) -> hi/lo [R][S*32]: out[r][s*32 + b] = in[s][r][b]
+__global__ void split_bf16_hist_kernel(const float* __restrict__ x, long long slot_stride, int S, int R,
+                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const size_t total = (size_t)S * R * 32;
+  const size_t ld = (size_t)S * 32;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i & 31); size_t e = i >> 5;
+    const int r = (int)(e % R); const int sidx = (int)(e / R);
+    const float v = x[(size_t)sidx * slot_stride + (size_t)r * 32 + b];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const size_t o = (size_t)r * ld + (size_t)sidx * 32 + b;
+    hi[o] = h;
+    if (lo) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
 static int encode_map(CUtensorMap* m, const void* base, int rows, int K, int ld_elems, int box_rows) {
   PFN_encodeTiled fn = get_encode_fn();
   ZCHECK_ARG(fn != nullptr, "tc_gemm: cuTensorMapEncodeTiled not available from the driver");
@@ -162,6 +199,61 @@ int tc_gemm_launch(int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bf
   count_launch();
   ZCHECK_LAUNCH();
   return ZEGGS_OK;
+}
+
+// ------------------------------------------------------------------ fp32-in / fp32-out front end
+// Caller-provided scratch for the bf16 operand copies (the library allocates nothing itself).
+static char* g_scratch = nullptr;
+static size_t g_scratch_bytes = 0;
+static int g_gemm_mode = 1;   // 0: fp32 SIMT everywhere, 1: tcgen05 split-bf16 (x3, ~fp32 accuracy), 2: tcgen05 plain bf16
+
+extern "C" int zeggs_set_scratch(void* p, size_t bytes) { g_scratch = (char*)p; g_scratch_bytes = bytes; return ZEGGS_OK; }
+extern "C" int zeggs_set_gemm_mode(int mode) {
+  ZCHECK_ARG(mode >= 0 && mode <= 2, "gemm mode must be 0 (fp32 SIMT), 1 (tcgen05 bf16x3) or 2 (tcgen05 bf16)");
+  g_gemm_mode = mode; return ZEGGS_OK;
+}
+int gemm_mode() { return g_gemm_mode; }
+char* scratch_base() { return g_scratch; }
+size_t scratch_bytes() { return g_scratch_bytes; }
+
+int split_hist_launch(const float* x, long long slot_stride, int S, int R, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t stream) {
+  split_bf16_hist_kernel<<<1184, 256, 0, stream>>>(x, slot_stride, S, R, hi, lo);
+  count_launch();
+  ZCHECK_LAUNCH();
+  return ZEGGS_OK;
+}
+
+// mode 0: C = act(A[M,K] B[N,K]^T + bias);  1: C = A[K,M]^T B[K,N];  2: C = A[M,K] B[K,N]   (all fp32, row-major)
+// Large products go through tcgen05 (operands split to bf16 hi/lo in the scratch buffer); small ones, or no scratch,
+// use the fp32 SIMT kernel.
+int gemm_f32_auto(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* bias,
+                  float* C, int ldc, int act, int accumulate, cudaStream_t stream) {
+  const int Kp = round_up(K, 8);
+  const size_t elems = (size_t)(M + N) * Kp;
+  const bool want_lo = g_gemm_mode == 1;
+  const size_t need = elems * 2 * (want_lo ? 2 : 1) + 1024;
+  if (g_gemm_mode == 0 || g_scratch == nullptr || need > g_scratch_bytes || (double)M * N * K < 4.0e6)
+    return sgemm_launch(mode, M, N, K, A, lda, B, ldb, bias, C, ldc, act, accumulate, stream);
+  char* p = g_scratch;
+  auto take = [&](size_t n) { __nv_bfloat16* r = (__nv_bfloat16*)p; p += ((n * 2 + 255) / 256) * 256; return r; };
+  __nv_bfloat16* Ah = take((size_t)M * Kp); __nv_bfloat16* Bh = take((size_t)N * Kp);
+  __nv_bfloat16* Al = want_lo ? take((size_t)M * Kp) : nullptr; __nv_bfloat16* Bl = want_lo ? take((size_t)N * Kp) : nullptr;
+  if ((size_t)(p - g_scratch) > g_scratch_bytes)
+    return sgemm_launch(mode, M, N, K, A, lda, B, ldb, bias, C, ldc, act, accumulate, stream);
+  const dim3 tb(32, 8);
+  if (mode == 1) split_bf16_t_kernel<<<dim3(ceil_div(M, 32), ceil_div(Kp, 32)), tb, 0, stream>>>(A, K, M, lda, Ah, Al, Kp);
+  else split_bf16_kernel<<<592, 256, 0, stream>>>(A, M, K, lda, Ah, Al, Kp);
+  count_launch();
+  if (mode == 0) split_bf16_kernel<<<592, 256, 0, stream>>>(B, N, K, ldb, Bh, Bl, Kp);
+  else split_bf16_t_kernel<<<dim3(ceil_div(N, 32), ceil_div(Kp, 32)), tb, 0, stream>>>(B, K, N, ldb, Bh, Bl, Kp);
+  count_launch();
+  ZCHECK_LAUNCH();
+  return tc_gemm_launch(M, N, K, Ah, Al, Kp, Bh, Bl, Kp, bias, C, ldc, act, accumulate, stream);
+}
+
+extern "C" int zeggs_gemm_f32(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* bias,
+                              float* C, int ldc, int act, int accumulate, void* stream) {
+  return gemm_f32_auto(mode, M, N, K, A, lda, B, ldb, bias, C, ldc, act, accumulate, (cudaStream_t)stream);
 }
 
 extern "C" int zeggs_tc_gemm_bf16(int M, int N, int K, const void* A_hi, const void* A_lo, int lda, const void* B_hi,

@@ -34,6 +34,21 @@ class _Workspace:
 
 WS = _Workspace()
 
+_scratch = {}
+
+
+def ensure_scratch(dev):
+    """Caller-owned scratch for the tcgen05 GEMM front end (bf16 operand copies); ZEGGS_SCRATCH_MB overrides the size."""
+    import os
+    key = str(dev)
+    if key not in _scratch:
+        mb = int(os.environ.get("ZEGGS_SCRATCH_MB", "1536"))
+        buf = torch.empty(mb << 20, dtype=torch.uint8, device=dev)
+        _lib.check(_lib.lib().zeggs_set_scratch(buf.data_ptr(), buf.numel()), "zeggs_set_scratch")
+        _scratch[key] = buf
+    return _scratch[key]
+
+
 _weights_epoch = 0
 
 
@@ -102,6 +117,7 @@ def decoder_window_forward(dec, root_pos0, root_rot0, pose0, gaze_pos, speech, s
     dev = speech.device
     if dev.type != "cuda":
         raise _lib.ZeggsError("zeggs_b200.Decoder runs on CUDA tensors only (no CPU fallback)")
+    ensure_scratch(dev)
     B, T = speech.shape[0], speech.shape[1]
     tensors = dict(root_pos0=_f32c(root_pos0, dev).reshape(B, 3), root_rot0=_f32c(root_rot0, dev).reshape(B, 4),
                    pose0=_f32c(pose0, dev).reshape(B, P_OUT), gaze_pos=_f32c(gaze_pos, dev).reshape(B, T, 3),
@@ -197,6 +213,7 @@ def speech_encoder(enc, x, masks=None):
     if x.device.type != "cuda":
         raise _lib.ZeggsError("zeggs_b200.SpeechEncoder runs on CUDA tensors only (no CPU fallback)")
     from .autograd import SpeechEncoderFn
+    ensure_scratch(x.device)
     B, T = x.shape[0], x.shape[1]
     H, O = enc.layer0.weight.shape[0], enc.layer1.weight.shape[0]
     if masks is None and enc.training:
@@ -238,6 +255,7 @@ def style_encoder(enc, x, temperature=1.0, eps=None, masks=None):
         raise _lib.ZeggsError("zeggs_b200.StyleEncoder runs on CUDA tensors only (no CPU fallback)")
     from .autograd import StyleEncoderFn
     dev = x.device
+    ensure_scratch(dev)
     B, T = x.shape[0], x.shape[1]
     Hs = enc.encoder.convs[0].conv.weight.shape[0]
     E = enc.encoder.convs[4].conv.weight.shape[0]
