@@ -197,9 +197,38 @@ def _load(mod, P, prefix, dev):
     return mod.to(dev)
 
 
+@pytest.fixture
+def gemm_mode(dev):
+    """Select the GEMM engine for one test and restore the default (1 = tcgen05 split-bf16) afterwards."""
+    from zeggs_b200 import _lib
+
+    def set_mode(m):
+        _lib.check(_lib.lib().zeggs_set_gemm_mode(m), "zeggs_set_gemm_mode")
+    yield set_mode
+    set_mode(1)
+
+
+def _grad_close(name, got, ref, mode, bad):
+    """mode 0 (fp32 SIMT): max-abs 3e-4 of max|ref|.  mode 1 (tcgen05 split-bf16, ~1e-5 relative products): relative L2 error
+    <= 2e-3 -- a ReLU/ELU gate whose pre-activation is within 1e-5 of zero can legitimately flip, which moves single
+    elements by O(1) of their size but leaves the L2 error tiny."""
+    err, sc = report(name, got, ref)
+    if mode == 0:
+        if not err <= 3e-4 * max(sc, 1e-6):
+            bad.append((name, err, sc))
+    else:
+        num = float((got.detach().cpu().double() - ref.double()).norm())
+        den = float(ref.double().norm())
+        if not num <= 2e-3 * max(den, 1e-9):
+            bad.append((name, "relL2", num / max(den, 1e-30)))
+
+
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("B,T,train", [(2, 6, False), (3, 40, True), (4, 97, True)])
-def test_speech_encoder_fwd_bwd(dev, B, T, train):
-    """abs <= 1e-5 forward, rel 2e-4 gradients vs oracle autograd (same injected dropout masks)."""
+def test_speech_encoder_fwd_bwd(dev, gemm_mode, B, T, train, mode):
+    """fp32 SIMT engine: abs <= 1e-5 forward, 3e-4 max-abs gradients; tcgen05 split-bf16 engine: abs <= 1e-4 forward, rel-L2
+    2e-3 gradients -- vs oracle autograd with the same injected dropout masks."""
+    gemm_mode(mode)
     from oracle import model_oracle as mo
     from zeggs_b200 import modules, synth
     P = synth.make_params(H=64, seed=21)
@@ -219,15 +248,19 @@ def test_speech_encoder_fwd_bwd(dev, B, T, train):
     named = dict(enc.named_parameters())
     g_got = torch.autograd.grad((out * cot.to(dev)).sum(), [named[k[len("speech_encoder."):]] for k in keys])
     err, sc = report(f"speech fwd B{B} T{T}", out, ref)
-    assert err <= 1e-5 * max(1.0, sc)
+    assert err <= (1e-5 if mode == 0 else 1e-4) * max(1.0, sc)
+    bad = []
     for k, a, b in zip(keys, g_got, g_ref):
-        err, sc = report(f"speech bwd {k}", a, b)
-        assert err <= 2e-4 * max(sc, 1e-6), k
+        _grad_close(f"speech bwd {k}", a, b, mode, bad)
+    assert not bad, bad
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("B,T,train", [(2, 16, False), (3, 33, True), (2, 130, True)])
-def test_style_encoder_fwd_bwd(dev, B, T, train):
-    """abs <= 2e-5 on (z, mu, logvar); rel 3e-4 gradients vs oracle autograd (injected eps and dropout masks)."""
+def test_style_encoder_fwd_bwd(dev, gemm_mode, B, T, train, mode):
+    """(z, mu, logvar): abs <= 2e-5 (fp32 SIMT engine) / 1e-4 (tcgen05 split-bf16); gradients as in _grad_close --
+    vs oracle autograd with injected eps and dropout masks."""
+    gemm_mode(mode)
     from oracle import model_oracle as mo
     from zeggs_b200 import modules, synth
     P = synth.make_params(H=64, seed=22)
@@ -253,12 +286,10 @@ def test_style_encoder_fwd_bwd(dev, B, T, train):
                                 [named[k[len("style_encoder."):]] for k in keys])
     for n, o, r in zip(("z", "mu", "logvar"), out, ref):
         err, sc = report(f"style fwd B{B} T{T} {n}", o, r)
-        assert err <= 2e-5 * max(1.0, sc), n
+        assert err <= (2e-5 if mode == 0 else 1e-4) * max(1.0, sc), n
     bad = []
     for k, a, b in zip(keys, g_got, g_ref):
-        err, sc = report(f"style bwd {k}", a, b)
-        if not err <= 3e-4 * max(sc, 1e-6):
-            bad.append((k, err, sc))
+        _grad_close(f"style bwd {k}", a, b, mode, bad)
     assert not bad, bad
 
 
@@ -282,10 +313,12 @@ def _batch(dev, B, T, T_ex, seed):
     return b
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("tag", ["h64", "h128"])
-def test_train_step_loss_and_gradients_vs_reference_golden(dev, golden_dir, tag):
+def test_train_step_loss_and_gradients_vs_reference_golden(dev, golden_dir, gemm_mode, tag, mode):
     """Whole step body (encoders -> decoder -> FK loss -> backward) against the reference's own loss / gradients
     (golden written by oracle/make_golden.py from the unmodified reference, eval-mode dropout, injected VAE eps)."""
+    gemm_mode(mode)
     g = np.load(os.path.join(golden_dir, f"train_{tag}.npz"))
     H, B, T, T_ex = int(g["H"]), int(g["B"]), int(g["T"]), int(g["T_ex"])
     step, P = _make_step(dev, H, int(g["param_seed"]))
@@ -296,24 +329,27 @@ def test_train_step_loss_and_gradients_vs_reference_golden(dev, golden_dir, tag)
     torch.cuda.synchronize()
     terms = step.terms.cpu().numpy()
     print(f"  loss {loss.item():.6f} vs golden {float(g['loss']):.6f}")
-    assert abs(loss.item() - float(g["loss"])) <= 2e-5 * abs(float(g["loss"]))
+    assert abs(loss.item() - float(g["loss"])) <= (2e-5 if mode == 0 else 2e-4) * abs(float(g["loss"]))
     names = ["root_pos", "root_rot", "root_vel", "root_vrt", "lpos", "lrot", "lvel", "lvrt", "cpos", "crot", "cvel", "cvrt",
              "ldvl", "ldvt", "cdvl", "cdvt", "gaze", "kl_div"]
     for i, n in enumerate(names):
         ref = float(g["loss_" + n])
-        assert abs(terms[1 + i] - ref) <= 3e-5 * max(1e-3, abs(ref)), (n, terms[1 + i], ref)
+        assert abs(terms[1 + i] - ref) <= (3e-5 if mode == 0 else 5e-4) * max(1e-3, abs(ref)), (n, terms[1 + i], ref)
     bad = []
     for prefix, net in (("speech_encoder.", step.se), ("decoder.", step.dec), ("style_encoder.", step.st)):
         for k, p in net.named_parameters():
             ref_n = float(g["gradnorm." + prefix + k])
             got_n = float(p.grad.double().norm())
-            if not abs(got_n - ref_n) <= 5e-4 * max(ref_n, 1e-7):
+            if not abs(got_n - ref_n) <= (5e-4 if mode == 0 else 3e-3) * max(ref_n, 1e-7):
                 bad.append((prefix + k, got_n, ref_n))
             if "grad." + prefix + k in g.files:
                 ref = g["grad." + prefix + k]
-                err = float(np.abs(p.grad.cpu().numpy() - ref).max())
-                if not err <= 5e-4 * max(float(np.abs(ref).max()), 1e-7):
-                    bad.append((prefix + k, "elementwise", err))
+                d = p.grad.cpu().numpy() - ref
+                if mode == 0:
+                    if not float(np.abs(d).max()) <= 5e-4 * max(float(np.abs(ref).max()), 1e-7):
+                        bad.append((prefix + k, "elementwise", float(np.abs(d).max())))
+                elif not float(np.linalg.norm(d)) <= 3e-3 * max(float(np.linalg.norm(ref)), 1e-9):
+                    bad.append((prefix + k, "relL2", float(np.linalg.norm(d))))
     assert not bad, bad
 
 
@@ -359,7 +395,7 @@ def test_fused_radam_vs_reference_golden(dev, golden_dir):
 
 @pytest.mark.parametrize("mode,M,N,K", [(0, 300, 200, 1000), (1, 512, 3402, 1536), (2, 700, 260, 129), (0, 12288 // 8, 512, 3402)])
 def test_gemm_f32_front_end_tcgen05(dev, mode, M, N, K):
-    """fp32 in/out GEMM through tcgen05 split-bf16 (default mode 1): <= 2e-5 relative to max|C| vs float64."""
+    """fp32 in/out GEMM through tcgen05 split-bf16 (default mode 1): <= 4e-5 relative to max|C| vs float64 (K up to 3402)."""
     from zeggs_b200 import _lib, ops
     ops.ensure_scratch(dev)
     g = torch.Generator().manual_seed(mode * 7 + M)
@@ -374,4 +410,4 @@ def test_gemm_f32_front_end_tcgen05(dev, mode, M, N, K):
     _lib.check(_lib.lib().zeggs_gemm_f32(mode, M, N, K, Ad.data_ptr(), Ad.stride(0), Bd.data_ptr(), Bd.stride(0), None,
                                          out.data_ptr(), N, 0, 0, _lib.stream_ptr()), "zeggs_gemm_f32")
     err, sc = report(f"gemm_f32 mode{mode} {M}x{N}x{K}", out, ref)
-    assert err <= 2e-5 * sc
+    assert err <= 4e-5 * sc
