@@ -1,0 +1,13 @@
+"""A short train-step run for ncu (launch list / full capture).  Sizes reduced in T so a replayed capture stays short."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+T = int(os.environ.get("PROF_T", "32")); steps = int(os.environ.get("PROF_STEPS", "2"))
+dev = torch.device("cuda:0")
+stepper, P, stats = bench.build_stepper(1024, dev, 1)
+batch = bench.synth_batch(32, T, 384, seed=1, device=dev)
+for _ in range(steps):
+    stepper.step(batch)
+torch.cuda.synchronize()
+print("done")

@@ -411,3 +411,58 @@ def test_gemm_f32_front_end_tcgen05(dev, mode, M, N, K):
                                          out.data_ptr(), N, 0, 0, _lib.stream_ptr()), "zeggs_gemm_f32")
     err, sc = report(f"gemm_f32 mode{mode} {M}x{N}x{K}", out, ref)
     assert err <= 4e-5 * sc
+
+
+# ---------------------------------------------------------------------------------------------- inference path (config 1)
+def test_generate_motion_end_to_end_vs_oracle(dev):
+    """WAV samples -> mel -> SpeechEncoder -> StyleEncoder (example) -> free-running decoder (B=1, 3 s clip), eval mode.
+    Per-pose-channel max-abs <= 5e-4 * max(1, max|ref|) in de-normalised units (default tcgen05 split-bf16 encoders,
+    fp32 recurrence)."""
+    from oracle import mel_oracle, model_oracle as mo
+    from zeggs_b200 import generate, modules, synth
+    H = 1024
+    P = synth.make_params(H=H, seed=77)
+    st = synth.load_stats()
+    nets = dict(speech_encoder=_load(modules.SpeechEncoder(81, 64, 64), P, "speech_encoder.", dev).eval(),
+                style_encoder=_load(modules.StyleEncoder(1134, 512, 64, type="attn", use_vae=True), P, "style_encoder.", dev).eval(),
+                decoder=_load(modules.Decoder(1134, 1131, 64, 64, H, 2), P, "decoder.", dev).eval())
+    wav = synth.make_waveforms(1, 48000, seed=9)[0]
+    ex = synth.make_style_example(1, 200, seed=9)[0]
+    win = synth.make_pose_windows(1, 2, seed=9)
+    fp = {k: win[k][0, 0] for k in NAMES}
+    from oracle.make_golden import audio_params
+    eps = np.zeros((1, 64), np.float32)
+    out, z = generate.generate_motion(nets, st, audio_params(200), wav, ex, fp, win["gaze_pos"][0, 0], float(st["dt"]),
+                                      temperature=1.0, eps=torch.zeros(1, 64, device=dev), device=dev)
+    torch.cuda.synchronize()
+    # oracle chain
+    f = lambda k: torch.as_tensor(st[k], dtype=torch.float32)
+    T = 180
+    Pt = tt(P)
+    with torch.no_grad():
+        feat = torch.from_numpy(mel_oracle.preprocess_audio(wav, 60, T))[None]
+        sp = mo.speech_encoder(Pt, (feat - f("audio_input_mean")) / f("audio_input_std"))
+        zz, mu, lv = mo.style_encoder(Pt, (torch.from_numpy(ex)[None] - f("anim_input_mean")) / f("anim_input_std"), eps=torch.from_numpy(eps))
+        gaze = torch.from_numpy(win["gaze_pos"][0, 0]).reshape(1, 1, 3).repeat(1, T, 1)
+        ref = mo.decoder_forward(Pt, *[torch.from_numpy(fp[k])[None] for k in NAMES], gaze, sp, zz.unsqueeze(1).repeat(1, T, 1),
+                                 f("anim_input_mean"), f("anim_input_std"), f("anim_output_mean"), f("anim_output_std"), float(st["dt"]))
+    err, sc = report("generate z", z, zz)
+    assert err <= 1e-4 * max(1.0, sc)
+    for n, o, r in zip(NAMES, out, ref):
+        assert tuple(o.shape) == tuple(r.shape)
+        err, sc = report(f"generate {n}", o, r)
+        assert err <= 5e-4 * max(1.0, sc), n
+
+
+def test_checkpoint_round_trip_whole_module_pickles(dev, tmp_path):
+    """train.py:482-509 / generate.py:130-138 artefact format: torch.save(module) -> load_networks -> same outputs."""
+    from zeggs_b200 import generate, modules, synth
+    P = synth.make_params(H=64, seed=5)
+    dec = _load(modules.Decoder(1134, 1131, 64, 64, 64, 2), P, "decoder.", dev).eval()
+    se = _load(modules.SpeechEncoder(81, 64, 64), P, "speech_encoder.", dev).eval()
+    torch.save(dec, tmp_path / "decoder.pt"); torch.save(se, tmp_path / "speech_encoder.pt")
+    nets = generate.load_networks(tmp_path, dev, with_style=False)
+    x = torch.randn(2, 9, 81, device=dev)
+    with torch.no_grad():
+        assert torch.equal(nets["speech_encoder"](x), se(x))
+    assert nets["decoder"].hidden_size == 64

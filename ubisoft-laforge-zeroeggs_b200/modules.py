@@ -59,12 +59,23 @@ class Decoder(nn.Module):
             raise _lib.ZeggsError("num_rnn_layers must be 2 (train.py:124-131 hard-codes it)")
         if pose_input_size != P_IN or pose_output_size != P_OUT:
             raise _lib.ZeggsError("pose layout must be the 75-joint 1134/1131 layout (modules.py:699-736)")
-        self.hidden_size = hidden_size
-        self.speech_encoding_size = speech_encoding_size
-        self.style_encoding_size = style_encoding_size
         self.recurrent_decoder = RecurrentDecoderNormal(
             pose_input_size, speech_encoding_size, style_encoding_size, pose_output_size, hidden_size, num_rnn_layers)
         self.cell_state_encoder = CellStateEncoder(pose_input_size + style_encoding_size, hidden_size, num_rnn_layers)
+
+    # sizes are read off the parameters so that instances un-pickled from the reference's whole-module checkpoints
+    # (generate.py:130-138; they carry no extra attributes) work unchanged
+    @property
+    def hidden_size(self):
+        return self.recurrent_decoder.layer0.weight.shape[0]
+
+    @property
+    def style_encoding_size(self):
+        return self.cell_state_encoder.layer0.weight.shape[1] - P_IN
+
+    @property
+    def speech_encoding_size(self):
+        return self.recurrent_decoder.layer0.weight.shape[1] - P_IN - self.style_encoding_size
 
     def _weights(self):
         r, c = self.recurrent_decoder, self.cell_state_encoder
@@ -157,7 +168,8 @@ class PositionalEncoding(nn.Module):
 
     def table(self, T):
         pos = torch.arange(0, T, dtype=torch.float).unsqueeze(1)
-        div_term = torch.exp(torch.arange(0, self.embed_dim, 2).float() * (-np.log(self.timestep) / self.embed_dim))
+        timestep = getattr(self, "timestep", 10000.0)   # absent on instances un-pickled from reference checkpoints
+        div_term = torch.exp(torch.arange(0, self.embed_dim, 2).float() * (-np.log(timestep) / self.embed_dim))
         pe = torch.zeros(T, self.embed_dim)
         pe[:, 0::2] = torch.sin(pos * div_term)
         pe[:, 1::2] = torch.cos(pos * div_term)
