@@ -102,20 +102,35 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
   const float m1 = s1 / D, m2 = s2 / D, rs = rstd[row];
   for (int i = lane; i < D; i += 32) dx[(size_t)row * D + i] = rs * (pd[i] * gamma[i] - m1 - px[i] * m2);
 }
-// dgamma[d] = sum_rows dy*xhat, dbeta[d] = sum_rows dy.   grid = ceil(D/32) x 1, block (32, 8)
-__global__ void layernorm_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ xhat, int rows, int D,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  __shared__ float sg[8][33], sb[8][33];
+// Column reductions over many rows, two stages (deterministic): stage 1 grid (ceil(D/32), RB), block (32,8) writes
+// partial[rb][2][D]; stage 2 sums the RB partials.  mode 0: out0 = sum_r a[r][d];  mode 1: out0 = sum a*b, out1 = sum a.
+constexpr int COLRED_RB = 64;
+__global__ void colred_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, int rows, int D, float* __restrict__ partial) {
+  __shared__ float s0[8][33], s1[8][33];
   const int d = blockIdx.x * 32 + threadIdx.x;
-  float g = 0.f, b = 0.f;
+  const int per = (rows + gridDim.y - 1) / gridDim.y;
+  const int r_lo = blockIdx.y * per, r_hi = min(rows, r_lo + per);
+  float x = 0.f, y = 0.f;
   if (d < D)
-    for (int r = threadIdx.y; r < rows; r += 8) { float v = dy[(size_t)r * D + d]; g += v * xhat[(size_t)r * D + d]; b += v; }
-  sg[threadIdx.y][threadIdx.x] = g; sb[threadIdx.y][threadIdx.x] = b;
+    for (int r = r_lo + threadIdx.y; r < r_hi; r += 8) {
+      const float v = a[(size_t)r * D + d];
+      if (b) { x += v * b[(size_t)r * D + d]; y += v; } else x += v;
+    }
+  s0[threadIdx.y][threadIdx.x] = x; s1[threadIdx.y][threadIdx.x] = y;
   __syncthreads();
   if (threadIdx.y == 0 && d < D) {
-    for (int r = 1; r < 8; ++r) { g += sg[r][threadIdx.x]; b += sb[r][threadIdx.x]; }
-    dgamma[d] = g; dbeta[d] = b;
+    for (int r = 1; r < 8; ++r) { x += s0[r][threadIdx.x]; y += s1[r][threadIdx.x]; }
+    partial[((size_t)blockIdx.y * 2) * D + d] = x;
+    partial[((size_t)blockIdx.y * 2 + 1) * D + d] = y;
   }
+}
+__global__ void colred_final_kernel(const float* __restrict__ partial, int RB, int D, float* __restrict__ out0, float* __restrict__ out1) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  float x = 0.f, y = 0.f;
+  for (int rb = 0; rb < RB; ++rb) { x += partial[((size_t)rb * 2) * D + d]; y += partial[((size_t)rb * 2 + 1) * D + d]; }
+  out0[d] = x;
+  if (out1) out1[d] = y;
 }
 // row-wise softmax (+ dropout multiplier) over rows of length L:  P = softmax(S);  Pd = P * mask
 __global__ void softmax_rows_kernel(const float* __restrict__ S, const float* __restrict__ mask, size_t rows, int L,
@@ -191,16 +206,6 @@ __global__ void vae_sample_bwd_kernel(const float* __restrict__ dz, const float*
   dpooled[(size_t)b * 2 * Z + j] = gm;
   dpooled[(size_t)b * 2 * Z + Z + j] = gl;
 }
-__global__ void colsum2_kernel(const float* __restrict__ x, int rows, int cols, float* __restrict__ out) {
-  __shared__ float sm[8][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  float s = 0.f;
-  if (c < cols) for (int r = threadIdx.y; r < rows; r += 8) s += x[(size_t)r * cols + c];
-  sm[threadIdx.y][threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.y == 0 && c < cols) { for (int r = 1; r < 8; ++r) s += sm[r][threadIdx.x]; out[c] = s; }
-}
-
 // ------------------------------------------------------------------ launch helpers
 struct Arena {
   char* base; size_t off;
@@ -224,11 +229,16 @@ static int ew_add(float* dst, const float* a, const float* b, size_t n, size_t p
   ew_add_kernel<<<GRID1(n), 256, 0, s>>>(dst, a, b, n, period); LAUNCH_OK(); return 0; }
 static int ln_fwd(const float* a, const float* res, const float* g, const float* b, int rows, int D, float* y, float* xh, float* rs, cudaStream_t s) {
   layernorm_fwd_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(a, res, g, b, rows, D, y, xh, rs); LAUNCH_OK(); return 0; }
+static float* g_redbuf = nullptr;   // [COLRED_RB][2][D <= 4096] scratch inside the calling module's workspace
+static int colred(const float* a, const float* b, int rows, int D, float* out0, float* out1, cudaStream_t s) {
+  ZCHECK_ARG(g_redbuf != nullptr && D <= 4096, "column reduction: scratch missing or D=%d too wide", D);
+  const int RB = rows < 8 * COLRED_RB ? ceil_div(rows, 8) : COLRED_RB;
+  colred_partial_kernel<<<dim3(ceil_div(D, 32), RB), dim3(32, 8), 0, s>>>(a, b, rows, D, g_redbuf); LAUNCH_OK();
+  colred_final_kernel<<<ceil_div(D, 256), 256, 0, s>>>(g_redbuf, RB, D, out0, out1); LAUNCH_OK(); return 0; }
 static int ln_bwd(const float* dy, const float* xh, const float* rs, const float* g, int rows, int D, float* dx, float* dg, float* db, cudaStream_t s) {
   layernorm_bwd_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(dy, xh, rs, g, rows, D, dx); LAUNCH_OK();
-  layernorm_wgrad_kernel<<<ceil_div(D, 32), dim3(32, 8), 0, s>>>(dy, xh, rows, D, dg, db); LAUNCH_OK(); return 0; }
-static int colsum(const float* x, int rows, int cols, float* out, cudaStream_t s) {
-  colsum2_kernel<<<ceil_div(cols, 32), dim3(32, 8), 0, s>>>(x, rows, cols, out); LAUNCH_OK(); return 0; }
+  return colred(dy, xh, rows, D, dg, db, s); }
+static int colsum(const float* x, int rows, int cols, float* out, cudaStream_t s) { return colred(x, nullptr, rows, cols, out, nullptr, s); }
 // Linear / conv-as-GEMM forward: y[M,N] = act(x[M,K] W[N,K]^T + b)
 static int lin_fwd(const float* x, const float* W, const float* b, float* y, int M, int N, int K, int act, cudaStream_t s) {
   return gemm_f32_auto(0, M, N, K, x, K, W, K, b, y, N, act, 0, s); }
@@ -241,12 +251,13 @@ static int lin_bwd(const float* dpre, const float* x, const float* W, float* dW,
 }
 
 // ================================================================== SpeechEncoder
-struct SpeechWs { float *h0, *h0d, *col1, *h1, *h1d, *t0, *t1, *dcol; size_t bytes; };
+struct SpeechWs { float *h0, *h0d, *col1, *h1, *h1d, *t0, *t1, *dcol, *red; size_t bytes; };
 static SpeechWs speech_ws(void* base, int B, int T, int Cin, int H, int O, int k) {
   Arena a{(char*)base, 0};
   SpeechWs w; const size_t R = (size_t)B * T;
   w.h0 = a.take(R * H); w.h0d = a.take(R * H); w.col1 = a.take(R * H * k); w.h1 = a.take(R * O); w.h1d = a.take(R * O);
   w.t0 = a.take(R * (H > O ? H : O)); w.t1 = a.take(R * (H > O ? H : O)); w.dcol = a.take(R * H * k);
+  w.red = a.take((size_t)COLRED_RB * 2 * 4096);
   w.bytes = a.off; return w;
 }
 extern "C" size_t zeggs_speech_enc_workspace_bytes(int B, int T, int Cin, int H, int O) {
@@ -274,6 +285,7 @@ extern "C" int zeggs_speech_enc_bwd(const zeggs_speech_enc_args* ap, const zeggs
   const zeggs_speech_enc_args& a = *ap; const zeggs_speech_enc_grads& g = *gp; cudaStream_t s = (cudaStream_t)stream_;
   const int B = a.B, T = a.T, Cin = a.C_in, H = a.H, O = a.O, k = 31, M = B * T;
   SpeechWs w = speech_ws(a.workspace, B, T, Cin, H, O, k);
+  g_redbuf = w.red;
   ScopedTimer tm("encoders_bwd", s);
   RC(ew_mul(w.t0, g.dy, nullptr, a.y, 1, (size_t)M * O, s));                        // dpre2 = dy * ELU'(y)
   RC(lin_bwd(w.t0, w.h1d, a.W2, g.dW2, g.db2, w.t1, M, O, O, s));                   // t1 = d h1d
@@ -289,7 +301,7 @@ extern "C" int zeggs_speech_enc_bwd(const zeggs_speech_enc_args* ap, const zeggs
 struct StyleWs {
   float *col0, *c1, *l1, *xh1, *rs1, *l1d, *col1, *c2, *l2, *xh2, *rs2, *l2d, *pe, *x0, *qkv, *S, *P, *Pd, *o, *ao, *aod,
         *x1, *xh3, *rs3, *colf, *f1, *colf2, *f2, *f2d, *x2, *xh4, *rs4, *pooled;
-  float *g0, *g1, *g2, *gqkv, *gcol;   // backward temporaries
+  float *g0, *g1, *g2, *gqkv, *gcol, *red;   // backward temporaries
   size_t bytes;
 };
 static StyleWs style_ws(void* base, int B, int T, int Cin, int Hs, int E, int nh) {
@@ -305,6 +317,7 @@ static StyleWs style_ws(void* base, int B, int T, int Cin, int Hs, int E, int nh
   const size_t big = Hs > 3 * E ? Hs : 3 * E;
   w.g0 = a.take(R * big); w.g1 = a.take(R * big); w.g2 = a.take(R * big); w.gqkv = a.take(R * 3 * E);
   w.gcol = a.take(R * (size_t)(Hs * 3 > E * 3 ? Hs * 3 : E * 3));
+  w.red = a.take((size_t)COLRED_RB * 2 * 4096);
   w.bytes = a.off; return w;
 }
 extern "C" size_t zeggs_style_enc_workspace_bytes(int B, int T, int Cin, int Hs, int E, int nheads) {
@@ -362,6 +375,7 @@ extern "C" int zeggs_style_enc_bwd(const zeggs_style_enc_args* ap, const zeggs_s
   StyleWs w = style_ws(a.workspace, B, T, Cin, Hs, E, nh);
   const long long TT = (long long)T * T;
   const size_t nE = (size_t)M * E;
+  g_redbuf = w.red;
   ScopedTimer tm("encoders_bwd", s);
   // VAE sample + mean pool
   vae_sample_bwd_kernel<<<ceil_div(B * (E / 2), 256), 256, 0, s>>>(g.dz, g.dmu, g.dlogvar, a.eps, a.logvar, B, E / 2, 1.0f / a.temperature, w.pooled); LAUNCH_OK();
