@@ -103,12 +103,19 @@ typedef struct {
   void* workspace;
   size_t workspace_bytes;
   int save_for_backward; /* 1: keep every step's activations in the workspace for zeggs_decoder_window_bwd */
+  int engine;            /* 0: fp32 SIMT recurrence (parity grade); 1: tcgen05 recurrence, bf16 operands / fp32 state (B <= 32) */
+  const void* packed_tc; /* engine 1: zeggs_decoder_pack_weights_tc output */
+  void* workspace_tc;    /* engine 1: zeggs_decoder_tc_workspace_bytes bytes (bf16 activation images) */
 } zeggs_decoder_fwd_args;
 
 size_t zeggs_decoder_packed_bytes(int H, int S, int Z);
 /* one-off re-layout of the decoder weights into per-CTA k-major slices (re-run after each optimizer step) */
 int zeggs_decoder_pack_weights(const zeggs_decoder_fwd_args* a, float* packed, void* stream);
 size_t zeggs_decoder_workspace_bytes(int B, int T, int H, int S, int Z, int save_for_backward);
+/* tensor-core engine: bf16 shared-memory images of the per-CTA weight slices + activation image buffers */
+size_t zeggs_decoder_packed_tc_bytes(int H, int S, int Z);
+size_t zeggs_decoder_tc_workspace_bytes(int H, int S, int Z);
+int zeggs_decoder_pack_weights_tc(const zeggs_decoder_fwd_args* a, void* packed, void* stream);
 int zeggs_decoder_window_fwd(const zeggs_decoder_fwd_args* a, void* stream);
 
 /* Backward of zeggs_decoder_window_fwd (the autograd of modules.py:47-162: full BPTT through the GRU stack,

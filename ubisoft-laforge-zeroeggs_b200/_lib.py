@@ -26,7 +26,8 @@ class DecoderFwdArgs(C.Structure):
                     "in_mean", "in_std", "out_mean", "out_std",
                     "root_pos0", "root_rot0", "pose0", "gaze_pos", "speech", "style",
                     "Y", "root_pos", "root_rot", "workspace")] +
-                [("workspace_bytes", C.c_size_t), ("save_for_backward", C.c_int)])
+                [("workspace_bytes", C.c_size_t), ("save_for_backward", C.c_int), ("engine", C.c_int),
+                 ("packed_tc", C.c_void_p), ("workspace_tc", C.c_void_p)])
 
 
 class DecoderBwdArgs(C.Structure):
@@ -75,6 +76,9 @@ SYMBOLS = [
     ("zeggs_decoder_pack_weights", C.c_int, [C.POINTER(DecoderFwdArgs), C.c_void_p, C.c_void_p]),
     ("zeggs_decoder_workspace_bytes", C.c_size_t, [C.c_int] * 6),
     ("zeggs_decoder_window_fwd", C.c_int, [C.POINTER(DecoderFwdArgs), C.c_void_p]),
+    ("zeggs_decoder_packed_tc_bytes", C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    ("zeggs_decoder_tc_workspace_bytes", C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    ("zeggs_decoder_pack_weights_tc", C.c_int, [C.POINTER(DecoderFwdArgs), C.c_void_p, C.c_void_p]),
     ("zeggs_decoder_packed_bwd_bytes", C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     ("zeggs_decoder_pack_weights_bwd", C.c_int, [C.POINTER(DecoderFwdArgs), C.c_void_p, C.c_void_p]),
     ("zeggs_decoder_bwd_workspace_bytes", C.c_size_t, [C.c_int] * 5),

@@ -105,6 +105,8 @@ inline DecWs make_ws(void* base, const DecGeom& g, int T, int save) {
   return w;
 }
 
+int decoder_fwd_tc_run(const zeggs_decoder_fwd_args& a, const DecGeom& g, const DecWs& w, cudaStream_t stream);
+
 // ------------------------------------------------------------------ skinny GEMM
 // One CTA (8 warps) computes out[r][b] = sum_k Wt[k][r] * x[k][b] for a tile of R = 4*RT rows and 32
 // batch columns.  Wt is the CTA's pre-packed k-major slice [K][R]; x is a k-major activation vector

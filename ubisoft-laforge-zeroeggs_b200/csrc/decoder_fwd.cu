@@ -348,7 +348,7 @@ extern "C" int zeggs_decoder_window_fwd(const zeggs_decoder_fwd_args* ap, void* 
   DecGeom g = make_geom(a.B, a.H, a.S, a.Z);
   DecWs w = make_ws(a.workspace, g, a.T, a.save_for_backward);
   ZCHECK_ARG(a.workspace != nullptr && a.workspace_bytes >= w.bytes, "decoder: workspace too small (%zu < %zu)", a.workspace_bytes, w.bytes);
-  ZCHECK_ARG(a.packed != nullptr, "decoder: packed weights missing (call zeggs_decoder_pack_weights)");
+  ZCHECK_ARG(a.engine == 1 || a.packed != nullptr, "decoder: packed weights missing (call zeggs_decoder_pack_weights)");
   // zero: barrier words, the x_pose slots (k padding rows / batch padding columns) and the h slot 0
   ZCHECK_CUDA(cudaMemsetAsync(w.bar, 0, 256, stream));
   ZCHECK_CUDA(cudaMemsetAsync(w.XP, 0, (size_t)w.TS * g.nbt * K1P * 32 * sizeof(float), stream));
@@ -372,8 +372,12 @@ extern "C" int zeggs_decoder_window_fwd(const zeggs_decoder_fwd_args* ap, void* 
     cond_precompute_kernel<<<dim3(a.T, g.nbt, ceil_div(4 * a.H, 64)), 256, sm, stream>>>(a, g, w.S01);
     count_launch();
     ZCHECK_LAUNCH();
-    { ScopedTimer tm("decoder_fwd", stream);
-      if (g.U == 4) rc = launch_fwd<4>(a, g, w, stream); else rc = launch_fwd<8>(a, g, w, stream); }
+    if (a.engine == 1) {
+      rc = decoder_fwd_tc_run(a, g, w, stream);
+    } else {
+      ScopedTimer tm("decoder_fwd", stream);
+      if (g.U == 4) rc = launch_fwd<4>(a, g, w, stream); else rc = launch_fwd<8>(a, g, w, stream);
+    }
     if (rc) return rc;
   }
   return ZEGGS_OK;

@@ -1,0 +1,511 @@
+// Decoder window forward on the 5th-gen tensor cores (engine 1): the same persistent, weight-stationary
+// partition as decoder_fwd.cu (CTA c owns U hidden units of layer0 / GRU0 / GRU1 and ceil(1131/G) layer2 rows,
+// four stages per step separated by a grid barrier) but every stage GEMM is a tcgen05.mma chain:
+//
+//   D[128 x N] (f32, TMEM) = X[128 x K] (bf16, smem)  *  Wslice[N x K]^T (bf16, smem)
+//
+//   * X = the stage's activation vector for the 32 samples of the batch tile.  Only rows 0..31 of the M = 128
+//     operand are real; the k-block tiles are packed 4 KB apart, so rows 32..127 of every tile alias the following
+//     k-blocks (any finite or non-finite garbage there only reaches accumulator rows that are never read).
+//   * Activations live in global memory as bf16 *shared-memory images* (128-byte rows, 16-byte chunks XOR-swizzled
+//     by row&7, i.e. the SWIZZLE_128B K-major canonical layout), written by the producing epilogue, so one
+//     cp.async.bulk per vector brings them in -- no tensor maps, no conversion passes.
+//   * Weight slices are pre-packed once per optimizer step into the same image format per (CTA, chain, k-block) and
+//     streamed through a 16-slot smem ring by a dedicated producer warp that runs ahead across grid barriers.
+//   * Warp roles (128 threads): warp 0 = epilogue (TMEM lanes 0..31 = the 32 samples: gates / ELU / pose integration
+//     in fp32, writes next activations as bf16 images + fp32 state/history), warp 1 = MMA issuer (one lane),
+//     warp 2 = weight producer, warp 3 = activation loader (waits on the grid barrier, then bulk-copies X).
+//   GRU state, gates, pose integration and all saved-for-backward tensors stay fp32; only the MMA operands are bf16.
+#include "decoder_common.cuh"
+#include "tc_common.cuh"
+
+namespace zeggs {
+
+constexpr int TC_RING = 16;             // weight ring slots (one k-block tile each)
+constexpr int TC_XKB = 18;              // k-blocks of the widest activation vector (x_pose: 1136 -> 1152)
+constexpr int TC_SLOT_BYTES = 4096;     // 32 rows x 128 B (N <= 32)
+
+struct TcGeom {
+  int NP;          // padded rows of a gate chain: round_up(3U,16)
+  int N1;          // rows of the stage-1 chain: 4U
+  int kbH, kbX;    // k-blocks of an H-vector / of x_pose
+  int n4t;         // 16-row tiles of layer2 per CTA
+  size_t chain_off[6];   // byte offset of chain c inside one CTA's packed block (chain 5 = first layer2 tile)
+  size_t cta_bytes;
+};
+
+__host__ __device__ inline size_t tc_tile_bytes(int N) { return (size_t)N * 128; }
+
+inline TcGeom make_tcgeom(const DecGeom& g) {
+  TcGeom t;
+  t.NP = round_up(3 * g.U, 16);
+  t.N1 = 4 * g.U;
+  t.kbH = ceil_div(g.H, 64);
+  t.kbX = ceil_div(K1P, 64);
+  t.n4t = g.n4t;
+  size_t off = 0;
+  t.chain_off[0] = off; off += (size_t)t.kbX * tc_tile_bytes(t.N1);     // S1   X = x_pose
+  t.chain_off[1] = off; off += (size_t)t.kbH * tc_tile_bytes(t.NP);     // gh0  X = h0(t-1)
+  t.chain_off[2] = off; off += (size_t)t.kbH * tc_tile_bytes(t.NP);     // gi0a X = a(t)
+  t.chain_off[3] = off; off += (size_t)t.kbH * tc_tile_bytes(t.NP);     // gh1  X = h1(t-1)
+  t.chain_off[4] = off; off += (size_t)t.kbH * tc_tile_bytes(t.NP);     // gi1  X = h0(t)
+  t.chain_off[5] = off; off += (size_t)t.n4t * t.kbH * tc_tile_bytes(16);  // y tiles X = h1(t)
+  t.cta_bytes = off;
+  return t;
+}
+
+// byte offset of element (row, k) inside an image whose k-block tiles have `rows` rows
+__host__ __device__ inline size_t img_off(int rows, int row, int k) {
+  const int kb = k >> 6, c = (k & 63) >> 3, e = k & 7;
+  return (size_t)kb * rows * 128 + (size_t)row * 128 + (size_t)((c ^ (row & 7)) << 4) + (size_t)e * 2;
+}
+
+// ------------------------------------------------------------------ packing (bf16 images of the weight slices)
+__global__ void pack_decoder_tc_kernel(DecGeom g, TcGeom tg, const float* __restrict__ W0, const float* __restrict__ Wih0,
+                                       const float* __restrict__ Whh0, const float* __restrict__ Wih1,
+                                       const float* __restrict__ Whh1, const float* __restrict__ W2, uint8_t* __restrict__ out) {
+  const int H = g.H, U = g.U, A = g.A;
+  const size_t total_elems = (size_t)g.G * tg.cta_bytes / 2;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_elems; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i / (tg.cta_bytes / 2));
+    size_t b = (i % (tg.cta_bytes / 2)) * 2;           // byte offset inside the CTA block
+    int chain = 5;
+    for (int q = 0; q < 5; ++q) if (b < tg.chain_off[q + 1]) { chain = q; break; }
+    b -= tg.chain_off[chain];
+    int N = chain == 0 ? tg.N1 : (chain == 5 ? 16 : tg.NP);
+    int tile = 0;
+    if (chain == 5) { tile = (int)(b / ((size_t)tg.kbH * tc_tile_bytes(16))); b -= (size_t)tile * tg.kbH * tc_tile_bytes(16); }
+    const int kb = (int)(b / tc_tile_bytes(N));
+    const int rb = (int)(b % tc_tile_bytes(N));
+    const int row = rb / 128, chunk_phys = (rb % 128) / 16, e = (rb % 16) / 2;
+    const int k = kb * 64 + ((chunk_phys ^ (row & 7)) << 3) + e;
+    float v = 0.f;
+    if (chain == 0) {
+      const int gi = row / U, j = c * U + row % U;
+      if (k < P_IN) v = gi == 0 ? W0[(size_t)j * A + k] : Wih0[(size_t)((gi - 1) * H + j) * (A + H) + H + k];
+    } else if (chain <= 4) {
+      if (row < 3 * U && k < H) {
+        const int gi = row / U, j = c * U + row % U;
+        const size_t r = (size_t)(gi * H + j);
+        v = chain == 1 ? Whh0[r * H + k] : chain == 2 ? Wih0[r * (A + H) + k] : chain == 3 ? Whh1[r * H + k] : Wih1[r * H + k];
+      }
+    } else {
+      const int lr = tile * 16 + row, n = c * g.rpc + lr;
+      if (lr < g.rpc && n < P_OUT && k < H) v = W2[(size_t)n * H + k];
+    }
+    reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// fp32 k-major vector [K][32] -> bf16 image (32 rows); K padded with zeros to kbs*64
+__global__ void image_from_kmajor_kernel(const float* __restrict__ src, int K, int kbs, uint8_t* __restrict__ img) {
+  const int total = kbs * 64 * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i & 31, k = i >> 5;
+    const float v = k < K ? src[(size_t)k * 32 + b] : 0.f;
+    *reinterpret_cast<__nv_bfloat16*>(img + img_off(32, b, k)) = __float2bfloat16_rn(v);
+  }
+}
+
+struct TcWs {
+  uint8_t *xpb[2], *ab, *h0b[2], *h1b[2];   // bf16 activation images
+  size_t bytes;
+};
+inline TcWs make_tcws(void* base, const DecGeom& g) {
+  TcWs w; size_t off = 0;
+  auto take = [&](size_t n) { uint8_t* p = base ? (uint8_t*)base + off : nullptr; off += ((n + 1023) / 1024) * 1024; return p; };
+  const size_t xb = (size_t)ceil_div(K1P, 64) * 4096, hb = (size_t)ceil_div(g.H, 64) * 4096;
+  w.xpb[0] = take(xb); w.xpb[1] = take(xb); w.ab = take(hb);
+  w.h0b[0] = take(hb); w.h0b[1] = take(hb); w.h1b[0] = take(hb); w.h1b[1] = take(hb);
+  w.bytes = off; return w;
+}
+
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+
+template <int NC>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[NC]);
+template <>
+__device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  tmem_ld_32x32b_x32(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <>
+__device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// grid barrier split in two halves: the epilogue warp arrives, the activation loader waits
+__device__ __forceinline__ void grid_arrive(unsigned* counter) {
+  __threadfence();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) atomicAdd(counter, 1u);
+}
+__device__ __forceinline__ void grid_wait(const unsigned* counter, unsigned target) {
+  long long t0 = clock64();
+  while (ld_acquire_u32(counter) < target) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+// write U consecutive bf16 values (units j0..j0+U-1 of sample row b) into an activation image
+template <int U>
+__device__ __forceinline__ void store_img_units(uint8_t* img, int b, int j0, const float (&h)[U]) {
+  __nv_bfloat16 t[U];
+#pragma unroll
+  for (int i = 0; i < U; ++i) t[i] = __float2bfloat16_rn(h[i]);
+  uint8_t* p = img + img_off(32, b, j0);
+  if (U == 8) *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(t);
+  else *reinterpret_cast<uint2*>(p) = *reinterpret_cast<const uint2*>(t);
+}
+
+template <int U>
+__global__ void __launch_bounds__(128, 1)
+decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, TcWs tw, const uint8_t* __restrict__ packed) {
+  constexpr int NP = (3 * U + 15) / 16 * 16;     // gate-chain rows (32 for U=8, 16 for U=4)
+  constexpr int N1 = 4 * U;                      // stage-1 rows
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // layout: XA | XB | ring | 12 KB slack (operand rows 32..127 of the last k-blocks alias whatever follows)
+  uint8_t* XA = smem;
+  uint8_t* XB = XA + TC_XKB * 4096;
+  uint8_t* ring = XB + tg.kbH * 4096;
+  uint8_t* tail = ring + TC_RING * TC_SLOT_BYTES + 12288;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* full = bars;                 // [TC_RING]
+  uint64_t* empty = bars + TC_RING;      // [TC_RING]
+  uint64_t* xa_full = bars + 2 * TC_RING;
+  uint64_t* xb_full = xa_full + 1;
+  uint64_t* xa_free = xa_full + 2;
+  uint64_t* xb_free = xa_full + 3;
+  uint64_t* d_full = xa_full + 4;        // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x, H = a.H, T = a.T;
+  const int kbH = tg.kbH, kbX = tg.kbX, n4t = tg.n4t;
+  const uint8_t* pk = packed + (size_t)c * tg.cta_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TC_RING; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(xa_full, 1); mbar_init(xb_full, 1); mbar_init(xa_free, 1); mbar_init(xb_free, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&d_full[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  // TMEM columns: chain q at q*32 (q < 5), layer2 tile i at 160 + 16*i
+  const size_t actH = (size_t)g.nbt * H * 32, actX = (size_t)g.nbt * K1P * 32;
+
+  if (warp == 2) {
+    // ================= weight producer: streams every chain's tiles in the MMA warp's consumption order
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = 1; t < T; ++t) {
+        // order: gh0(1), S1(0), gh1(3), gi0a(2), gi1(4), y tiles(5)
+        const int order[5] = {1, 0, 3, 2, 4};
+        for (int oi = 0; oi < 5 + n4t; ++oi) {
+          const int chain = oi < 5 ? order[oi] : 5;
+          const int tile = oi < 5 ? 0 : oi - 5;
+          const int N = chain == 0 ? N1 : (chain == 5 ? 16 : NP);
+          const int nkb = chain == 0 ? kbX : kbH;
+          const uint8_t* src = pk + tg.chain_off[chain] + (size_t)tile * kbH * tc_tile_bytes(16);
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = it % TC_RING; const uint32_t ph = (it / TC_RING) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full[s], (uint32_t)tc_tile_bytes(N));
+            bulk_g2s(ring + s * TC_SLOT_BYTES, src + (size_t)kb * tc_tile_bytes(N), (uint32_t)tc_tile_bytes(N), &full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ================= activation loader
+    if (lane == 0) {
+      uint32_t xa_n = 0, xb_n = 0;        // loads issued so far into XA / XB
+      auto load_xa = [&](const uint8_t* img, int nkb) {
+        if (xa_n > 0) mbar_wait(xa_free, (xa_n - 1) & 1);
+        fence_proxy_async();
+        mbar_arrive_expect_tx(xa_full, (uint32_t)nkb * 4096);
+        bulk_g2s(XA, img, (uint32_t)nkb * 4096, xa_full);
+        ++xa_n;
+      };
+      auto load_xb = [&](const uint8_t* img) {
+        if (xb_n > 0) mbar_wait(xb_free, (xb_n - 1) & 1);
+        fence_proxy_async();
+        mbar_arrive_expect_tx(xb_full, (uint32_t)kbH * 4096);
+        bulk_g2s(XB, img, (uint32_t)kbH * 4096, xb_full);
+        ++xb_n;
+      };
+      unsigned epoch = 0;
+      for (int t = 1; t < T; ++t) {
+        load_xb(tw.h0b[(t - 1) & 1]);                               // h0(t-1): complete since barrier B2 of step t-1
+        if (t > 1) grid_wait(w.bar, (++epoch) * gridDim.x);          // B4(t-1): x_pose(t) complete
+        load_xa(tw.xpb[t & 1], kbX);
+        load_xb(tw.h1b[(t - 1) & 1]);                               // h1(t-1)
+        grid_wait(w.bar, (++epoch) * gridDim.x);                    // B1
+        load_xa(tw.ab, kbH);
+        grid_wait(w.bar, (++epoch) * gridDim.x);                    // B2
+        load_xa(tw.h0b[t & 1], kbH);
+        grid_wait(w.bar, (++epoch) * gridDim.x);                    // B3
+        load_xa(tw.h1b[t & 1], kbH);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer
+    uint32_t it = 0, xa_n = 0, xb_n = 0;
+    auto chain_mma = [&](const uint8_t* X, int nkb, int N, uint32_t dcol) {
+      const uint32_t idesc = make_idesc_bf16_f32(128, N);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % TC_RING; const uint32_t ph = (it / TC_RING) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after_sync();
+        if (lane == 0) {
+          const uint64_t da = make_smem_desc_sw128(X + (size_t)kb * 4096);
+          const uint64_t db = make_smem_desc_sw128(ring + s * TC_SLOT_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem + dcol, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          umma_commit(&empty[s]);
+        }
+        __syncwarp();
+      }
+    };
+    for (int t = 1; t < T; ++t) {
+      mbar_wait(xb_full, xb_n & 1); ++xb_n; tc_fence_after_sync();
+      chain_mma(XB, kbH, NP, 1 * 32);                                   // gh0
+      if (lane == 0) umma_commit(xb_free);
+      mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
+      chain_mma(XA, kbX, N1, 0 * 32);                                   // S1
+      if (lane == 0) { umma_commit(xa_free); umma_commit(&d_full[0]); }
+      mbar_wait(xb_full, xb_n & 1); ++xb_n; tc_fence_after_sync();
+      chain_mma(XB, kbH, NP, 3 * 32);                                   // gh1
+      if (lane == 0) umma_commit(xb_free);
+      mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
+      chain_mma(XA, kbH, NP, 2 * 32);                                   // gi0a
+      if (lane == 0) { umma_commit(xa_free); umma_commit(&d_full[1]); }
+      mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
+      chain_mma(XA, kbH, NP, 4 * 32);                                   // gi1
+      if (lane == 0) { umma_commit(xa_free); umma_commit(&d_full[2]); }
+      mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
+      for (int tile = 0; tile < n4t; ++tile) chain_mma(XA, kbH, 16, 160 + 16 * tile);   // y
+      if (lane == 0) { umma_commit(xa_free); umma_commit(&d_full[3]); }
+      __syncwarp();
+    }
+  } else {
+    // ================= epilogue warp (TMEM lanes 0..31 = samples)
+    const int b = lane;
+    const bool live = b < a.B;
+    const int j0 = c * U;
+    float gi0p[3 * U];
+    for (int t = 1; t < T; ++t) {
+      const uint32_t ph = (t - 1) & 1;
+      const int ts = w.save ? t : (t & 1), tp = w.save ? t - 1 : ((t - 1) & 1), tn = w.save ? t + 1 : ((t + 1) & 1);
+      // ---------------- stage 1
+      mbar_wait(&d_full[0], ph);
+      tc_fence_after_sync();
+      {
+        float v[N1];
+        tmem_ld_cols<N1>(tmem + 0 * 32, v);
+        const float* S = w.S01 + ((size_t)t * g.nbt) * 4 * H * 32;
+        float av[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          av[u] = elu_f(v[u] + S[(size_t)(j0 + u) * 32 + b]);
+          w.A[ts * actH + (size_t)(j0 + u) * 32 + b] = av[u];
+#pragma unroll
+          for (int q = 0; q < 3; ++q) gi0p[q * U + u] = v[(1 + q) * U + u] + S[(size_t)(H + q * H + j0 + u) * 32 + b];
+        }
+        store_img_units<U>(tw.ab, b, j0, av);
+      }
+      tc_fence_before_sync();
+      grid_arrive(w.bar);
+      // ---------------- stage 2 (GRU layer 0)
+      mbar_wait(&d_full[1], ph);
+      tc_fence_after_sync();
+      {
+        float gh[NP], gi[NP];
+        tmem_ld_cols<NP>(tmem + 1 * 32, gh);
+        tmem_ld_cols<NP>(tmem + 2 * 32, gi);
+        float hv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + u;
+          const float r = sigmoid_f(gi[u] + gi0p[u] + gh[u] + a.b_hh0[j]);
+          const float z = sigmoid_f(gi[U + u] + gi0p[U + u] + gh[U + u] + a.b_hh0[H + j]);
+          const float ghn = gh[2 * U + u] + a.b_hh0[2 * H + j];
+          const float n = tanhf(gi[2 * U + u] + gi0p[2 * U + u] + r * ghn);
+          const float hp = w.H0[tp * actH + (size_t)j * 32 + b];
+          hv[u] = (1.f - z) * n + z * hp;
+          w.H0[ts * actH + (size_t)j * 32 + b] = hv[u];
+          if (w.save) {
+            float* G = w.G0 + ((size_t)t * g.nbt) * 4 * H * 32;
+            G[(size_t)(0 * H + j) * 32 + b] = r; G[(size_t)(1 * H + j) * 32 + b] = z;
+            G[(size_t)(2 * H + j) * 32 + b] = n; G[(size_t)(3 * H + j) * 32 + b] = ghn;
+          }
+        }
+        store_img_units<U>(tw.h0b[t & 1], b, j0, hv);
+      }
+      tc_fence_before_sync();
+      grid_arrive(w.bar);
+      // ---------------- stage 3 (GRU layer 1)
+      mbar_wait(&d_full[2], ph);
+      tc_fence_after_sync();
+      {
+        float gh[NP], gi[NP];
+        tmem_ld_cols<NP>(tmem + 3 * 32, gh);
+        tmem_ld_cols<NP>(tmem + 4 * 32, gi);
+        float hv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + u;
+          const float r = sigmoid_f(gi[u] + a.b_ih1[j] + gh[u] + a.b_hh1[j]);
+          const float z = sigmoid_f(gi[U + u] + a.b_ih1[H + j] + gh[U + u] + a.b_hh1[H + j]);
+          const float ghn = gh[2 * U + u] + a.b_hh1[2 * H + j];
+          const float n = tanhf(gi[2 * U + u] + a.b_ih1[2 * H + j] + r * ghn);
+          const float hp = w.H1[tp * actH + (size_t)j * 32 + b];
+          hv[u] = (1.f - z) * n + z * hp;
+          w.H1[ts * actH + (size_t)j * 32 + b] = hv[u];
+          if (w.save) {
+            float* G = w.G1 + ((size_t)t * g.nbt) * 4 * H * 32;
+            G[(size_t)(0 * H + j) * 32 + b] = r; G[(size_t)(1 * H + j) * 32 + b] = z;
+            G[(size_t)(2 * H + j) * 32 + b] = n; G[(size_t)(3 * H + j) * 32 + b] = ghn;
+          }
+        }
+        store_img_units<U>(tw.h1b[t & 1], b, j0, hv);
+      }
+      tc_fence_before_sync();
+      grid_arrive(w.bar);
+      // ---------------- stage 4 (layer2, de-normalise, pose integration, next x_pose)
+      mbar_wait(&d_full[3], ph);
+      tc_fence_after_sync();
+      {
+        uint8_t* xpn = tw.xpb[(t + 1) & 1];
+        float* xpf = w.XP + tn * actX;
+        float root6[6];
+        for (int tile = 0; tile < n4t; ++tile) {
+          float y[16];
+          tmem_ld_cols<16>(tmem + 160 + 16 * tile, y);
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            const int lr = tile * 16 + r, n = c * g.rpc + lr;
+            if (lr < g.rpc && n < P_OUT) {
+              const float p = (y[r] + a.b2[n]) * a.out_std[n] + a.out_mean[n];
+              if (live) a.Y[((size_t)b * T + t) * P_OUT + n] = p;
+              if (t + 1 < T) {
+                const float xn = (p - a.in_mean[n]) / a.in_std[n];
+                *reinterpret_cast<__nv_bfloat16*>(xpn + img_off(32, b, n)) = __float2bfloat16_rn(xn);
+                if (w.save) xpf[(size_t)n * 32 + b] = xn;
+              }
+              if (n < 6) root6[n] = p;
+            }
+          }
+        }
+        if (c == 0 && live) {
+          const float* rp = a.root_pos + ((size_t)b * T + (t - 1)) * 3;
+          const float* rq = a.root_rot + ((size_t)b * T + (t - 1)) * 4;
+          V3 pos = v3(rp[0], rp[1], rp[2]);
+          Q4 q; q.w = rq[0]; q.x = rq[1]; q.y = rq[2]; q.z = rq[3];
+          V3 npos = quat_mul_vec(q, a.dt * v3(root6[0], root6[1], root6[2])) + pos;
+          Q4 nq = quat_mul(quat_from_helical(quat_mul_vec(q, a.dt * v3(root6[3], root6[4], root6[5]))), q);
+          float* op = a.root_pos + ((size_t)b * T + t) * 3;
+          float* oq = a.root_rot + ((size_t)b * T + t) * 4;
+          op[0] = npos.x; op[1] = npos.y; op[2] = npos.z;
+          oq[0] = nq.w; oq[1] = nq.x; oq[2] = nq.y; oq[3] = nq.z;
+          if (t + 1 < T) {
+            const float* gp = a.gaze_pos + ((size_t)b * T + (t + 1)) * 3;
+            V3 gd = quat_mul_vec(quat_inv(nq), v3(gp[0], gp[1], gp[2]) - npos);
+            const float gx[3] = {gd.x, gd.y, gd.z};
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              const float xn = (gx[d] - a.in_mean[P_OUT + d]) / a.in_std[P_OUT + d];
+              *reinterpret_cast<__nv_bfloat16*>(xpn + img_off(32, b, P_OUT + d)) = __float2bfloat16_rn(xn);
+              if (w.save) xpf[(size_t)(P_OUT + d) * 32 + b] = xn;
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      if (t + 1 < T) grid_arrive(w.bar);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem, 256); }
+}
+
+// ------------------------------------------------------------------ host
+extern "C" size_t zeggs_decoder_packed_tc_bytes(int H, int S, int Z) {
+  if (H % 16 != 0 || pick_U(H) <= 0) return 0;
+  DecGeom g = make_geom(1, H, S, Z);
+  return (size_t)g.G * make_tcgeom(g).cta_bytes;
+}
+extern "C" size_t zeggs_decoder_tc_workspace_bytes(int H, int S, int Z) {
+  if (H % 16 != 0 || pick_U(H) <= 0) return 0;
+  DecGeom g = make_geom(1, H, S, Z);
+  return make_tcws(nullptr, g).bytes;
+}
+extern "C" int zeggs_decoder_pack_weights_tc(const zeggs_decoder_fwd_args* a, void* packed, void* stream_) {
+  ZCHECK_ARG(a && packed && a->H % 16 == 0 && pick_U(a->H) > 0, "decoder tc pack: bad arguments");
+  DecGeom g = make_geom(a->B, a->H, a->S, a->Z);
+  TcGeom tg = make_tcgeom(g);
+  ZCHECK_ARG(tg.n4t <= 6, "decoder tc: hidden size %d too small for the tensor-core engine", a->H);
+  pack_decoder_tc_kernel<<<592, 256, 0, (cudaStream_t)stream_>>>(g, tg, a->W0, a->W_ih0, a->W_hh0, a->W_ih1, a->W_hh1, a->W2, (uint8_t*)packed);
+  count_launch();
+  ZCHECK_LAUNCH();
+  return ZEGGS_OK;
+}
+
+template <int U>
+static int launch_tc(const zeggs_decoder_fwd_args& a, const DecGeom& g, const TcGeom& tg, const DecWs& w, const TcWs& tw,
+                     const uint8_t* packed, cudaStream_t stream) {
+  const size_t smem = 1024 + (size_t)TC_XKB * 4096 + (size_t)tg.kbH * 4096 + TC_RING * TC_SLOT_BYTES + 12288 + 512;
+  ZCHECK_CUDA(cudaFuncSetAttribute(decoder_fwd_tc_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, nsm = 0, occ = 0;
+  ZCHECK_CUDA(cudaGetDevice(&dev));
+  ZCHECK_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  ZCHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decoder_fwd_tc_kernel<U>, 128, smem));
+  ZCHECK_ARG(occ * nsm >= g.G, "decoder tc: cooperative grid of %d CTAs does not fit", g.G);
+  void* args[] = {(void*)&a, (void*)&g, (void*)&tg, (void*)&w, (void*)&tw, (void*)&packed};
+  ZCHECK_CUDA(cudaLaunchCooperativeKernel((void*)decoder_fwd_tc_kernel<U>, dim3(g.G), dim3(128), args, smem, stream));
+  count_launch();
+  return ZEGGS_OK;
+}
+
+// called by zeggs_decoder_window_fwd after the prologue / CellStateEncoder / cond pre-pass when engine == 1
+int decoder_fwd_tc_run(const zeggs_decoder_fwd_args& a, const DecGeom& g, const DecWs& w, cudaStream_t stream) {
+  TcGeom tg = make_tcgeom(g);
+  ZCHECK_ARG(g.nbt == 1, "decoder tc engine handles one 32-sample batch tile (B <= 32); got B=%d", a.B);
+  ZCHECK_ARG(a.packed_tc && a.workspace_tc, "decoder tc: packed_tc / workspace_tc missing");
+  ZCHECK_ARG(tg.n4t <= 6 && tg.kbH <= 16, "decoder tc: unsupported hidden size %d", a.H);
+  TcWs tw = make_tcws(a.workspace_tc, g);
+  const size_t xb = (size_t)tg.kbX * 4096, hb = (size_t)tg.kbH * 4096;
+  ZCHECK_CUDA(cudaMemsetAsync(tw.xpb[0], 0, xb, stream));
+  ZCHECK_CUDA(cudaMemsetAsync(tw.xpb[1], 0, xb, stream));
+  // images of x_pose(1), h0(0), h1(0) from the fp32 k-major buffers the prologue / CellStateEncoder wrote
+  image_from_kmajor_kernel<<<64, 256, 0, stream>>>(w.XP + (size_t)1 * g.nbt * K1P * 32, K1P, tg.kbX, tw.xpb[1]); count_launch();
+  image_from_kmajor_kernel<<<64, 256, 0, stream>>>(w.H0, a.H, tg.kbH, tw.h0b[0]); count_launch();
+  image_from_kmajor_kernel<<<64, 256, 0, stream>>>(w.H1, a.H, tg.kbH, tw.h1b[0]); count_launch();
+  ZCHECK_LAUNCH();
+  (void)hb;
+  ScopedTimer tm("decoder_fwd", stream);
+  return g.U == 4 ? launch_tc<4>(a, g, tg, w, tw, (const uint8_t*)a.packed_tc, stream)
+                  : launch_tc<8>(a, g, tg, w, tw, (const uint8_t*)a.packed_tc, stream);
+}
+
+}  // namespace zeggs

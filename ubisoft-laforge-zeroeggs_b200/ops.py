@@ -51,6 +51,16 @@ def ensure_scratch(dev):
 
 _weights_epoch = 0
 
+# decoder recurrence engine: "fp32" (SIMT, parity grade) or "tc" (tcgen05, bf16 operands / fp32 state; B <= 32)
+DECODER_ENGINE = __import__("os").environ.get("ZEGGS_DECODER_ENGINE", "fp32")
+
+
+def set_decoder_engine(name):
+    global DECODER_ENGINE
+    if name not in ("fp32", "tc"):
+        raise _lib.ZeggsError("decoder engine must be 'fp32' or 'tc'")
+    DECODER_ENGINE = name
+
 
 def bump_weights_epoch():
     """Called by anything that rewrites parameters without going through torch (the fused optimizer)."""
@@ -104,6 +114,17 @@ def _decoder_args(dec, B, T, dev, tensors, stats, dt, save):
         cache = dec.__dict__["_zeggs_packed"]
     a.packed = cache[1].data_ptr()
     keep.append(cache[1])
+    if DECODER_ENGINE == "tc" and B <= 32:
+        tcc = dec.__dict__.get("_zeggs_packed_tc")
+        if tcc is None or tcc[0] != ver or tcc[1].device != dev:
+            nb = l.zeggs_decoder_packed_tc_bytes(H, S, Z)
+            ptc = torch.empty(nb, dtype=torch.uint8, device=dev)
+            _lib.check(l.zeggs_decoder_pack_weights_tc(a, ptc.data_ptr(), _lib.stream_ptr()), "zeggs_decoder_pack_weights_tc")
+            dec.__dict__["_zeggs_packed_tc"] = (ver, ptc)
+            tcc = dec.__dict__["_zeggs_packed_tc"]
+        wtc = WS.get("dec_tc", l.zeggs_decoder_tc_workspace_bytes(H, S, Z), dev)
+        a.engine, a.packed_tc, a.workspace_tc = 1, tcc[1].data_ptr(), wtc.data_ptr()
+        keep += [tcc[1], wtc]
     wsb = l.zeggs_decoder_workspace_bytes(B, T, H, S, Z, int(save))
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if save else WS.get("dec_fwd", wsb, dev)
     a.workspace = ws.data_ptr()
