@@ -116,6 +116,9 @@ size_t zeggs_decoder_workspace_bytes(int B, int T, int H, int S, int Z, int save
 size_t zeggs_decoder_packed_tc_bytes(int H, int S, int Z);
 size_t zeggs_decoder_tc_workspace_bytes(int H, int S, int Z);
 int zeggs_decoder_pack_weights_tc(const zeggs_decoder_fwd_args* a, void* packed, void* stream);
+/* development aid: device buffer [64][32] of int64 receiving CTA 0's per-step phase timestamps (NULL = off) */
+void zeggs_debug_set_tc_trace(void* device_buffer);
+void zeggs_debug_set_tc_nacc(int n); /* development aid: accumulators per MMA chain (1, 2, 4, 8; 0 = default) */
 int zeggs_decoder_window_fwd(const zeggs_decoder_fwd_args* a, void* stream);
 
 /* Backward of zeggs_decoder_window_fwd (the autograd of modules.py:47-162: full BPTT through the GRU stack,

@@ -30,6 +30,7 @@ struct TcGeom {
   int N1;          // rows of the stage-1 chain: 4U
   int kbH, kbX;    // k-blocks of an H-vector / of x_pose
   int n4t;         // 16-row tiles of layer2 per CTA
+  int nacc;        // independent TMEM accumulators per chain (breaks the MMA->MMA accumulate dependency)
   size_t chain_off[6];   // byte offset of chain c inside one CTA's packed block (chain 5 = first layer2 tile)
   size_t cta_bytes;
 };
@@ -43,6 +44,7 @@ inline TcGeom make_tcgeom(const DecGeom& g) {
   t.kbH = ceil_div(g.H, 64);
   t.kbX = ceil_div(K1P, 64);
   t.n4t = g.n4t;
+  t.nacc = 4;
   size_t off = 0;
   t.chain_off[0] = off; off += (size_t)t.kbX * tc_tile_bytes(t.N1);     // S1   X = x_pose
   t.chain_off[1] = off; off += (size_t)t.kbH * tc_tile_bytes(t.NP);     // gh0  X = h0(t-1)
@@ -109,6 +111,7 @@ __global__ void image_from_kmajor_kernel(const float* __restrict__ src, int K, i
 
 struct TcWs {
   uint8_t *xpb[2], *ab, *h0b[2], *h1b[2];   // bf16 activation images
+  long long* dbg;                            // optional per-step phase timestamps of CTA 0 (clock64), [T][32]
   size_t bytes;
 };
 inline TcWs make_tcws(void* base, const DecGeom& g) {
@@ -117,6 +120,7 @@ inline TcWs make_tcws(void* base, const DecGeom& g) {
   const size_t xb = (size_t)ceil_div(K1P, 64) * 4096, hb = (size_t)ceil_div(g.H, 64) * 4096;
   w.xpb[0] = take(xb); w.xpb[1] = take(xb); w.ab = take(hb);
   w.h0b[0] = take(hb); w.h0b[1] = take(hb); w.h1b[0] = take(hb); w.h1b[1] = take(hb);
+  w.dbg = nullptr;
   w.bytes = off; return w;
 }
 
@@ -172,6 +176,8 @@ __device__ __forceinline__ void store_img_units(uint8_t* img, int b, int j0, con
   else *reinterpret_cast<uint2*>(p) = *reinterpret_cast<const uint2*>(t);
 }
 
+#define TCDBG(ev) do { if (tw.dbg && c == 0 && lane == 0 && t < 64) tw.dbg[t * 32 + (ev)] = clock64(); } while (0)
+
 template <int U>
 __global__ void __launch_bounds__(128, 1)
 decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, TcWs tw, const uint8_t* __restrict__ packed) {
@@ -179,7 +185,7 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
   constexpr int N1 = 4 * U;                      // stage-1 rows
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // layout: XA | XB | ring | 12 KB slack (operand rows 32..127 of the last k-blocks alias whatever follows)
+  // layout: XA | XB | ring | 12 KB slack (operand rows 32..127 of the last k-blocks alias whatever follows) | barriers | constants
   uint8_t* XA = smem;
   uint8_t* XB = XA + TC_XKB * 4096;
   uint8_t* ring = XB + tg.kbH * 4096;
@@ -193,10 +199,17 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
   uint64_t* xb_free = xa_full + 3;
   uint64_t* d_full = xa_full + 4;        // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 4);
+  float* cst = reinterpret_cast<float*>(tail + 512);   // per-CTA constants (biases, normalisation rows)
+  const int R4 = tg.n4t * 16;
+  float* c_bhh0 = cst;            // [3U]
+  float* c_bih1 = cst + 3 * U;    // [3U]
+  float* c_bhh1 = cst + 6 * U;    // [3U]
+  float* c_b2 = cst + 9 * U;      // [R4]  then out_std, out_mean, in_mean, in_std (R4 each), then gaze in_mean/in_std (3+3)
+  float* c_os = c_b2 + R4; float* c_om = c_os + R4; float* c_im = c_om + R4; float* c_is = c_im + R4; float* c_gz = c_is + R4;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x, H = a.H, T = a.T;
-  const int kbH = tg.kbH, kbX = tg.kbX, n4t = tg.n4t;
+  const int kbH = tg.kbH, kbX = tg.kbX, n4t = tg.n4t, nacc = tg.nacc;
   const uint8_t* pk = packed + (size_t)c * tg.cta_bytes;
 
   if (threadIdx.x == 0) {
@@ -205,34 +218,44 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
     for (int i = 0; i < 4; ++i) mbar_init(&d_full[i], 1);
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  for (int i = threadIdx.x; i < 3 * U; i += blockDim.x) {
+    const int j = (i / U) * H + c * U + (i % U);
+    c_bhh0[i] = a.b_hh0[j]; c_bih1[i] = a.b_ih1[j]; c_bhh1[i] = a.b_hh1[j];
+  }
+  for (int i = threadIdx.x; i < R4; i += blockDim.x) {
+    const int n = c * g.rpc + i;
+    const bool ok = i < g.rpc && n < P_OUT;
+    c_b2[i] = ok ? a.b2[n] : 0.f; c_os[i] = ok ? a.out_std[n] : 0.f; c_om[i] = ok ? a.out_mean[n] : 0.f;
+    c_im[i] = ok ? a.in_mean[n] : 0.f; c_is[i] = ok ? a.in_std[n] : 1.f;
+  }
+  if (threadIdx.x < 3) { c_gz[threadIdx.x] = a.in_mean[P_OUT + threadIdx.x]; c_gz[3 + threadIdx.x] = a.in_std[P_OUT + threadIdx.x]; }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  // TMEM columns: chain q at q*32 (q < 5), layer2 tile i at 160 + 16*i
+  // TMEM regions (columns): gh0 [0,128) | gh1 [128,256) | S1 / gi0a / gi1 / y [256,512); accumulator q of a chain at +q*N
+  constexpr uint32_t R_GH0 = 0, R_GH1 = 128, R_MAIN = 256;
   const size_t actH = (size_t)g.nbt * H * 32, actX = (size_t)g.nbt * K1P * 32;
 
   if (warp == 2) {
     // ================= weight producer: streams every chain's tiles in the MMA warp's consumption order
     if (lane == 0) {
       uint32_t it = 0;
-      for (int t = 1; t < T; ++t) {
-        // order: gh0(1), S1(0), gh1(3), gi0a(2), gi1(4), y tiles(5)
-        const int order[5] = {1, 0, 3, 2, 4};
-        for (int oi = 0; oi < 5 + n4t; ++oi) {
-          const int chain = oi < 5 ? order[oi] : 5;
-          const int tile = oi < 5 ? 0 : oi - 5;
-          const int N = chain == 0 ? N1 : (chain == 5 ? 16 : NP);
-          const int nkb = chain == 0 ? kbX : kbH;
-          const uint8_t* src = pk + tg.chain_off[chain] + (size_t)tile * kbH * tc_tile_bytes(16);
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
-            const int s = it % TC_RING; const uint32_t ph = (it / TC_RING) & 1;
-            mbar_wait(&empty[s], ph ^ 1);
-            mbar_arrive_expect_tx(&full[s], (uint32_t)tc_tile_bytes(N));
-            bulk_g2s(ring + s * TC_SLOT_BYTES, src + (size_t)kb * tc_tile_bytes(N), (uint32_t)tc_tile_bytes(N), &full[s]);
-          }
+      auto stream = [&](int chain, int tile) {
+        const int N = chain == 0 ? N1 : (chain == 5 ? 16 : NP);
+        const int nkb = chain == 0 ? kbX : kbH;
+        const uint8_t* src = pk + tg.chain_off[chain] + (size_t)tile * kbH * tc_tile_bytes(16);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % TC_RING; const uint32_t ph = (it / TC_RING) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], (uint32_t)tc_tile_bytes(N));
+          bulk_g2s(ring + s * TC_SLOT_BYTES, src + (size_t)kb * tc_tile_bytes(N), (uint32_t)tc_tile_bytes(N), &full[s]);
         }
+      };
+      for (int t = 1; t < T; ++t) {   // order: gh0(1), S1(0), gh1(3), gi0a(2), gi1(4), y tiles(5)
+        stream(1, 0); stream(0, 0); stream(3, 0); stream(2, 0); stream(4, 0);
+        for (int tile = 0; tile < n4t; ++tile) stream(5, tile);
       }
     }
   } else if (warp == 3) {
@@ -257,20 +280,26 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
       for (int t = 1; t < T; ++t) {
         load_xb(tw.h0b[(t - 1) & 1]);                               // h0(t-1): complete since barrier B2 of step t-1
         if (t > 1) grid_wait(w.bar, (++epoch) * gridDim.x);          // B4(t-1): x_pose(t) complete
+        TCDBG(0);
         load_xa(tw.xpb[t & 1], kbX);
         load_xb(tw.h1b[(t - 1) & 1]);                               // h1(t-1)
         grid_wait(w.bar, (++epoch) * gridDim.x);                    // B1
+        TCDBG(8);
         load_xa(tw.ab, kbH);
         grid_wait(w.bar, (++epoch) * gridDim.x);                    // B2
+        TCDBG(14);
         load_xa(tw.h0b[t & 1], kbH);
         grid_wait(w.bar, (++epoch) * gridDim.x);                    // B3
+        TCDBG(20);
         load_xa(tw.h1b[t & 1], kbH);
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer
     uint32_t it = 0, xa_n = 0, xb_n = 0;
-    auto chain_mma = [&](const uint8_t* X, int nkb, int N, uint32_t dcol) {
+    // k-step k of k-block kb accumulates into accumulator (kb*4 + k) % na of the chain's TMEM region: independent
+    // accumulators let consecutive MMAs overlap instead of serialising on the accumulate dependency
+    auto chain_mma = [&](const uint8_t* X, int nkb, int N, uint32_t dcol, int na) {
       const uint32_t idesc = make_idesc_bf16_f32(128, N);
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % TC_RING; const uint32_t ph = (it / TC_RING) & 1;
@@ -280,30 +309,41 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
           const uint64_t da = make_smem_desc_sw128(X + (size_t)kb * 4096);
           const uint64_t db = make_smem_desc_sw128(ring + s * TC_SLOT_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem + dcol, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) {
+            const int q = (kb * 4 + k) % na;
+            umma_bf16(tmem + dcol + (uint32_t)(q * N), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb * 4 + k) >= na);
+          }
           umma_commit(&empty[s]);
         }
         __syncwarp();
       }
     };
+    const int na_main = nacc > 8 ? 8 : nacc, na_side = nacc > 4 ? 4 : nacc;
     for (int t = 1; t < T; ++t) {
       mbar_wait(xb_full, xb_n & 1); ++xb_n; tc_fence_after_sync();
-      chain_mma(XB, kbH, NP, 1 * 32);                                   // gh0
+      chain_mma(XB, kbH, NP, R_GH0, na_side);                           // gh0
       if (lane == 0) umma_commit(xb_free);
       mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
-      chain_mma(XA, kbX, N1, 0 * 32);                                   // S1
+      TCDBG(3);
+      chain_mma(XA, kbX, N1, R_MAIN, na_main);                          // S1
       if (lane == 0) { umma_commit(xa_free); umma_commit(&d_full[0]); }
+      TCDBG(4);
       mbar_wait(xb_full, xb_n & 1); ++xb_n; tc_fence_after_sync();
-      chain_mma(XB, kbH, NP, 3 * 32);                                   // gh1
+      chain_mma(XB, kbH, NP, R_GH1, na_side);                           // gh1
       if (lane == 0) umma_commit(xb_free);
       mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
-      chain_mma(XA, kbH, NP, 2 * 32);                                   // gi0a
+      TCDBG(10);
+      chain_mma(XA, kbH, NP, R_MAIN, na_main);                          // gi0a
       if (lane == 0) { umma_commit(xa_free); umma_commit(&d_full[1]); }
+      TCDBG(11);
       mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
-      chain_mma(XA, kbH, NP, 4 * 32);                                   // gi1
+      TCDBG(15);
+      chain_mma(XA, kbH, NP, R_MAIN, na_main);                          // gi1
       if (lane == 0) { umma_commit(xa_free); umma_commit(&d_full[2]); }
+      TCDBG(16);
       mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
-      for (int tile = 0; tile < n4t; ++tile) chain_mma(XA, kbH, 16, 160 + 16 * tile);   // y
+      TCDBG(21);
+      for (int tile = 0; tile < n4t; ++tile) chain_mma(XA, kbH, 16, R_MAIN + (uint32_t)(tile * na_side * 16), na_side);   // y
       if (lane == 0) { umma_commit(xa_free); umma_commit(&d_full[3]); }
       __syncwarp();
     }
@@ -312,128 +352,184 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
     const int b = lane;
     const bool live = b < a.B;
     const int j0 = c * U;
+    const int na_main = nacc > 8 ? 8 : nacc, na_side = nacc > 4 ? 4 : nacc;
+    auto ld_sum = [&](uint32_t col, int na, float (&v)[NP]) {     // sum of a gate chain's accumulators
+      tmem_ld_cols<NP>(tmem + col, v);
+      for (int q = 1; q < na; ++q) {
+        float u_[NP];
+        tmem_ld_cols<NP>(tmem + col + (uint32_t)(q * NP), u_);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) v[i] += u_[i];
+      }
+    };
     float gi0p[3 * U];
     for (int t = 1; t < T; ++t) {
       const uint32_t ph = (t - 1) & 1;
       const int ts = w.save ? t : (t & 1), tp = w.save ? t - 1 : ((t - 1) & 1), tn = w.save ? t + 1 : ((t + 1) & 1);
-      // ---------------- stage 1
+      // ---------------- stage 1   (operands that do not depend on the MMA are fetched before the wait)
+      float sv[4 * U];
+      {
+        const float* S = w.S01 + ((size_t)t * g.nbt) * 4 * H * 32;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          sv[u] = __ldg(S + (size_t)(j0 + u) * 32 + b);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) sv[(1 + q) * U + u] = __ldg(S + (size_t)(H + q * H + j0 + u) * 32 + b);
+        }
+      }
       mbar_wait(&d_full[0], ph);
       tc_fence_after_sync();
+      TCDBG(5);
       {
         float v[N1];
-        tmem_ld_cols<N1>(tmem + 0 * 32, v);
-        const float* S = w.S01 + ((size_t)t * g.nbt) * 4 * H * 32;
+        tmem_ld_cols<N1>(tmem + R_MAIN, v);
+        for (int q = 1; q < na_main; ++q) {
+          float u_[N1];
+          tmem_ld_cols<N1>(tmem + R_MAIN + (uint32_t)(q * N1), u_);
+#pragma unroll
+          for (int i = 0; i < N1; ++i) v[i] += u_[i];
+        }
         float av[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          av[u] = elu_f(v[u] + S[(size_t)(j0 + u) * 32 + b]);
-          w.A[ts * actH + (size_t)(j0 + u) * 32 + b] = av[u];
+          av[u] = elu_f(v[u] + sv[u]);
 #pragma unroll
-          for (int q = 0; q < 3; ++q) gi0p[q * U + u] = v[(1 + q) * U + u] + S[(size_t)(H + q * H + j0 + u) * 32 + b];
+          for (int q = 0; q < 3; ++q) gi0p[q * U + u] = v[(1 + q) * U + u] + sv[(1 + q) * U + u];
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u) w.A[ts * actH + (size_t)(j0 + u) * 32 + b] = av[u];
         store_img_units<U>(tw.ab, b, j0, av);
       }
       tc_fence_before_sync();
+      TCDBG(6);
       grid_arrive(w.bar);
+      TCDBG(7);
       // ---------------- stage 2 (GRU layer 0)
+      float hp[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) hp[u] = w.H0[tp * actH + (size_t)(j0 + u) * 32 + b];
       mbar_wait(&d_full[1], ph);
       tc_fence_after_sync();
+      TCDBG(12);
       {
         float gh[NP], gi[NP];
-        tmem_ld_cols<NP>(tmem + 1 * 32, gh);
-        tmem_ld_cols<NP>(tmem + 2 * 32, gi);
-        float hv[U];
+        ld_sum(R_GH0, na_side, gh);
+        ld_sum(R_MAIN, na_main, gi);
+        float hv[U], rr[U], zz[U], nn[U], gn[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int j = j0 + u;
-          const float r = sigmoid_f(gi[u] + gi0p[u] + gh[u] + a.b_hh0[j]);
-          const float z = sigmoid_f(gi[U + u] + gi0p[U + u] + gh[U + u] + a.b_hh0[H + j]);
-          const float ghn = gh[2 * U + u] + a.b_hh0[2 * H + j];
-          const float n = tanhf(gi[2 * U + u] + gi0p[2 * U + u] + r * ghn);
-          const float hp = w.H0[tp * actH + (size_t)j * 32 + b];
-          hv[u] = (1.f - z) * n + z * hp;
-          w.H0[ts * actH + (size_t)j * 32 + b] = hv[u];
-          if (w.save) {
-            float* G = w.G0 + ((size_t)t * g.nbt) * 4 * H * 32;
-            G[(size_t)(0 * H + j) * 32 + b] = r; G[(size_t)(1 * H + j) * 32 + b] = z;
-            G[(size_t)(2 * H + j) * 32 + b] = n; G[(size_t)(3 * H + j) * 32 + b] = ghn;
+          rr[u] = sigmoid_f(gi[u] + gi0p[u] + gh[u] + c_bhh0[u]);
+          zz[u] = sigmoid_f(gi[U + u] + gi0p[U + u] + gh[U + u] + c_bhh0[U + u]);
+          gn[u] = gh[2 * U + u] + c_bhh0[2 * U + u];
+          nn[u] = tanhf(gi[2 * U + u] + gi0p[2 * U + u] + rr[u] * gn[u]);
+          hv[u] = (1.f - zz[u]) * nn[u] + zz[u] * hp[u];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) w.H0[ts * actH + (size_t)(j0 + u) * 32 + b] = hv[u];
+        store_img_units<U>(tw.h0b[t & 1], b, j0, hv);
+        if (w.save) {
+          float* G = w.G0 + ((size_t)t * g.nbt) * 4 * H * 32;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int j = j0 + u;
+            G[(size_t)(0 * H + j) * 32 + b] = rr[u]; G[(size_t)(1 * H + j) * 32 + b] = zz[u];
+            G[(size_t)(2 * H + j) * 32 + b] = nn[u]; G[(size_t)(3 * H + j) * 32 + b] = gn[u];
           }
         }
-        store_img_units<U>(tw.h0b[t & 1], b, j0, hv);
       }
       tc_fence_before_sync();
+      TCDBG(13);
       grid_arrive(w.bar);
       // ---------------- stage 3 (GRU layer 1)
+#pragma unroll
+      for (int u = 0; u < U; ++u) hp[u] = w.H1[tp * actH + (size_t)(j0 + u) * 32 + b];
       mbar_wait(&d_full[2], ph);
       tc_fence_after_sync();
+      TCDBG(17);
       {
         float gh[NP], gi[NP];
-        tmem_ld_cols<NP>(tmem + 3 * 32, gh);
-        tmem_ld_cols<NP>(tmem + 4 * 32, gi);
-        float hv[U];
+        ld_sum(R_GH1, na_side, gh);
+        ld_sum(R_MAIN, na_main, gi);
+        float hv[U], rr[U], zz[U], nn[U], gn[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int j = j0 + u;
-          const float r = sigmoid_f(gi[u] + a.b_ih1[j] + gh[u] + a.b_hh1[j]);
-          const float z = sigmoid_f(gi[U + u] + a.b_ih1[H + j] + gh[U + u] + a.b_hh1[H + j]);
-          const float ghn = gh[2 * U + u] + a.b_hh1[2 * H + j];
-          const float n = tanhf(gi[2 * U + u] + a.b_ih1[2 * H + j] + r * ghn);
-          const float hp = w.H1[tp * actH + (size_t)j * 32 + b];
-          hv[u] = (1.f - z) * n + z * hp;
-          w.H1[ts * actH + (size_t)j * 32 + b] = hv[u];
-          if (w.save) {
-            float* G = w.G1 + ((size_t)t * g.nbt) * 4 * H * 32;
-            G[(size_t)(0 * H + j) * 32 + b] = r; G[(size_t)(1 * H + j) * 32 + b] = z;
-            G[(size_t)(2 * H + j) * 32 + b] = n; G[(size_t)(3 * H + j) * 32 + b] = ghn;
+          rr[u] = sigmoid_f(gi[u] + c_bih1[u] + gh[u] + c_bhh1[u]);
+          zz[u] = sigmoid_f(gi[U + u] + c_bih1[U + u] + gh[U + u] + c_bhh1[U + u]);
+          gn[u] = gh[2 * U + u] + c_bhh1[2 * U + u];
+          nn[u] = tanhf(gi[2 * U + u] + c_bih1[2 * U + u] + rr[u] * gn[u]);
+          hv[u] = (1.f - zz[u]) * nn[u] + zz[u] * hp[u];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) w.H1[ts * actH + (size_t)(j0 + u) * 32 + b] = hv[u];
+        store_img_units<U>(tw.h1b[t & 1], b, j0, hv);
+        if (w.save) {
+          float* G = w.G1 + ((size_t)t * g.nbt) * 4 * H * 32;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int j = j0 + u;
+            G[(size_t)(0 * H + j) * 32 + b] = rr[u]; G[(size_t)(1 * H + j) * 32 + b] = zz[u];
+            G[(size_t)(2 * H + j) * 32 + b] = nn[u]; G[(size_t)(3 * H + j) * 32 + b] = gn[u];
           }
         }
-        store_img_units<U>(tw.h1b[t & 1], b, j0, hv);
       }
       tc_fence_before_sync();
+      TCDBG(18);
       grid_arrive(w.bar);
+      TCDBG(19);
       // ---------------- stage 4 (layer2, de-normalise, pose integration, next x_pose)
+      V3 pos = v3(0, 0, 0), gzp = v3(0, 0, 0);
+      Q4 q; q.w = 1.f; q.x = q.y = q.z = 0.f;
+      if (c == 0 && live) {
+        const float* rp = a.root_pos + ((size_t)b * T + (t - 1)) * 3;
+        const float* rq = a.root_rot + ((size_t)b * T + (t - 1)) * 4;
+        pos = v3(rp[0], rp[1], rp[2]);
+        q.w = rq[0]; q.x = rq[1]; q.y = rq[2]; q.z = rq[3];
+        if (t + 1 < T) { const float* gp = a.gaze_pos + ((size_t)b * T + (t + 1)) * 3; gzp = v3(gp[0], gp[1], gp[2]); }
+      }
       mbar_wait(&d_full[3], ph);
       tc_fence_after_sync();
+      TCDBG(22);
       {
         uint8_t* xpn = tw.xpb[(t + 1) & 1];
         float* xpf = w.XP + tn * actX;
-        float root6[6];
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f, r5 = 0.f;
         for (int tile = 0; tile < n4t; ++tile) {
           float y[16];
-          tmem_ld_cols<16>(tmem + 160 + 16 * tile, y);
+          tmem_ld_cols<16>(tmem + R_MAIN + (uint32_t)(tile * na_side * 16), y);
+          for (int qa = 1; qa < na_side; ++qa) {
+            float u_[16];
+            tmem_ld_cols<16>(tmem + R_MAIN + (uint32_t)((tile * na_side + qa) * 16), u_);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[i] += u_[i];
+          }
 #pragma unroll
           for (int r = 0; r < 16; ++r) {
             const int lr = tile * 16 + r, n = c * g.rpc + lr;
             if (lr < g.rpc && n < P_OUT) {
-              const float p = (y[r] + a.b2[n]) * a.out_std[n] + a.out_mean[n];
+              const float p = (y[r] + c_b2[lr]) * c_os[lr] + c_om[lr];
               if (live) a.Y[((size_t)b * T + t) * P_OUT + n] = p;
               if (t + 1 < T) {
-                const float xn = (p - a.in_mean[n]) / a.in_std[n];
+                const float xn = (p - c_im[lr]) / c_is[lr];
                 *reinterpret_cast<__nv_bfloat16*>(xpn + img_off(32, b, n)) = __float2bfloat16_rn(xn);
                 if (w.save) xpf[(size_t)n * 32 + b] = xn;
               }
-              if (n < 6) root6[n] = p;
+              if (tile == 0) { if (r == 0) r0 = p; if (r == 1) r1 = p; if (r == 2) r2 = p; if (r == 3) r3 = p; if (r == 4) r4 = p; if (r == 5) r5 = p; }
             }
           }
         }
         if (c == 0 && live) {
-          const float* rp = a.root_pos + ((size_t)b * T + (t - 1)) * 3;
-          const float* rq = a.root_rot + ((size_t)b * T + (t - 1)) * 4;
-          V3 pos = v3(rp[0], rp[1], rp[2]);
-          Q4 q; q.w = rq[0]; q.x = rq[1]; q.y = rq[2]; q.z = rq[3];
-          V3 npos = quat_mul_vec(q, a.dt * v3(root6[0], root6[1], root6[2])) + pos;
-          Q4 nq = quat_mul(quat_from_helical(quat_mul_vec(q, a.dt * v3(root6[3], root6[4], root6[5]))), q);
+          V3 npos = quat_mul_vec(q, a.dt * v3(r0, r1, r2)) + pos;
+          Q4 nq = quat_mul(quat_from_helical(quat_mul_vec(q, a.dt * v3(r3, r4, r5))), q);
           float* op = a.root_pos + ((size_t)b * T + t) * 3;
           float* oq = a.root_rot + ((size_t)b * T + t) * 4;
           op[0] = npos.x; op[1] = npos.y; op[2] = npos.z;
           oq[0] = nq.w; oq[1] = nq.x; oq[2] = nq.y; oq[3] = nq.z;
           if (t + 1 < T) {
-            const float* gp = a.gaze_pos + ((size_t)b * T + (t + 1)) * 3;
-            V3 gd = quat_mul_vec(quat_inv(nq), v3(gp[0], gp[1], gp[2]) - npos);
+            V3 gd = quat_mul_vec(quat_inv(nq), gzp - npos);
             const float gx[3] = {gd.x, gd.y, gd.z};
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
-              const float xn = (gx[d] - a.in_mean[P_OUT + d]) / a.in_std[P_OUT + d];
+              const float xn = (gx[d] - c_gz[d]) / c_gz[3 + d];
               *reinterpret_cast<__nv_bfloat16*>(xpn + img_off(32, b, P_OUT + d)) = __float2bfloat16_rn(xn);
               if (w.save) xpf[(size_t)(P_OUT + d) * 32 + b] = xn;
             }
@@ -441,12 +537,14 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
         }
       }
       tc_fence_before_sync();
+      TCDBG(23);
       if (t + 1 < T) grid_arrive(w.bar);
+      TCDBG(24);
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem, 256); }
+  if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem, 512); }
 }
 
 // ------------------------------------------------------------------ host
@@ -464,7 +562,7 @@ extern "C" int zeggs_decoder_pack_weights_tc(const zeggs_decoder_fwd_args* a, vo
   ZCHECK_ARG(a && packed && a->H % 16 == 0 && pick_U(a->H) > 0, "decoder tc pack: bad arguments");
   DecGeom g = make_geom(a->B, a->H, a->S, a->Z);
   TcGeom tg = make_tcgeom(g);
-  ZCHECK_ARG(tg.n4t <= 6, "decoder tc: hidden size %d too small for the tensor-core engine", a->H);
+  ZCHECK_ARG(tg.n4t <= 4, "decoder tc: hidden size %d too small for the tensor-core engine", a->H);
   pack_decoder_tc_kernel<<<592, 256, 0, (cudaStream_t)stream_>>>(g, tg, a->W0, a->W_ih0, a->W_hh0, a->W_ih1, a->W_hh1, a->W2, (uint8_t*)packed);
   count_launch();
   ZCHECK_LAUNCH();
@@ -474,7 +572,8 @@ extern "C" int zeggs_decoder_pack_weights_tc(const zeggs_decoder_fwd_args* a, vo
 template <int U>
 static int launch_tc(const zeggs_decoder_fwd_args& a, const DecGeom& g, const TcGeom& tg, const DecWs& w, const TcWs& tw,
                      const uint8_t* packed, cudaStream_t stream) {
-  const size_t smem = 1024 + (size_t)TC_XKB * 4096 + (size_t)tg.kbH * 4096 + TC_RING * TC_SLOT_BYTES + 12288 + 512;
+  const size_t smem = 1024 + (size_t)TC_XKB * 4096 + (size_t)tg.kbH * 4096 + TC_RING * TC_SLOT_BYTES + 12288 + 512 +
+                      (size_t)(9 * U + 5 * tg.n4t * 16 + 8) * sizeof(float);
   ZCHECK_CUDA(cudaFuncSetAttribute(decoder_fwd_tc_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, nsm = 0, occ = 0;
   ZCHECK_CUDA(cudaGetDevice(&dev));
@@ -487,13 +586,20 @@ static int launch_tc(const zeggs_decoder_fwd_args& a, const DecGeom& g, const Tc
   return ZEGGS_OK;
 }
 
+static long long* g_tc_dbg = nullptr;
+static int g_tc_nacc = 0;
+extern "C" void zeggs_debug_set_tc_nacc(int n) { g_tc_nacc = n; }
+extern "C" void zeggs_debug_set_tc_trace(void* p) { g_tc_dbg = (long long*)p; }
+
 // called by zeggs_decoder_window_fwd after the prologue / CellStateEncoder / cond pre-pass when engine == 1
 int decoder_fwd_tc_run(const zeggs_decoder_fwd_args& a, const DecGeom& g, const DecWs& w, cudaStream_t stream) {
   TcGeom tg = make_tcgeom(g);
   ZCHECK_ARG(g.nbt == 1, "decoder tc engine handles one 32-sample batch tile (B <= 32); got B=%d", a.B);
   ZCHECK_ARG(a.packed_tc && a.workspace_tc, "decoder tc: packed_tc / workspace_tc missing");
-  ZCHECK_ARG(tg.n4t <= 6 && tg.kbH <= 16, "decoder tc: unsupported hidden size %d", a.H);
+  ZCHECK_ARG(tg.n4t <= 4 && tg.kbH <= 16, "decoder tc: unsupported hidden size %d", a.H);
+  if (g_tc_nacc > 0) tg.nacc = g_tc_nacc;
   TcWs tw = make_tcws(a.workspace_tc, g);
+  tw.dbg = g_tc_dbg;
   const size_t xb = (size_t)tg.kbX * 4096, hb = (size_t)tg.kbH * 4096;
   ZCHECK_CUDA(cudaMemsetAsync(tw.xpb[0], 0, xb, stream));
   ZCHECK_CUDA(cudaMemsetAsync(tw.xpb[1], 0, xb, stream));
