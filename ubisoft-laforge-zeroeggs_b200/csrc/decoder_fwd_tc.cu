@@ -21,9 +21,9 @@
 
 namespace zeggs {
 
-constexpr int TC_RING = 16;             // weight ring slots (one k-block tile each)
+constexpr int TC_RING = 8;              // weight ring slots (two k-block tiles each)
 constexpr int TC_XKB = 18;              // k-blocks of the widest activation vector (x_pose: 1136 -> 1152)
-constexpr int TC_SLOT_BYTES = 4096;     // 32 rows x 128 B (N <= 32)
+constexpr int TC_SLOT_BYTES = 8192;     // 2 k-blocks x (32 rows x 128 B) (N <= 32)
 
 struct TcGeom {
   int NP;          // padded rows of a gate chain: round_up(3U,16)
@@ -209,7 +209,7 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x, H = a.H, T = a.T;
-  const int kbH = tg.kbH, kbX = tg.kbX, n4t = tg.n4t, nacc = tg.nacc;
+  const int kbH = tg.kbH, kbX = tg.kbX, n4t = tg.n4t;
   const uint8_t* pk = packed + (size_t)c * tg.cta_bytes;
 
   if (threadIdx.x == 0) {
@@ -246,11 +246,12 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
         const int N = chain == 0 ? N1 : (chain == 5 ? 16 : NP);
         const int nkb = chain == 0 ? kbX : kbH;
         const uint8_t* src = pk + tg.chain_off[chain] + (size_t)tile * kbH * tc_tile_bytes(16);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % TC_RING; const uint32_t ph = (it / TC_RING) & 1;
+        for (int kb = 0; kb < nkb; kb += 2, ++it) {
+          const int s = it & (TC_RING - 1); const uint32_t ph = (it / TC_RING) & 1;
+          const uint32_t bytes = (uint32_t)((nkb - kb >= 2 ? 2 : 1) * tc_tile_bytes(N));
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], (uint32_t)tc_tile_bytes(N));
-          bulk_g2s(ring + s * TC_SLOT_BYTES, src + (size_t)kb * tc_tile_bytes(N), (uint32_t)tc_tile_bytes(N), &full[s]);
+          mbar_arrive_expect_tx(&full[s], bytes);
+          bulk_g2s(ring + s * TC_SLOT_BYTES, src + (size_t)kb * tc_tile_bytes(N), bytes, &full[s]);
         }
       };
       for (int t = 1; t < T; ++t) {   // order: gh0(1), S1(0), gh1(3), gi0a(2), gi1(4), y tiles(5)
@@ -295,64 +296,67 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer
-    uint32_t it = 0, xa_n = 0, xb_n = 0;
-    // k-step k of k-block kb accumulates into accumulator (kb*4 + k) % na of the chain's TMEM region: independent
-    // accumulators let consecutive MMAs overlap instead of serialising on the accumulate dependency
-    auto chain_mma = [&](const uint8_t* X, int nkb, int N, uint32_t dcol, int na) {
-      const uint32_t idesc = make_idesc_bf16_f32(128, N);
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % TC_RING; const uint32_t ph = (it / TC_RING) & 1;
-        mbar_wait(&full[s], ph);
-        tc_fence_after_sync();
-        if (lane == 0) {
-          const uint64_t da = make_smem_desc_sw128(X + (size_t)kb * 4096);
-          const uint64_t db = make_smem_desc_sw128(ring + s * TC_SLOT_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int q = (kb * 4 + k) % na;
-            umma_bf16(tmem + dcol + (uint32_t)(q * N), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb * 4 + k) >= na);
+    // ================= MMA issuer (one lane; the loop is kept lean: descriptors are advanced by constants, the four
+    // k-steps of a k-block go to four independent TMEM accumulators so consecutive MMAs never wait on each other)
+    if (lane == 0) {
+      uint32_t it = 0, xa_n = 0, xb_n = 0;
+      const uint64_t dXA = make_smem_desc_sw128(XA), dXB = make_smem_desc_sw128(XB), dRing = make_smem_desc_sw128(ring);
+      auto chain_mma = [&](uint64_t dx, int nkb, int N, uint32_t d0) {
+        const uint32_t idesc = make_idesc_bf16_f32(128, N);
+        const uint64_t bstep = (uint64_t)(N * 8);            // one k-block tile of the weight slice, in 16-byte units
+        for (int kb = 0; kb < nkb; kb += 2, ++it) {
+          const uint32_t s = it & (TC_RING - 1), ph = (it / TC_RING) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after_sync();
+          const uint64_t da = dx + (uint64_t)kb * 256, db = dRing + (uint64_t)s * (TC_SLOT_BYTES >> 4);
+          const uint32_t acc0 = kb > 0 ? 1u : 0u;
+          umma_bf16(d0 + 0 * N, da + 0, db + 0, idesc, acc0);
+          umma_bf16(d0 + 1 * N, da + 2, db + 2, idesc, acc0);
+          umma_bf16(d0 + 2 * N, da + 4, db + 4, idesc, acc0);
+          umma_bf16(d0 + 3 * N, da + 6, db + 6, idesc, acc0);
+          if (kb + 1 < nkb) {
+            umma_bf16(d0 + 0 * N, da + 256 + 0, db + bstep + 0, idesc, 1u);
+            umma_bf16(d0 + 1 * N, da + 256 + 2, db + bstep + 2, idesc, 1u);
+            umma_bf16(d0 + 2 * N, da + 256 + 4, db + bstep + 4, idesc, 1u);
+            umma_bf16(d0 + 3 * N, da + 256 + 6, db + bstep + 6, idesc, 1u);
           }
           umma_commit(&empty[s]);
         }
-        __syncwarp();
+      };
+      for (int t = 1; t < T; ++t) {
+        mbar_wait(xb_full, xb_n & 1); ++xb_n; tc_fence_after_sync();
+        chain_mma(dXB, kbH, NP, tmem + R_GH0);                            // gh0
+        umma_commit(xb_free);
+        mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
+        TCDBG(3);
+        chain_mma(dXA, kbX, N1, tmem + R_MAIN);                           // S1
+        umma_commit(xa_free); umma_commit(&d_full[0]);
+        TCDBG(4);
+        mbar_wait(xb_full, xb_n & 1); ++xb_n; tc_fence_after_sync();
+        chain_mma(dXB, kbH, NP, tmem + R_GH1);                            // gh1
+        umma_commit(xb_free);
+        mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
+        TCDBG(10);
+        chain_mma(dXA, kbH, NP, tmem + R_MAIN);                           // gi0a
+        umma_commit(xa_free); umma_commit(&d_full[1]);
+        TCDBG(11);
+        mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
+        TCDBG(15);
+        chain_mma(dXA, kbH, NP, tmem + R_MAIN);                           // gi1
+        umma_commit(xa_free); umma_commit(&d_full[2]);
+        TCDBG(16);
+        mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
+        TCDBG(21);
+        for (int tile = 0; tile < n4t; ++tile) chain_mma(dXA, kbH, 16, tmem + R_MAIN + (uint32_t)(tile * 64));   // y
+        umma_commit(xa_free); umma_commit(&d_full[3]);
       }
-    };
-    const int na_main = nacc > 8 ? 8 : nacc, na_side = nacc > 4 ? 4 : nacc;
-    for (int t = 1; t < T; ++t) {
-      mbar_wait(xb_full, xb_n & 1); ++xb_n; tc_fence_after_sync();
-      chain_mma(XB, kbH, NP, R_GH0, na_side);                           // gh0
-      if (lane == 0) umma_commit(xb_free);
-      mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
-      TCDBG(3);
-      chain_mma(XA, kbX, N1, R_MAIN, na_main);                          // S1
-      if (lane == 0) { umma_commit(xa_free); umma_commit(&d_full[0]); }
-      TCDBG(4);
-      mbar_wait(xb_full, xb_n & 1); ++xb_n; tc_fence_after_sync();
-      chain_mma(XB, kbH, NP, R_GH1, na_side);                           // gh1
-      if (lane == 0) umma_commit(xb_free);
-      mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
-      TCDBG(10);
-      chain_mma(XA, kbH, NP, R_MAIN, na_main);                          // gi0a
-      if (lane == 0) { umma_commit(xa_free); umma_commit(&d_full[1]); }
-      TCDBG(11);
-      mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
-      TCDBG(15);
-      chain_mma(XA, kbH, NP, R_MAIN, na_main);                          // gi1
-      if (lane == 0) { umma_commit(xa_free); umma_commit(&d_full[2]); }
-      TCDBG(16);
-      mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
-      TCDBG(21);
-      for (int tile = 0; tile < n4t; ++tile) chain_mma(XA, kbH, 16, R_MAIN + (uint32_t)(tile * na_side * 16), na_side);   // y
-      if (lane == 0) { umma_commit(xa_free); umma_commit(&d_full[3]); }
-      __syncwarp();
     }
   } else {
     // ================= epilogue warp (TMEM lanes 0..31 = samples)
     const int b = lane;
     const bool live = b < a.B;
     const int j0 = c * U;
-    const int na_main = nacc > 8 ? 8 : nacc, na_side = nacc > 4 ? 4 : nacc;
+    constexpr int na_main = 4, na_side = 4;
     auto ld_sum = [&](uint32_t col, int na, float (&v)[NP]) {     // sum of a gate chain's accumulators
       tmem_ld_cols<NP>(tmem + col, v);
       for (int q = 1; q < na; ++q) {
