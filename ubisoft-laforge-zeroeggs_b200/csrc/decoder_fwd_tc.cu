@@ -233,7 +233,11 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem = *tmem_slot;
+  // The CTA allocates all 512 TMEM columns (1 CTA/SM), so the allocation base is column 0 / lane 0.  Using the literal
+  // keeps every tcgen05 address operand provably warp-uniform: otherwise the compiler wraps each UTCHMMA in an
+  // ELECT / R2UR.BROADCAST waterfall loop (~90 cycles per MMA, the issue-bound regime seen in the first trace).
+  if (*tmem_slot != 0u) __trap();
+  constexpr uint32_t tmem = 0u;
   // TMEM regions (columns): gh0 [0,128) | gh1 [128,256) | S1 / gi0a / gi1 / y [256,512); accumulator q of a chain at +q*N
   constexpr uint32_t R_GH0 = 0, R_GH1 = 128, R_MAIN = 256;
   const size_t actH = (size_t)g.nbt * H * 32, actX = (size_t)g.nbt * K1P * 32;
@@ -296,9 +300,9 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (one lane; the loop is kept lean: descriptors are advanced by constants, the four
-    // k-steps of a k-block go to four independent TMEM accumulators so consecutive MMAs never wait on each other)
-    if (lane == 0) {
+    // ================= MMA issuer.  The warp runs the loops converged; one elected lane issues.  Descriptors advance by
+    // constants and the four k-steps of a k-block go to four independent TMEM accumulators.
+    {
       uint32_t it = 0, xa_n = 0, xb_n = 0;
       const uint64_t dXA = make_smem_desc_sw128(XA), dXB = make_smem_desc_sw128(XB), dRing = make_smem_desc_sw128(ring);
       auto chain_mma = [&](uint64_t dx, int nkb, int N, uint32_t d0) {
@@ -309,46 +313,53 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
           mbar_wait(&full[s], ph);
           tc_fence_after_sync();
           const uint64_t da = dx + (uint64_t)kb * 256, db = dRing + (uint64_t)s * (TC_SLOT_BYTES >> 4);
-          const uint32_t acc0 = kb > 0 ? 1u : 0u;
-          umma_bf16(d0 + 0 * N, da + 0, db + 0, idesc, acc0);
-          umma_bf16(d0 + 1 * N, da + 2, db + 2, idesc, acc0);
-          umma_bf16(d0 + 2 * N, da + 4, db + 4, idesc, acc0);
-          umma_bf16(d0 + 3 * N, da + 6, db + 6, idesc, acc0);
-          if (kb + 1 < nkb) {
-            umma_bf16(d0 + 0 * N, da + 256 + 0, db + bstep + 0, idesc, 1u);
-            umma_bf16(d0 + 1 * N, da + 256 + 2, db + bstep + 2, idesc, 1u);
-            umma_bf16(d0 + 2 * N, da + 256 + 4, db + bstep + 4, idesc, 1u);
-            umma_bf16(d0 + 3 * N, da + 256 + 6, db + bstep + 6, idesc, 1u);
+          const bool acc0 = kb > 0, two = kb + 1 < nkb;
+          if (elect_one_sync()) {
+            umma_bf16(d0 + 0 * N, da + 0, db + 0, idesc, acc0);
+            umma_bf16(d0 + 1 * N, da + 2, db + 2, idesc, acc0);
+            umma_bf16(d0 + 2 * N, da + 4, db + 4, idesc, acc0);
+            umma_bf16(d0 + 3 * N, da + 6, db + 6, idesc, acc0);
+            if (two) {
+              umma_bf16(d0 + 0 * N, da + 256 + 0, db + bstep + 0, idesc, true);
+              umma_bf16(d0 + 1 * N, da + 256 + 2, db + bstep + 2, idesc, true);
+              umma_bf16(d0 + 2 * N, da + 256 + 4, db + bstep + 4, idesc, true);
+              umma_bf16(d0 + 3 * N, da + 256 + 6, db + bstep + 6, idesc, true);
+            }
+            umma_commit(&empty[s]);
           }
-          umma_commit(&empty[s]);
+          __syncwarp();
         }
+      };
+      auto commit2 = [&](uint64_t* b0, uint64_t* b1) {
+        if (elect_one_sync()) { umma_commit(b0); if (b1) umma_commit(b1); }
+        __syncwarp();
       };
       for (int t = 1; t < T; ++t) {
         mbar_wait(xb_full, xb_n & 1); ++xb_n; tc_fence_after_sync();
         chain_mma(dXB, kbH, NP, tmem + R_GH0);                            // gh0
-        umma_commit(xb_free);
+        commit2(xb_free, nullptr);
         mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
         TCDBG(3);
         chain_mma(dXA, kbX, N1, tmem + R_MAIN);                           // S1
-        umma_commit(xa_free); umma_commit(&d_full[0]);
+        commit2(xa_free, &d_full[0]);
         TCDBG(4);
         mbar_wait(xb_full, xb_n & 1); ++xb_n; tc_fence_after_sync();
         chain_mma(dXB, kbH, NP, tmem + R_GH1);                            // gh1
-        umma_commit(xb_free);
+        commit2(xb_free, nullptr);
         mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
         TCDBG(10);
         chain_mma(dXA, kbH, NP, tmem + R_MAIN);                           // gi0a
-        umma_commit(xa_free); umma_commit(&d_full[1]);
+        commit2(xa_free, &d_full[1]);
         TCDBG(11);
         mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
         TCDBG(15);
         chain_mma(dXA, kbH, NP, tmem + R_MAIN);                           // gi1
-        umma_commit(xa_free); umma_commit(&d_full[2]);
+        commit2(xa_free, &d_full[2]);
         TCDBG(16);
         mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
         TCDBG(21);
         for (int tile = 0; tile < n4t; ++tile) chain_mma(dXA, kbH, 16, tmem + R_MAIN + (uint32_t)(tile * 64));   // y
-        umma_commit(xa_free); umma_commit(&d_full[3]);
+        commit2(xa_free, &d_full[3]);
       }
     }
   } else {
