@@ -22,6 +22,7 @@
 namespace zeggs {
 
 constexpr int TC_RING = 8;              // weight ring slots (two k-block tiles each)
+constexpr int TC_XCH = 5;               // chunks (of 4 k-blocks) of an XA load
 constexpr int TC_XKB = 18;              // k-blocks of the widest activation vector (x_pose: 1136 -> 1152)
 constexpr int TC_SLOT_BYTES = 8192;     // 2 k-blocks x (32 rows x 128 B) (N <= 32)
 
@@ -152,6 +153,10 @@ __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, float (&v)[16])
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// bf16-engine gate math: exp via the SFU (relative error ~1e-6, far below the bf16 operand rounding)
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+
 // grid barrier split in two halves: the epilogue warp arrives, the activation loader waits
 __device__ __forceinline__ void grid_arrive(unsigned* counter) {
   __threadfence();
@@ -193,11 +198,11 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
   uint64_t* full = bars;                 // [TC_RING]
   uint64_t* empty = bars + TC_RING;      // [TC_RING]
-  uint64_t* xa_full = bars + 2 * TC_RING;
-  uint64_t* xb_full = xa_full + 1;
-  uint64_t* xa_free = xa_full + 2;
-  uint64_t* xb_free = xa_full + 3;
-  uint64_t* d_full = xa_full + 4;        // [4]
+  uint64_t* xa_full = bars + 2 * TC_RING;   // [TC_XCH] one per 4-k-block chunk of XA: the MMA chain starts on chunk 0
+  uint64_t* xb_full = xa_full + TC_XCH;
+  uint64_t* xa_free = xb_full + 1;
+  uint64_t* xb_free = xb_full + 2;
+  uint64_t* d_full = xb_full + 3;        // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 4);
   float* cst = reinterpret_cast<float*>(tail + 512);   // per-CTA constants (biases, normalisation rows)
   const int R4 = tg.n4t * 16;
@@ -214,7 +219,8 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_RING; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(xa_full, 1); mbar_init(xb_full, 1); mbar_init(xa_free, 1); mbar_init(xb_free, 1);
+    for (int i = 0; i < TC_XCH; ++i) mbar_init(&xa_full[i], 1);
+    mbar_init(xb_full, 1); mbar_init(xa_free, 1); mbar_init(xb_free, 1);
     for (int i = 0; i < 4; ++i) mbar_init(&d_full[i], 1);
     fence_mbar_init();
   }
@@ -270,8 +276,12 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
       auto load_xa = [&](const uint8_t* img, int nkb) {
         if (xa_n > 0) mbar_wait(xa_free, (xa_n - 1) & 1);
         fence_proxy_async();
-        mbar_arrive_expect_tx(xa_full, (uint32_t)nkb * 4096);
-        bulk_g2s(XA, img, (uint32_t)nkb * 4096, xa_full);
+        for (int ch = 0; ch * 4 < nkb; ++ch) {
+          const uint32_t bytes = (uint32_t)((nkb - ch * 4 >= 4 ? 4 : nkb - ch * 4) * 4096);
+          mbar_arrive_expect_tx(&xa_full[ch], bytes);
+          bulk_g2s(XA + ch * 16384, img + (size_t)ch * 16384, bytes, &xa_full[ch]);
+        }
+        for (int ch = (nkb + 3) / 4; ch < TC_XCH; ++ch) mbar_arrive(&xa_full[ch]);   // keep every chunk barrier in phase
         ++xa_n;
       };
       auto load_xb = [&](const uint8_t* img) {
@@ -305,11 +315,12 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
     {
       uint32_t it = 0, xa_n = 0, xb_n = 0;
       const uint64_t dXA = make_smem_desc_sw128(XA), dXB = make_smem_desc_sw128(XB), dRing = make_smem_desc_sw128(ring);
-      auto chain_mma = [&](uint64_t dx, int nkb, int N, uint32_t d0) {
+      auto chain_mma = [&](uint64_t dx, int nkb, int N, uint32_t d0, int xph) {   // xph >= 0: X arrives in chunks (XA)
         const uint32_t idesc = make_idesc_bf16_f32(128, N);
         const uint64_t bstep = (uint64_t)(N * 8);            // one k-block tile of the weight slice, in 16-byte units
         for (int kb = 0; kb < nkb; kb += 2, ++it) {
           const uint32_t s = it & (TC_RING - 1), ph = (it / TC_RING) & 1;
+          if (xph >= 0 && (kb & 3) == 0) mbar_wait(&xa_full[kb >> 2], (uint32_t)xph);
           mbar_wait(&full[s], ph);
           tc_fence_after_sync();
           const uint64_t da = dx + (uint64_t)kb * 256, db = dRing + (uint64_t)s * (TC_SLOT_BYTES >> 4);
@@ -336,29 +347,26 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
       };
       for (int t = 1; t < T; ++t) {
         mbar_wait(xb_full, xb_n & 1); ++xb_n; tc_fence_after_sync();
-        chain_mma(dXB, kbH, NP, tmem + R_GH0);                            // gh0
+        chain_mma(dXB, kbH, NP, tmem + R_GH0, -1);                        // gh0
         commit2(xb_free, nullptr);
-        mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
         TCDBG(3);
-        chain_mma(dXA, kbX, N1, tmem + R_MAIN);                           // S1
+        chain_mma(dXA, kbX, N1, tmem + R_MAIN, xa_n & 1); ++xa_n;         // S1
         commit2(xa_free, &d_full[0]);
         TCDBG(4);
         mbar_wait(xb_full, xb_n & 1); ++xb_n; tc_fence_after_sync();
-        chain_mma(dXB, kbH, NP, tmem + R_GH1);                            // gh1
+        chain_mma(dXB, kbH, NP, tmem + R_GH1, -1);                        // gh1
         commit2(xb_free, nullptr);
-        mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
         TCDBG(10);
-        chain_mma(dXA, kbH, NP, tmem + R_MAIN);                           // gi0a
+        chain_mma(dXA, kbH, NP, tmem + R_MAIN, xa_n & 1); ++xa_n;         // gi0a
         commit2(xa_free, &d_full[1]);
         TCDBG(11);
-        mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
         TCDBG(15);
-        chain_mma(dXA, kbH, NP, tmem + R_MAIN);                           // gi1
+        chain_mma(dXA, kbH, NP, tmem + R_MAIN, xa_n & 1); ++xa_n;         // gi1
         commit2(xa_free, &d_full[2]);
         TCDBG(16);
-        mbar_wait(xa_full, xa_n & 1); ++xa_n; tc_fence_after_sync();
         TCDBG(21);
-        for (int tile = 0; tile < n4t; ++tile) chain_mma(dXA, kbH, 16, tmem + R_MAIN + (uint32_t)(tile * 64));   // y
+        for (int tile = 0; tile < n4t; ++tile) chain_mma(dXA, kbH, 16, tmem + R_MAIN + (uint32_t)(tile * 64), tile == 0 ? (int)(xa_n & 1) : -1);   // y
+        ++xa_n;
         commit2(xa_free, &d_full[3]);
       }
     }
@@ -411,14 +419,14 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
 #pragma unroll
           for (int q = 0; q < 3; ++q) gi0p[q * U + u] = v[(1 + q) * U + u] + sv[(1 + q) * U + u];
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) w.A[ts * actH + (size_t)(j0 + u) * 32 + b] = av[u];
         store_img_units<U>(tw.ab, b, j0, av);
+        tc_fence_before_sync();
+        TCDBG(6);
+        grid_arrive(w.bar);                     // only the bf16 image feeds other CTAs: publish it first ...
+        TCDBG(7);
+#pragma unroll
+        for (int u = 0; u < U; ++u) w.A[ts * actH + (size_t)(j0 + u) * 32 + b] = av[u];   // ... fp32 history afterwards
       }
-      tc_fence_before_sync();
-      TCDBG(6);
-      grid_arrive(w.bar);
-      TCDBG(7);
       // ---------------- stage 2 (GRU layer 0)
       float hp[U];
 #pragma unroll
@@ -433,15 +441,18 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
         float hv[U], rr[U], zz[U], nn[U], gn[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          rr[u] = sigmoid_f(gi[u] + gi0p[u] + gh[u] + c_bhh0[u]);
-          zz[u] = sigmoid_f(gi[U + u] + gi0p[U + u] + gh[U + u] + c_bhh0[U + u]);
+          rr[u] = fast_sigmoid(gi[u] + gi0p[u] + gh[u] + c_bhh0[u]);
+          zz[u] = fast_sigmoid(gi[U + u] + gi0p[U + u] + gh[U + u] + c_bhh0[U + u]);
           gn[u] = gh[2 * U + u] + c_bhh0[2 * U + u];
-          nn[u] = tanhf(gi[2 * U + u] + gi0p[2 * U + u] + rr[u] * gn[u]);
+          nn[u] = fast_tanh(gi[2 * U + u] + gi0p[2 * U + u] + rr[u] * gn[u]);
           hv[u] = (1.f - zz[u]) * nn[u] + zz[u] * hp[u];
         }
+        store_img_units<U>(tw.h0b[t & 1], b, j0, hv);
+        tc_fence_before_sync();
+        TCDBG(13);
+        grid_arrive(w.bar);
 #pragma unroll
         for (int u = 0; u < U; ++u) w.H0[ts * actH + (size_t)(j0 + u) * 32 + b] = hv[u];
-        store_img_units<U>(tw.h0b[t & 1], b, j0, hv);
         if (w.save) {
           float* G = w.G0 + ((size_t)t * g.nbt) * 4 * H * 32;
 #pragma unroll
@@ -452,9 +463,6 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
           }
         }
       }
-      tc_fence_before_sync();
-      TCDBG(13);
-      grid_arrive(w.bar);
       // ---------------- stage 3 (GRU layer 1)
 #pragma unroll
       for (int u = 0; u < U; ++u) hp[u] = w.H1[tp * actH + (size_t)(j0 + u) * 32 + b];
@@ -468,15 +476,19 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
         float hv[U], rr[U], zz[U], nn[U], gn[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          rr[u] = sigmoid_f(gi[u] + c_bih1[u] + gh[u] + c_bhh1[u]);
-          zz[u] = sigmoid_f(gi[U + u] + c_bih1[U + u] + gh[U + u] + c_bhh1[U + u]);
+          rr[u] = fast_sigmoid(gi[u] + c_bih1[u] + gh[u] + c_bhh1[u]);
+          zz[u] = fast_sigmoid(gi[U + u] + c_bih1[U + u] + gh[U + u] + c_bhh1[U + u]);
           gn[u] = gh[2 * U + u] + c_bhh1[2 * U + u];
-          nn[u] = tanhf(gi[2 * U + u] + c_bih1[2 * U + u] + rr[u] * gn[u]);
+          nn[u] = fast_tanh(gi[2 * U + u] + c_bih1[2 * U + u] + rr[u] * gn[u]);
           hv[u] = (1.f - zz[u]) * nn[u] + zz[u] * hp[u];
         }
+        store_img_units<U>(tw.h1b[t & 1], b, j0, hv);
+        tc_fence_before_sync();
+        TCDBG(18);
+        grid_arrive(w.bar);
+        TCDBG(19);
 #pragma unroll
         for (int u = 0; u < U; ++u) w.H1[ts * actH + (size_t)(j0 + u) * 32 + b] = hv[u];
-        store_img_units<U>(tw.h1b[t & 1], b, j0, hv);
         if (w.save) {
           float* G = w.G1 + ((size_t)t * g.nbt) * 4 * H * 32;
 #pragma unroll
@@ -487,10 +499,6 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
           }
         }
       }
-      tc_fence_before_sync();
-      TCDBG(18);
-      grid_arrive(w.bar);
-      TCDBG(19);
       // ---------------- stage 4 (layer2, de-normalise, pose integration, next x_pose)
       V3 pos = v3(0, 0, 0), gzp = v3(0, 0, 0);
       Q4 q; q.w = 1.f; q.x = q.y = q.z = 0.f;
