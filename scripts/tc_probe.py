@@ -33,7 +33,7 @@ def case(H, B, T, seed=3, time_it=False):
         a, b = outs["tc"][i].cpu(), outs["fp32"][i].cpu()
         d = (a - b).abs()
         print(f"  H{H} B{B} T{T} {n:9s} max|tc-fp32| {d.max().item():.3e} (ref max {b.abs().max().item():.3e}) nan={torch.isnan(a).sum().item()}  last-frame err {d[:, -1].max().item():.3e}")
-for cfg in [(128, 4, 9), (64, 2, 6), (512, 16, 12), (1024, 32, 8)]:
+for cfg in [(128, 4, 9), (512, 16, 12), (1024, 32, 8)]:
     case(*cfg)
 case(1024, 32, 128, time_it=True)
 case(512, 16, 120, time_it=True)

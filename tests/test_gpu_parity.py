@@ -466,3 +466,61 @@ def test_checkpoint_round_trip_whole_module_pickles(dev, tmp_path):
     with torch.no_grad():
         assert torch.equal(nets["speech_encoder"](x), se(x))
     assert nets["decoder"].hidden_size == 64
+
+
+# ---------------------------------------------------------------------------------------------- tensor-core recurrence engine
+@pytest.fixture
+def decoder_engine():
+    from zeggs_b200 import ops
+
+    def set_engine(name):
+        ops.set_decoder_engine(name)
+    yield set_engine
+    ops.set_decoder_engine("fp32")
+
+
+@pytest.mark.parametrize("H,B,T", [(128, 4, 9), (512, 16, 40), (1024, 32, 24), (1024, 7, 64)])
+def test_decoder_forward_tc_engine_vs_oracle(dev, decoder_engine, H, B, T):
+    """tcgen05 recurrence (bf16 MMA operands, fp32 accumulate/state): free-running per-pose-channel max-abs
+    <= 2e-2 * max(1, max|ref|) in de-normalised units (bf16 operand rounding, 2^-9 relative, compounds over the window)."""
+    decoder_engine("tc")
+    out, ref = _decoder_case(dev, H, B, T, seed=500 + H + B)
+    for n, o, r in zip(NAMES, out, ref):
+        err, sc = report(f"decoder[tc] H{H} B{B} T{T} {n}", o, r)
+        assert torch.isfinite(o).all()
+        assert err <= 2e-2 * max(1.0, sc), n
+
+
+@pytest.mark.parametrize("H,B,T", [(512, 16, 12), (1024, 32, 10)])
+def test_decoder_training_with_tc_forward(dev, decoder_engine, H, B, T):
+    """Forward on the tensor-core engine (saved fp32 activations) + BPTT kernel: gradients vs oracle autograd, relative L2 <= 3e-2
+    (mixed-precision training numerics: the backward differentiates the bf16-operand forward)."""
+    from oracle import model_oracle as mo
+    from zeggs_b200 import synth
+    decoder_engine("tc")
+    seed = 700 + H
+    st = stats_tensors()
+    P = synth.make_params(H=H, seed=seed, with_style=False)
+    win = tt(synth.make_pose_windows(B, T, seed=seed))
+    rs = np.random.RandomState(seed)
+    speech = torch.from_numpy((rs.randn(B, T, 64) * 0.5).astype(np.float32))
+    style = torch.from_numpy(rs.randn(B, T, 64).astype(np.float32))
+    cot = [torch.from_numpy(rs.randn(*win[n].shape).astype(np.float32)) for n in NAMES]
+    Pt = {k: v.clone().requires_grad_(True) for k, v in tt(P).items() if k.startswith("decoder.")}
+    ref = mo.decoder_forward(Pt, *[win[n][:, 0] for n in NAMES], win["gaze_pos"], speech, style, st["anim_input_mean"],
+                             st["anim_input_std"], st["anim_output_mean"], st["anim_output_std"], st["dt"])
+    keys = sorted(Pt.keys())
+    g_ref = torch.autograd.grad(sum((o * c).sum() for o, c in zip(ref, cot)), [Pt[k] for k in keys])
+    dec = make_decoder(P, H, device=dev).train()
+    out = dec(*[win[n][:, 0].to(dev) for n in NAMES], win["gaze_pos"].to(dev), speech.to(dev), style.to(dev), st["parents"],
+              st["anim_input_mean"].to(dev), st["anim_input_std"].to(dev), st["anim_output_mean"].to(dev),
+              st["anim_output_std"].to(dev), st["dt"])
+    named = dict(dec.named_parameters())
+    g_got = torch.autograd.grad(sum((o * c.to(dev)).sum() for o, c in zip(out, cot)), [named[k[len("decoder."):]] for k in keys])
+    bad = []
+    for k, a, b in zip(keys, g_got, g_ref):
+        num = float((a.cpu().double() - b.double()).norm()); den = float(b.double().norm())
+        print(f"  [tc-train H{H} {k}] relL2 {num / max(den, 1e-30):.3e}")
+        if not num <= 3e-2 * max(den, 1e-9):
+            bad.append((k, num / max(den, 1e-30)))
+    assert not bad, bad
