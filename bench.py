@@ -129,8 +129,9 @@ def run_ours(args):
         ge.build()
     if world > 1:
         torch.distributed.barrier()
-    from zeggs_b200 import _lib
+    from zeggs_b200 import _lib, ops
     lib = _lib.lib()
+    ops.set_decoder_engine(args.engine)
     wl = WORKLOADS[args.workload]
     B, T, H, T_ex = wl["B"], wl["T"], wl["H"], wl["T_ex"]
     K, W = args.steps, max(args.warmup, 3)
@@ -204,12 +205,14 @@ def run_ours(args):
                     unit="TFLOP/s", frac=round(achieved / peaks["bf16_tflops_sustained"], 5), traffic=None,
                     peak_source=peaks["src"] + " (cuBLAS bf16, sustained)", ms_per_launch=round(dom_ms, 3),
                     weight_stream_gbs=round(wbytes * (T - 1) / (dom_ms * 1e-3) / 1e9, 1),
-                    note="fp32 SIMT recurrence this round (tcgen05 only in the batched GEMM); per-step arithmetic intensity at B=32 is 16 FLOP/B, "
-                         "see DESIGN.md")
+                    note=("decoder forward recurrence on tcgen05 (bf16 operands, fp32 state); BPTT recurrence fp32 SIMT; batched GEMMs tcgen05 split-bf16; "
+                          if args.engine == "tc" else "fp32 SIMT recurrence; batched GEMMs tcgen05 split-bf16; ") +
+                         "per-step arithmetic intensity at B=32 is 16-32 FLOP/B (weight streaming from L2), see DESIGN.md")
     out = dict(metric="frames/sec (train step, 60fps 75-joint pose)", value=round(value, 1), unit="frames/s", n_gpus=world, steps=K, warmup=W,
-               ms_per_step=round(r["ms"] / K, 3), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+               ms_per_step=round(r["ms"] / K, 3), higher_is_better=True, scaling="weak", vs_baseline=None,
+               dtype=("bf16" if args.engine == "tc" else "f32"), data="synthetic",
                config=dict(workload=wl["desc"], per_gpu_batch=B, global_batch=world * B, window=T, hidden=H, style_example_len=T_ex,
-                           parallelism=f"dp{world}", l2="per-step working set ~1.4 GB of saved activations >> 126 MB L2 (no explicit flush)"),
+                           parallelism=f"dp{world}", decoder_engine=args.engine, l2="per-step working set ~1.4 GB of saved activations >> 126 MB L2 (no explicit flush)"),
                e2e=dict(value=round(frames / (r["e2e_ms"] / K) * 1e3, 1), unit="frames/s", h2d_bytes_per_step=r["h2d"], d2h_bytes_per_step=4),
                gpu_launches=r["launches"], clocks=r["clocks"], roofline=roofline,
                kernel_ms_per_step={k: round(v["ms_per_step"], 3) for k, v in r["spans"].items()}, loss=r["loss"])
@@ -272,6 +275,7 @@ if __name__ == "__main__":
     ap.add_argument("--workload", default="train_v1", choices=list(WORKLOADS))
     ap.add_argument("--alt", type=int, default=1, help="also time the BASELINE.json-worded sizes (reported under alt_config)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--engine", default="tc", choices=["tc", "fp32"], help="decoder recurrence engine: tcgen05 bf16 (default) or fp32 SIMT")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
