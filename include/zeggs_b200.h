@@ -136,11 +136,16 @@ typedef struct {
   float* dStyle;  /* [B,T,Z] or NULL */
   void* workspace;
   size_t workspace_bytes;
+  const void* packed_bwd_tc; /* tensor-core engine (fwd args' engine == 1): zeggs_decoder_pack_weights_bwd_tc output, or NULL */
+  void* workspace_tc;        /* zeggs_decoder_bwd_tc_workspace_bytes bytes (bf16 gradient images) */
 } zeggs_decoder_bwd_args;
 size_t zeggs_decoder_packed_bwd_bytes(int H, int S, int Z);
 int zeggs_decoder_pack_weights_bwd(const zeggs_decoder_fwd_args* a, float* packed, void* stream);
 size_t zeggs_decoder_bwd_workspace_bytes(int B, int T, int H, int S, int Z);
 int zeggs_decoder_window_bwd(const zeggs_decoder_fwd_args* f, const zeggs_decoder_bwd_args* b, void* stream);
+size_t zeggs_decoder_packed_bwd_tc_bytes(int H, int S, int Z);
+size_t zeggs_decoder_bwd_tc_workspace_bytes(int H, int S, int Z);
+int zeggs_decoder_pack_weights_bwd_tc(const zeggs_decoder_fwd_args* a, void* packed, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SpeechEncoder (modules.py:249-272): conv k1 + ELU + drop -> conv k31 (replicate 'same') + ELU + drop -> Linear + ELU.

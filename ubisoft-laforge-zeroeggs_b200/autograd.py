@@ -47,6 +47,16 @@ class DecoderWindowFn(torch.autograd.Function):
             dec.__dict__["_zeggs_packed_bwd"] = (ver, packed)
             cache = dec.__dict__["_zeggs_packed_bwd"]
         b.packed_bwd = cache[1].data_ptr()
+        if a.engine == 1 and l.zeggs_decoder_packed_bwd_tc_bytes(H, S, Z) > 0 and H >= 288:
+            tcc = dec.__dict__.get("_zeggs_packed_bwd_tc")
+            if tcc is None or tcc[0] != ver or tcc[1].device != dev:
+                ptc = torch.empty(l.zeggs_decoder_packed_bwd_tc_bytes(H, S, Z), dtype=torch.uint8, device=dev)
+                _lib.check(l.zeggs_decoder_pack_weights_bwd_tc(a, ptc.data_ptr(), _lib.stream_ptr()), "zeggs_decoder_pack_weights_bwd_tc")
+                dec.__dict__["_zeggs_packed_bwd_tc"] = (ver, ptc)
+                tcc = dec.__dict__["_zeggs_packed_bwd_tc"]
+            wtc = ops.WS.get("dec_bwd_tc", l.zeggs_decoder_bwd_tc_workspace_bytes(H, S, Z), dev)
+            b.packed_bwd_tc, b.workspace_tc = tcc[1].data_ptr(), wtc.data_ptr()
+            hold += [tcc[1], wtc]
         grads = [torch.empty_like(w, dtype=torch.float32, memory_format=torch.contiguous_format) for w in ctx.weights]
         for n, g in zip(_DEC_GRAD_NAMES, grads):
             setattr(b, n, g.data_ptr())

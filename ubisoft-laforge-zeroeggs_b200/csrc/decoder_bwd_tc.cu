@@ -1,0 +1,537 @@
+// Decoder BPTT recurrence on the tensor cores (engine 1).  Same stage structure as decoder_bwd.cu (B1..B4 + R per
+// reverse step, grid barrier between stages) with every transposed GEMM as a tcgen05.mma chain.
+//
+// The gradient w.r.t. a GRU layer's gate pre-activations is four H-vectors per sample: dpr, dpz, dpn (= d gi) and
+// dpn*r (the n-block of d gh).  They are stored as ONE bf16 image of 128 rows = 4 blocks x 32 samples, K = H, so
+// the M = 128 operand of the MMA is fully used and the K = 3H contractions of the SIMT formulation
+// (dh_below = W_ih^T dgi, dh_prev = W_hh^T dgh) collapse into a single K = H chain per layer:
+//     D[(blk,b)][(w,j)] = sum_k img[(blk,b)][k] * Wt[(w,j)][k],      w in {ih_r, ih_z, ih_n, hh_r, hh_z, hh_n (, x_pose rows)}
+// and the wanted sums are the block-diagonal entries (pr with *_r, pz with *_z, pn with ih_n, pnr with hh_n), added
+// up across the four TMEM lane quadrants by the four epilogue warps through shared memory.
+//   B1  A = dY image [32 x 1152] (rows 32..127 alias),  B = W2^T slice            -> dh1 -> GRU1 gate adjoint -> G1 image
+//   B2  A = G1 image [128 x H],                         B = [W_ih1^T | W_hh1^T]   -> dh0 (+GRU0 adjoint -> G0 image), dh1(t-1)
+//   B3  A = G0 image [128 x H],                         B = [W_ih0a^T | W_hh0^T | W_ih0p^T] -> d pre_a image, dh0(t-1), dxp part
+//   B4  A = d pre_a image [32 x H],                     B = W0p^T slice           -> dxp -> R(t-1): dY image of step t-1, root adjoint
+// Warps: 0..3 epilogue (TMEM quadrants), 4 MMA issuer, 5 weight producer (runs ahead across barriers), 6 activation
+// loader (grid-barrier waiter; streams the A images through a 4 x 16 KB ring).  fp32 histories for the weight
+// gradients are written in the same k-major layout as the SIMT kernel, so the batched wgrad code is shared.
+#include "decoder_bwd_common.cuh"
+#include "tc_dec_common.cuh"
+
+namespace zeggs {
+
+constexpr int BT_XRING = 4;
+constexpr int BT_XSLOT = 16384;
+
+struct BtGeom {
+  int N1, N2, N3, N4, P6;
+  int kbH, kbX, rpcb;
+  int wslot, wring;       // weight ring slot bytes / slots
+  int nacc3;
+  size_t off[4];
+  size_t cta_bytes;
+};
+
+inline BtGeom make_btgeom(const DecGeom& g, const BwdGeom& bg) {
+  BtGeom t;
+  t.N1 = 16; t.P6 = round_up(6 * g.U, 16); t.N2 = t.P6; t.N3 = t.P6 + 48; t.N4 = 16;
+  t.kbH = ceil_div(g.H, 64); t.kbX = ceil_div(K1P, 64); t.rpcb = bg.rpcb;
+  t.wslot = round_up(t.N3 * 128, 1024);
+  t.wring = 98304 / t.wslot; if (t.wring > 8) t.wring = 8;
+  t.nacc3 = 4 * t.N3 <= 512 ? 4 : 2;
+  size_t off = 0;
+  t.off[0] = off; off += (size_t)t.kbX * t.N1 * 128;
+  t.off[1] = off; off += (size_t)t.kbH * t.N2 * 128;
+  t.off[2] = off; off += (size_t)t.kbH * t.N3 * 128;
+  t.off[3] = off; off += (size_t)t.kbH * t.N4 * 128;
+  t.cta_bytes = off;
+  return t;
+}
+
+__global__ void pack_decoder_bwd_tc_kernel(DecGeom g, BtGeom tg, const float* __restrict__ W0, const float* __restrict__ Wih0,
+                                           const float* __restrict__ Whh0, const float* __restrict__ Wih1,
+                                           const float* __restrict__ Whh1, const float* __restrict__ W2, uint8_t* __restrict__ out) {
+  const int H = g.H, U = g.U, A = g.A;
+  const size_t per = tg.cta_bytes / 2, total = (size_t)g.G * per;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i / per);
+    size_t b = (i % per) * 2;
+    int chain = 3;
+    for (int q = 0; q < 3; ++q) if (b < tg.off[q + 1]) { chain = q; break; }
+    b -= tg.off[chain];
+    const int N = chain == 0 ? tg.N1 : chain == 1 ? tg.N2 : chain == 2 ? tg.N3 : tg.N4;
+    const int kb = (int)(b / ((size_t)N * 128)), rb = (int)(b % ((size_t)N * 128));
+    const int row = rb / 128, cp = (rb % 128) / 16, e = (rb % 16) / 2;
+    const int k = kb * 64 + ((cp ^ (row & 7)) << 3) + e;
+    float v = 0.f;
+    if (chain == 0) {                         // W2^T: k = output channel n
+      if (row < U && k < P_OUT) v = W2[(size_t)k * H + c * U + row];
+    } else if (chain == 1 || chain == 2) {    // gate-row transposes: k = k' in [0,H)
+      if (k < H) {
+        if (row < 6 * U) {
+          const int wsel = row / U, u = row % U, gq = wsel % 3, j = c * U + u;
+          const size_t r = (size_t)(gq * H + k);
+          if (chain == 1) v = wsel < 3 ? Wih1[r * H + j] : Whh1[r * H + j];
+          else            v = wsel < 3 ? Wih0[r * (A + H) + j] : Whh0[r * H + j];
+        } else if (chain == 2 && row >= tg.P6) {
+          const int rr = row - tg.P6, gq = rr / 16, lr = rr % 16, m = c * tg.rpcb + lr;
+          if (lr < tg.rpcb && m < P_IN) v = Wih0[(size_t)(gq * H + k) * (A + H) + H + xp_perm(m)];
+        }
+      }
+    } else {                                  // W0p^T: k = hidden unit of pre_a
+      const int m = c * tg.rpcb + row;
+      if (row < tg.rpcb && m < P_IN && k < H) v = W0[(size_t)k * A + xp_perm(m)];
+    }
+    reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+  }
+}
+
+struct BtWs { uint8_t *dyimg, *g1img, *g0img, *dpaimg; size_t bytes; };
+inline BtWs make_btws(void* base, const DecGeom& g) {
+  BtWs w; size_t off = 0;
+  auto take = [&](size_t n) { uint8_t* p = base ? (uint8_t*)base + off : nullptr; off += ((n + 1023) / 1024) * 1024; return p; };
+  const size_t kbH = ceil_div(g.H, 64), kbX = ceil_div(K1P, 64);
+  w.dyimg = take(kbX * 4096); w.g1img = take(kbH * 16384); w.g0img = take(kbH * 16384); w.dpaimg = take(kbH * 4096);
+  w.bytes = off; return w;
+}
+
+// store U bf16 values at (row, k = j0..j0+U-1) of an image with `rows`-row tiles
+template <int U>
+__device__ __forceinline__ void store_img_row(uint8_t* img, int rows, int row, int j0, const float (&h)[U]) {
+  __nv_bfloat16 t[U];
+#pragma unroll
+  for (int i = 0; i < U; ++i) t[i] = __float2bfloat16_rn(h[i]);
+  uint8_t* p = img + img_off(rows, row, j0);
+  if (U == 8) *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(t);
+  else *reinterpret_cast<uint2*>(p) = *reinterpret_cast<const uint2*>(t);
+}
+__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;\n" ::"r"(id) : "memory"); }
+
+template <int U>
+__global__ void __launch_bounds__(224, 1)
+decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg, DecWs w, BwdWs bw, BtWs iw, BwdArgsDev d,
+                      const uint8_t* __restrict__ packed) {
+  constexpr int PW = 2 * U + 16;            // floats of the cross-quadrant exchange per (warp, sample)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* xring = smem;                                        // 4 x 16 KB activation tiles
+  uint8_t* wring = xring + BT_XRING * BT_XSLOT;                 // weight tiles (rows 32..127 of 4 KB A tiles alias into here)
+  uint8_t* tail = wring + tg.wring * tg.wslot;
+  uint64_t* xfull = reinterpret_cast<uint64_t*>(tail);          // [4]
+  uint64_t* xempty = xfull + BT_XRING;                          // [4]
+  uint64_t* wfull = xempty + BT_XRING;                          // [8]
+  uint64_t* wempty = wfull + 8;                                 // [8]
+  uint64_t* d_full = wempty + 8;                                // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 4);
+  float* part = reinterpret_cast<float*>(tail + 512);           // [4][32][PW]
+  float* c_is = part + 4 * 32 * PW;                             // [16] in_std of this CTA's x_pose rows, then out_std [16]
+  float* c_os = c_is + 16;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x, H = a.H, T = a.T;
+  const int kbH = tg.kbH, kbX = tg.kbX;
+  const uint8_t* pk = packed + (size_t)c * tg.cta_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < BT_XRING; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(&d_full[i], 1);
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 16) {
+    const int m = c * tg.rpcb + threadIdx.x;
+    const bool ok = threadIdx.x < tg.rpcb && m < P_IN;
+    const int n = ok ? xp_perm(m) : 0;
+    c_is[threadIdx.x] = ok ? a.in_std[n] : 1.f;
+    c_os[threadIdx.x] = (ok && n < P_OUT) ? a.out_std[n] : 0.f;
+  }
+  if (warp == 4) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  if (*tmem_slot != 0u) __trap();           // whole-TMEM allocation: base 0 keeps tcgen05 operands warp-uniform
+  constexpr uint32_t tmem = 0u;
+  const size_t actH = (size_t)g.nbt * H * 32, act3 = (size_t)g.nbt * 3 * H * 32, actX = (size_t)g.nbt * K1P * 32, act4 = (size_t)g.nbt * 4 * H * 32;
+
+  if (warp == 5) {
+    // ================= weight producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      auto stream = [&](int chain, int nkb, int N) {
+        const uint8_t* src = pk + tg.off[chain];
+        const uint32_t bytes = (uint32_t)N * 128;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t s = it % (uint32_t)tg.wring, ph = (it / (uint32_t)tg.wring) & 1;
+          mbar_wait(&wempty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&wfull[s], bytes);
+          bulk_g2s(wring + (size_t)s * tg.wslot, src + (size_t)kb * bytes, bytes, &wfull[s]);
+        }
+      };
+      for (int t = T - 1; t >= 1; --t) {
+        stream(0, kbX, tg.N1); stream(1, kbH, tg.N2); stream(2, kbH, tg.N3);
+        if (t > 1) stream(3, kbH, tg.N4);
+      }
+    }
+  } else if (warp == 6) {
+    // ================= activation loader
+    if (lane == 0) {
+      uint32_t it = 0; unsigned epoch = 0;
+      auto stream = [&](const uint8_t* img, int nkb, uint32_t tile_bytes) {
+        grid_wait(bw.bar, (++epoch) * gridDim.x);
+        fence_proxy_async();
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t s = it % BT_XRING, ph = (it / BT_XRING) & 1;
+          mbar_wait(&xempty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&xfull[s], tile_bytes);
+          bulk_g2s(xring + s * BT_XSLOT, img + (size_t)kb * tile_bytes, tile_bytes, &xfull[s]);
+        }
+      };
+      for (int t = T - 1; t >= 1; --t) {
+        stream(iw.dyimg, kbX, 4096);
+        stream(iw.g1img, kbH, 16384);
+        stream(iw.g0img, kbH, 16384);
+        if (t > 1) stream(iw.dpaimg, kbH, 4096);
+      }
+    }
+  } else if (warp == 4) {
+    // ================= MMA issuer
+    uint32_t itx = 0, itw = 0;
+    const uint64_t dX = make_smem_desc_sw128(xring), dW = make_smem_desc_sw128(wring);
+    const uint32_t wstep = (uint32_t)(tg.wslot >> 4);
+    auto chain_mma = [&](int nkb, int N, int nacc) {
+      const uint32_t idesc = make_idesc_bf16_f32(128, N);
+      for (int kb = 0; kb < nkb; ++kb, ++itx, ++itw) {
+        const uint32_t sx = itx % BT_XRING, phx = (itx / BT_XRING) & 1;
+        const uint32_t sw = itw % (uint32_t)tg.wring, phw = (itw / (uint32_t)tg.wring) & 1;
+        mbar_wait(&xfull[sx], phx);
+        mbar_wait(&wfull[sw], phw);
+        tc_fence_after_sync();
+        const uint64_t da = dX + (uint64_t)sx * (BT_XSLOT >> 4), db = dW + (uint64_t)sw * wstep;
+        const bool acc0 = kb > 0;
+        if (elect_one_sync()) {
+          if (nacc == 4) {
+            umma_bf16(tmem + 0 * N, da + 0, db + 0, idesc, acc0);
+            umma_bf16(tmem + 1 * N, da + 2, db + 2, idesc, acc0);
+            umma_bf16(tmem + 2 * N, da + 4, db + 4, idesc, acc0);
+            umma_bf16(tmem + 3 * N, da + 6, db + 6, idesc, acc0);
+          } else {
+            umma_bf16(tmem + 0 * N, da + 0, db + 0, idesc, acc0);
+            umma_bf16(tmem + 1 * N, da + 2, db + 2, idesc, acc0);
+            umma_bf16(tmem + 0 * N, da + 4, db + 4, idesc, true);
+            umma_bf16(tmem + 1 * N, da + 6, db + 6, idesc, true);
+          }
+          umma_commit(&xempty[sx]);
+          umma_commit(&wempty[sw]);
+        }
+        __syncwarp();
+      }
+    };
+    auto commit_d = [&](int i) { if (elect_one_sync()) umma_commit(&d_full[i]); __syncwarp(); };
+    for (int t = T - 1; t >= 1; --t) {
+      chain_mma(kbX, tg.N1, 4); commit_d(0);
+      chain_mma(kbH, tg.N2, 4); commit_d(1);
+      chain_mma(kbH, tg.N3, tg.nacc3); commit_d(2);
+      if (t > 1) { chain_mma(kbH, tg.N4, 4); commit_d(3); }
+    }
+  } else {
+    // ================= epilogue warps 0..3 (TMEM lane quadrant = warp index)
+    const int b = lane, q = warp;
+    const bool live = b < a.B;
+    const int j0 = c * U;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float* mypart = part + ((size_t)q * 32 + b) * PW;
+    // sum of the chain's accumulators for a U-wide column group starting at `col`
+    auto ld_units = [&](uint32_t col, int N, int nacc, float (&v)[U]) {
+      tmem_ld_cols<U>(lane_base + col, v);
+      for (int k = 1; k < nacc; ++k) {
+        float u_[U];
+        tmem_ld_cols<U>(lane_base + col + (uint32_t)(k * N), u_);
+#pragma unroll
+        for (int i = 0; i < U; ++i) v[i] += u_[i];
+      }
+    };
+    auto ld16 = [&](uint32_t col, int N, int nacc, float (&v)[16]) {
+      tmem_ld_cols<16>(lane_base + col, v);
+      for (int k = 1; k < nacc; ++k) {
+        float u_[16];
+        tmem_ld_cols<16>(lane_base + col + (uint32_t)(k * N), u_);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += u_[i];
+      }
+    };
+    // ---- R(t): finalise dY_acc[t] (this CTA's x_pose rows) from dxp; root / gaze adjoint on CTA 0.  warp 0 only.
+    float dpq[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // running d root_pos(3) / d root_rot(4) of this sample (CTA 0)
+    auto phase_R = [&](int t, const float (&dxp)[16], bool have_dxp) {
+      float rootg[9];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const int m = c * tg.rpcb + r;
+        if (r >= tg.rpcb || m >= P_IN) continue;
+        const int n = xp_perm(m);
+        const float dx = have_dxp ? dxp[r] / c_is[r] : 0.f;                       // modules.py:713
+        if (m < 9) { rootg[m < 9 ? m : 0] = dx; continue; }
+        const float ext = (d.dY && live) ? d.dY[((size_t)b * T + t) * P_OUT + n] : 0.f;
+        const float v = (ext + dx) * c_os[r];                                     // modules.py:728
+        *reinterpret_cast<__nv_bfloat16*>(iw.dyimg + img_off(32, b, n)) = __float2bfloat16_rn(v);
+        bw.DY[t * actX + (size_t)n * 32 + b] = v;
+      }
+      if (c == 0) {
+        float dch[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (live) {
+          V3 dp; Q4 dq;
+          if (!have_dxp) {
+            dp = d.dRootPos ? v3(d.dRootPos[((size_t)b * T + t) * 3 + 0], d.dRootPos[((size_t)b * T + t) * 3 + 1], d.dRootPos[((size_t)b * T + t) * 3 + 2]) : v3(0, 0, 0);
+            if (d.dRootRot) { const float* e = d.dRootRot + ((size_t)b * T + t) * 4; dq.w = e[0]; dq.x = e[1]; dq.y = e[2]; dq.z = e[3]; }
+            else { dq.w = dq.x = dq.y = dq.z = 0.f; }
+          } else {
+            dp = v3(dpq[0], dpq[1], dpq[2]); dq.w = dpq[3]; dq.x = dpq[4]; dq.y = dpq[5]; dq.z = dpq[6];
+          }
+          const float* rp = a.root_pos + ((size_t)b * T + t) * 3;
+          const float* rq = a.root_rot + ((size_t)b * T + t) * 4;
+          Q4 qt; qt.w = rq[0]; qt.x = rq[1]; qt.y = rq[2]; qt.z = rq[3];
+          if (have_dxp) {       // gaze_dir(t+1) = R(q_t)^-1 (gaze_pos[t+1] - p_t)
+            const float* gp = a.gaze_pos + ((size_t)b * T + (t + 1)) * 3;
+            V3 u = v3(gp[0] - rp[0], gp[1] - rp[1], gp[2] - rp[2]);
+            Q4 dqc; V3 du;
+            quat_mul_vec_bwd(quat_inv(qt), u, v3(rootg[6], rootg[7], rootg[8]), dqc, du);
+            dq.w += dqc.w; dq.x -= dqc.x; dq.y -= dqc.y; dq.z -= dqc.z;
+            dp = dp - du;
+          }
+          const float* rq1 = a.root_rot + ((size_t)b * T + (t - 1)) * 4;
+          Q4 q1; q1.w = rq1[0]; q1.x = rq1[1]; q1.y = rq1[2]; q1.z = rq1[3];
+          const float* yt = a.Y + ((size_t)b * T + t) * P_OUT;
+          V3 a1 = a.dt * v3(yt[0], yt[1], yt[2]);
+          V3 a2 = a.dt * v3(yt[3], yt[4], yt[5]);
+          Q4 dq_a, dq_b, dq_c, dE; V3 da1, da2;
+          quat_mul_vec_bwd(q1, a1, dp, dq_a, da1);
+          V3 wv = quat_mul_vec(q1, a2);
+          Q4 E = quat_from_helical(wv);
+          quat_mul_bwd(E, q1, dq, dE, dq_b);
+          V3 dw = quat_from_helical_bwd(wv, dE);
+          quat_mul_vec_bwd(q1, a2, dw, dq_c, da2);
+          dch[0] = a.dt * da1.x; dch[1] = a.dt * da1.y; dch[2] = a.dt * da1.z; dch[3] = a.dt * da2.x; dch[4] = a.dt * da2.y; dch[5] = a.dt * da2.z;
+          V3 dp1 = dp; Q4 dq1;
+          dq1.w = dq_a.w + dq_b.w + dq_c.w; dq1.x = dq_a.x + dq_b.x + dq_c.x; dq1.y = dq_a.y + dq_b.y + dq_c.y; dq1.z = dq_a.z + dq_b.z + dq_c.z;
+          if (d.dRootPos) { const float* e = d.dRootPos + ((size_t)b * T + (t - 1)) * 3; dp1 = dp1 + v3(e[0], e[1], e[2]); }
+          if (d.dRootRot) { const float* e = d.dRootRot + ((size_t)b * T + (t - 1)) * 4; dq1.w += e[0]; dq1.x += e[1]; dq1.y += e[2]; dq1.z += e[3]; }
+          dpq[0] = dp1.x; dpq[1] = dp1.y; dpq[2] = dp1.z; dpq[3] = dq1.w; dpq[4] = dq1.x; dpq[5] = dq1.y; dpq[6] = dq1.z;
+        }
+#pragma unroll
+        for (int n = 0; n < 6; ++n) {
+          const float ext = (d.dY && live) ? d.dY[((size_t)b * T + t) * P_OUT + n] : 0.f;
+          const float dx = have_dxp ? rootg[n] : 0.f;
+          const float v = live ? (ext + dx + dch[n]) * c_os[n] : 0.f;
+          *reinterpret_cast<__nv_bfloat16*>(iw.dyimg + img_off(32, b, n)) = __float2bfloat16_rn(v);
+          bw.DY[t * actX + (size_t)n * 32 + b] = v;
+        }
+      }
+    };
+
+    float dhz1[U], dhz0[U], dxp1[16];
+    if (q == 0) {
+      const float zero16[16] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      phase_R(T - 1, zero16, false);
+      grid_arrive(bw.bar);
+    }
+    for (int t = T - 1; t >= 1; --t) {
+      const uint32_t ph = (uint32_t)((T - 1 - t) & 1);
+      // ------------------------------------------------------------ B1 epilogue (quadrant 0 holds the 32 samples)
+      if (q == 0) {
+        float gr[U], gz[U], gn[U], ghn[U], hp[U], acc[U];
+        const float* G = w.G1 + t * act4;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + u;
+          gr[u] = G[(size_t)(0 * H + j) * 32 + b]; gz[u] = G[(size_t)(1 * H + j) * 32 + b];
+          gn[u] = G[(size_t)(2 * H + j) * 32 + b]; ghn[u] = G[(size_t)(3 * H + j) * 32 + b];
+          hp[u] = w.H1[(t - 1) * actH + (size_t)j * 32 + b];
+          acc[u] = t == T - 1 ? 0.f : bw.DH1[(size_t)j * 32 + b];
+        }
+        mbar_wait(&d_full[0], ph);
+        tc_fence_after_sync();
+        float v[U];
+        ld_units(0, tg.N1, 4, v);
+        float pr[U], pz[U], pn[U], pnr[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          float dgi[3], dgh[3];
+          gru_gate_bwd(v[u] + acc[u], gr[u], gz[u], gn[u], ghn[u], hp[u], dgi, dgh, dhz1[u]);
+          pr[u] = dgi[0]; pz[u] = dgi[1]; pn[u] = dgi[2]; pnr[u] = dgh[2];
+        }
+        store_img_row<U>(iw.g1img, 128, 0 * 32 + b, j0, pr); store_img_row<U>(iw.g1img, 128, 1 * 32 + b, j0, pz);
+        store_img_row<U>(iw.g1img, 128, 2 * 32 + b, j0, pn); store_img_row<U>(iw.g1img, 128, 3 * 32 + b, j0, pnr);
+        tc_fence_before_sync();
+        grid_arrive(bw.bar);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + u;
+          bw.DGI1[t * act3 + (size_t)(0 * H + j) * 32 + b] = pr[u]; bw.DGI1[t * act3 + (size_t)(1 * H + j) * 32 + b] = pz[u];
+          bw.DGI1[t * act3 + (size_t)(2 * H + j) * 32 + b] = pn[u];
+          bw.DGH1[t * act3 + (size_t)(0 * H + j) * 32 + b] = pr[u]; bw.DGH1[t * act3 + (size_t)(1 * H + j) * 32 + b] = pz[u];
+          bw.DGH1[t * act3 + (size_t)(2 * H + j) * 32 + b] = pnr[u];
+        }
+      }
+      // ------------------------------------------------------------ B2 epilogue (4 quadrants = blocks pr, pz, pn, pnr)
+      float gr[U], gz[U], gn[U], ghn[U], hp[U], acc[U];
+      if (q == 0) {
+        const float* G = w.G0 + t * act4;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + u;
+          gr[u] = G[(size_t)(0 * H + j) * 32 + b]; gz[u] = G[(size_t)(1 * H + j) * 32 + b];
+          gn[u] = G[(size_t)(2 * H + j) * 32 + b]; ghn[u] = G[(size_t)(3 * H + j) * 32 + b];
+          hp[u] = w.H0[(t - 1) * actH + (size_t)j * 32 + b];
+          acc[u] = t == T - 1 ? 0.f : bw.DH0[(size_t)j * 32 + b];
+        }
+      }
+      mbar_wait(&d_full[1], ph);
+      tc_fence_after_sync();
+      {
+        float v0[U], v1[U];
+        if (q < 3) ld_units((uint32_t)(q * U), tg.N2, 4, v0);               // ih_g
+        if (q != 2) ld_units((uint32_t)((3 + (q == 3 ? 2 : q)) * U), tg.N2, 4, v1);   // hh_g (quadrant 3 = pnr pairs with hh_n)
+#pragma unroll
+        for (int u = 0; u < U; ++u) { mypart[u] = q < 3 ? v0[u] : 0.f; mypart[U + u] = q != 2 ? v1[u] : 0.f; }
+      }
+      tc_fence_before_sync();
+      epi_bar(1);
+      if (q == 0) {
+        float pr[U], pz[U], pn[U], pnr[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          float oa = 0.f, ob = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) { oa += part[((size_t)qq * 32 + b) * PW + u]; ob += part[((size_t)qq * 32 + b) * PW + U + u]; }
+          float dgi[3], dgh[3];
+          gru_gate_bwd(oa + acc[u], gr[u], gz[u], gn[u], ghn[u], hp[u], dgi, dgh, dhz0[u]);
+          pr[u] = dgi[0]; pz[u] = dgi[1]; pn[u] = dgi[2]; pnr[u] = dgh[2];
+          bw.DH1[(size_t)(j0 + u) * 32 + b] = ob + dhz1[u];               // dh1(t-1) = dh1*z1 + W_hh1^T dgh1
+        }
+        store_img_row<U>(iw.g0img, 128, 0 * 32 + b, j0, pr); store_img_row<U>(iw.g0img, 128, 1 * 32 + b, j0, pz);
+        store_img_row<U>(iw.g0img, 128, 2 * 32 + b, j0, pn); store_img_row<U>(iw.g0img, 128, 3 * 32 + b, j0, pnr);
+        grid_arrive(bw.bar);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + u;
+          bw.DGI0[t * act3 + (size_t)(0 * H + j) * 32 + b] = pr[u]; bw.DGI0[t * act3 + (size_t)(1 * H + j) * 32 + b] = pz[u];
+          bw.DGI0[t * act3 + (size_t)(2 * H + j) * 32 + b] = pn[u];
+          bw.DGH0[t * act3 + (size_t)(0 * H + j) * 32 + b] = pr[u]; bw.DGH0[t * act3 + (size_t)(1 * H + j) * 32 + b] = pz[u];
+          bw.DGH0[t * act3 + (size_t)(2 * H + j) * 32 + b] = pnr[u];
+        }
+      }
+      epi_bar(2);
+      // ------------------------------------------------------------ B3 epilogue
+      float av[U];
+      if (q == 0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) av[u] = w.A[t * actH + (size_t)(j0 + u) * 32 + b];
+      }
+      mbar_wait(&d_full[2], ph);
+      tc_fence_after_sync();
+      {
+        float v0[U], v1[U], vx[16];
+        if (q < 3) { ld_units((uint32_t)(q * U), tg.N3, tg.nacc3, v0); ld16((uint32_t)(tg.P6 + q * 16), tg.N3, tg.nacc3, vx); }
+        if (q != 2) ld_units((uint32_t)((3 + (q == 3 ? 2 : q)) * U), tg.N3, tg.nacc3, v1);
+#pragma unroll
+        for (int u = 0; u < U; ++u) { mypart[u] = q < 3 ? v0[u] : 0.f; mypart[U + u] = q != 2 ? v1[u] : 0.f; }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) mypart[2 * U + r] = q < 3 ? vx[r] : 0.f;
+      }
+      tc_fence_before_sync();
+      epi_bar(1);
+      if (q == 0) {
+        float dpa[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          float da = 0.f, ob = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) { da += part[((size_t)qq * 32 + b) * PW + u]; ob += part[((size_t)qq * 32 + b) * PW + U + u]; }
+          dpa[u] = da * (av[u] > 0.f ? 1.f : av[u] + 1.f);                 // ELU'(pre) = a + 1 for pre <= 0
+          bw.DH0[(size_t)(j0 + u) * 32 + b] = ob + dhz0[u];
+        }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          float s = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < 3; ++qq) s += part[((size_t)qq * 32 + b) * PW + 2 * U + r];
+          dxp1[r] = s;
+        }
+        store_img_row<U>(iw.dpaimg, 32, b, j0, dpa);
+        if (t > 1) grid_arrive(bw.bar);
+#pragma unroll
+        for (int u = 0; u < U; ++u) bw.DPA[t * actH + (size_t)(j0 + u) * 32 + b] = dpa[u];
+      }
+      epi_bar(2);
+      if (t == 1) break;
+      // ------------------------------------------------------------ B4 epilogue + R(t-1)
+      if (q == 0) {
+        mbar_wait(&d_full[3], ph);
+        tc_fence_after_sync();
+        float dxp[16];
+        ld16(0, tg.N4, 4, dxp);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) dxp[r] += dxp1[r];
+        phase_R(t - 1, dxp, true);
+        tc_fence_before_sync();
+        grid_arrive(bw.bar);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) { tc_fence_after_sync(); tmem_dealloc(tmem, 512); }
+}
+
+// ------------------------------------------------------------------ host
+extern "C" size_t zeggs_decoder_packed_bwd_tc_bytes(int H, int S, int Z) {
+  if (H % 16 != 0 || pick_U(H) <= 0) return 0;
+  DecGeom g = make_geom(1, H, S, Z);
+  return (size_t)g.G * make_btgeom(g, make_bgeom(g)).cta_bytes;
+}
+extern "C" size_t zeggs_decoder_bwd_tc_workspace_bytes(int H, int S, int Z) {
+  if (H % 16 != 0 || pick_U(H) <= 0) return 0;
+  return make_btws(nullptr, make_geom(1, H, S, Z)).bytes;
+}
+extern "C" int zeggs_decoder_pack_weights_bwd_tc(const zeggs_decoder_fwd_args* a, void* packed, void* stream_) {
+  ZCHECK_ARG(a && packed && a->H % 16 == 0 && pick_U(a->H) > 0, "decoder bwd tc pack: bad arguments");
+  DecGeom g = make_geom(a->B, a->H, a->S, a->Z);
+  BwdGeom bg = make_bgeom(g);
+  ZCHECK_ARG(bg.n4b == 1, "decoder bwd tc: hidden size %d too small for the tensor-core engine", a->H);
+  BtGeom tg = make_btgeom(g, bg);
+  pack_decoder_bwd_tc_kernel<<<592, 256, 0, (cudaStream_t)stream_>>>(g, tg, a->W0, a->W_ih0, a->W_hh0, a->W_ih1, a->W_hh1, a->W2, (uint8_t*)packed);
+  count_launch();
+  ZCHECK_LAUNCH();
+  return ZEGGS_OK;
+}
+
+template <int U>
+static int launch_bt(const zeggs_decoder_fwd_args& a, const DecGeom& g, const BwdGeom& bg, const BtGeom& tg, const DecWs& w,
+                     const BwdWs& bw, const BtWs& iw, const BwdArgsDev& d, const uint8_t* packed, cudaStream_t stream) {
+  const size_t smem = 1024 + (size_t)BT_XRING * BT_XSLOT + (size_t)tg.wring * tg.wslot + 512 + (size_t)(4 * 32 * (2 * U + 16) + 32) * sizeof(float);
+  ZCHECK_CUDA(cudaFuncSetAttribute(decoder_bwd_tc_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, nsm = 0, occ = 0;
+  ZCHECK_CUDA(cudaGetDevice(&dev));
+  ZCHECK_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  ZCHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decoder_bwd_tc_kernel<U>, 224, smem));
+  ZCHECK_ARG(occ * nsm >= g.G, "decoder bwd tc: cooperative grid of %d CTAs does not fit", g.G);
+  void* args[] = {(void*)&a, (void*)&g, (void*)&bg, (void*)&tg, (void*)&w, (void*)&bw, (void*)&iw, (void*)&d, (void*)&packed};
+  ZCHECK_CUDA(cudaLaunchCooperativeKernel((void*)decoder_bwd_tc_kernel<U>, dim3(g.G), dim3(224), args, smem, stream));
+  count_launch();
+  return ZEGGS_OK;
+}
+
+int decoder_bwd_tc_run(const zeggs_decoder_fwd_args& a, const zeggs_decoder_bwd_args& b, const DecGeom& g, const DecWs& w,
+                       const BwdWs& bw, cudaStream_t stream) {
+  BwdGeom bg = make_bgeom(g);
+  ZCHECK_ARG(g.nbt == 1 && bg.n4b == 1, "decoder bwd tc engine needs B <= 32 and H >= 284 (got B=%d H=%d)", a.B, a.H);
+  ZCHECK_ARG(b.packed_bwd_tc && b.workspace_tc, "decoder bwd tc: packed_bwd_tc / workspace_tc missing");
+  BtGeom tg = make_btgeom(g, bg);
+  ZCHECK_ARG(tg.wring >= 2 && 4 * tg.N2 <= 512, "decoder bwd tc: unsupported geometry");
+  BtWs iw = make_btws(b.workspace_tc, g);
+  ZCHECK_CUDA(cudaMemsetAsync(iw.dyimg, 0, (size_t)tg.kbX * 4096, stream));
+  BwdArgsDev d; d.dY = b.dY; d.dRootPos = b.dRootPos; d.dRootRot = b.dRootRot; d.packed = nullptr;
+  return g.U == 4 ? launch_bt<4>(a, g, bg, tg, w, bw, iw, d, (const uint8_t*)b.packed_bwd_tc, stream)
+                  : launch_bt<8>(a, g, bg, tg, w, bw, iw, d, (const uint8_t*)b.packed_bwd_tc, stream);
+}
+
+}  // namespace zeggs

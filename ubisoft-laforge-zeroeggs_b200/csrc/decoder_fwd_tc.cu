@@ -18,6 +18,7 @@
 //   GRU state, gates, pose integration and all saved-for-backward tensors stay fp32; only the MMA operands are bf16.
 #include "decoder_common.cuh"
 #include "tc_common.cuh"
+#include "tc_dec_common.cuh"
 
 namespace zeggs {
 
@@ -55,12 +56,6 @@ inline TcGeom make_tcgeom(const DecGeom& g) {
   t.chain_off[5] = off; off += (size_t)t.n4t * t.kbH * tc_tile_bytes(16);  // y tiles X = h1(t)
   t.cta_bytes = off;
   return t;
-}
-
-// byte offset of element (row, k) inside an image whose k-block tiles have `rows` rows
-__host__ __device__ inline size_t img_off(int rows, int row, int k) {
-  const int kb = k >> 6, c = (k & 63) >> 3, e = k & 7;
-  return (size_t)kb * rows * 128 + (size_t)row * 128 + (size_t)((c ^ (row & 7)) << 4) + (size_t)e * 2;
 }
 
 // ------------------------------------------------------------------ packing (bf16 images of the weight slices)
@@ -123,62 +118,6 @@ inline TcWs make_tcws(void* base, const DecGeom& g) {
   w.h0b[0] = take(hb); w.h0b[1] = take(hb); w.h1b[0] = take(hb); w.h1b[1] = take(hb);
   w.dbg = nullptr;
   w.bytes = off; return w;
-}
-
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
-
-template <int NC>
-__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[NC]);
-template <>
-__device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  tmem_ld_32x32b_x32(taddr, r);
-  tmem_ld_wait();
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-template <>
-__device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-               : "r"(taddr) : "memory");
-  tmem_ld_wait();
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// bf16-engine gate math: exp via the SFU (relative error ~1e-6, far below the bf16 operand rounding)
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
-
-// grid barrier split in two halves: the epilogue warp arrives, the activation loader waits
-__device__ __forceinline__ void grid_arrive(unsigned* counter) {
-  __threadfence();
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0) atomicAdd(counter, 1u);
-}
-__device__ __forceinline__ void grid_wait(const unsigned* counter, unsigned target) {
-  long long t0 = clock64();
-  while (ld_acquire_u32(counter) < target) {
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-
-// write U consecutive bf16 values (units j0..j0+U-1 of sample row b) into an activation image
-template <int U>
-__device__ __forceinline__ void store_img_units(uint8_t* img, int b, int j0, const float (&h)[U]) {
-  __nv_bfloat16 t[U];
-#pragma unroll
-  for (int i = 0; i < U; ++i) t[i] = __float2bfloat16_rn(h[i]);
-  uint8_t* p = img + img_off(32, b, j0);
-  if (U == 8) *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(t);
-  else *reinterpret_cast<uint2*>(p) = *reinterpret_cast<const uint2*>(t);
 }
 
 #define TCDBG(ev) do { if (tw.dbg && c == 0 && lane == 0 && t < 64) tw.dbg[t * 32 + (ev)] = clock64(); } while (0)
