@@ -13,14 +13,14 @@
 //   B3  A = G0 image [128 x H],                         B = [W_ih0a^T | W_hh0^T | W_ih0p^T] -> d pre_a image, dh0(t-1), dxp part
 //   B4  A = d pre_a image [32 x H],                     B = W0p^T slice           -> dxp -> R(t-1): dY image of step t-1, root adjoint
 // Warps: 0..3 epilogue (TMEM quadrants), 4 MMA issuer, 5 weight producer (runs ahead across barriers), 6 activation
-// loader (grid-barrier waiter; streams the A images through a 4 x 16 KB ring).  fp32 histories for the weight
+// loader (grid-barrier waiter; streams the A images through an 8 x 16 KB ring).  fp32 histories for the weight
 // gradients are written in the same k-major layout as the SIMT kernel, so the batched wgrad code is shared.
 #include "decoder_bwd_common.cuh"
 #include "tc_dec_common.cuh"
 
 namespace zeggs {
 
-constexpr int BT_XRING = 4;
+constexpr int BT_XRING = 8;
 constexpr int BT_XSLOT = 16384;
 
 struct BtGeom {
@@ -37,7 +37,7 @@ inline BtGeom make_btgeom(const DecGeom& g, const BwdGeom& bg) {
   t.N1 = 16; t.P6 = round_up(6 * g.U, 16); t.N2 = t.P6; t.N3 = t.P6 + 48; t.N4 = 16;
   t.kbH = ceil_div(g.H, 64); t.kbX = ceil_div(K1P, 64); t.rpcb = bg.rpcb;
   t.wslot = round_up(t.N3 * 128, 1024);
-  t.wring = 98304 / t.wslot; if (t.wring > 8) t.wring = 8;
+  t.wring = 73728 / t.wslot; if (t.wring > 8) t.wring = 8;
   t.nacc3 = 4 * t.N3 <= 512 ? 4 : 2;
   size_t off = 0;
   t.off[0] = off; off += (size_t)t.kbX * t.N1 * 128;
@@ -114,11 +114,11 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
   constexpr int PW = 2 * U + 16;            // floats of the cross-quadrant exchange per (warp, sample)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* xring = smem;                                        // 4 x 16 KB activation tiles
+  uint8_t* xring = smem;                                        // 8 x 16 KB activation tiles
   uint8_t* wring = xring + BT_XRING * BT_XSLOT;                 // weight tiles (rows 32..127 of 4 KB A tiles alias into here)
   uint8_t* tail = wring + tg.wring * tg.wslot;
-  uint64_t* xfull = reinterpret_cast<uint64_t*>(tail);          // [4]
-  uint64_t* xempty = xfull + BT_XRING;                          // [4]
+  uint64_t* xfull = reinterpret_cast<uint64_t*>(tail);          // [8]
+  uint64_t* xempty = xfull + BT_XRING;                          // [8]
   uint64_t* wfull = xempty + BT_XRING;                          // [8]
   uint64_t* wempty = wfull + 8;                                 // [8]
   uint64_t* d_full = wempty + 8;                                // [4]
