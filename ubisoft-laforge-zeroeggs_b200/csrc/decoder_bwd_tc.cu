@@ -86,14 +86,18 @@ __global__ void pack_decoder_bwd_tc_kernel(DecGeom g, BtGeom tg, const float* __
   }
 }
 
-struct BtWs { uint8_t *dyimg, *g1img, *g0img, *dpaimg; size_t bytes; };
+struct BtWs { uint8_t *dyimg, *g1img, *g0img, *dpaimg; long long* dbg; size_t bytes; };
+long long* tc_debug_buffer();
 inline BtWs make_btws(void* base, const DecGeom& g) {
   BtWs w; size_t off = 0;
   auto take = [&](size_t n) { uint8_t* p = base ? (uint8_t*)base + off : nullptr; off += ((n + 1023) / 1024) * 1024; return p; };
   const size_t kbH = ceil_div(g.H, 64), kbX = ceil_div(K1P, 64);
   w.dyimg = take(kbX * 4096); w.g1img = take(kbH * 16384); w.g0img = take(kbH * 16384); w.dpaimg = take(kbH * 4096);
+  w.dbg = nullptr;
   w.bytes = off; return w;
 }
+
+#define BTDBG(ev) do { if (iw.dbg && c == 0 && lane == 0 && (T - 1 - t) < 64) iw.dbg[(T - 1 - t) * 32 + (ev)] = clock64(); } while (0)
 
 // store U bf16 values at (row, k = j0..j0+U-1) of an image with `rows`-row tiles
 template <int U>
@@ -176,8 +180,11 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
     // ================= activation loader
     if (lane == 0) {
       uint32_t it = 0; unsigned epoch = 0;
+      int t = T - 1; int sidx = 0;
       auto stream = [&](const uint8_t* img, int nkb, uint32_t tile_bytes) {
         grid_wait(bw.bar, (++epoch) * gridDim.x);
+        if (iw.dbg && c == 0 && (T - 1 - t) < 64) iw.dbg[(T - 1 - t) * 32 + 2 * (sidx & 3)] = clock64();
+        ++sidx;
         fence_proxy_async();
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const uint32_t s = it % BT_XRING, ph = (it / BT_XRING) & 1;
@@ -186,11 +193,12 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
           bulk_g2s(xring + s * BT_XSLOT, img + (size_t)kb * tile_bytes, tile_bytes, &xfull[s]);
         }
       };
-      for (int t = T - 1; t >= 1; --t) {
-        stream(iw.dyimg, kbX, 4096);
-        stream(iw.g1img, kbH, 16384);
-        stream(iw.g0img, kbH, 16384);
-        if (t > 1) stream(iw.dpaimg, kbH, 4096);
+      for (t = T - 1; t >= 1; --t) {
+        sidx = 0;
+        stream(iw.dyimg, kbX, 4096); BTDBG(1);
+        stream(iw.g1img, kbH, 16384); BTDBG(3);
+        stream(iw.g0img, kbH, 16384); BTDBG(5);
+        if (t > 1) { stream(iw.dpaimg, kbH, 4096); BTDBG(7); }
       }
     }
   } else if (warp == 4) {
@@ -228,10 +236,10 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
     };
     auto commit_d = [&](int i) { if (elect_one_sync()) umma_commit(&d_full[i]); __syncwarp(); };
     for (int t = T - 1; t >= 1; --t) {
-      chain_mma(kbX, tg.N1, 4); commit_d(0);
-      chain_mma(kbH, tg.N2, 4); commit_d(1);
-      chain_mma(kbH, tg.N3, tg.nacc3); commit_d(2);
-      if (t > 1) { chain_mma(kbH, tg.N4, 4); commit_d(3); }
+      chain_mma(kbX, tg.N1, 4); commit_d(0); BTDBG(8);
+      chain_mma(kbH, tg.N2, 4); commit_d(1); BTDBG(9);
+      chain_mma(kbH, tg.N3, tg.nacc3); commit_d(2); BTDBG(10);
+      if (t > 1) { chain_mma(kbH, tg.N4, 4); commit_d(3); BTDBG(11); }
     }
   } else {
     // ================= epilogue warps 0..3 (TMEM lane quadrant = warp index)
@@ -349,6 +357,7 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
         }
         mbar_wait(&d_full[0], ph);
         tc_fence_after_sync();
+        BTDBG(12);
         float v[U];
         ld_units(0, tg.N1, 4, v);
         float pr[U], pz[U], pn[U], pnr[U];
@@ -361,6 +370,7 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
         store_img_row<U>(iw.g1img, 128, 0 * 32 + b, j0, pr); store_img_row<U>(iw.g1img, 128, 1 * 32 + b, j0, pz);
         store_img_row<U>(iw.g1img, 128, 2 * 32 + b, j0, pn); store_img_row<U>(iw.g1img, 128, 3 * 32 + b, j0, pnr);
         tc_fence_before_sync();
+        BTDBG(13);
         grid_arrive(bw.bar);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -386,6 +396,7 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
       }
       mbar_wait(&d_full[1], ph);
       tc_fence_after_sync();
+      if (q == 0) BTDBG(14);
       {
         float v0[U], v1[U];
         if (q < 3) ld_units((uint32_t)(q * U), tg.N2, 4, v0);               // ih_g
@@ -409,6 +420,7 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
         }
         store_img_row<U>(iw.g0img, 128, 0 * 32 + b, j0, pr); store_img_row<U>(iw.g0img, 128, 1 * 32 + b, j0, pz);
         store_img_row<U>(iw.g0img, 128, 2 * 32 + b, j0, pn); store_img_row<U>(iw.g0img, 128, 3 * 32 + b, j0, pnr);
+        BTDBG(16);
         grid_arrive(bw.bar);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -428,6 +440,7 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
       }
       mbar_wait(&d_full[2], ph);
       tc_fence_after_sync();
+      if (q == 0) BTDBG(17);
       {
         float v0[U], v1[U], vx[16];
         if (q < 3) { ld_units((uint32_t)(q * U), tg.N3, tg.nacc3, v0); ld16((uint32_t)(tg.P6 + q * 16), tg.N3, tg.nacc3, vx); }
@@ -457,6 +470,7 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
           dxp1[r] = s;
         }
         store_img_row<U>(iw.dpaimg, 32, b, j0, dpa);
+        BTDBG(18);
         if (t > 1) grid_arrive(bw.bar);
 #pragma unroll
         for (int u = 0; u < U; ++u) bw.DPA[t * actH + (size_t)(j0 + u) * 32 + b] = dpa[u];
@@ -467,12 +481,14 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
       if (q == 0) {
         mbar_wait(&d_full[3], ph);
         tc_fence_after_sync();
+        BTDBG(19);
         float dxp[16];
         ld16(0, tg.N4, 4, dxp);
 #pragma unroll
         for (int r = 0; r < 16; ++r) dxp[r] += dxp1[r];
         phase_R(t - 1, dxp, true);
         tc_fence_before_sync();
+        BTDBG(20);
         grid_arrive(bw.bar);
       }
     }
@@ -528,6 +544,7 @@ int decoder_bwd_tc_run(const zeggs_decoder_fwd_args& a, const zeggs_decoder_bwd_
   BtGeom tg = make_btgeom(g, bg);
   ZCHECK_ARG(tg.wring >= 2 && 4 * tg.N2 <= 512, "decoder bwd tc: unsupported geometry");
   BtWs iw = make_btws(b.workspace_tc, g);
+  iw.dbg = tc_debug_buffer();
   ZCHECK_CUDA(cudaMemsetAsync(iw.dyimg, 0, (size_t)tg.kbX * 4096, stream));
   BwdArgsDev d; d.dY = b.dY; d.dRootPos = b.dRootPos; d.dRootRot = b.dRootRot; d.packed = nullptr;
   return g.U == 4 ? launch_bt<4>(a, g, bg, tg, w, bw, iw, d, (const uint8_t*)b.packed_bwd_tc, stream)

@@ -551,6 +551,7 @@ static int launch_tc(const zeggs_decoder_fwd_args& a, const DecGeom& g, const Tc
 static long long* g_tc_dbg = nullptr;
 static int g_tc_nacc = 0;
 extern "C" void zeggs_debug_set_tc_nacc(int n) { g_tc_nacc = n; }
+long long* tc_debug_buffer() { return g_tc_dbg; }
 extern "C" void zeggs_debug_set_tc_trace(void* p) { g_tc_dbg = (long long*)p; }
 
 // called by zeggs_decoder_window_fwd after the prologue / CellStateEncoder / cond pre-pass when engine == 1
