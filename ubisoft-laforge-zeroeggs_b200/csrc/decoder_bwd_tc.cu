@@ -20,13 +20,14 @@
 
 namespace zeggs {
 
-constexpr int BT_XRING = 8;
-constexpr int BT_XSLOT = 16384;
+constexpr int BT_RING = 3;               // unified operand ring: each slot = 2 k-blocks of (A tile 16 KB | B tile)
+constexpr int BT_XPART = 32768;          // bytes of the A part of a slot
 
 struct BtGeom {
   int N1, N2, N3, N4, P6;
   int kbH, kbX, rpcb;
-  int wslot, wring;       // weight ring slot bytes / slots
+  int wslot;              // bytes of one weight k-block tile slot (max N * 128, 1 KB aligned)
+  int slot_bytes;         // BT_XPART + 2 * wslot
   int nacc3;
   size_t off[4];
   size_t cta_bytes;
@@ -37,7 +38,7 @@ inline BtGeom make_btgeom(const DecGeom& g, const BwdGeom& bg) {
   t.N1 = 16; t.P6 = round_up(6 * g.U, 16); t.N2 = t.P6; t.N3 = t.P6 + 48; t.N4 = 16;
   t.kbH = ceil_div(g.H, 64); t.kbX = ceil_div(K1P, 64); t.rpcb = bg.rpcb;
   t.wslot = round_up(t.N3 * 128, 1024);
-  t.wring = 73728 / t.wslot; if (t.wring > 8) t.wring = 8;
+  t.slot_bytes = BT_XPART + 2 * t.wslot;
   t.nacc3 = 4 * t.N3 <= 512 ? 4 : 2;
   size_t off = 0;
   t.off[0] = off; off += (size_t)t.kbX * t.N1 * 128;
@@ -97,6 +98,7 @@ inline BtWs make_btws(void* base, const DecGeom& g) {
   w.bytes = off; return w;
 }
 
+#define BTDBG1(ev) do { if (iw.dbg && c == 1 && lane == 0 && (T - 1 - t) < 64) iw.dbg[(T - 1 - t) * 32 + (ev)] = clock64(); } while (0)
 #define BTDBG(ev) do { if (iw.dbg && c == 0 && lane == 0 && (T - 1 - t) < 64) iw.dbg[(T - 1 - t) * 32 + (ev)] = clock64(); } while (0)
 
 // store U bf16 values at (row, k = j0..j0+U-1) of an image with `rows`-row tiles
@@ -118,14 +120,11 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
   constexpr int PW = 2 * U + 16;            // floats of the cross-quadrant exchange per (warp, sample)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* xring = smem;                                        // 8 x 16 KB activation tiles
-  uint8_t* wring = xring + BT_XRING * BT_XSLOT;                 // weight tiles (rows 32..127 of 4 KB A tiles alias into here)
-  uint8_t* tail = wring + tg.wring * tg.wslot;
-  uint64_t* xfull = reinterpret_cast<uint64_t*>(tail);          // [8]
-  uint64_t* xempty = xfull + BT_XRING;                          // [8]
-  uint64_t* wfull = xempty + BT_XRING;                          // [8]
-  uint64_t* wempty = wfull + 8;                                 // [8]
-  uint64_t* d_full = wempty + 8;                                // [4]
+  uint8_t* ring = smem;                                         // BT_RING slots: [A kb0 | A kb1 | B kb0 | B kb1]
+  uint8_t* tail = ring + (size_t)BT_RING * tg.slot_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);           // [BT_RING]  two producers (activations, weights) arrive on each
+  uint64_t* empty = full + BT_RING;                             // [BT_RING]
+  uint64_t* d_full = empty + BT_RING;                           // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 4);
   float* part = reinterpret_cast<float*>(tail + 512);           // [4][32][PW]
   float* c_is = part + 4 * 32 * PW;                             // [16] in_std of this CTA's x_pose rows, then out_std [16]
@@ -137,8 +136,7 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
   const uint8_t* pk = packed + (size_t)c * tg.cta_bytes;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < BT_XRING; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
-    for (int i = 0; i < 8; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+    for (int i = 0; i < BT_RING; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 4; ++i) mbar_init(&d_full[i], 1);
     fence_mbar_init();
   }
@@ -158,22 +156,23 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
   const size_t actH = (size_t)g.nbt * H * 32, act3 = (size_t)g.nbt * 3 * H * 32, actX = (size_t)g.nbt * K1P * 32, act4 = (size_t)g.nbt * 4 * H * 32;
 
   if (warp == 5) {
-    // ================= weight producer
+    // ================= weight producer (its half of every slot may be filled before the stage's grid barrier)
     if (lane == 0) {
       uint32_t it = 0;
-      auto stream = [&](int chain, int nkb, int N) {
+      auto stream = [&](int chain, int nkb, int N, int kps) {
         const uint8_t* src = pk + tg.off[chain];
-        const uint32_t bytes = (uint32_t)N * 128;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t s = it % (uint32_t)tg.wring, ph = (it / (uint32_t)tg.wring) & 1;
-          mbar_wait(&wempty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&wfull[s], bytes);
-          bulk_g2s(wring + (size_t)s * tg.wslot, src + (size_t)kb * bytes, bytes, &wfull[s]);
+        const uint32_t tile = (uint32_t)N * 128;
+        for (int kb = 0; kb < nkb; kb += kps, ++it) {
+          const uint32_t s = it % BT_RING, ph = (it / BT_RING) & 1;
+          const uint32_t bytes = (uint32_t)min(kps, nkb - kb) * tile;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], bytes);
+          bulk_g2s(ring + (size_t)s * tg.slot_bytes + BT_XPART, src + (size_t)kb * tile, bytes, &full[s]);
         }
       };
       for (int t = T - 1; t >= 1; --t) {
-        stream(0, kbX, tg.N1); stream(1, kbH, tg.N2); stream(2, kbH, tg.N3);
-        if (t > 1) stream(3, kbH, tg.N4);
+        stream(0, kbX, tg.N1, 8); stream(1, kbH, tg.N2, 2); stream(2, kbH, tg.N3, 2);
+        if (t > 1) stream(3, kbH, tg.N4, 8);
       }
     }
   } else if (warp == 6) {
@@ -186,11 +185,13 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
         if (iw.dbg && c == 0 && (T - 1 - t) < 64) iw.dbg[(T - 1 - t) * 32 + 2 * (sidx & 3)] = clock64();
         ++sidx;
         fence_proxy_async();
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t s = it % BT_XRING, ph = (it / BT_XRING) & 1;
-          mbar_wait(&xempty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&xfull[s], tile_bytes);
-          bulk_g2s(xring + s * BT_XSLOT, img + (size_t)kb * tile_bytes, tile_bytes, &xfull[s]);
+        const int kps = BT_XPART / (int)tile_bytes;               // 2 k-blocks of a 128-row image, 8 of a 32-row image
+        for (int kb = 0; kb < nkb; kb += kps, ++it) {
+          const uint32_t s = it % BT_RING, ph = (it / BT_RING) & 1;
+          const uint32_t bytes = (uint32_t)min(kps, nkb - kb) * tile_bytes;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], bytes);
+          bulk_g2s(ring + (size_t)s * tg.slot_bytes, img + (size_t)kb * tile_bytes, bytes, &full[s]);
         }
       };
       for (t = T - 1; t >= 1; --t) {
@@ -202,44 +203,48 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
       }
     }
   } else if (warp == 4) {
-    // ================= MMA issuer
-    uint32_t itx = 0, itw = 0;
-    const uint64_t dX = make_smem_desc_sw128(xring), dW = make_smem_desc_sw128(wring);
-    const uint32_t wstep = (uint32_t)(tg.wslot >> 4);
-    auto chain_mma = [&](int nkb, int N, int nacc) {
+    // ================= MMA issuer: one wait + one commit per slot (8 MMAs)
+    uint32_t it = 0;
+    const uint64_t dR = make_smem_desc_sw128(ring);
+    const uint32_t sstep = (uint32_t)(tg.slot_bytes >> 4);
+    auto chain_mma = [&](int nkb, int N, int nacc, int kps, uint32_t atile) {
       const uint32_t idesc = make_idesc_bf16_f32(128, N);
-      for (int kb = 0; kb < nkb; ++kb, ++itx, ++itw) {
-        const uint32_t sx = itx % BT_XRING, phx = (itx / BT_XRING) & 1;
-        const uint32_t sw = itw % (uint32_t)tg.wring, phw = (itw / (uint32_t)tg.wring) & 1;
-        mbar_wait(&xfull[sx], phx);
-        mbar_wait(&wfull[sw], phw);
+      const uint32_t astep = atile >> 4, wstep = (uint32_t)(N * 128) >> 4;
+      for (int kb = 0; kb < nkb; kb += kps, ++it) {
+        const uint32_t s = it % BT_RING, ph = (it / BT_RING) & 1;
+        const int nk = min(kps, nkb - kb);
+        mbar_wait(&full[s], ph);
         tc_fence_after_sync();
-        const uint64_t da = dX + (uint64_t)sx * (BT_XSLOT >> 4), db = dW + (uint64_t)sw * wstep;
-        const bool acc0 = kb > 0;
+        uint64_t da = dR + (uint64_t)s * sstep, db = da + (BT_XPART >> 4);
         if (elect_one_sync()) {
           if (nacc == 4) {
-            umma_bf16(tmem + 0 * N, da + 0, db + 0, idesc, acc0);
-            umma_bf16(tmem + 1 * N, da + 2, db + 2, idesc, acc0);
-            umma_bf16(tmem + 2 * N, da + 4, db + 4, idesc, acc0);
-            umma_bf16(tmem + 3 * N, da + 6, db + 6, idesc, acc0);
+            for (int kk = 0; kk < nk; ++kk, da += astep, db += wstep) {
+              const bool acc = (kb + kk) > 0;
+              umma_bf16(tmem + 0 * N, da + 0, db + 0, idesc, acc);
+              umma_bf16(tmem + 1 * N, da + 2, db + 2, idesc, acc);
+              umma_bf16(tmem + 2 * N, da + 4, db + 4, idesc, acc);
+              umma_bf16(tmem + 3 * N, da + 6, db + 6, idesc, acc);
+            }
           } else {
-            umma_bf16(tmem + 0 * N, da + 0, db + 0, idesc, acc0);
-            umma_bf16(tmem + 1 * N, da + 2, db + 2, idesc, acc0);
-            umma_bf16(tmem + 0 * N, da + 4, db + 4, idesc, true);
-            umma_bf16(tmem + 1 * N, da + 6, db + 6, idesc, true);
+            for (int kk = 0; kk < nk; ++kk, da += astep, db += wstep) {
+              const bool acc = (kb + kk) > 0;
+              umma_bf16(tmem + 0 * N, da + 0, db + 0, idesc, acc);
+              umma_bf16(tmem + 1 * N, da + 2, db + 2, idesc, acc);
+              umma_bf16(tmem + 0 * N, da + 4, db + 4, idesc, true);
+              umma_bf16(tmem + 1 * N, da + 6, db + 6, idesc, true);
+            }
           }
-          umma_commit(&xempty[sx]);
-          umma_commit(&wempty[sw]);
+          umma_commit(&empty[s]);
         }
         __syncwarp();
       }
     };
     auto commit_d = [&](int i) { if (elect_one_sync()) umma_commit(&d_full[i]); __syncwarp(); };
     for (int t = T - 1; t >= 1; --t) {
-      chain_mma(kbX, tg.N1, 4); commit_d(0); BTDBG(8);
-      chain_mma(kbH, tg.N2, 4); commit_d(1); BTDBG(9);
-      chain_mma(kbH, tg.N3, tg.nacc3); commit_d(2); BTDBG(10);
-      if (t > 1) { chain_mma(kbH, tg.N4, 4); commit_d(3); BTDBG(11); }
+      chain_mma(kbX, tg.N1, 4, 8, 4096); commit_d(0); BTDBG(8);
+      chain_mma(kbH, tg.N2, 4, 2, 16384); commit_d(1); BTDBG(9);
+      chain_mma(kbH, tg.N3, tg.nacc3, 2, 16384); commit_d(2); BTDBG(10);
+      if (t > 1) { chain_mma(kbH, tg.N4, 4, 8, 4096); commit_d(3); BTDBG(11); }
     }
   } else {
     // ================= epilogue warps 0..3 (TMEM lane quadrant = warp index)
@@ -247,7 +252,7 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
     const bool live = b < a.B;
     const int j0 = c * U;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    float* mypart = part + ((size_t)q * 32 + b) * PW;
+    float* mypart = part + (size_t)q * PW * 32 + b;            // part[q][col][b]: lanes hit distinct banks
     // sum of the chain's accumulators for a U-wide column group starting at `col`
     auto ld_units = [&](uint32_t col, int N, int nacc, float (&v)[U]) {
       tmem_ld_cols<U>(lane_base + col, v);
@@ -269,6 +274,61 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
     };
     // ---- R(t): finalise dY_acc[t] (this CTA's x_pose rows) from dxp; root / gaze adjoint on CTA 0.  warp 0 only.
     float dpq[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // running d root_pos(3) / d root_rot(4) of this sample (CTA 0)
+    // All global operands of R(t) are fetched into registers by R_prefetch (issued before the wait on the B4
+    // accumulator) so that the adjoint itself is pure arithmetic + stores.
+    float ext[16], ext6[6], rpv[3], rqv[4], gpv[3], rq1v[4], ytv[6], e1p[3], e1q[4], e0p[3], e0q[4];
+    // gradient-independent part of the root adjoint (R_precompute, also before the wait)
+    Q4 r_qinv, r_q1, r_E; V3 r_u, r_a1, r_a2, r_x; float r_k0, r_k1, r_k2;
+    auto R_precompute = [&]() {
+      if (c != 0 || !live) return;
+      Q4 qt; qt.w = rqv[0]; qt.x = rqv[1]; qt.y = rqv[2]; qt.z = rqv[3];
+      r_qinv = quat_inv(qt);
+      r_u = v3(gpv[0] - rpv[0], gpv[1] - rpv[1], gpv[2] - rpv[2]);
+      r_q1.w = rq1v[0]; r_q1.x = rq1v[1]; r_q1.y = rq1v[2]; r_q1.z = rq1v[3];
+      r_a1 = a.dt * v3(ytv[0], ytv[1], ytv[2]);
+      r_a2 = a.dt * v3(ytv[3], ytv[4], ytv[5]);
+      const V3 wv = quat_mul_vec(r_q1, r_a2);
+      r_E = quat_from_helical(wv);
+      // quat_from_helical_bwd is linear in dE: dx = k0 * dEv + (k1 * dE.w + k2 * dot(dEv, x)) * x   (common.cuh)
+      r_x = 0.5f * wv;
+      const float a2 = dot(r_x, r_x), an = sqrtf(a2);
+      if (an < 1e-5f) {
+        const float rn = sqrtf(1.0f + a2), n = rn + 1e-5f;
+        r_k0 = 1.0f / n; r_k1 = -1.0f / (n * n * rn); r_k2 = r_k1;
+      } else {
+        const float sn = sinf(an), cs = cosf(an);
+        r_k0 = sn / an; r_k1 = -sn / an; r_k2 = (an * cs - sn) / (a2 * an);
+      }
+    };
+    auto R_prefetch = [&](int t, bool have_dxp) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const int m = c * tg.rpcb + r;
+        const bool use = r < tg.rpcb && m < P_IN && m >= 9 && d.dY && live;
+        ext[r] = use ? d.dY[((size_t)b * T + t) * P_OUT + xp_perm(m)] : 0.f;
+      }
+      if (c == 0 && live) {
+        const size_t bt = (size_t)b * T + t;
+#pragma unroll
+        for (int n = 0; n < 6; ++n) ext6[n] = d.dY ? d.dY[bt * P_OUT + n] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          rpv[i] = a.root_pos[bt * 3 + i];
+          gpv[i] = have_dxp ? a.gaze_pos[(bt + 1) * 3 + i] : 0.f;
+          e1p[i] = d.dRootPos ? d.dRootPos[(bt - 1) * 3 + i] : 0.f;
+          e0p[i] = (!have_dxp && d.dRootPos) ? d.dRootPos[bt * 3 + i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          rqv[i] = a.root_rot[bt * 4 + i];
+          rq1v[i] = a.root_rot[(bt - 1) * 4 + i];
+          e1q[i] = d.dRootRot ? d.dRootRot[(bt - 1) * 4 + i] : 0.f;
+          e0q[i] = (!have_dxp && d.dRootRot) ? d.dRootRot[bt * 4 + i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ytv[i] = a.Y[bt * P_OUT + i];
+      }
+    };
     auto phase_R = [&](int t, const float (&dxp)[16], bool have_dxp) {
       float rootg[9];
 #pragma unroll
@@ -277,9 +337,8 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
         if (r >= tg.rpcb || m >= P_IN) continue;
         const int n = xp_perm(m);
         const float dx = have_dxp ? dxp[r] / c_is[r] : 0.f;                       // modules.py:713
-        if (m < 9) { rootg[m < 9 ? m : 0] = dx; continue; }
-        const float ext = (d.dY && live) ? d.dY[((size_t)b * T + t) * P_OUT + n] : 0.f;
-        const float v = (ext + dx) * c_os[r];                                     // modules.py:728
+        if (m < 9) { if (r < 9) rootg[r] = dx; continue; }           // m < 9 only on CTA 0, where m == r
+        const float v = (ext[r] + dx) * c_os[r];                                  // modules.py:728
         *reinterpret_cast<__nv_bfloat16*>(iw.dyimg + img_off(32, b, n)) = __float2bfloat16_rn(v);
         bw.DY[t * actX + (size_t)n * 32 + b] = v;
       }
@@ -288,47 +347,31 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
         if (live) {
           V3 dp; Q4 dq;
           if (!have_dxp) {
-            dp = d.dRootPos ? v3(d.dRootPos[((size_t)b * T + t) * 3 + 0], d.dRootPos[((size_t)b * T + t) * 3 + 1], d.dRootPos[((size_t)b * T + t) * 3 + 2]) : v3(0, 0, 0);
-            if (d.dRootRot) { const float* e = d.dRootRot + ((size_t)b * T + t) * 4; dq.w = e[0]; dq.x = e[1]; dq.y = e[2]; dq.z = e[3]; }
-            else { dq.w = dq.x = dq.y = dq.z = 0.f; }
+            dp = v3(e0p[0], e0p[1], e0p[2]); dq.w = e0q[0]; dq.x = e0q[1]; dq.y = e0q[2]; dq.z = e0q[3];
           } else {
             dp = v3(dpq[0], dpq[1], dpq[2]); dq.w = dpq[3]; dq.x = dpq[4]; dq.y = dpq[5]; dq.z = dpq[6];
           }
-          const float* rp = a.root_pos + ((size_t)b * T + t) * 3;
-          const float* rq = a.root_rot + ((size_t)b * T + t) * 4;
-          Q4 qt; qt.w = rq[0]; qt.x = rq[1]; qt.y = rq[2]; qt.z = rq[3];
           if (have_dxp) {       // gaze_dir(t+1) = R(q_t)^-1 (gaze_pos[t+1] - p_t)
-            const float* gp = a.gaze_pos + ((size_t)b * T + (t + 1)) * 3;
-            V3 u = v3(gp[0] - rp[0], gp[1] - rp[1], gp[2] - rp[2]);
             Q4 dqc; V3 du;
-            quat_mul_vec_bwd(quat_inv(qt), u, v3(rootg[6], rootg[7], rootg[8]), dqc, du);
+            quat_mul_vec_bwd(r_qinv, r_u, v3(rootg[6], rootg[7], rootg[8]), dqc, du);
             dq.w += dqc.w; dq.x -= dqc.x; dq.y -= dqc.y; dq.z -= dqc.z;
             dp = dp - du;
           }
-          const float* rq1 = a.root_rot + ((size_t)b * T + (t - 1)) * 4;
-          Q4 q1; q1.w = rq1[0]; q1.x = rq1[1]; q1.y = rq1[2]; q1.z = rq1[3];
-          const float* yt = a.Y + ((size_t)b * T + t) * P_OUT;
-          V3 a1 = a.dt * v3(yt[0], yt[1], yt[2]);
-          V3 a2 = a.dt * v3(yt[3], yt[4], yt[5]);
           Q4 dq_a, dq_b, dq_c, dE; V3 da1, da2;
-          quat_mul_vec_bwd(q1, a1, dp, dq_a, da1);
-          V3 wv = quat_mul_vec(q1, a2);
-          Q4 E = quat_from_helical(wv);
-          quat_mul_bwd(E, q1, dq, dE, dq_b);
-          V3 dw = quat_from_helical_bwd(wv, dE);
-          quat_mul_vec_bwd(q1, a2, dw, dq_c, da2);
+          quat_mul_vec_bwd(r_q1, r_a1, dp, dq_a, da1);
+          quat_mul_bwd(r_E, r_q1, dq, dE, dq_b);
+          const V3 dEv = v3(dE.x, dE.y, dE.z);
+          const V3 dw = 0.5f * (r_k0 * dEv + (r_k1 * dE.w + r_k2 * dot(dEv, r_x)) * r_x);
+          quat_mul_vec_bwd(r_q1, r_a2, dw, dq_c, da2);
           dch[0] = a.dt * da1.x; dch[1] = a.dt * da1.y; dch[2] = a.dt * da1.z; dch[3] = a.dt * da2.x; dch[4] = a.dt * da2.y; dch[5] = a.dt * da2.z;
-          V3 dp1 = dp; Q4 dq1;
-          dq1.w = dq_a.w + dq_b.w + dq_c.w; dq1.x = dq_a.x + dq_b.x + dq_c.x; dq1.y = dq_a.y + dq_b.y + dq_c.y; dq1.z = dq_a.z + dq_b.z + dq_c.z;
-          if (d.dRootPos) { const float* e = d.dRootPos + ((size_t)b * T + (t - 1)) * 3; dp1 = dp1 + v3(e[0], e[1], e[2]); }
-          if (d.dRootRot) { const float* e = d.dRootRot + ((size_t)b * T + (t - 1)) * 4; dq1.w += e[0]; dq1.x += e[1]; dq1.y += e[2]; dq1.z += e[3]; }
-          dpq[0] = dp1.x; dpq[1] = dp1.y; dpq[2] = dp1.z; dpq[3] = dq1.w; dpq[4] = dq1.x; dpq[5] = dq1.y; dpq[6] = dq1.z;
+          dpq[0] = dp.x + e1p[0]; dpq[1] = dp.y + e1p[1]; dpq[2] = dp.z + e1p[2];
+          dpq[3] = dq_a.w + dq_b.w + dq_c.w + e1q[0]; dpq[4] = dq_a.x + dq_b.x + dq_c.x + e1q[1];
+          dpq[5] = dq_a.y + dq_b.y + dq_c.y + e1q[2]; dpq[6] = dq_a.z + dq_b.z + dq_c.z + e1q[3];
         }
 #pragma unroll
         for (int n = 0; n < 6; ++n) {
-          const float ext = (d.dY && live) ? d.dY[((size_t)b * T + t) * P_OUT + n] : 0.f;
           const float dx = have_dxp ? rootg[n] : 0.f;
-          const float v = live ? (ext + dx + dch[n]) * c_os[n] : 0.f;
+          const float v = live ? (ext6[n] + dx + dch[n]) * c_os[n] : 0.f;
           *reinterpret_cast<__nv_bfloat16*>(iw.dyimg + img_off(32, b, n)) = __float2bfloat16_rn(v);
           bw.DY[t * actX + (size_t)n * 32 + b] = v;
         }
@@ -338,6 +381,7 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
     float dhz1[U], dhz0[U], dxp1[16];
     if (q == 0) {
       const float zero16[16] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      R_prefetch(T - 1, false); R_precompute();
       phase_R(T - 1, zero16, false);
       grid_arrive(bw.bar);
     }
@@ -402,26 +446,28 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
         if (q < 3) ld_units((uint32_t)(q * U), tg.N2, 4, v0);               // ih_g
         if (q != 2) ld_units((uint32_t)((3 + (q == 3 ? 2 : q)) * U), tg.N2, 4, v1);   // hh_g (quadrant 3 = pnr pairs with hh_n)
 #pragma unroll
-        for (int u = 0; u < U; ++u) { mypart[u] = q < 3 ? v0[u] : 0.f; mypart[U + u] = q != 2 ? v1[u] : 0.f; }
+        for (int u = 0; u < U; ++u) { mypart[u * 32] = q < 3 ? v0[u] : 0.f; mypart[(U + u) * 32] = q != 2 ? v1[u] : 0.f; }
       }
       tc_fence_before_sync();
       epi_bar(1);
       if (q == 0) {
-        float pr[U], pz[U], pn[U], pnr[U];
+        float pr[U], pz[U], pn[U], pnr[U], dh1n[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           float oa = 0.f, ob = 0.f;
 #pragma unroll
-          for (int qq = 0; qq < 4; ++qq) { oa += part[((size_t)qq * 32 + b) * PW + u]; ob += part[((size_t)qq * 32 + b) * PW + U + u]; }
+          for (int qq = 0; qq < 4; ++qq) { oa += part[((size_t)qq * PW + u) * 32 + b]; ob += part[((size_t)qq * PW + U + u) * 32 + b]; }
           float dgi[3], dgh[3];
           gru_gate_bwd(oa + acc[u], gr[u], gz[u], gn[u], ghn[u], hp[u], dgi, dgh, dhz0[u]);
           pr[u] = dgi[0]; pz[u] = dgi[1]; pn[u] = dgi[2]; pnr[u] = dgh[2];
-          bw.DH1[(size_t)(j0 + u) * 32 + b] = ob + dhz1[u];               // dh1(t-1) = dh1*z1 + W_hh1^T dgh1
+          dh1n[u] = ob + dhz1[u];                                         // dh1(t-1) = dh1*z1 + W_hh1^T dgh1
         }
         store_img_row<U>(iw.g0img, 128, 0 * 32 + b, j0, pr); store_img_row<U>(iw.g0img, 128, 1 * 32 + b, j0, pz);
         store_img_row<U>(iw.g0img, 128, 2 * 32 + b, j0, pn); store_img_row<U>(iw.g0img, 128, 3 * 32 + b, j0, pnr);
         BTDBG(16);
         grid_arrive(bw.bar);
+#pragma unroll
+        for (int u = 0; u < U; ++u) bw.DH1[(size_t)(j0 + u) * 32 + b] = dh1n[u];   // private to this thread: no ordering needed
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int j = j0 + u;
@@ -446,49 +492,50 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
         if (q < 3) { ld_units((uint32_t)(q * U), tg.N3, tg.nacc3, v0); ld16((uint32_t)(tg.P6 + q * 16), tg.N3, tg.nacc3, vx); }
         if (q != 2) ld_units((uint32_t)((3 + (q == 3 ? 2 : q)) * U), tg.N3, tg.nacc3, v1);
 #pragma unroll
-        for (int u = 0; u < U; ++u) { mypart[u] = q < 3 ? v0[u] : 0.f; mypart[U + u] = q != 2 ? v1[u] : 0.f; }
+        for (int u = 0; u < U; ++u) { mypart[u * 32] = q < 3 ? v0[u] : 0.f; mypart[(U + u) * 32] = q != 2 ? v1[u] : 0.f; }
 #pragma unroll
-        for (int r = 0; r < 16; ++r) mypart[2 * U + r] = q < 3 ? vx[r] : 0.f;
+        for (int r = 0; r < 16; ++r) mypart[(2 * U + r) * 32] = q < 3 ? vx[r] : 0.f;
       }
       tc_fence_before_sync();
       epi_bar(1);
       if (q == 0) {
-        float dpa[U];
+        float dpa[U], dh0n[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           float da = 0.f, ob = 0.f;
 #pragma unroll
-          for (int qq = 0; qq < 4; ++qq) { da += part[((size_t)qq * 32 + b) * PW + u]; ob += part[((size_t)qq * 32 + b) * PW + U + u]; }
+          for (int qq = 0; qq < 4; ++qq) { da += part[((size_t)qq * PW + u) * 32 + b]; ob += part[((size_t)qq * PW + U + u) * 32 + b]; }
           dpa[u] = da * (av[u] > 0.f ? 1.f : av[u] + 1.f);                 // ELU'(pre) = a + 1 for pre <= 0
-          bw.DH0[(size_t)(j0 + u) * 32 + b] = ob + dhz0[u];
+          dh0n[u] = ob + dhz0[u];
         }
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
           float s = 0.f;
 #pragma unroll
-          for (int qq = 0; qq < 3; ++qq) s += part[((size_t)qq * 32 + b) * PW + 2 * U + r];
+          for (int qq = 0; qq < 3; ++qq) s += part[((size_t)qq * PW + 2 * U + r) * 32 + b];
           dxp1[r] = s;
         }
         store_img_row<U>(iw.dpaimg, 32, b, j0, dpa);
         BTDBG(18);
         if (t > 1) grid_arrive(bw.bar);
 #pragma unroll
-        for (int u = 0; u < U; ++u) bw.DPA[t * actH + (size_t)(j0 + u) * 32 + b] = dpa[u];
+        for (int u = 0; u < U; ++u) { bw.DH0[(size_t)(j0 + u) * 32 + b] = dh0n[u]; bw.DPA[t * actH + (size_t)(j0 + u) * 32 + b] = dpa[u]; }
       }
       epi_bar(2);
       if (t == 1) break;
       // ------------------------------------------------------------ B4 epilogue + R(t-1)
       if (q == 0) {
+        R_prefetch(t - 1, true); R_precompute();
         mbar_wait(&d_full[3], ph);
         tc_fence_after_sync();
-        BTDBG(19);
+        BTDBG(19); BTDBG1(21);
         float dxp[16];
         ld16(0, tg.N4, 4, dxp);
 #pragma unroll
         for (int r = 0; r < 16; ++r) dxp[r] += dxp1[r];
         phase_R(t - 1, dxp, true);
         tc_fence_before_sync();
-        BTDBG(20);
+        BTDBG(20); BTDBG1(22);
         grid_arrive(bw.bar);
       }
     }
@@ -523,7 +570,7 @@ extern "C" int zeggs_decoder_pack_weights_bwd_tc(const zeggs_decoder_fwd_args* a
 template <int U>
 static int launch_bt(const zeggs_decoder_fwd_args& a, const DecGeom& g, const BwdGeom& bg, const BtGeom& tg, const DecWs& w,
                      const BwdWs& bw, const BtWs& iw, const BwdArgsDev& d, const uint8_t* packed, cudaStream_t stream) {
-  const size_t smem = 1024 + (size_t)BT_XRING * BT_XSLOT + (size_t)tg.wring * tg.wslot + 512 + (size_t)(4 * 32 * (2 * U + 16) + 32) * sizeof(float);
+  const size_t smem = 1024 + (size_t)BT_RING * tg.slot_bytes + 512 + (size_t)(4 * 32 * (2 * U + 16) + 32) * sizeof(float);
   ZCHECK_CUDA(cudaFuncSetAttribute(decoder_bwd_tc_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, nsm = 0, occ = 0;
   ZCHECK_CUDA(cudaGetDevice(&dev));
@@ -542,7 +589,7 @@ int decoder_bwd_tc_run(const zeggs_decoder_fwd_args& a, const zeggs_decoder_bwd_
   ZCHECK_ARG(g.nbt == 1 && bg.n4b == 1, "decoder bwd tc engine needs B <= 32 and H >= 284 (got B=%d H=%d)", a.B, a.H);
   ZCHECK_ARG(b.packed_bwd_tc && b.workspace_tc, "decoder bwd tc: packed_bwd_tc / workspace_tc missing");
   BtGeom tg = make_btgeom(g, bg);
-  ZCHECK_ARG(tg.wring >= 2 && 4 * tg.N2 <= 512, "decoder bwd tc: unsupported geometry");
+  ZCHECK_ARG(4 * tg.N2 <= 512 && (tg.kbH % 2) == 0, "decoder bwd tc: unsupported geometry");
   BtWs iw = make_btws(b.workspace_tc, g);
   iw.dbg = tc_debug_buffer();
   ZCHECK_CUDA(cudaMemsetAsync(iw.dyimg, 0, (size_t)tg.kbX * 4096, stream));

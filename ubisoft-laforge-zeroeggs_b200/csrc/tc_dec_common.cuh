@@ -65,9 +65,8 @@ __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2
 
 // grid barrier split in two halves: the epilogue warp arrives, the activation loader waits
 __device__ __forceinline__ void grid_arrive(unsigned* counter) {
-  __threadfence();
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0) atomicAdd(counter, 1u);
+  __syncwarp();   // the lanes' stores happen-before lane 0's release (cumulative at gpu scope)
+  if ((threadIdx.x & 31) == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
 }
 __device__ __forceinline__ void grid_wait(const unsigned* counter, unsigned target) {
   long long t0 = clock64();
