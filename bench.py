@@ -195,17 +195,20 @@ def run_ours(args):
     frames = world * B * T
     value = frames / (r["ms"] / K) * 1e3
     peaks = load_peaks()
-    # roofline of the dominant kernel (the persistent BPTT kernel): algorithmic FLOPs = the transposed GEMMs of every step
+    # roofline of the dominant kernel (the slower of the two persistent recurrence kernels): algorithmic FLOPs = the
+    # (transposed) GEMMs of every step
     fl_step = decoder_flops_per_frame(H) - 2 * 128 * 4 * H          # the speech/style columns are hoisted out of the recurrence
     dom = "decoder_bwd" if r["spans"]["decoder_bwd"]["ms_per_step"] >= r["spans"]["decoder_fwd"]["ms_per_step"] else "decoder_fwd"
     dom_ms = r["spans"][dom]["ms_per_step"]
     achieved = fl_step * B * (T - 1) / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
     wbytes = (fl_step / 2) * 4                                      # fp32 weights streamed per step (L2 resident)
-    roofline = dict(bound="tensor", kernel=f"{dom}_kernel", achieved=round(achieved, 3), peak=peaks["bf16_tflops_sustained"],
+    roofline = dict(bound="tensor", kernel=(f"{dom}_tc_kernel" if args.engine == "tc" else f"{dom}_kernel"), achieved=round(achieved, 3), peak=peaks["bf16_tflops_sustained"],
                     unit="TFLOP/s", frac=round(achieved / peaks["bf16_tflops_sustained"], 5), traffic=None,
                     peak_source=peaks["src"] + " (cuBLAS bf16, sustained)", ms_per_launch=round(dom_ms, 3),
                     weight_stream_gbs=round(wbytes * (T - 1) / (dom_ms * 1e-3) / 1e9, 1),
-                    note=("decoder forward recurrence on tcgen05 (bf16 operands, fp32 state); BPTT recurrence fp32 SIMT; batched GEMMs tcgen05 split-bf16; "
+                    note=("decoder forward and BPTT recurrences on tcgen05 (bf16 operands from smem images, fp32 accumulators in TMEM, fp32 state); "
+                          "weight-gradient GEMMs tcgen05 bf16, encoder GEMMs tcgen05 split-bf16; only 32 of the 128 MMA rows carry samples (B=32), "
+                          "the step is bound by 4 grid barriers + operand streaming from L2, not by tensor peak; "
                           if args.engine == "tc" else "fp32 SIMT recurrence; batched GEMMs tcgen05 split-bf16; ") +
                          "per-step arithmetic intensity at B=32 is 16-32 FLOP/B (weight streaming from L2), see DESIGN.md")
     out = dict(metric="frames/sec (train step, 60fps 75-joint pose)", value=round(value, 1), unit="frames/s", n_gpus=world, steps=K, warmup=W,

@@ -210,8 +210,10 @@ def gemm_mode(dev):
 
 def _grad_close(name, got, ref, mode, bad):
     """mode 0 (fp32 SIMT): max-abs 3e-4 of max|ref|.  mode 1 (tcgen05 split-bf16, ~1e-5 relative products): relative L2 error
-    <= 1e-2 -- a ReLU/ELU gate whose pre-activation is within 1e-5 of zero can legitimately flip (about one element per
-    100k), which moves the affected rows by O(1) of their size but leaves the L2 error small."""
+    <= 3e-2 -- a ReLU/ELU gate whose pre-activation is within 1e-5 of zero can legitimately flip (about one element per
+    100k), which moves the affected rows by O(1) of their size but leaves the L2 error small (on the smallest case, 32
+    rows, ONE flip is 1.5-2.6e-2 of a bias-gradient norm; which element flips depends on the summation order, e.g. split-K).
+    The backward algebra itself is pinned by mode 0 and the GEMM by test_gemm_f32_front_end_tcgen05 (4e-5)."""
     err, sc = report(name, got, ref)
     if mode == 0:
         if not err <= 3e-4 * max(sc, 1e-6):
@@ -219,7 +221,7 @@ def _grad_close(name, got, ref, mode, bad):
     else:
         num = float((got.detach().cpu().double() - ref.double()).norm())
         den = float(ref.double().norm())
-        if not num <= 1e-2 * max(den, 1e-9):
+        if not num <= 3e-2 * max(den, 1e-9):
             bad.append((name, "relL2", num / max(den, 1e-30)))
 
 
@@ -393,7 +395,8 @@ def test_fused_radam_vs_reference_golden(dev, golden_dir):
         assert np.abs(p.detach().cpu().numpy() - g["traj"][i]).max() <= 2e-7, i
 
 
-@pytest.mark.parametrize("mode,M,N,K", [(0, 300, 200, 1000), (1, 512, 3402, 1536), (2, 700, 260, 129), (0, 12288 // 8, 512, 3402)])
+@pytest.mark.parametrize("mode,M,N,K", [(0, 300, 200, 1000), (1, 512, 3402, 1536), (2, 700, 260, 129), (0, 12288 // 8, 512, 3402),
+                                        (0, 32, 512, 3402), (1, 128, 384, 12288), (2, 32, 1198, 2048), (1, 64, 64, 12288)])   # last four: split-K
 def test_gemm_f32_front_end_tcgen05(dev, mode, M, N, K):
     """fp32 in/out GEMM through tcgen05 split-bf16 (default mode 1): <= 4e-5 relative to max|C| vs float64 (K up to 3402)."""
     from zeggs_b200 import _lib, ops
@@ -410,6 +413,21 @@ def test_gemm_f32_front_end_tcgen05(dev, mode, M, N, K):
     _lib.check(_lib.lib().zeggs_gemm_f32(mode, M, N, K, Ad.data_ptr(), Ad.stride(0), Bd.data_ptr(), Bd.stride(0), None,
                                          out.data_ptr(), N, 0, 0, _lib.stream_ptr()), "zeggs_gemm_f32")
     err, sc = report(f"gemm_f32 mode{mode} {M}x{N}x{K}", out, ref)
+    assert err <= 4e-5 * sc
+
+
+def test_gemm_f32_splitk_epilogue(dev):
+    """split-K path (few output tiles, long K): bias + ELU + accumulate are applied once, by the reduction kernel."""
+    from zeggs_b200 import _lib, ops
+    ops.ensure_scratch(dev)
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 32, 300, 4096
+    A, B, bias, C0 = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    ref = C0.double() + torch.nn.functional.elu(A.double() @ B.double().T + bias.double())
+    Ad, Bd, bd, out = A.to(dev), B.to(dev), bias.to(dev), C0.to(dev).clone()
+    _lib.check(_lib.lib().zeggs_gemm_f32(0, M, N, K, Ad.data_ptr(), K, Bd.data_ptr(), K, bd.data_ptr(), out.data_ptr(), N, 1, 1,
+                                         _lib.stream_ptr()), "zeggs_gemm_f32")
+    err, sc = report("gemm_f32 split-K bias+elu+accumulate", out, ref)
     assert err <= 4e-5 * sc
 
 

@@ -483,47 +483,51 @@ extern "C" int zeggs_decoder_window_bwd(const zeggs_decoder_fwd_args* ap, const 
   // K = (T-1)*nbt*32; "previous step" operands are the same buffer shifted by one slot (32*nbt columns).
   bool tc_done = false;
   if (gemm_mode() != 0 && scratch_base() != nullptr) {
-    const bool want_lo = gemm_mode() == 1;
+    // the tc engine's recurrence already runs on bf16 operands: a single bf16 pass matches its accuracy
+    const bool want_lo = gemm_mode() == 1 && !use_tc;
     const int S = T * nbt;                       // slots per history
     const size_t ld = (size_t)S * 32;
     char* p = scratch_base();
-    struct Hist { const float* src; long long stride; int rows; __nv_bfloat16 *hi, *lo; };
+    struct Hist { const float* src; long long stride; int rows; __nv_bfloat16 *hi, *lo; float* db; };
     Hist hs[11] = {
-      {bw.DY, sX, P_OUT, nullptr, nullptr}, {bw.DGI1, s3, 3 * H, nullptr, nullptr}, {bw.DGH1, s3, 3 * H, nullptr, nullptr},
-      {bw.DGI0, s3, 3 * H, nullptr, nullptr}, {bw.DGH0, s3, 3 * H, nullptr, nullptr}, {bw.DPA, sH, H, nullptr, nullptr},
-      {w.H0, sH, H, nullptr, nullptr}, {w.H1, sH, H, nullptr, nullptr}, {w.A, sH, H, nullptr, nullptr},
-      {w.XP, sX, P_IN, nullptr, nullptr}, {bw.COND, sC, C, nullptr, nullptr}};
+      {bw.DY, sX, P_OUT, nullptr, nullptr, b.db2}, {bw.DGI1, s3, 3 * H, nullptr, nullptr, b.db_ih1}, {bw.DGH1, s3, 3 * H, nullptr, nullptr, b.db_hh1},
+      {bw.DGI0, s3, 3 * H, nullptr, nullptr, b.db_ih0}, {bw.DGH0, s3, 3 * H, nullptr, nullptr, b.db_hh0}, {bw.DPA, sH, H, nullptr, nullptr, b.db0},
+      {w.H0, sH, H, nullptr, nullptr, nullptr}, {w.H1, sH, H, nullptr, nullptr, nullptr}, {w.A, sH, H, nullptr, nullptr, nullptr},
+      {w.XP, sX, P_IN, nullptr, nullptr, nullptr}, {bw.COND, sC, C, nullptr, nullptr, nullptr}};
     size_t need = 0;
-    for (auto& h : hs) need += (((size_t)h.rows * ld * 2 + 255) / 256) * 256 * (want_lo ? 2 : 1);
+    for (auto& h : hs) need += (size_t)h.rows * ld * 2 * (want_lo ? 2 : 1);
     if (need <= scratch_bytes()) {
+      // all hi parts first, then all lo parts: (ld * 2) bytes per row, 16 B aligned, so consecutive histories stack into ONE
+      // row-contiguous operand ([a | x_pose | cond] is the input of layer0 / GRU0 in the weights' own column order)
+      for (auto& h : hs) { h.hi = (__nv_bfloat16*)p; p += (size_t)h.rows * ld * 2; }
+      if (want_lo) for (auto& h : hs) { h.lo = (__nv_bfloat16*)p; p += (size_t)h.rows * ld * 2; }
       for (auto& h : hs) {
-        h.hi = (__nv_bfloat16*)p; p += (((size_t)h.rows * ld * 2 + 255) / 256) * 256;
-        if (want_lo) { h.lo = (__nv_bfloat16*)p; p += (((size_t)h.rows * ld * 2 + 255) / 256) * 256; }
         // per-slot stride of the fp32 history is (stride / nbt) floats: slots (t,bt) are contiguous
-        rc = split_hist_launch(h.src, h.stride / nbt, S, h.rows, h.hi, h.lo, stream); if (rc) return rc;
+        // gradient histories: the same pass returns the bias gradient (sum over slots t >= 1, i.e. s >= nbt)
+        rc = split_hist_launch(h.src, h.stride / nbt, S, h.rows, h.hi, h.lo, stream, h.db, nbt); if (rc) return rc;
       }
+      char* ws_p = (char*)(((uintptr_t)p + 255) & ~(uintptr_t)255);             // split-K partials behind the histories
+      const size_t ws_bytes = (size_t)(scratch_base() + scratch_bytes() - ws_p);
       const int Kc = nT * nbt * 32;
       const int cur = nbt * 32;                  // column offset of slot t = 1
       auto G = [&](const Hist& ga, int ga_off, int N, const Hist& xb, int xb_off, int K, float* dW, int ldw) {
         return tc_gemm_launch(N, K, Kc, ga.hi + ga_off, want_lo ? ga.lo + ga_off : nullptr, (int)ld,
-                              xb.hi + xb_off, want_lo ? xb.lo + xb_off : nullptr, (int)ld, nullptr, dW, ldw, 0, 0, stream);
+                              xb.hi + xb_off, want_lo ? xb.lo + xb_off : nullptr, (int)ld, nullptr, dW, ldw, 0, 0, stream,
+                              (float*)ws_p, ws_bytes);
       };
       const Hist &hDY = hs[0], &hGI1 = hs[1], &hGH1 = hs[2], &hGI0 = hs[3], &hGH0 = hs[4], &hPA = hs[5], &hH0 = hs[6], &hH1 = hs[7],
-                 &hA = hs[8], &hXP = hs[9], &hCO = hs[10];
+                 &hA = hs[8], &hXP = hs[9];
       if ((rc = G(hDY, cur, P_OUT, hH1, cur, H, b.dW2, H))) return rc;
       if ((rc = G(hGI1, cur, 3 * H, hH0, cur, H, b.dW_ih1, H))) return rc;
       if ((rc = G(hGH1, cur, 3 * H, hH1, 0, H, b.dW_hh1, H))) return rc;
-      if ((rc = G(hGI0, cur, 3 * H, hA, cur, H, b.dW_ih0, A + H))) return rc;
-      if ((rc = G(hGI0, cur, 3 * H, hXP, cur, P_IN, b.dW_ih0 + H, A + H))) return rc;
-      if ((rc = G(hGI0, cur, 3 * H, hCO, cur, C, b.dW_ih0 + H + P_IN, A + H))) return rc;
+      if ((rc = G(hGI0, cur, 3 * H, hA, cur, H + P_IN + C, b.dW_ih0, A + H))) return rc;     // [a | x_pose | cond] stacked
       if ((rc = G(hGH0, cur, 3 * H, hH0, 0, H, b.dW_hh0, H))) return rc;
-      if ((rc = G(hPA, cur, H, hXP, cur, P_IN, b.dW0, A))) return rc;
-      if ((rc = G(hPA, cur, H, hCO, cur, C, b.dW0 + P_IN, A))) return rc;
+      if ((rc = G(hPA, cur, H, hXP, cur, P_IN + C, b.dW0, A))) return rc;                    // [x_pose | cond] stacked
       tc_done = true;
     }
   }
 #define WG(...) do { if (!tc_done) { rc = wgrad(__VA_ARGS__); if (rc) return rc; } } while (0)
-#define RS(...) do { rc = rowsum(__VA_ARGS__); if (rc) return rc; } while (0)
+#define RS(...) do { if (!tc_done) { rc = rowsum(__VA_ARGS__); if (rc) return rc; } } while (0)
   // layer2: dW2 = DY . H1[t]^T
   WG(bw.DY + sX, sX, (long long)K1P * 32, P_OUT, w.H1 + sH, sH, (long long)H * 32, H, nT, nbt, b.dW2, H, stream);
   RS(bw.DY + sX, sX, (long long)K1P * 32, P_OUT, nT, nbt, b.db2, stream);
@@ -554,15 +558,15 @@ extern "C" int zeggs_decoder_window_bwd(const zeggs_decoder_fwd_args* ap, const 
   count_launch();
   rc = sgemm_launch(1, 2 * H, H, a.B, bw.cse_dout, 2 * H, w.cse_h2, H, nullptr, b.dWc2, H, 0, 0, stream); if (rc) return rc;
   colsum_kernel<<<ceil_div(2 * H, 256), 256, 0, stream>>>(bw.cse_dout, a.B, 2 * H, b.dbc2); count_launch();
-  rc = sgemm_launch(2, a.B, H, 2 * H, bw.cse_dout, 2 * H, a.Wc2, H, nullptr, bw.cse_d2, H, 0, 0, stream); if (rc) return rc;
+  rc = gemm_f32_auto(2, a.B, H, 2 * H, bw.cse_dout, 2 * H, a.Wc2, H, nullptr, bw.cse_d2, H, 0, 0, stream); if (rc) return rc;
   elu_bwd_kernel<<<ceil_div(a.B * H, 256), 256, 0, stream>>>(bw.cse_d2, w.cse_h2, (size_t)a.B * H); count_launch();
   rc = sgemm_launch(1, H, H, a.B, bw.cse_d2, H, w.cse_h1, H, nullptr, b.dWc1, H, 0, 0, stream); if (rc) return rc;
   colsum_kernel<<<ceil_div(H, 256), 256, 0, stream>>>(bw.cse_d2, a.B, H, b.dbc1); count_launch();
-  rc = sgemm_launch(2, a.B, H, H, bw.cse_d2, H, a.Wc1, H, nullptr, bw.cse_d1, H, 0, 0, stream); if (rc) return rc;
+  rc = gemm_f32_auto(2, a.B, H, H, bw.cse_d2, H, a.Wc1, H, nullptr, bw.cse_d1, H, 0, 0, stream); if (rc) return rc;
   elu_bwd_kernel<<<ceil_div(a.B * H, 256), 256, 0, stream>>>(bw.cse_d1, w.cse_h1, (size_t)a.B * H); count_launch();
   rc = sgemm_launch(1, H, Kin, a.B, bw.cse_d1, H, w.cse_in, Kin, nullptr, b.dWc0, Kin, 0, 0, stream); if (rc) return rc;
   colsum_kernel<<<ceil_div(H, 256), 256, 0, stream>>>(bw.cse_d1, a.B, H, b.dbc0); count_launch();
-  rc = sgemm_launch(2, a.B, Kin, H, bw.cse_d1, H, a.Wc0, Kin, nullptr, bw.cse_din, Kin, 0, 0, stream); if (rc) return rc;
+  rc = gemm_f32_auto(2, a.B, Kin, H, bw.cse_d1, H, a.Wc0, Kin, nullptr, bw.cse_din, Kin, 0, 0, stream); if (rc) return rc;
   dcond_scatter_kernel<<<592, 256, 0, stream>>>(a, g, bw.DCOND, bw.cse_din, b.dSpeech, b.dStyle);
   count_launch();
   ZCHECK_LAUNCH();

@@ -276,7 +276,7 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
     float dpq[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // running d root_pos(3) / d root_rot(4) of this sample (CTA 0)
     // All global operands of R(t) are fetched into registers by R_prefetch (issued before the wait on the B4
     // accumulator) so that the adjoint itself is pure arithmetic + stores.
-    float ext[16], ext6[6], rpv[3], rqv[4], gpv[3], rq1v[4], ytv[6], e1p[3], e1q[4], e0p[3], e0q[4];
+    float ext[16], ext6[6], rpv[3] = {}, rqv[4] = {}, gpv[3] = {}, rq1v[4] = {}, ytv[6] = {}, e1p[3], e1q[4], e0p[3], e0q[4];
     // gradient-independent part of the root adjoint (R_precompute, also before the wait)
     Q4 r_qinv, r_q1, r_E; V3 r_u, r_a1, r_a2, r_x; float r_k0, r_k1, r_k2;
     auto R_precompute = [&]() {

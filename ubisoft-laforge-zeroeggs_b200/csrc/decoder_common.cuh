@@ -27,10 +27,12 @@ int gemm_f32_auto(int mode, int M, int N, int K, const float* A, int lda, const 
 int gemm_mode();
 char* scratch_base();
 size_t scratch_bytes();
-int split_hist_launch(const float* x, long long slot_stride, int S, int R, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t stream);
+int split_hist_launch(const float* x, long long slot_stride, int S, int R, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t stream,
+                      float* rowsum = nullptr, int s_begin = 0);
 int tc_gemm_launch(int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, int lda,
                    const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, const float* bias,
-                   float* C, int ldc, int act, int accumulate, cudaStream_t stream);
+                   float* C, int ldc, int act, int accumulate, cudaStream_t stream, float* splitk_ws = nullptr,
+                   size_t splitk_ws_bytes = 0);
 int sgemm_batched2_launch(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                           const float* bias, float* C, int ldc, int act, int accumulate, int batch,
                           long long sA, long long sB, long long sC, int inner, long long iA, long long iB, long long iC,
@@ -70,7 +72,8 @@ inline DecGeom make_geom(int B, int H, int S, int Z) {
 struct DecWs {
   unsigned* bar;
   float *cse_in, *cse_h1, *cse_h2, *cse_out;
-  float *S01;  // [T][nbt][4H][32]   hoisted speech/style contributions (+ b0 / b_ih0)
+  float *S01;  // [T][nbt][4H][32]   hoisted speech/style contributions (+ b0 / b_ih0); tc engine: [T][32][4H]
+  float *CONDR;  // [T][nbt*32][S+Z]  cond rows (tc engine: A operand of the hoisted GEMM)
   float *XP;   // [TS][nbt][K1P][32] normalised pose input of step t
   float *A;    // [TS][nbt][H][32]   ELU(layer0)
   float *H0, *H1;  // [TS][nbt][H][32]  GRU states (slot 0 = CellStateEncoder output)
@@ -101,6 +104,7 @@ inline DecWs make_ws(void* base, const DecGeom& g, int T, int save) {
   w.H1 = take((size_t)w.TS * g.nbt * g.H * 32);
   w.G0 = take(save ? (size_t)T * g.nbt * 4 * g.H * 32 : 64);
   w.G1 = take(save ? (size_t)T * g.nbt * 4 * g.H * 32 : 64);
+  w.CONDR = take((size_t)T * g.nbt * 32 * (g.S + g.Z));
   w.bytes = off;
   return w;
 }

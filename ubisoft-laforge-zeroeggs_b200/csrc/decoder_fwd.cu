@@ -139,6 +139,19 @@ __global__ void __launch_bounds__(256) cond_precompute_kernel(zeggs_decoder_fwd_
   }
 }
 
+// cond rows for the tc engine: R[(t*32 + b)][c] = [speech[b,t,:] | style[b,t,:]] (zero rows for b >= B)
+__global__ void cond_rows_kernel(zeggs_decoder_fwd_args a, float* __restrict__ R) {
+  const int C = a.S + a.Z, T = a.T;
+  const size_t total = (size_t)T * 32 * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % C); const size_t e = i / C;
+    const int b = (int)(e & 31), t = (int)(e >> 5);
+    float v = 0.f;
+    if (b < a.B) v = cc < a.S ? a.speech[((size_t)b * T + t) * a.S + cc] : a.style[((size_t)b * T + t) * a.Z + (cc - a.S)];
+    R[i] = v;
+  }
+}
+
 // ------------------------------------------------------------------ the persistent kernel
 template <int U>
 __global__ void __launch_bounds__(256, 1) decoder_fwd_kernel(zeggs_decoder_fwd_args a, DecGeom g, DecWs w) {
@@ -359,22 +372,30 @@ extern "C" int zeggs_decoder_window_fwd(const zeggs_decoder_fwd_args* ap, void* 
   count_launch();
   ZCHECK_LAUNCH();
   // CellStateEncoder (modules.py:238-243)
-  rc = sgemm_launch(0, a.B, a.H, P_IN + a.Z, w.cse_in, P_IN + a.Z, a.Wc0, P_IN + a.Z, a.bc0, w.cse_h1, a.H, 1, 0, stream); if (rc) return rc;
-  rc = sgemm_launch(0, a.B, a.H, a.H, w.cse_h1, a.H, a.Wc1, a.H, a.bc1, w.cse_h2, a.H, 1, 0, stream); if (rc) return rc;
-  rc = sgemm_launch(0, a.B, 2 * a.H, a.H, w.cse_h2, a.H, a.Wc2, a.H, a.bc2, w.cse_out, 2 * a.H, 0, 0, stream); if (rc) return rc;
+  rc = gemm_f32_auto(0, a.B, a.H, P_IN + a.Z, w.cse_in, P_IN + a.Z, a.Wc0, P_IN + a.Z, a.bc0, w.cse_h1, a.H, 1, 0, stream); if (rc) return rc;
+  rc = gemm_f32_auto(0, a.B, a.H, a.H, w.cse_h1, a.H, a.Wc1, a.H, a.bc1, w.cse_h2, a.H, 1, 0, stream); if (rc) return rc;
+  rc = gemm_f32_auto(0, a.B, 2 * a.H, a.H, w.cse_h2, a.H, a.Wc2, a.H, a.bc2, w.cse_out, 2 * a.H, 0, 0, stream); if (rc) return rc;
   cse_scatter_kernel<<<ceil_div(a.B * 2 * a.H, 256), 256, 0, stream>>>(a.B, a.H, w.cse_out, w.H0, w.H1);
   count_launch();
   ZCHECK_LAUNCH();
   if (a.T > 1) {
     const int C = a.S + a.Z;
     size_t sm = (size_t)(C * 33 + 64 * (C + 1)) * sizeof(float);
-    ZCHECK_CUDA(cudaFuncSetAttribute(cond_precompute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    cond_precompute_kernel<<<dim3(a.T, g.nbt, ceil_div(4 * a.H, 64)), 256, sm, stream>>>(a, g, w.S01);
-    count_launch();
-    ZCHECK_LAUNCH();
     if (a.engine == 1) {
+      // hoisted speech/style terms as two GEMMs (tcgen05 when a scratch buffer is set): S01[(t,b)][4H] =
+      // cond_rows [(t,b)][C] . [W0[:, 1134:] ; W_ih0[:, H+1134:]]^T + [b0 ; b_ih0]
+      ZCHECK_ARG(g.nbt == 1, "decoder tc engine handles one 32-sample batch tile (B <= 32); got B=%d", a.B);
+      cond_rows_kernel<<<592, 256, 0, stream>>>(a, w.CONDR);
+      count_launch();
+      ZCHECK_LAUNCH();
+      rc = gemm_f32_auto(0, a.T * 32, a.H, C, w.CONDR, C, a.W0 + P_IN, g.A, a.b0, w.S01, 4 * a.H, 0, 0, stream); if (rc) return rc;
+      rc = gemm_f32_auto(0, a.T * 32, 3 * a.H, C, w.CONDR, C, a.W_ih0 + a.H + P_IN, g.A + a.H, a.b_ih0, w.S01 + a.H, 4 * a.H, 0, 0, stream); if (rc) return rc;
       rc = decoder_fwd_tc_run(a, g, w, stream);
     } else {
+      ZCHECK_CUDA(cudaFuncSetAttribute(cond_precompute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      cond_precompute_kernel<<<dim3(a.T, g.nbt, ceil_div(4 * a.H, 64)), 256, sm, stream>>>(a, g, w.S01);
+      count_launch();
+      ZCHECK_LAUNCH();
       ScopedTimer tm("decoder_fwd", stream);
       if (g.U == 4) rc = launch_fwd<4>(a, g, w, stream); else rc = launch_fwd<8>(a, g, w, stream);
     }

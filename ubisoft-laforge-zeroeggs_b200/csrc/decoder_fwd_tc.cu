@@ -331,12 +331,14 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
       // ---------------- stage 1   (operands that do not depend on the MMA are fetched before the wait)
       float sv[4 * U];
       {
-        const float* S = w.S01 + ((size_t)t * g.nbt) * 4 * H * 32;
+        const float* S = w.S01 + ((size_t)t * 32 + b) * 4 * H + j0;      // [t][b][4H]: U consecutive floats per gate block
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          sv[u] = __ldg(S + (size_t)(j0 + u) * 32 + b);
+        for (int q = 0; q < 4; ++q) {
 #pragma unroll
-          for (int q = 0; q < 3; ++q) sv[(1 + q) * U + u] = __ldg(S + (size_t)(H + q * H + j0 + u) * 32 + b);
+          for (int u4 = 0; u4 < U; u4 += 4) {
+            const float4 v4 = __ldg(reinterpret_cast<const float4*>(S + (size_t)q * H + u4));
+            sv[q * U + u4 + 0] = v4.x; sv[q * U + u4 + 1] = v4.y; sv[q * U + u4 + 2] = v4.z; sv[q * U + u4 + 3] = v4.w;
+          }
         }
       }
       mbar_wait(&d_full[0], ph);

@@ -22,7 +22,8 @@ struct TcGemmMaps {
 
 __global__ void __launch_bounds__(192, 1)
 tc_gemm_kernel(const __grid_constant__ TcGemmMaps maps, int M, int N, int K, int passes,
-               const float* __restrict__ bias, float* __restrict__ C, int ldc, int act, int accumulate) {
+               const float* __restrict__ bias, float* __restrict__ C, int ldc, int act, int accumulate,
+               float* __restrict__ part, int kb_per_split) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -34,7 +35,9 @@ tc_gemm_kernel(const __grid_constant__ TcGemmMaps maps, int M, int N, int K, int
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TG_BM, n0 = blockIdx.x * TG_BN;
-  const int kblocks = ceil_div(K, TG_BK);
+  // split-K: blockIdx.z owns k-blocks [kb0, kb0 + kblocks); its raw fp32 tile goes to part[z][M][N] (reduced afterwards)
+  const int kb0 = blockIdx.z * kb_per_split;
+  const int kblocks = min(kb_per_split, ceil_div(K, TG_BK) - kb0);
   // pass order: (A0,B0), (A1,B0), (A0,B1)
   const int total = kblocks * (passes == 1 ? 1 : 3);
 
@@ -55,7 +58,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmMaps maps, int M, int N, int K, int
       for (int it = 0; it < total; ++it) {
         const int s = it % TG_STAGES, ph = (it / TG_STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
-        const int p = it / kblocks, kb = it - p * kblocks;
+        const int p = it / kblocks, kb = kb0 + it - p * kblocks;
         const CUtensorMap* ma = &maps.a[p == 1 ? 1 : 0];
         const CUtensorMap* mb = &maps.b[p == 2 ? 1 : 0];
         mbar_arrive_expect_tx(&full[s], TG_A_BYTES + TG_B_BYTES);
@@ -91,7 +94,12 @@ tc_gemm_kernel(const __grid_constant__ TcGemmMaps maps, int M, int N, int K, int
       uint32_t v[32];
       tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
-      if (m < M) {
+      if (m < M && part) {
+        float* prow = part + ((size_t)blockIdx.z * M + m) * N + n0 + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + c0 + j < N) prow[j] = __uint_as_float(v[j]);
+      } else if (m < M) {
         float* crow = C + (size_t)m * ldc + n0 + c0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -110,6 +118,21 @@ tc_gemm_kernel(const __grid_constant__ TcGemmMaps maps, int M, int N, int K, int
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem_base, TG_BN); }
+}
+
+// sum of the split-K partial tiles + the epilogue of the un-split kernel (deterministic order)
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N, const float* __restrict__ bias,
+                                     float* __restrict__ C, int ldc, int act, int accumulate) {
+  const size_t total = (size_t)M * N;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / N), n = (int)(i % N);
+    float x = 0.f;
+    for (int z = 0; z < splits; ++z) x += part[(size_t)z * total + i];
+    if (bias) x += bias[n];
+    if (act == 1) x = elu_f(x); else if (act == 2) x = fmaxf(x, 0.f);
+    float* c = C + (size_t)m * ldc + n;
+    *c = accumulate ? *c + x : x;
+  }
 }
 
 // fp32 -> (hi, lo) bf16 split, row-major, optional zero padding of the row to ld_out
@@ -146,19 +169,45 @@ __global__ void split_bf16_t_kernel(const float* __restrict__ x, int rows, int c
   }
 }
 
-// k-major history [S][R_src][32] (slot stride given) -> hi/lo [R][S*32]: out[r][s*32 + b] = in[s][r][b]
-__global__ void split_bf16_hist_kernel(const float* __restrict__ x, long long slot_stride, int S, int R,
-                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-  const size_t total = (size_t)S * R * 32;
+// k-major history [S][R_src][32] (slot stride given) -> hi/lo [R][S*32]: out[r][s*32 + b] = in[s][r][b].
+// One warp per history row r: lanes = samples b, the warp walks the slots (128 B in, 64 B out per slot, both streams
+// sequential) and, when `rowsum` is given, also returns sum over slots s >= s_begin and samples of in[s][r][b] (the bias
+// gradient of that row) -- fixed summation order, no atomics.
+__global__ void __launch_bounds__(256) split_bf16_hist_kernel(const float* __restrict__ x, long long slot_stride, int S, int R,
+                                                              __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                              float* __restrict__ rowsum, int s_begin) {
+  const int lane = threadIdx.x & 31;
   const size_t ld = (size_t)S * 32;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int b = (int)(i & 31); size_t e = i >> 5;
-    const int r = (int)(e % R); const int sidx = (int)(e / R);
-    const float v = x[(size_t)sidx * slot_stride + (size_t)r * 32 + b];
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const size_t o = (size_t)r * ld + (size_t)sidx * 32 + b;
-    hi[o] = h;
-    if (lo) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+  for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < R; r += gridDim.x * 8) {
+    const float* src = x + (size_t)r * 32 + lane;
+    __nv_bfloat16* oh = hi + (size_t)r * ld + lane;
+    __nv_bfloat16* ol = lo ? lo + (size_t)r * ld + lane : nullptr;
+    float acc = 0.f;
+    int sidx = 0;
+    for (; sidx + 8 <= S; sidx += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __ldg(src + (size_t)(sidx + i) * slot_stride);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v[i]);
+        oh[(size_t)(sidx + i) * 32] = h;
+        if (ol) ol[(size_t)(sidx + i) * 32] = __float2bfloat16_rn(v[i] - __bfloat162float(h));
+        if (sidx + i >= s_begin) acc += v[i];
+      }
+    }
+    for (; sidx < S; ++sidx) {
+      const float v = __ldg(src + (size_t)sidx * slot_stride);
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      oh[(size_t)sidx * 32] = h;
+      if (ol) ol[(size_t)sidx * 32] = __float2bfloat16_rn(v - __bfloat162float(h));
+      if (sidx >= s_begin) acc += v;
+    }
+    if (rowsum) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) rowsum[r] = acc;
+    }
   }
 }
 
@@ -178,7 +227,7 @@ static int encode_map(CUtensorMap* m, const void* base, int rows, int K, int ld_
 
 int tc_gemm_launch(int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, int lda,
                    const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, const float* bias,
-                   float* C, int ldc, int act, int accumulate, cudaStream_t stream) {
+                   float* C, int ldc, int act, int accumulate, cudaStream_t stream, float* splitk_ws, size_t splitk_ws_bytes) {
   ZCHECK_ARG(M > 0 && N > 0 && K > 0 && A_hi && B_hi && C, "tc_gemm: bad arguments");
   ZCHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "tc_gemm: leading dimensions must be multiples of 8 bf16 (16 B)");
   ZCHECK_ARG(((uintptr_t)A_hi & 15) == 0 && ((uintptr_t)B_hi & 15) == 0, "tc_gemm: operands must be 16-byte aligned");
@@ -195,8 +244,27 @@ int tc_gemm_launch(int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bf
   const size_t smem = 1024 + TG_STAGES * (TG_A_BYTES + TG_B_BYTES) + (2 * TG_STAGES + 1) * 8 + 16;
   ZCHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(N, TG_BN), ceil_div(M, TG_BM));
-  tc_gemm_kernel<<<grid, 192, smem, stream>>>(maps, M, N, K, passes, bias, C, ldc, act, accumulate);
-  count_launch();
+  // split-K when the output has too few tiles to fill the 148 SMs and the contraction is long
+  const int tiles = (int)(grid.x * grid.y), kblocks = ceil_div(K, TG_BK);
+  int splits = 1;
+  if (splitk_ws && tiles <= 74 && kblocks >= 8) {
+    splits = std::min(std::max(1, 148 / tiles), kblocks / 2);
+    const size_t per = (size_t)M * N * sizeof(float);
+    if ((size_t)splits * per > splitk_ws_bytes) splits = (int)(splitk_ws_bytes / per);
+  }
+  if (splits <= 1) {
+    tc_gemm_kernel<<<grid, 192, smem, stream>>>(maps, M, N, K, passes, bias, C, ldc, act, accumulate, nullptr, kblocks);
+    count_launch();
+  } else {
+    const int kbs = ceil_div(kblocks, splits);
+    splits = ceil_div(kblocks, kbs);                      // every z gets at least one k-block
+    grid.z = splits;
+    tc_gemm_kernel<<<grid, 192, smem, stream>>>(maps, M, N, K, passes, nullptr, C, ldc, 0, 0, splitk_ws, kbs);
+    count_launch();
+    const size_t total = (size_t)M * N;
+    splitk_reduce_kernel<<<(int)std::min<size_t>(1184, (total + 255) / 256), 256, 0, stream>>>(splitk_ws, splits, M, N, bias, C, ldc, act, accumulate);
+    count_launch();
+  }
   ZCHECK_LAUNCH();
   return ZEGGS_OK;
 }
@@ -216,8 +284,9 @@ int gemm_mode() { return g_gemm_mode; }
 char* scratch_base() { return g_scratch; }
 size_t scratch_bytes() { return g_scratch_bytes; }
 
-int split_hist_launch(const float* x, long long slot_stride, int S, int R, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t stream) {
-  split_bf16_hist_kernel<<<1184, 256, 0, stream>>>(x, slot_stride, S, R, hi, lo);
+int split_hist_launch(const float* x, long long slot_stride, int S, int R, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t stream,
+                      float* rowsum, int s_begin) {
+  split_bf16_hist_kernel<<<std::min(ceil_div(R, 8), 1184), 256, 0, stream>>>(x, slot_stride, S, R, hi, lo, rowsum, s_begin);
   count_launch();
   ZCHECK_LAUNCH();
   return ZEGGS_OK;
@@ -248,7 +317,9 @@ int gemm_f32_auto(int mode, int M, int N, int K, const float* A, int lda, const 
   else split_bf16_t_kernel<<<dim3(ceil_div(N, 32), ceil_div(Kp, 32)), tb, 0, stream>>>(B, K, N, ldb, Bh, Bl, Kp);
   count_launch();
   ZCHECK_LAUNCH();
-  return tc_gemm_launch(M, N, K, Ah, Al, Kp, Bh, Bl, Kp, bias, C, ldc, act, accumulate, stream);
+  p = (char*)(((uintptr_t)p + 255) & ~(uintptr_t)255);
+  return tc_gemm_launch(M, N, K, Ah, Al, Kp, Bh, Bl, Kp, bias, C, ldc, act, accumulate, stream, (float*)p,
+                        (size_t)(g_scratch + g_scratch_bytes - p));
 }
 
 extern "C" int zeggs_gemm_f32(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* bias,
