@@ -39,15 +39,18 @@ class DecoderWindowFn(torch.autograd.Function):
                 setattr(b, name, g.data_ptr())
         # transposed weight slices for the backward recurrence (cached on the module like the forward pack)
         ver = ops.weights_key(dec._weights())
-        cache = dec.__dict__.get("_zeggs_packed_bwd")
-        if cache is None or cache[0] != ver or cache[1].device != dev:
-            nb = l.zeggs_decoder_packed_bwd_bytes(H, S, Z)
-            packed = torch.empty(nb // 4, dtype=torch.float32, device=dev)
-            _lib.check(l.zeggs_decoder_pack_weights_bwd(a, packed.data_ptr(), _lib.stream_ptr()), "zeggs_decoder_pack_weights_bwd")
-            dec.__dict__["_zeggs_packed_bwd"] = (ver, packed)
-            cache = dec.__dict__["_zeggs_packed_bwd"]
-        b.packed_bwd = cache[1].data_ptr()
-        if a.engine == 1 and l.zeggs_decoder_packed_bwd_tc_bytes(H, S, Z) > 0 and H >= 288:
+        use_tc = a.engine == 1 and l.zeggs_decoder_packed_bwd_tc_bytes(H, S, Z) > 0 and H >= 288
+        if not use_tc:
+            cache = dec.__dict__.get("_zeggs_packed_bwd")
+            if cache is None or cache[0] != ver or cache[1].device != dev:
+                nb = l.zeggs_decoder_packed_bwd_bytes(H, S, Z)
+                packed = torch.empty(nb // 4, dtype=torch.float32, device=dev)
+                _lib.check(l.zeggs_decoder_pack_weights_bwd(a, packed.data_ptr(), _lib.stream_ptr()), "zeggs_decoder_pack_weights_bwd")
+                dec.__dict__["_zeggs_packed_bwd"] = (ver, packed)
+                cache = dec.__dict__["_zeggs_packed_bwd"]
+            b.packed_bwd = cache[1].data_ptr()
+            hold.append(cache[1])
+        if use_tc:
             tcc = dec.__dict__.get("_zeggs_packed_bwd_tc")
             if tcc is None or tcc[0] != ver or tcc[1].device != dev:
                 ptc = torch.empty(l.zeggs_decoder_packed_bwd_tc_bytes(H, S, Z), dtype=torch.uint8, device=dev)

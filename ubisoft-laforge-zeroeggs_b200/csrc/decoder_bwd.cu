@@ -358,15 +358,16 @@ __global__ void cond_kmajor_kernel(zeggs_decoder_fwd_args a, DecGeom g, float* _
 }
 
 // dSpeech/dStyle[b][t][c] from DCOND[t][bt][c][32] (t>=1) ; t = 0: zero for speech, CellStateEncoder input grad for style
+// rows != 0: DCOND is [(t*32 + b)][c] (tc engine, nbt == 1)
 __global__ void dcond_scatter_kernel(zeggs_decoder_fwd_args a, DecGeom g, const float* __restrict__ DCOND, const float* __restrict__ cse_din,
-                                     float* __restrict__ dSpeech, float* __restrict__ dStyle) {
+                                     float* __restrict__ dSpeech, float* __restrict__ dStyle, int rows) {
   const int C = a.S + a.Z;
   const size_t total = (size_t)a.B * a.T * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int cc = i % C; size_t e = i / C;
     int t = e % a.T; int b = e / a.T;
     float v = 0.f;
-    if (t >= 1) v = DCOND[(((size_t)t * g.nbt + b / 32) * C + cc) * 32 + (b % 32)];
+    if (t >= 1) v = rows ? DCOND[((size_t)t * 32 + b) * C + cc] : DCOND[(((size_t)t * g.nbt + b / 32) * C + cc) * 32 + (b % 32)];
     else if (cc >= a.S) v = cse_din[(size_t)b * (P_IN + a.Z) + P_IN + (cc - a.S)];
     if (cc < a.S) { if (dSpeech) dSpeech[((size_t)b * a.T + t) * a.S + cc] = v; }
     else if (dStyle) dStyle[((size_t)b * a.T + t) * a.Z + (cc - a.S)] = v;
@@ -481,7 +482,7 @@ extern "C" int zeggs_decoder_window_bwd(const zeggs_decoder_fwd_args* ap, const 
   // ---- weight gradients (slots t = 1..T-1).  tcgen05 path: every history is re-laid out once as bf16 (hi, lo)
   // [rows][(T*nbt)*32] (contraction index contiguous) in the scratch buffer, then each dW is one NT GEMM with
   // K = (T-1)*nbt*32; "previous step" operands are the same buffer shifted by one slot (32*nbt columns).
-  bool tc_done = false;
+  bool tc_done = false, dcond_rows = false;
   if (gemm_mode() != 0 && scratch_base() != nullptr) {
     // the tc engine's recurrence already runs on bf16 operands: a single bf16 pass matches its accuracy
     const bool want_lo = gemm_mode() == 1 && !use_tc;
@@ -524,6 +525,24 @@ extern "C" int zeggs_decoder_window_bwd(const zeggs_decoder_fwd_args* ap, const 
       if ((rc = G(hGH0, cur, 3 * H, hH0, 0, H, b.dW_hh0, H))) return rc;
       if ((rc = G(hPA, cur, H, hXP, cur, P_IN + C, b.dW0, A))) return rc;                    // [x_pose | cond] stacked
       tc_done = true;
+      // ---- d cond on tcgen05 (single-pass bf16, tc engine): transpose the dpa / dgi0 histories to [(t,b)][row] and contract
+      // them with the transposed cond columns of W0 / W_ih0:  DCOND[(t,b)][c] = dpa^T W0[:, 1134+c] + dgi0^T W_ih0[:, H+1134+c]
+      if (!want_lo && nbt == 1 && H % 64 == 0) {
+        char* q = ws_p;
+        auto takeq = [&](size_t bytes) { char* r = q; q += (bytes + 255) / 256 * 256; return (__nv_bfloat16*)r; };
+        __nv_bfloat16* paT = takeq(ld * H * 2); __nv_bfloat16* giT = takeq(ld * 3 * H * 2);
+        __nv_bfloat16* w0T = takeq((size_t)C * H * 2); __nv_bfloat16* wiT = takeq((size_t)C * 3 * H * 2);
+        if ((size_t)(q - scratch_base()) <= scratch_bytes()) {
+          if ((rc = transpose_bf16_launch(hPA.hi, H, (int)ld, ld, paT, H, stream))) return rc;
+          if ((rc = transpose_bf16_launch(hGI0.hi, 3 * H, (int)ld, ld, giT, 3 * H, stream))) return rc;
+          if ((rc = split_t_launch(a.W0 + P_IN, H, C, A, w0T, nullptr, H, stream))) return rc;
+          if ((rc = split_t_launch(a.W_ih0 + H + P_IN, 3 * H, C, A + H, wiT, nullptr, 3 * H, stream))) return rc;
+          float* out = bw.DCOND + (size_t)cur * C;
+          if ((rc = tc_gemm_launch(Kc, C, H, paT + (size_t)cur * H, nullptr, H, w0T, nullptr, H, nullptr, out, C, 0, 0, stream))) return rc;
+          if ((rc = tc_gemm_launch(Kc, C, 3 * H, giT + (size_t)cur * 3 * H, nullptr, 3 * H, wiT, nullptr, 3 * H, nullptr, out, C, 0, 1, stream))) return rc;
+          dcond_rows = true;
+        }
+      }
     }
   }
 #define WG(...) do { if (!tc_done) { rc = wgrad(__VA_ARGS__); if (rc) return rc; } } while (0)
@@ -550,8 +569,10 @@ extern "C" int zeggs_decoder_window_bwd(const zeggs_decoder_fwd_args* ap, const 
 #undef WG
 #undef RS
   // ---- d cond[t] = W0[:, 1134:]^T dpre_a + W_ih0[:, H+1134:]^T dgi0   (batched over slots t >= 1)
-  rc = sgemm_batched_launch(1, C, 32, H, a.W0 + P_IN, A, bw.DPA + sH, 32, nullptr, bw.DCOND + sC, 32, 0, 0, nT * nbt, 0, (long long)H * 32, (long long)C * 32, stream); if (rc) return rc;
-  rc = sgemm_batched_launch(1, C, 32, 3 * H, a.W_ih0 + H + P_IN, A + H, bw.DGI0 + s3, 32, nullptr, bw.DCOND + sC, 32, 0, 1, nT * nbt, 0, (long long)3 * H * 32, (long long)C * 32, stream); if (rc) return rc;
+  if (!dcond_rows) {
+    rc = sgemm_batched_launch(1, C, 32, H, a.W0 + P_IN, A, bw.DPA + sH, 32, nullptr, bw.DCOND + sC, 32, 0, 0, nT * nbt, 0, (long long)H * 32, (long long)C * 32, stream); if (rc) return rc;
+    rc = sgemm_batched_launch(1, C, 32, 3 * H, a.W_ih0 + H + P_IN, A + H, bw.DGI0 + s3, 32, nullptr, bw.DCOND + sC, 32, 0, 1, nT * nbt, 0, (long long)3 * H * 32, (long long)C * 32, stream); if (rc) return rc;
+  }
   // ---- CellStateEncoder backward (modules.py:238-243)
   const int Kin = P_IN + a.Z;
   cse_gather_kernel<<<ceil_div(a.B * 2 * H, 256), 256, 0, stream>>>(a.B, H, bw.DH0, bw.DH1, bw.cse_dout);
@@ -567,7 +588,7 @@ extern "C" int zeggs_decoder_window_bwd(const zeggs_decoder_fwd_args* ap, const 
   rc = sgemm_launch(1, H, Kin, a.B, bw.cse_d1, H, w.cse_in, Kin, nullptr, b.dWc0, Kin, 0, 0, stream); if (rc) return rc;
   colsum_kernel<<<ceil_div(H, 256), 256, 0, stream>>>(bw.cse_d1, a.B, H, b.dbc0); count_launch();
   rc = gemm_f32_auto(2, a.B, Kin, H, bw.cse_d1, H, a.Wc0, Kin, nullptr, bw.cse_din, Kin, 0, 0, stream); if (rc) return rc;
-  dcond_scatter_kernel<<<592, 256, 0, stream>>>(a, g, bw.DCOND, bw.cse_din, b.dSpeech, b.dStyle);
+  dcond_scatter_kernel<<<592, 256, 0, stream>>>(a, g, bw.DCOND, bw.cse_din, b.dSpeech, b.dStyle, dcond_rows ? 1 : 0);
   count_launch();
   ZCHECK_LAUNCH();
   return ZEGGS_OK;

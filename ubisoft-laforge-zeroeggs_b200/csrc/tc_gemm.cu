@@ -211,6 +211,40 @@ __global__ void __launch_bounds__(256) split_bf16_hist_kernel(const float* __res
   }
 }
 
+// bf16 transpose: in[R][ld_in] (first Ncols columns) -> out[Ncols][ld_out]; 64x64 tiles, 4-byte accesses both ways
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const uint16_t* __restrict__ in, int R, int Ncols, size_t ld_in,
+                                                             uint16_t* __restrict__ out, size_t ld_out) {
+  __shared__ uint16_t tile[64][66];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  for (int r = ty; r < 64; r += 8) {
+    const int rr = r0 + r, cc = c0 + 2 * tx;
+    uint32_t v = 0;
+    if (rr < R && cc + 1 < Ncols) v = *reinterpret_cast<const uint32_t*>(in + (size_t)rr * ld_in + cc);
+    else if (rr < R && cc < Ncols) v = in[(size_t)rr * ld_in + cc];
+    tile[r][2 * tx] = (uint16_t)(v & 0xffffu); tile[r][2 * tx + 1] = (uint16_t)(v >> 16);
+  }
+  __syncthreads();
+  for (int c = ty; c < 64; c += 8) {
+    const int cc = c0 + c, rr = r0 + 2 * tx;
+    if (cc >= Ncols) continue;
+    const uint32_t v = (uint32_t)tile[2 * tx][c] | ((uint32_t)tile[2 * tx + 1][c] << 16);
+    if (rr + 1 < R) *reinterpret_cast<uint32_t*>(out + (size_t)cc * ld_out + rr) = v;
+    else if (rr < R) out[(size_t)cc * ld_out + rr] = (uint16_t)(v & 0xffffu);
+  }
+}
+
+int transpose_bf16_launch(const __nv_bfloat16* in, int R, int Ncols, size_t ld_in, __nv_bfloat16* out, size_t ld_out, cudaStream_t stream) {
+  ZCHECK_ARG((ld_in % 2) == 0 && (ld_out % 2) == 0 && ((uintptr_t)in & 3) == 0 && ((uintptr_t)out & 3) == 0, "transpose_bf16: 4-byte alignment");
+  transpose_bf16_kernel<<<dim3(ceil_div(Ncols, 64), ceil_div(R, 64)), 256, 0, stream>>>((const uint16_t*)in, R, Ncols, ld_in, (uint16_t*)out, ld_out);
+  count_launch();
+  ZCHECK_LAUNCH();
+  return ZEGGS_OK;
+}
+
+// transposing split of a weight sub-block: x[rows][cols] (ld_in) -> hi [cols][ld_out] bf16
+int split_t_launch(const float* x, int rows, int cols, int ld_in, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_out, cudaStream_t stream);
+
 static int encode_map(CUtensorMap* m, const void* base, int rows, int K, int ld_elems, int box_rows) {
   PFN_encodeTiled fn = get_encode_fn();
   ZCHECK_ARG(fn != nullptr, "tc_gemm: cuTensorMapEncodeTiled not available from the driver");
@@ -265,6 +299,13 @@ int tc_gemm_launch(int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bf
     splitk_reduce_kernel<<<(int)std::min<size_t>(1184, (total + 255) / 256), 256, 0, stream>>>(splitk_ws, splits, M, N, bias, C, ldc, act, accumulate);
     count_launch();
   }
+  ZCHECK_LAUNCH();
+  return ZEGGS_OK;
+}
+
+int split_t_launch(const float* x, int rows, int cols, int ld_in, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_out, cudaStream_t stream) {
+  split_bf16_t_kernel<<<dim3(ceil_div(cols, 32), ceil_div(ld_out, 32)), dim3(32, 8), 0, stream>>>(x, rows, cols, ld_in, hi, lo, ld_out);
+  count_launch();
   ZCHECK_LAUNCH();
   return ZEGGS_OK;
 }

@@ -101,20 +101,22 @@ def _decoder_args(dec, B, T, dev, tensors, stats, dt, save):
     for n, t in tensors.items():
         setattr(a, n, _lib.ptr(t))
         keep.append(t)
-    # packed weights: re-packed whenever any parameter's version counter moved
+    # packed weights: re-packed whenever any parameter's version counter moved (each engine packs only its own slices)
     ver = weights_key(dec._weights())
-    cache = getattr(dec, "_zeggs_packed", None)
-    if cache is None or cache[0] != ver or cache[1].device != dev:
-        nbytes = l.zeggs_decoder_packed_bytes(H, S, Z)
-        if nbytes == 0:
-            raise _lib.ZeggsError(f"decoder hidden size {H} unsupported")
-        packed = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
-        _lib.check(l.zeggs_decoder_pack_weights(a, packed.data_ptr(), _lib.stream_ptr()), "zeggs_decoder_pack_weights")
-        dec.__dict__["_zeggs_packed"] = (ver, packed)
-        cache = dec.__dict__["_zeggs_packed"]
-    a.packed = cache[1].data_ptr()
-    keep.append(cache[1])
-    if DECODER_ENGINE == "tc" and B <= 32:
+    use_tc = DECODER_ENGINE == "tc" and B <= 32 and l.zeggs_decoder_packed_tc_bytes(H, S, Z) > 0 and H >= 288
+    if not use_tc:
+        cache = getattr(dec, "_zeggs_packed", None)
+        if cache is None or cache[0] != ver or cache[1].device != dev:
+            nbytes = l.zeggs_decoder_packed_bytes(H, S, Z)
+            if nbytes == 0:
+                raise _lib.ZeggsError(f"decoder hidden size {H} unsupported")
+            packed = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+            _lib.check(l.zeggs_decoder_pack_weights(a, packed.data_ptr(), _lib.stream_ptr()), "zeggs_decoder_pack_weights")
+            dec.__dict__["_zeggs_packed"] = (ver, packed)
+            cache = dec.__dict__["_zeggs_packed"]
+        a.packed = cache[1].data_ptr()
+        keep.append(cache[1])
+    if use_tc:
         tcc = dec.__dict__.get("_zeggs_packed_tc")
         if tcc is None or tcc[0] != ver or tcc[1].device != dev:
             nb = l.zeggs_decoder_packed_tc_bytes(H, S, Z)
