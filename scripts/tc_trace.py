@@ -13,7 +13,7 @@ dec = make_decoder(P, H, device=dev)
 args = [win[n][:, 0].to(dev) for n in NAMES] + [win["gaze_pos"].to(dev), speech.to(dev), style.to(dev), st["parents"]] + \
        [st[k].to(dev) for k in ("anim_input_mean", "anim_input_std", "anim_output_mean", "anim_output_std")] + [st["dt"]]
 ops.set_decoder_engine("tc")
-_lib.lib().zeggs_debug_set_tc_nacc(int(os.environ.get("NACC", "0")))
+_lib.lib().zeggs_debug_set_tc_cluster(int(os.environ.get("CLUSTER", "8")))
 with torch.no_grad(): dec(*args)
 buf = torch.zeros(64 * 32, dtype=torch.int64, device=dev)
 _lib.lib().zeggs_debug_set_tc_trace(buf.data_ptr())
@@ -21,9 +21,10 @@ with torch.no_grad(): dec(*args)
 torch.cuda.synchronize()
 _lib.lib().zeggs_debug_set_tc_trace(None)
 tr = buf.cpu().numpy().reshape(64, 32)
-names = {0:"L:B4 seen",1:"L:xp load issued",2:"M:before xa wait",3:"M:xa(S1) ready",4:"M:S1 issued",5:"E:d0 ready",6:"E:s1 done",7:"E:arrived B1",8:"L:B1 seen",
-         9:"M:before xa wait",10:"M:xa(a) ready",11:"M:gi0a issued",12:"E:d1 ready",13:"E:s2 done",14:"L:B2 seen",15:"M:xa(h0) ready",16:"M:gi1 issued",17:"E:d2 ready",
-         18:"E:s3 done",19:"E:arrived B3",20:"L:B3 seen",21:"M:xa(h1) ready",22:"E:d3 ready",23:"E:s4 done",24:"E:arrived B4"}
+print("cluster size used:", _lib.lib().zeggs_debug_get_tc_cluster())
+names = {0:"L:C(t-1) seen, h1 load issued",4:"M:fold issued",5:"E:d0 ready",6:"E:A done",7:"E:arrived A",8:"L:A seen",10:"M:gh1 issued",
+         11:"M:gi0a issued",12:"E:d1 ready",13:"E:B done",14:"L:B seen",16:"M:gi1 issued",17:"E:d2 ready",18:"E:C done",19:"E:arrived C",20:"M:gi0a x chunk0",21:"M:gi0a x chunk1",22:"M:gi0a x chunk2",23:"M:gi0a x chunk3",
+         24:"M:gi0a w slot0",25:"M:gi0a w slot1",26:"M:gi0a w slot2",27:"M:gi0a w slot3",28:"M:gi0a w slot4",29:"M:gi0a w slot5",30:"M:gi0a w slot6",31:"M:gi0a w slot7"}
 for t in (10, 20):
     base = tr[t, 0]
     print(f"step {t}: (cycles since 'B4 seen'; 1 us ~ 1900 cyc)")

@@ -5,7 +5,7 @@
 #include "../../ubisoft-laforge-zeroeggs_b200/csrc/tc_common.cuh"
 using namespace zeggs;
 __device__ size_t img_off(int row, int k) { int kb = k >> 6, c = (k & 63) >> 3, e = k & 7; return (size_t)kb * 0 + (size_t)row * 128 + (size_t)((c ^ (row & 7)) << 4) + e * 2; }
-__global__ void __launch_bounds__(128, 1) k(int M, int nmma, float* out, long long* tm) {
+__global__ void __launch_bounds__(128, 1) k(int M, int nmma, float* out, long long* tm, int N = 32) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar; __shared__ uint32_t slot;
@@ -20,15 +20,15 @@ __global__ void __launch_bounds__(128, 1) k(int M, int nmma, float* out, long lo
   tc_fence_before_sync(); __syncthreads(); tc_fence_after_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) {
-    const uint32_t idesc = make_idesc_bf16_f32(M, 32);
+    const uint32_t idesc = make_idesc_bf16_f32(M, N);
     const uint64_t da = make_smem_desc_sw128(A), db = make_smem_desc_sw128(B);
     long long t0 = clock64();
     for (int i = 0; i < nmma; i += 4) {
       if (elect_one_sync()) {
         umma_bf16(0, da, db, idesc, i > 0);
-        umma_bf16(32, da + 2, db + 2, idesc, i > 0);
-        umma_bf16(64, da + 4, db + 4, idesc, i > 0);
-        umma_bf16(96, da + 6, db + 6, idesc, i > 0);
+        umma_bf16(N, da + 2, db + 2, idesc, i > 0);
+        umma_bf16(2 * N, da + 4, db + 4, idesc, i > 0);
+        umma_bf16(3 * N, da + 6, db + 6, idesc, i > 0);
       }
       __syncwarp();
     }
@@ -61,6 +61,12 @@ int main() {
     cudaDeviceSynchronize();
     cudaMemcpy(ht, t, 16, cudaMemcpyDeviceToHost);
     printf("M=%d N=32: issue %.1f cyc/mma, complete %.1f cyc/mma\n", M, ht[0] / 4096.0, ht[1] / 4096.0);
+    for (int N : {16, 48, 64, 128}) {
+      k<<<1, 128, 200 * 1024>>>(M, 4096, d, t, N);
+      cudaDeviceSynchronize();
+      cudaMemcpy(ht, t, 16, cudaMemcpyDeviceToHost);
+      printf("M=%d N=%d: issue %.1f cyc/mma, complete %.1f cyc/mma\n", M, N, ht[0] / 4096.0, ht[1] / 4096.0);
+    }
   }
   return 0;
 }

@@ -80,6 +80,11 @@ struct DecWs {
   float *A;    // [TS][nbt][H][32]   ELU(layer0)
   float *H0, *H1;  // [TS][nbt][H][32]  GRU states (slot 0 = CellStateEncoder output)
   float *G0, *G1;  // [T][nbt][4][H][32] r,z,n,(W_hn h + b_hn)   (save only)
+  // tc engine (layer2 folded into the next step's layer0/GRU0 input GEMM, see decoder_fwd_tc.cu)
+  void* H1B;       // bf16 [T*32][H]     row-major history of h1(t): A operand of the batched layer2 GEMM
+  float* YC;       // [T*32][1131]       raw layer2 outputs of the batched GEMM (rows (t,b))
+  float* Y6;       // [T][32][8]         de-normalised root velocity channels the in-kernel root integration used
+  float* GZ;       // [T][32][4]         normalised gaze direction fed to step t
   int TS, save;
   size_t bytes;
 };
@@ -107,10 +112,15 @@ inline DecWs make_ws(void* base, const DecGeom& g, int T, int save) {
   w.G0 = take(save ? (size_t)T * g.nbt * 4 * g.H * 32 : 64);
   w.G1 = take(save ? (size_t)T * g.nbt * 4 * g.H * 32 : 64);
   w.CONDR = take((size_t)T * g.nbt * 32 * (g.S + g.Z));
+  w.H1B = (void*)take((size_t)T * 32 * g.H / 2);
+  w.YC = take((size_t)T * 32 * P_OUT);
+  w.Y6 = take((size_t)T * 32 * 8);
+  w.GZ = take((size_t)T * 32 * 4);
   w.bytes = off;
   return w;
 }
 
+int decoder_fwd_tc_hoist(const zeggs_decoder_fwd_args& a, const DecGeom& g, const DecWs& w, cudaStream_t stream);
 int decoder_fwd_tc_run(const zeggs_decoder_fwd_args& a, const DecGeom& g, const DecWs& w, cudaStream_t stream);
 
 // ------------------------------------------------------------------ skinny GEMM

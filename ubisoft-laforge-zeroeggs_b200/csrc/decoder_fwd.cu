@@ -388,8 +388,7 @@ extern "C" int zeggs_decoder_window_fwd(const zeggs_decoder_fwd_args* ap, void* 
       cond_rows_kernel<<<592, 256, 0, stream>>>(a, w.CONDR);
       count_launch();
       ZCHECK_LAUNCH();
-      rc = gemm_f32_auto(0, a.T * 32, a.H, C, w.CONDR, C, a.W0 + P_IN, g.A, a.b0, w.S01, 4 * a.H, 0, 0, stream); if (rc) return rc;
-      rc = gemm_f32_auto(0, a.T * 32, 3 * a.H, C, w.CONDR, C, a.W_ih0 + a.H + P_IN, g.A + a.H, a.b_ih0, w.S01 + a.H, 4 * a.H, 0, 0, stream); if (rc) return rc;
+      rc = decoder_fwd_tc_hoist(a, g, w, stream); if (rc) return rc;
       rc = decoder_fwd_tc_run(a, g, w, stream);
     } else {
       ZCHECK_CUDA(cudaFuncSetAttribute(cond_precompute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));

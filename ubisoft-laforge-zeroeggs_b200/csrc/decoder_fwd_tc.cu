@@ -1,20 +1,35 @@
-// Decoder window forward on the 5th-gen tensor cores (engine 1): the same persistent, weight-stationary
-// partition as decoder_fwd.cu (CTA c owns U hidden units of layer0 / GRU0 / GRU1 and ceil(1131/G) layer2 rows,
-// four stages per step separated by a grid barrier) but every stage GEMM is a tcgen05.mma chain:
+// Decoder window forward on the 5th-gen tensor cores (engine 1).
 //
-//   D[128 x N] (f32, TMEM) = X[128 x K] (bf16, smem)  *  Wslice[N x K]^T (bf16, smem)
+// Same persistent, weight-stationary partition as decoder_fwd.cu (CTA c owns U hidden units of layer0 / GRU0 / GRU1),
+// but (1) every stage GEMM is a tcgen05.mma chain and (2) layer2 is FOLDED out of the recurrence:
 //
-//   * X = the stage's activation vector for the 32 samples of the batch tile.  Only rows 0..31 of the M = 128
-//     operand are real; the k-block tiles are packed 4 KB apart, so rows 32..127 of every tile alias the following
-//     k-blocks (any finite or non-finite garbage there only reaches accumulator rows that are never read).
+//   x(t+1)[n] = ((W2 h1(t) + b2)[n] * os[n] + om[n] - im[n]) / is[n]          n < 1131     (modules.py:728, :713)
+//   [pre_a ; gi0](t+1) = Wx x(t+1) + cond terms,   Wx = [W0[:, :1134] ; W_ih0[:, H:H+1134]]   (modules.py:172-175)
+//
+// is linear in h1(t) apart from the three gaze columns, so with  Mfold = (Wx[:, :1131] diag(os/is)) W2   [4H x H]
+//   [pre_a ; gi0](t+1) = Mfold h1(t) + cfold + Wx[:, 1131:1134] gaze(t+1) + S01[t+1]
+// and a step needs only THREE all-to-all exchanges (a, h0, h1) instead of four.  The gaze direction needs the root
+// state, i.e. y(t)[0:6] = W2[0:6] h1(t): six extra rows in every CTA's fold chain, and every CTA integrates the root
+// trajectory of the 32 samples redundantly (modules.py:739-740, :696).  y(t) itself, the pose outputs and the x_pose
+// history for the backward pass are produced AFTER the recurrence by one batched tcgen05 GEMM over the bf16 h1 history
+// (zeggs tc_gemm) + one elementwise pass.
+//
+// MMA shape: D[64 x N] (f32, TMEM) = X[64 x K] (bf16, smem) * Wslice[N x K]^T (bf16, smem), M = 64: rows 0..31 of the
+// A operand are the 32 samples (TMEM lanes 0..15 and 32..47), rows 32..63 alias the following k-block (their
+// accumulator rows are never read).  M = 64 halves the shared-memory read of the A operand per MMA, which is what
+// bounds these skinny products (measured: 24 cycles per M=64,N=32,K=16 MMA against 40 at M=128).
+//
 //   * Activations live in global memory as bf16 *shared-memory images* (128-byte rows, 16-byte chunks XOR-swizzled
-//     by row&7, i.e. the SWIZZLE_128B K-major canonical layout), written by the producing epilogue, so one
-//     cp.async.bulk per vector brings them in -- no tensor maps, no conversion passes.
+//     by row&7 = SWIZZLE_128B K-major canonical layout), written by the producing epilogue: one cp.async.bulk per
+//     16 KB chunk brings them in -- no tensor maps, no conversion passes.  Each stage loads ONE vector and runs the
+//     critical chain plus the next consumer of the same vector from the same shared-memory copy
+//     (h1(t-1): fold chain + gh1;  a(t): gi0a;  h0(t): gi1 + gh0 of step t+1).
 //   * Weight slices are pre-packed once per optimizer step into the same image format per (CTA, chain, k-block) and
-//     streamed through a 16-slot smem ring by a dedicated producer warp that runs ahead across grid barriers.
-//   * Warp roles (128 threads): warp 0 = epilogue (TMEM lanes 0..31 = the 32 samples: gates / ELU / pose integration
-//     in fp32, writes next activations as bf16 images + fp32 state/history), warp 1 = MMA issuer (one lane),
-//     warp 2 = weight producer, warp 3 = activation loader (waits on the grid barrier, then bulk-copies X).
+//     streamed through a shared-memory ring by a dedicated producer warp that runs ahead across grid barriers.
+//   * Warp roles (160 threads): warps 0,1 = epilogue (TMEM lanes 0..15 of quadrants 0/1 = samples 0..15 / 16..31:
+//     gates / ELU / root integration in fp32, writes next activations as bf16 images + fp32 state/history),
+//     warp 2 = MMA issuer (one elected lane), warp 3 = weight producer, warp 4 = activation loader (waits on the grid
+//     barrier, then bulk-copies X).
 //   GRU state, gates, pose integration and all saved-for-backward tensors stay fp32; only the MMA operands are bf16.
 #include "decoder_common.cuh"
 #include "tc_common.cuh"
@@ -22,44 +37,94 @@
 
 namespace zeggs {
 
-constexpr int TC_RING = 8;              // weight ring slots (two k-block tiles each)
-constexpr int TC_XCH = 5;               // chunks (of 4 k-blocks) of an XA load
-constexpr int TC_XKB = 18;              // k-blocks of the widest activation vector (x_pose: 1136 -> 1152)
-constexpr int TC_SLOT_BYTES = 8192;     // 2 k-blocks x (32 rows x 128 B) (N <= 32)
+constexpr int TC_RING = 6;              // weight ring slots (two k-block tiles each)
+constexpr int TC_XCH = 4;               // 4-k-block chunks of an activation load (kbH <= 16)
+constexpr int TC_NEPI = 2;              // epilogue warps (grid-barrier arrivals per CTA and stage)
 
 struct TcGeom {
-  int NP;          // padded rows of a gate chain: round_up(3U,16)
-  int N1;          // rows of the stage-1 chain: 4U
-  int kbH, kbX;    // k-blocks of an H-vector / of x_pose
-  int n4t;         // 16-row tiles of layer2 per CTA
-  int nacc;        // independent TMEM accumulators per chain (breaks the MMA->MMA accumulate dependency)
-  size_t chain_off[6];   // byte offset of chain c inside one CTA's packed block (chain 5 = first layer2 tile)
+  int NP;          // rows of a gate chain: round_up(3U,8)
+  int N1;          // rows of the fold chain: 4U + 8 (6 used: W2[0:6])
+  int kbH;         // k-blocks of an H-vector
+  int slot_bytes;  // ring slot: two k-block tiles of the widest chain
+  size_t chain_off[6];   // byte offset of chain c inside one CTA's packed block
   size_t cta_bytes;
+  // tail of the packed buffer (after G * cta_bytes)
+  size_t off_mfold, off_wxdt, off_cfold, off_bfold, off_w2b, total_bytes;
 };
 
 __host__ __device__ inline size_t tc_tile_bytes(int N) { return (size_t)N * 128; }
 
 inline TcGeom make_tcgeom(const DecGeom& g) {
   TcGeom t;
-  t.NP = round_up(3 * g.U, 16);
-  t.N1 = 4 * g.U;
+  t.NP = round_up(3 * g.U, 8);      // M = 64 allows N % 8 == 0: no padding rows at U = 8
+  t.N1 = 4 * g.U + 8;
   t.kbH = ceil_div(g.H, 64);
-  t.kbX = ceil_div(K1P, 64);
-  t.n4t = g.n4t;
-  t.nacc = 4;
+  t.slot_bytes = 2 * (int)tc_tile_bytes(t.N1);
   size_t off = 0;
-  t.chain_off[0] = off; off += (size_t)t.kbX * tc_tile_bytes(t.N1);     // S1   X = x_pose
-  t.chain_off[1] = off; off += (size_t)t.kbH * tc_tile_bytes(t.NP);     // gh0  X = h0(t-1)
-  t.chain_off[2] = off; off += (size_t)t.kbH * tc_tile_bytes(t.NP);     // gi0a X = a(t)
-  t.chain_off[3] = off; off += (size_t)t.kbH * tc_tile_bytes(t.NP);     // gh1  X = h1(t-1)
-  t.chain_off[4] = off; off += (size_t)t.kbH * tc_tile_bytes(t.NP);     // gi1  X = h0(t)
-  t.chain_off[5] = off; off += (size_t)t.n4t * t.kbH * tc_tile_bytes(16);  // y tiles X = h1(t)
+  t.chain_off[0] = off; off += (size_t)t.kbH * tc_tile_bytes(t.N1);     // fold  X = h1(t-1)
+  t.chain_off[1] = off; off += (size_t)t.kbH * tc_tile_bytes(t.NP);     // gh0   X = h0(t-1)
+  t.chain_off[2] = off; off += (size_t)t.kbH * tc_tile_bytes(t.NP);     // gi0a  X = a(t)
+  t.chain_off[3] = off; off += (size_t)t.kbH * tc_tile_bytes(t.NP);     // gh1   X = h1(t-1)
+  t.chain_off[4] = off; off += (size_t)t.kbH * tc_tile_bytes(t.NP);     // gi1   X = h0(t)
+  t.chain_off[5] = off;
   t.cta_bytes = off;
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  size_t o = al((size_t)g.G * t.cta_bytes);
+  t.off_mfold = o; o = al(o + (size_t)4 * g.H * g.H * 4);
+  t.off_wxdt = o;  o = al(o + (size_t)P_OUT * 4 * g.H * 4);
+  t.off_cfold = o; o = al(o + (size_t)4 * g.H * 4);
+  t.off_bfold = o; o = al(o + (size_t)4 * g.H * 4);
+  t.off_w2b = o;   o = al(o + (size_t)round_up(P_OUT, 128) * g.H * 2);
+  t.total_bytes = o;
   return t;
 }
 
+// ------------------------------------------------------------------ fold preparation (once per weight version)
+// WxDt[n][row] = Wx[row][n] * os[n] / is[n],  n < 1131, row < 4H   (transposed so the fold product is one TN GEMM)
+__global__ void fold_wxdt_kernel(int H, int A, const float* __restrict__ W0, const float* __restrict__ Wih0,
+                                 const float* __restrict__ os, const float* __restrict__ is, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int row = r0 + i, n = n0 + threadIdx.x;
+    float v = 0.f;
+    if (row < 4 * H && n < P_OUT) v = row < H ? W0[(size_t)row * A + n] : Wih0[(size_t)(row - H) * (A + H) + H + n];
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int n = n0 + i, row = r0 + threadIdx.x;
+    if (n < P_OUT && row < 4 * H) out[(size_t)n * 4 * H + row] = tile[threadIdx.x][i] * os[n] / is[n];
+  }
+}
+// cfold[row] = sum_n Wx[row][n] (b2[n] os[n] + om[n] - im[n]) / is[n];  bfold = [b0 ; b_ih0] + cfold.  One warp per row.
+__global__ void fold_const_kernel(int H, int A, const float* __restrict__ W0, const float* __restrict__ Wih0,
+                                  const float* __restrict__ b0, const float* __restrict__ bih0, const float* __restrict__ b2,
+                                  const float* __restrict__ os, const float* __restrict__ om, const float* __restrict__ im,
+                                  const float* __restrict__ is, float* __restrict__ cfold, float* __restrict__ bfold) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= 4 * H) return;
+  const float* wr = row < H ? W0 + (size_t)row * A : Wih0 + (size_t)(row - H) * (A + H) + H;
+  float acc = 0.f;
+  for (int n = lane; n < P_OUT; n += 32) acc = fmaf(wr[n], (b2[n] * os[n] + om[n] - im[n]) / is[n], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) { cfold[row] = acc; bfold[row] = acc + (row < H ? b0[row] : bih0[row - H]); }
+}
+// S01[1][b][row] += Wx[row] . x(1)[:, b] - cfold[row]   (the first step consumes the given pose, not h1(0))
+__global__ void fold_first_step_kernel(int H, int A, const float* __restrict__ W0, const float* __restrict__ Wih0,
+                                       const float* __restrict__ xp1 /* [K1P][32] */, const float* __restrict__ cfold,
+                                       float* __restrict__ S01_t1 /* [32][4H] */) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), b = threadIdx.x & 31;
+  if (row >= 4 * H) return;
+  const float* wr = row < H ? W0 + (size_t)row * A : Wih0 + (size_t)(row - H) * (A + H) + H;
+  float acc = 0.f;
+  for (int n = 0; n < P_IN; ++n) acc = fmaf(__ldg(wr + n), xp1[(size_t)n * 32 + b], acc);
+  S01_t1[(size_t)b * 4 * H + row] += acc - cfold[row];
+}
+
 // ------------------------------------------------------------------ packing (bf16 images of the weight slices)
-__global__ void pack_decoder_tc_kernel(DecGeom g, TcGeom tg, const float* __restrict__ W0, const float* __restrict__ Wih0,
+__global__ void pack_decoder_tc_kernel(DecGeom g, TcGeom tg, const float* __restrict__ Mfold, const float* __restrict__ Wih0,
                                        const float* __restrict__ Whh0, const float* __restrict__ Wih1,
                                        const float* __restrict__ Whh1, const float* __restrict__ W2, uint8_t* __restrict__ out) {
   const int H = g.H, U = g.U, A = g.A;
@@ -67,29 +132,24 @@ __global__ void pack_decoder_tc_kernel(DecGeom g, TcGeom tg, const float* __rest
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_elems; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i / (tg.cta_bytes / 2));
     size_t b = (i % (tg.cta_bytes / 2)) * 2;           // byte offset inside the CTA block
-    int chain = 5;
-    for (int q = 0; q < 5; ++q) if (b < tg.chain_off[q + 1]) { chain = q; break; }
+    int chain = 4;
+    for (int q = 0; q < 4; ++q) if (b < tg.chain_off[q + 1]) { chain = q; break; }
     b -= tg.chain_off[chain];
-    int N = chain == 0 ? tg.N1 : (chain == 5 ? 16 : tg.NP);
-    int tile = 0;
-    if (chain == 5) { tile = (int)(b / ((size_t)tg.kbH * tc_tile_bytes(16))); b -= (size_t)tile * tg.kbH * tc_tile_bytes(16); }
+    const int N = chain == 0 ? tg.N1 : tg.NP;
     const int kb = (int)(b / tc_tile_bytes(N));
     const int rb = (int)(b % tc_tile_bytes(N));
     const int row = rb / 128, chunk_phys = (rb % 128) / 16, e = (rb % 16) / 2;
     const int k = kb * 64 + ((chunk_phys ^ (row & 7)) << 3) + e;
     float v = 0.f;
-    if (chain == 0) {
-      const int gi = row / U, j = c * U + row % U;
-      if (k < P_IN) v = gi == 0 ? W0[(size_t)j * A + k] : Wih0[(size_t)((gi - 1) * H + j) * (A + H) + H + k];
-    } else if (chain <= 4) {
-      if (row < 3 * U && k < H) {
+    if (k < H) {
+      if (chain == 0) {
+        if (row < 4 * U) { const int gi = row / U, j = c * U + row % U; v = Mfold[(size_t)(gi * H + j) * H + k]; }
+        else if (row < 4 * U + 6) v = W2[(size_t)(row - 4 * U) * H + k];
+      } else if (row < 3 * U) {
         const int gi = row / U, j = c * U + row % U;
         const size_t r = (size_t)(gi * H + j);
         v = chain == 1 ? Whh0[r * H + k] : chain == 2 ? Wih0[r * (A + H) + k] : chain == 3 ? Whh1[r * H + k] : Wih1[r * H + k];
       }
-    } else {
-      const int lr = tile * 16 + row, n = c * g.rpc + lr;
-      if (lr < g.rpc && n < P_OUT && k < H) v = W2[(size_t)n * H + k];
     }
     reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
   }
@@ -106,477 +166,606 @@ __global__ void image_from_kmajor_kernel(const float* __restrict__ src, int K, i
 }
 
 struct TcWs {
-  uint8_t *xpb[2], *ab, *h0b[2], *h1b[2];   // bf16 activation images
+  uint8_t *ab, *h0b[2], *h1b[2];            // bf16 activation images
   long long* dbg;                            // optional per-step phase timestamps of CTA 0 (clock64), [T][32]
   size_t bytes;
 };
 inline TcWs make_tcws(void* base, const DecGeom& g) {
   TcWs w; size_t off = 0;
   auto take = [&](size_t n) { uint8_t* p = base ? (uint8_t*)base + off : nullptr; off += ((n + 1023) / 1024) * 1024; return p; };
-  const size_t xb = (size_t)ceil_div(K1P, 64) * 4096, hb = (size_t)ceil_div(g.H, 64) * 4096;
-  w.xpb[0] = take(xb); w.xpb[1] = take(xb); w.ab = take(hb);
+  const size_t hb = (size_t)ceil_div(g.H, 64) * 4096;
+  w.ab = take(hb);
   w.h0b[0] = take(hb); w.h0b[1] = take(hb); w.h1b[0] = take(hb); w.h1b[1] = take(hb);
   w.dbg = nullptr;
   w.bytes = off; return w;
 }
 
-#define TCDBG(ev) do { if (tw.dbg && c == 0 && lane == 0 && t < 64) tw.dbg[t * 32 + (ev)] = clock64(); } while (0)
+#define TCDBG(ev) do { if (tw.dbg && c == 0 && warp_lane0 && t < 64) tw.dbg[t * 32 + (ev)] = clock64(); } while (0)
 
 template <int U>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(160, 1)
 decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, TcWs tw, const uint8_t* __restrict__ packed) {
-  constexpr int NP = (3 * U + 15) / 16 * 16;     // gate-chain rows (32 for U=8, 16 for U=4)
-  constexpr int N1 = 4 * U;                      // stage-1 rows
+  constexpr int NP = (3 * U + 7) / 8 * 8;        // gate-chain rows (24 for U=8, 16 for U=4)
+  constexpr int N1 = 4 * U + 8;                  // fold-chain rows
+  constexpr int SLOT = 2 * N1 * 128;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // layout: XA | XB | ring | 12 KB slack (operand rows 32..127 of the last k-blocks alias whatever follows) | barriers | constants
-  uint8_t* XA = smem;
-  uint8_t* XB = XA + TC_XKB * 4096;
-  uint8_t* ring = XB + tg.kbH * 4096;
-  uint8_t* tail = ring + TC_RING * TC_SLOT_BYTES + 12288;
+  // layout: X0 | X1 | ring | 4 KB slack | barriers | constants   (operand rows 32..63 of the last k-block alias what follows)
+  const int kbH = tg.kbH;
+  uint8_t* X0 = smem;
+  uint8_t* X1 = X0 + kbH * 4096;
+  uint8_t* ring = X1 + kbH * 4096;
+  uint8_t* tail = ring + TC_RING * SLOT + 4096;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* full = bars;                 // [TC_RING]
-  uint64_t* empty = bars + TC_RING;      // [TC_RING]
-  uint64_t* xa_full = bars + 2 * TC_RING;   // [TC_XCH] one per 4-k-block chunk of XA: the MMA chain starts on chunk 0
-  uint64_t* xb_full = xa_full + TC_XCH;
-  uint64_t* xa_free = xb_full + 1;
-  uint64_t* xb_free = xb_full + 2;
-  uint64_t* d_full = xb_full + 3;        // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 4);
-  float* cst = reinterpret_cast<float*>(tail + 512);   // per-CTA constants (biases, normalisation rows)
-  const int R4 = tg.n4t * 16;
+  uint64_t* full = bars;                        // [TC_RING]
+  uint64_t* empty = bars + TC_RING;             // [TC_RING]
+  uint64_t* x_full = empty + TC_RING;           // [2][TC_XCH]
+  uint64_t* x_free = x_full + 2 * TC_XCH;       // [2]
+  uint64_t* d_full = x_free + 2;                // [3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 3);
+  float* cst = reinterpret_cast<float*>(tail + 512);   // per-CTA constants
   float* c_bhh0 = cst;            // [3U]
   float* c_bih1 = cst + 3 * U;    // [3U]
   float* c_bhh1 = cst + 6 * U;    // [3U]
-  float* c_b2 = cst + 9 * U;      // [R4]  then out_std, out_mean, in_mean, in_std (R4 each), then gaze in_mean/in_std (3+3)
-  float* c_os = c_b2 + R4; float* c_om = c_os + R4; float* c_im = c_om + R4; float* c_is = c_im + R4; float* c_gz = c_is + R4;
+  float* c_wgz = cst + 12 * U;    // [4U][4]  gaze columns of Wx for this CTA's fold rows (16-byte rows)
+  float* c_y6 = c_wgz + 16 * U;   // b2[0:6], out_std[0:6], out_mean[0:6]
+  float* c_gz = c_y6 + 18;        // in_mean[1131:1134], 1 / in_std[1131:1134]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool warp_lane0 = lane == 0;
   const int c = blockIdx.x, H = a.H, T = a.T;
-  const int kbH = tg.kbH, kbX = tg.kbX, n4t = tg.n4t;
   const uint8_t* pk = packed + (size_t)c * tg.cta_bytes;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_RING; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < TC_XCH; ++i) mbar_init(&xa_full[i], 1);
-    mbar_init(xb_full, 1); mbar_init(xa_free, 1); mbar_init(xb_free, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&d_full[i], 1);
+    for (int i = 0; i < 2 * TC_XCH; ++i) mbar_init(&x_full[i], 1);
+    mbar_init(&x_free[0], 1); mbar_init(&x_free[1], 1);
+    for (int i = 0; i < 3; ++i) mbar_init(&d_full[i], 1);
     fence_mbar_init();
   }
   for (int i = threadIdx.x; i < 3 * U; i += blockDim.x) {
     const int j = (i / U) * H + c * U + (i % U);
     c_bhh0[i] = a.b_hh0[j]; c_bih1[i] = a.b_ih1[j]; c_bhh1[i] = a.b_hh1[j];
   }
-  for (int i = threadIdx.x; i < R4; i += blockDim.x) {
-    const int n = c * g.rpc + i;
-    const bool ok = i < g.rpc && n < P_OUT;
-    c_b2[i] = ok ? a.b2[n] : 0.f; c_os[i] = ok ? a.out_std[n] : 0.f; c_om[i] = ok ? a.out_mean[n] : 0.f;
-    c_im[i] = ok ? a.in_mean[n] : 0.f; c_is[i] = ok ? a.in_std[n] : 1.f;
+  for (int i = threadIdx.x; i < 16 * U; i += blockDim.x) {
+    const int row = i / 4, d = i % 4, gi = row / U, j = c * U + row % U;
+    c_wgz[i] = d == 3 ? 0.f : gi == 0 ? a.W0[(size_t)j * g.A + P_OUT + d] : a.W_ih0[(size_t)((gi - 1) * H + j) * (g.A + H) + H + P_OUT + d];
   }
-  if (threadIdx.x < 3) { c_gz[threadIdx.x] = a.in_mean[P_OUT + threadIdx.x]; c_gz[3 + threadIdx.x] = a.in_std[P_OUT + threadIdx.x]; }
-  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (threadIdx.x < 6) {
+    c_y6[threadIdx.x] = a.b2[threadIdx.x]; c_y6[6 + threadIdx.x] = a.out_std[threadIdx.x]; c_y6[12 + threadIdx.x] = a.out_mean[threadIdx.x];
+  }
+  if (threadIdx.x < 3) { c_gz[threadIdx.x] = a.in_mean[P_OUT + threadIdx.x]; c_gz[3 + threadIdx.x] = 1.0f / a.in_std[P_OUT + threadIdx.x]; }
+  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   // The CTA allocates all 512 TMEM columns (1 CTA/SM), so the allocation base is column 0 / lane 0.  Using the literal
   // keeps every tcgen05 address operand provably warp-uniform: otherwise the compiler wraps each UTCHMMA in an
-  // ELECT / R2UR.BROADCAST waterfall loop (~90 cycles per MMA, the issue-bound regime seen in the first trace).
+  // ELECT / R2UR.BROADCAST waterfall loop (~90 cycles per MMA).
   if (*tmem_slot != 0u) __trap();
   constexpr uint32_t tmem = 0u;
-  // TMEM regions (columns): gh0 [0,128) | gh1 [128,256) | S1 / gi0a / gi1 / y [256,512); accumulator q of a chain at +q*N
+  // Cluster of `csize` consecutive CTAs: every activation vector is read from L2 once per cluster -- CTA rank r fetches
+  // 1/csize of each 16 KB chunk and multicasts it into all members' X buffers (same smem offsets, each member's own
+  // mbarrier gets the bytes).  Re-use of an X buffer needs no cluster handshake: a load is only issued after a grid
+  // barrier whose epilogues waited on commits covering every MMA that read the previous contents, in every CTA.
+  const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
+  if (csize > 1) cluster_sync_all();          // peers' mbarriers are initialised before any multicast can land
+  // TMEM regions (columns): gh0 [0,128) | gh1 [128,256) | fold / gi0a / gi1 [256, 256 + 4*N1); accumulator q at +q*N
   constexpr uint32_t R_GH0 = 0, R_GH1 = 128, R_MAIN = 256;
-  const size_t actH = (size_t)g.nbt * H * 32, actX = (size_t)g.nbt * K1P * 32;
+  static_assert(4 * N1 <= 256 && 4 * NP <= 128, "TMEM budget");
+  const size_t actH = (size_t)g.nbt * H * 32;
+  const unsigned bar_n = gridDim.x * TC_NEPI;
 
-  if (warp == 2) {
+  if (warp == 3) {
     // ================= weight producer: streams every chain's tiles in the MMA warp's consumption order
     if (lane == 0) {
       uint32_t it = 0;
-      auto stream = [&](int chain, int tile) {
-        const int N = chain == 0 ? N1 : (chain == 5 ? 16 : NP);
-        const int nkb = chain == 0 ? kbX : kbH;
-        const uint8_t* src = pk + tg.chain_off[chain] + (size_t)tile * kbH * tc_tile_bytes(16);
-        for (int kb = 0; kb < nkb; kb += 2, ++it) {
-          const int s = it & (TC_RING - 1); const uint32_t ph = (it / TC_RING) & 1;
-          const uint32_t bytes = (uint32_t)((nkb - kb >= 2 ? 2 : 1) * tc_tile_bytes(N));
+      auto stream = [&](int chain) {
+        const int N = chain == 0 ? N1 : NP;
+        const uint8_t* src = pk + tg.chain_off[chain];
+        for (int kb = 0; kb < kbH; kb += 2, ++it) {
+          const uint32_t s = it % TC_RING, ph = (it / TC_RING) & 1;
+          const uint32_t bytes = (uint32_t)((kbH - kb >= 2 ? 2 : 1) * tc_tile_bytes(N));
           mbar_wait(&empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&full[s], bytes);
-          bulk_g2s(ring + s * TC_SLOT_BYTES, src + (size_t)kb * tc_tile_bytes(N), bytes, &full[s]);
+          bulk_g2s(ring + (size_t)s * SLOT, src + (size_t)kb * tc_tile_bytes(N), bytes, &full[s]);
         }
       };
-      for (int t = 1; t < T; ++t) {   // order: gh0(1), S1(0), gh1(3), gi0a(2), gi1(4), y tiles(5)
-        stream(1, 0); stream(0, 0); stream(3, 0); stream(2, 0); stream(4, 0);
-        for (int tile = 0; tile < n4t; ++tile) stream(5, tile);
+      stream(1);                                       // gh0 of step 1
+      for (int t = 1; t < T; ++t) {                    // per step: fold(0), gh1(3), gi0a(2), gi1(4), gh0 of t+1 (1)
+        stream(0); stream(3); stream(2); stream(4);
+        if (t + 1 < T) stream(1);
       }
+      stream(0);                                       // y(T-1)[0:6] for the last root integration
     }
-  } else if (warp == 3) {
-    // ================= activation loader
+  } else if (warp == 4) {
+    // ================= activation loader.  Load n goes to buffer n&1; it is the (n>>1)-th use of that buffer.
     if (lane == 0) {
-      uint32_t xa_n = 0, xb_n = 0;        // loads issued so far into XA / XB
-      auto load_xa = [&](const uint8_t* img, int nkb) {
-        if (xa_n > 0) mbar_wait(xa_free, (xa_n - 1) & 1);
+      uint32_t n = 0;
+      auto load = [&](const uint8_t* img) {
+        uint8_t* X = (n & 1) ? X1 : X0;
+        uint64_t* xf = x_full + (n & 1) * TC_XCH;
+        if (n >= 2) mbar_wait(&x_free[n & 1], ((n >> 1) - 1) & 1);
         fence_proxy_async();
-        for (int ch = 0; ch * 4 < nkb; ++ch) {
-          const uint32_t bytes = (uint32_t)((nkb - ch * 4 >= 4 ? 4 : nkb - ch * 4) * 4096);
-          mbar_arrive_expect_tx(&xa_full[ch], bytes);
-          bulk_g2s(XA + ch * 16384, img + (size_t)ch * 16384, bytes, &xa_full[ch]);
+        for (int ch = 0; ch < TC_XCH; ++ch) {
+          const int k0 = ch * 4;
+          if (k0 < kbH) {
+            const uint32_t bytes = (uint32_t)((kbH - k0 >= 4 ? 4 : kbH - k0) * 4096);
+            mbar_arrive_expect_tx(&xf[ch], bytes);
+            if (csize == 1) {
+              bulk_g2s(X + (size_t)k0 * 4096, img + (size_t)k0 * 4096, bytes, &xf[ch]);
+            } else {
+              const uint32_t part = bytes / csize, o = (uint32_t)k0 * 4096 + crank * part;
+              bulk_g2s_multicast(X + o, img + o, part, &xf[ch], (uint16_t)((1u << csize) - 1u));
+            }
+          } else {
+            mbar_arrive(&xf[ch]);                      // keep every chunk barrier in phase
+          }
         }
-        for (int ch = (nkb + 3) / 4; ch < TC_XCH; ++ch) mbar_arrive(&xa_full[ch]);   // keep every chunk barrier in phase
-        ++xa_n;
+        ++n;
       };
-      auto load_xb = [&](const uint8_t* img) {
-        if (xb_n > 0) mbar_wait(xb_free, (xb_n - 1) & 1);
-        fence_proxy_async();
-        mbar_arrive_expect_tx(xb_full, (uint32_t)kbH * 4096);
-        bulk_g2s(XB, img, (uint32_t)kbH * 4096, xb_full);
-        ++xb_n;
-      };
-      unsigned epoch = 0;
+      load(tw.h0b[0]);                                              // h0(0) for gh0 of step 1
       for (int t = 1; t < T; ++t) {
-        load_xb(tw.h0b[(t - 1) & 1]);                               // h0(t-1): complete since barrier B2 of step t-1
-        if (t > 1) grid_wait(w.bar, (++epoch) * gridDim.x);          // B4(t-1): x_pose(t) complete
-        TCDBG(0);
-        load_xa(tw.xpb[t & 1], kbX);
-        load_xb(tw.h1b[(t - 1) & 1]);                               // h1(t-1)
-        grid_wait(w.bar, (++epoch) * gridDim.x);                    // B1
-        TCDBG(8);
-        load_xa(tw.ab, kbH);
-        grid_wait(w.bar, (++epoch) * gridDim.x);                    // B2
-        TCDBG(14);
-        load_xa(tw.h0b[t & 1], kbH);
-        grid_wait(w.bar, (++epoch) * gridDim.x);                    // B3
-        TCDBG(20);
-        load_xa(tw.h1b[t & 1], kbH);
+        if (t > 1) grid_wait(w.bar, (unsigned)(3 * (t - 1)) * bar_n);           // C(t-1): h1(t-1) complete
+        if (tw.dbg && c == 0 && t < 64) tw.dbg[t * 32 + 0] = clock64();
+        load(tw.h1b[(t - 1) & 1]);
+        grid_wait(w.bar, (unsigned)(3 * (t - 1) + 1) * bar_n);                  // A(t): a(t) complete
+        if (tw.dbg && c == 0 && t < 64) tw.dbg[t * 32 + 8] = clock64();
+        load(tw.ab);
+        grid_wait(w.bar, (unsigned)(3 * (t - 1) + 2) * bar_n);                  // B(t): h0(t) complete
+        if (tw.dbg && c == 0 && t < 64) tw.dbg[t * 32 + 14] = clock64();
+        load(tw.h0b[t & 1]);
       }
+      grid_wait(w.bar, (unsigned)(3 * (T - 1)) * bar_n);
+      load(tw.h1b[(T - 1) & 1]);
     }
-  } else if (warp == 1) {
+  } else if (warp == 2) {
     // ================= MMA issuer.  The warp runs the loops converged; one elected lane issues.  Descriptors advance by
     // constants and the four k-steps of a k-block go to four independent TMEM accumulators.
-    {
-      uint32_t it = 0, xa_n = 0, xb_n = 0;
-      const uint64_t dXA = make_smem_desc_sw128(XA), dXB = make_smem_desc_sw128(XB), dRing = make_smem_desc_sw128(ring);
-      auto chain_mma = [&](uint64_t dx, int nkb, int N, uint32_t d0, int xph) {   // xph >= 0: X arrives in chunks (XA)
-        const uint32_t idesc = make_idesc_bf16_f32(128, N);
-        const uint64_t bstep = (uint64_t)(N * 8);            // one k-block tile of the weight slice, in 16-byte units
-        for (int kb = 0; kb < nkb; kb += 2, ++it) {
-          const uint32_t s = it & (TC_RING - 1), ph = (it / TC_RING) & 1;
-          if (xph >= 0 && (kb & 3) == 0) mbar_wait(&xa_full[kb >> 2], (uint32_t)xph);
-          mbar_wait(&full[s], ph);
-          tc_fence_after_sync();
-          const uint64_t da = dx + (uint64_t)kb * 256, db = dRing + (uint64_t)s * (TC_SLOT_BYTES >> 4);
-          const bool acc0 = kb > 0, two = kb + 1 < nkb;
-          if (elect_one_sync()) {
-            umma_bf16(d0 + 0 * N, da + 0, db + 0, idesc, acc0);
-            umma_bf16(d0 + 1 * N, da + 2, db + 2, idesc, acc0);
-            umma_bf16(d0 + 2 * N, da + 4, db + 4, idesc, acc0);
-            umma_bf16(d0 + 3 * N, da + 6, db + 6, idesc, acc0);
-            if (two) {
-              umma_bf16(d0 + 0 * N, da + 256 + 0, db + bstep + 0, idesc, true);
-              umma_bf16(d0 + 1 * N, da + 256 + 2, db + bstep + 2, idesc, true);
-              umma_bf16(d0 + 2 * N, da + 256 + 4, db + bstep + 4, idesc, true);
-              umma_bf16(d0 + 3 * N, da + 256 + 6, db + bstep + 6, idesc, true);
-            }
-            umma_commit(&empty[s]);
-          }
-          __syncwarp();
+    uint32_t it = 0, n = 0;
+    const uint64_t dX0 = make_smem_desc_sw128(X0), dX1 = make_smem_desc_sw128(X1), dRing = make_smem_desc_sw128(ring);
+    int dbg_t = -1;                                  // >= 0: trace this chain's operand arrivals (events 20..31)
+    auto chain_mma = [&](int N, uint32_t d0) {       // consumes load n (buffer n&1)
+      const uint32_t idesc = make_idesc_bf16_f32(64, N);
+      const uint64_t dx = (n & 1) ? dX1 : dX0;
+      uint64_t* xf = x_full + (n & 1) * TC_XCH;
+      const uint32_t xph = (n >> 1) & 1;
+      const uint64_t bstep = (uint64_t)(N * 8);            // one k-block tile of the weight slice, in 16-byte units
+      for (int kb = 0; kb < kbH; kb += 2, ++it) {
+        const uint32_t s = it % TC_RING, ph = (it / TC_RING) & 1;
+        if ((kb & 3) == 0) {
+          mbar_wait(&xf[kb >> 2], xph);
+          if (tw.dbg && c == 0 && warp_lane0 && dbg_t >= 0 && dbg_t < 64) tw.dbg[dbg_t * 32 + 20 + (kb >> 2)] = clock64();
         }
-      };
-      auto commit2 = [&](uint64_t* b0, uint64_t* b1) {
-        if (elect_one_sync()) { umma_commit(b0); if (b1) umma_commit(b1); }
+        mbar_wait(&full[s], ph);
+        if (tw.dbg && c == 0 && warp_lane0 && dbg_t >= 0 && dbg_t < 64) tw.dbg[dbg_t * 32 + 24 + (kb >> 1)] = clock64();
+        tc_fence_after_sync();
+        const uint64_t da = dx + (uint64_t)kb * 256, db = dRing + (uint64_t)s * (SLOT >> 4);
+        const bool acc0 = kb > 0, two = kb + 1 < kbH;
+        if (elect_one_sync()) {
+          umma_bf16(d0 + 0 * N, da + 0, db + 0, idesc, acc0);
+          umma_bf16(d0 + 1 * N, da + 2, db + 2, idesc, acc0);
+          umma_bf16(d0 + 2 * N, da + 4, db + 4, idesc, acc0);
+          umma_bf16(d0 + 3 * N, da + 6, db + 6, idesc, acc0);
+          if (two) {
+            umma_bf16(d0 + 0 * N, da + 256 + 0, db + bstep + 0, idesc, true);
+            umma_bf16(d0 + 1 * N, da + 256 + 2, db + bstep + 2, idesc, true);
+            umma_bf16(d0 + 2 * N, da + 256 + 4, db + bstep + 4, idesc, true);
+            umma_bf16(d0 + 3 * N, da + 256 + 6, db + bstep + 6, idesc, true);
+          }
+          umma_commit(&empty[s]);
+        }
         __syncwarp();
-      };
-      for (int t = 1; t < T; ++t) {
-        mbar_wait(xb_full, xb_n & 1); ++xb_n; tc_fence_after_sync();
-        chain_mma(dXB, kbH, NP, tmem + R_GH0, -1);                        // gh0
-        commit2(xb_free, nullptr);
-        TCDBG(3);
-        chain_mma(dXA, kbX, N1, tmem + R_MAIN, xa_n & 1); ++xa_n;         // S1
-        commit2(xa_free, &d_full[0]);
-        TCDBG(4);
-        mbar_wait(xb_full, xb_n & 1); ++xb_n; tc_fence_after_sync();
-        chain_mma(dXB, kbH, NP, tmem + R_GH1, -1);                        // gh1
-        commit2(xb_free, nullptr);
-        TCDBG(10);
-        chain_mma(dXA, kbH, NP, tmem + R_MAIN, xa_n & 1); ++xa_n;         // gi0a
-        commit2(xa_free, &d_full[1]);
-        TCDBG(11);
-        TCDBG(15);
-        chain_mma(dXA, kbH, NP, tmem + R_MAIN, xa_n & 1); ++xa_n;         // gi1
-        commit2(xa_free, &d_full[2]);
-        TCDBG(16);
-        TCDBG(21);
-        for (int tile = 0; tile < n4t; ++tile) chain_mma(dXA, kbH, 16, tmem + R_MAIN + (uint32_t)(tile * 64), tile == 0 ? (int)(xa_n & 1) : -1);   // y
-        ++xa_n;
-        commit2(xa_free, &d_full[3]);
-      }
-    }
-  } else {
-    // ================= epilogue warp (TMEM lanes 0..31 = samples)
-    const int b = lane;
-    const bool live = b < a.B;
-    const int j0 = c * U;
-    constexpr int na_main = 4, na_side = 4;
-    auto ld_sum = [&](uint32_t col, int na, float (&v)[NP]) {     // sum of a gate chain's accumulators
-      tmem_ld_cols<NP>(tmem + col, v);
-      for (int q = 1; q < na; ++q) {
-        float u_[NP];
-        tmem_ld_cols<NP>(tmem + col + (uint32_t)(q * NP), u_);
-#pragma unroll
-        for (int i = 0; i < NP; ++i) v[i] += u_[i];
       }
     };
-    float gi0p[3 * U];
+    auto commit2 = [&](uint64_t* b0, uint64_t* b1) {
+      if (elect_one_sync()) { if (b0) umma_commit(b0); if (b1) umma_commit(b1); }
+      __syncwarp();
+    };
+    chain_mma(NP, tmem + R_GH0);                                        // gh0 of step 1 from h0(0)
+    commit2(&x_free[n & 1], nullptr); ++n;
     for (int t = 1; t < T; ++t) {
+      chain_mma(N1, tmem + R_MAIN);                                     // fold: [pre_a ; gi0 ; y6] from h1(t-1)
+      commit2(&d_full[0], nullptr);
+      TCDBG(4);
+      chain_mma(NP, tmem + R_GH1);                                      // gh1 from h1(t-1)
+      commit2(&x_free[n & 1], nullptr); ++n;
+      TCDBG(10);
+      dbg_t = t;
+      chain_mma(NP, tmem + R_MAIN);                                     // gi0a from a(t)
+      dbg_t = -1;
+      commit2(&d_full[1], &x_free[n & 1]); ++n;
+      TCDBG(11);
+      chain_mma(NP, tmem + R_MAIN);                                     // gi1 from h0(t)
+      commit2(&d_full[2], nullptr);
+      TCDBG(16);
+      if (t + 1 < T) chain_mma(NP, tmem + R_GH0);                       // gh0 of step t+1 from h0(t)
+      commit2(&x_free[n & 1], nullptr); ++n;
+    }
+    chain_mma(N1, tmem + R_MAIN);                                       // y(T-1)[0:6]
+    commit2(&d_full[0], nullptr);
+  } else {
+    // ================= epilogue warps 0,1: TMEM lanes 0..15 of quadrant `warp` = samples 16*warp .. 16*warp+15
+    const bool act = lane < 16;
+    const int b = warp * 16 + (lane & 15);
+    const bool live = act && b < a.B;
+    const int j0 = c * U;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    // root state of sample b (every CTA integrates it redundantly; CTA 0 writes it out)
+    V3 pos = v3(0.f, 0.f, 0.f);
+    Q4 q; q.w = 1.f; q.x = q.y = q.z = 0.f;
+    if (live) {
+      pos = v3(a.root_pos0[b * 3 + 0], a.root_pos0[b * 3 + 1], a.root_pos0[b * 3 + 2]);
+      q.w = a.root_rot0[b * 4 + 0]; q.x = a.root_rot0[b * 4 + 1]; q.y = a.root_rot0[b * 4 + 2]; q.z = a.root_rot0[b * 4 + 3];
+    }
+    float gi0p[3 * U];
+    for (int t = 1; t <= T; ++t) {
       const uint32_t ph = (t - 1) & 1;
-      const int ts = w.save ? t : (t & 1), tp = w.save ? t - 1 : ((t - 1) & 1), tn = w.save ? t + 1 : ((t + 1) & 1);
-      // ---------------- stage 1   (operands that do not depend on the MMA are fetched before the wait)
+      const int ts = w.save ? t : (t & 1), tp = w.save ? t - 1 : ((t - 1) & 1);
+      // ---------------- stage A   (operands that do not depend on the MMA are fetched before the wait)
       float sv[4 * U];
-      {
-        const float* S = w.S01 + ((size_t)t * 32 + b) * 4 * H + j0;      // [t][b][4H]: U consecutive floats per gate block
+      V3 gzp = v3(0.f, 0.f, 0.f);
+      if (t < T) {
+        const float* S = w.S01 + ((size_t)t * 32 + (b & 31)) * 4 * H + j0;      // [t][b][4H]: U consecutive floats per gate block
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int qq = 0; qq < 4; ++qq) {
 #pragma unroll
           for (int u4 = 0; u4 < U; u4 += 4) {
-            const float4 v4 = __ldg(reinterpret_cast<const float4*>(S + (size_t)q * H + u4));
-            sv[q * U + u4 + 0] = v4.x; sv[q * U + u4 + 1] = v4.y; sv[q * U + u4 + 2] = v4.z; sv[q * U + u4 + 3] = v4.w;
+            const float4 v4 = __ldg(reinterpret_cast<const float4*>(S + (size_t)qq * H + u4));
+            sv[qq * U + u4 + 0] = v4.x; sv[qq * U + u4 + 1] = v4.y; sv[qq * U + u4 + 2] = v4.z; sv[qq * U + u4 + 3] = v4.w;
           }
         }
+        if (live) { const float* gp = a.gaze_pos + ((size_t)b * T + t) * 3; gzp = v3(gp[0], gp[1], gp[2]); }
       }
       mbar_wait(&d_full[0], ph);
       tc_fence_after_sync();
       TCDBG(5);
       {
-        float v[N1];
-        tmem_ld_cols<N1>(tmem + R_MAIN, v);
-        for (int q = 1; q < na_main; ++q) {
-          float u_[N1];
-          tmem_ld_cols<N1>(tmem + R_MAIN + (uint32_t)(q * N1), u_);
+        // y6 columns and the fold columns (+ hoisted terms) first; the serial root / gaze chain then overlaps nothing else
+        float y8[8];
+        tmem_ld4_sum<8>(tmem + lane_base + R_MAIN + 4 * U, N1, y8);
+        if (t >= 2 && t < T) {
 #pragma unroll
-          for (int i = 0; i < N1; ++i) v[i] += u_[i];
+          for (int qq = 0; qq < 4; ++qq) {
+            float v[U];
+            tmem_ld4_sum<U>(tmem + lane_base + R_MAIN + qq * U, N1, v);
+#pragma unroll
+            for (int u = 0; u < U; ++u) sv[qq * U + u] += v[u];
+          }
+        }
+        float p6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gzn[3] = {0.f, 0.f, 0.f};
+        if (t >= 2) {
+          // y(t-1)[0:6] -> root(t-1)   (modules.py:728, :739-740); SFU sin/cos/rsqrt like the gate math of this engine
+#pragma unroll
+          for (int i = 0; i < 6; ++i) p6[i] = (y8[i] + c_y6[i]) * c_y6[6 + i] + c_y6[12 + i];
+          const V3 npos = quat_mul_vec(q, a.dt * v3(p6[0], p6[1], p6[2])) + pos;
+          const V3 hx = (0.5f * a.dt) * quat_mul_vec(q, v3(p6[3], p6[4], p6[5]));
+          const float a2 = dot(hx, hx);
+          Q4 e;
+          if (a2 < 1e-10f) {
+            const float rn = __fdividef(1.0f, sqrtf(1.0f + a2) + 1e-5f);
+            e.w = rn; e.x = hx.x * rn; e.y = hx.y * rn; e.z = hx.z * rn;
+          } else {
+            const float ri = rsqrtf(a2), ha = a2 * ri, sc = __sinf(ha) * ri;
+            e.w = __cosf(ha); e.x = hx.x * sc; e.y = hx.y * sc; e.z = hx.z * sc;
+          }
+          const Q4 nq = quat_mul(e, q);
+          pos = npos; q = nq;
+        }
+        if (t == T) {
+          if (c == 0 && live) {
+            float* op = a.root_pos + ((size_t)b * T + (t - 1)) * 3;
+            float* oq = a.root_rot + ((size_t)b * T + (t - 1)) * 4;
+            op[0] = pos.x; op[1] = pos.y; op[2] = pos.z;
+            oq[0] = q.w; oq[1] = q.x; oq[2] = q.y; oq[3] = q.z;
+            float* y6 = w.Y6 + ((size_t)(t - 1) * 32 + b) * 8;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) y6[i] = p6[i];
+          }
+          break;
         }
         float av[U];
+        if (t >= 2) {
+          const V3 gd = quat_mul_vec(quat_inv(q), gzp - pos);          // modules.py:696
+          gzn[0] = (gd.x - c_gz[0]) * c_gz[3]; gzn[1] = (gd.y - c_gz[1]) * c_gz[4]; gzn[2] = (gd.z - c_gz[2]) * c_gz[5];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          av[u] = elu_f(v[u] + sv[u]);
-#pragma unroll
-          for (int q = 0; q < 3; ++q) gi0p[q * U + u] = v[(1 + q) * U + u] + sv[(1 + q) * U + u];
+          for (int i = 0; i < 4 * U; ++i) {
+            const float4 wg = *reinterpret_cast<const float4*>(c_wgz + 4 * i);
+            sv[i] += wg.x * gzn[0] + wg.y * gzn[1] + wg.z * gzn[2];
+          }
         }
-        store_img_units<U>(tw.ab, b, j0, av);
+#pragma unroll
+        for (int u = 0; u < U; ++u) av[u] = sv[u] > 0.f ? sv[u] : __expf(sv[u]) - 1.0f;   // ELU (modules.py:183)
+#pragma unroll
+        for (int i = 0; i < 3 * U; ++i) gi0p[i] = sv[U + i];
+        if (act) store_img_units<U>(tw.ab, b, j0, av);
         tc_fence_before_sync();
         TCDBG(6);
         grid_arrive(w.bar);                     // only the bf16 image feeds other CTAs: publish it first ...
         TCDBG(7);
+        if (act) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) w.A[ts * actH + (size_t)(j0 + u) * 32 + b] = av[u];   // ... fp32 history afterwards
+          for (int u = 0; u < U; ++u) w.A[ts * actH + (size_t)(j0 + u) * 32 + b] = av[u];   // ... fp32 history afterwards
+        }
+        if (c == 0 && live && t >= 2) {
+          float* op = a.root_pos + ((size_t)b * T + (t - 1)) * 3;
+          float* oq = a.root_rot + ((size_t)b * T + (t - 1)) * 4;
+          op[0] = pos.x; op[1] = pos.y; op[2] = pos.z;
+          oq[0] = q.w; oq[1] = q.x; oq[2] = q.y; oq[3] = q.z;
+          float* y6 = w.Y6 + ((size_t)(t - 1) * 32 + b) * 8;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) y6[i] = p6[i];
+          float* gz = w.GZ + ((size_t)t * 32 + b) * 4; gz[0] = gzn[0]; gz[1] = gzn[1]; gz[2] = gzn[2];
+        }
       }
-      // ---------------- stage 2 (GRU layer 0)
+      // ---------------- stage B (GRU layer 0)
       float hp[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) hp[u] = w.H0[tp * actH + (size_t)(j0 + u) * 32 + b];
+      for (int u = 0; u < U; ++u) hp[u] = w.H0[tp * actH + (size_t)(j0 + u) * 32 + (b & 31)];
       mbar_wait(&d_full[1], ph);
       tc_fence_after_sync();
       TCDBG(12);
       {
-        float gh[NP], gi[NP];
-        ld_sum(R_GH0, na_side, gh);
-        ld_sum(R_MAIN, na_main, gi);
         float hv[U], rr[U], zz[U], nn[U], gn[U];
+        {
+          float gh[U], gi[U];
+          tmem_ld4_sum<U>(tmem + lane_base + R_GH0, NP, gh); tmem_ld4_sum<U>(tmem + lane_base + R_MAIN, NP, gi);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          rr[u] = fast_sigmoid(gi[u] + gi0p[u] + gh[u] + c_bhh0[u]);
-          zz[u] = fast_sigmoid(gi[U + u] + gi0p[U + u] + gh[U + u] + c_bhh0[U + u]);
-          gn[u] = gh[2 * U + u] + c_bhh0[2 * U + u];
-          nn[u] = fast_tanh(gi[2 * U + u] + gi0p[2 * U + u] + rr[u] * gn[u]);
-          hv[u] = (1.f - zz[u]) * nn[u] + zz[u] * hp[u];
+          for (int u = 0; u < U; ++u) rr[u] = fast_sigmoid(gi[u] + gi0p[u] + gh[u] + c_bhh0[u]);
+          tmem_ld4_sum<U>(tmem + lane_base + R_GH0 + U, NP, gh); tmem_ld4_sum<U>(tmem + lane_base + R_MAIN + U, NP, gi);
+#pragma unroll
+          for (int u = 0; u < U; ++u) zz[u] = fast_sigmoid(gi[u] + gi0p[U + u] + gh[u] + c_bhh0[U + u]);
+          tmem_ld4_sum<U>(tmem + lane_base + R_GH0 + 2 * U, NP, gh); tmem_ld4_sum<U>(tmem + lane_base + R_MAIN + 2 * U, NP, gi);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            gn[u] = gh[u] + c_bhh0[2 * U + u];
+            nn[u] = fast_tanh(gi[u] + gi0p[2 * U + u] + rr[u] * gn[u]);
+            hv[u] = (1.f - zz[u]) * nn[u] + zz[u] * hp[u];
+          }
         }
-        store_img_units<U>(tw.h0b[t & 1], b, j0, hv);
+        if (act) store_img_units<U>(tw.h0b[t & 1], b, j0, hv);
         tc_fence_before_sync();
         TCDBG(13);
         grid_arrive(w.bar);
+        if (act) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) w.H0[ts * actH + (size_t)(j0 + u) * 32 + b] = hv[u];
-        if (w.save) {
-          float* G = w.G0 + ((size_t)t * g.nbt) * 4 * H * 32;
+          for (int u = 0; u < U; ++u) w.H0[ts * actH + (size_t)(j0 + u) * 32 + b] = hv[u];
+          if (w.save) {
+            float* G = w.G0 + ((size_t)t * g.nbt) * 4 * H * 32;
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int j = j0 + u;
-            G[(size_t)(0 * H + j) * 32 + b] = rr[u]; G[(size_t)(1 * H + j) * 32 + b] = zz[u];
-            G[(size_t)(2 * H + j) * 32 + b] = nn[u]; G[(size_t)(3 * H + j) * 32 + b] = gn[u];
+            for (int u = 0; u < U; ++u) {
+              const int j = j0 + u;
+              G[(size_t)(0 * H + j) * 32 + b] = rr[u]; G[(size_t)(1 * H + j) * 32 + b] = zz[u];
+              G[(size_t)(2 * H + j) * 32 + b] = nn[u]; G[(size_t)(3 * H + j) * 32 + b] = gn[u];
+            }
           }
         }
       }
-      // ---------------- stage 3 (GRU layer 1)
+      // ---------------- stage C (GRU layer 1)
 #pragma unroll
-      for (int u = 0; u < U; ++u) hp[u] = w.H1[tp * actH + (size_t)(j0 + u) * 32 + b];
+      for (int u = 0; u < U; ++u) hp[u] = w.H1[tp * actH + (size_t)(j0 + u) * 32 + (b & 31)];
       mbar_wait(&d_full[2], ph);
       tc_fence_after_sync();
       TCDBG(17);
       {
-        float gh[NP], gi[NP];
-        ld_sum(R_GH1, na_side, gh);
-        ld_sum(R_MAIN, na_main, gi);
         float hv[U], rr[U], zz[U], nn[U], gn[U];
+        {
+          float gh[U], gi[U];
+          tmem_ld4_sum<U>(tmem + lane_base + R_GH1, NP, gh); tmem_ld4_sum<U>(tmem + lane_base + R_MAIN, NP, gi);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          rr[u] = fast_sigmoid(gi[u] + c_bih1[u] + gh[u] + c_bhh1[u]);
-          zz[u] = fast_sigmoid(gi[U + u] + c_bih1[U + u] + gh[U + u] + c_bhh1[U + u]);
-          gn[u] = gh[2 * U + u] + c_bhh1[2 * U + u];
-          nn[u] = fast_tanh(gi[2 * U + u] + c_bih1[2 * U + u] + rr[u] * gn[u]);
-          hv[u] = (1.f - zz[u]) * nn[u] + zz[u] * hp[u];
+          for (int u = 0; u < U; ++u) rr[u] = fast_sigmoid(gi[u] + c_bih1[u] + gh[u] + c_bhh1[u]);
+          tmem_ld4_sum<U>(tmem + lane_base + R_GH1 + U, NP, gh); tmem_ld4_sum<U>(tmem + lane_base + R_MAIN + U, NP, gi);
+#pragma unroll
+          for (int u = 0; u < U; ++u) zz[u] = fast_sigmoid(gi[u] + c_bih1[U + u] + gh[u] + c_bhh1[U + u]);
+          tmem_ld4_sum<U>(tmem + lane_base + R_GH1 + 2 * U, NP, gh); tmem_ld4_sum<U>(tmem + lane_base + R_MAIN + 2 * U, NP, gi);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            gn[u] = gh[u] + c_bhh1[2 * U + u];
+            nn[u] = fast_tanh(gi[u] + c_bih1[2 * U + u] + rr[u] * gn[u]);
+            hv[u] = (1.f - zz[u]) * nn[u] + zz[u] * hp[u];
+          }
         }
-        store_img_units<U>(tw.h1b[t & 1], b, j0, hv);
+        if (act) store_img_units<U>(tw.h1b[t & 1], b, j0, hv);
         tc_fence_before_sync();
         TCDBG(18);
         grid_arrive(w.bar);
         TCDBG(19);
+        if (act) {
+          // bf16 row of the h1 history: A operand of the batched layer2 GEMM (rows (t,b))
+          __nv_bfloat16 hb[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) w.H1[ts * actH + (size_t)(j0 + u) * 32 + b] = hv[u];
-        if (w.save) {
-          float* G = w.G1 + ((size_t)t * g.nbt) * 4 * H * 32;
+          for (int u = 0; u < U; ++u) hb[u] = __float2bfloat16_rn(hv[u]);
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(w.H1B) + ((size_t)t * 32 + b) * H + j0;
+          if (U == 8) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hb);
+          else *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(hb);
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int j = j0 + u;
-            G[(size_t)(0 * H + j) * 32 + b] = rr[u]; G[(size_t)(1 * H + j) * 32 + b] = zz[u];
-            G[(size_t)(2 * H + j) * 32 + b] = nn[u]; G[(size_t)(3 * H + j) * 32 + b] = gn[u];
-          }
-        }
-      }
-      // ---------------- stage 4 (layer2, de-normalise, pose integration, next x_pose)
-      V3 pos = v3(0, 0, 0), gzp = v3(0, 0, 0);
-      Q4 q; q.w = 1.f; q.x = q.y = q.z = 0.f;
-      if (c == 0 && live) {
-        const float* rp = a.root_pos + ((size_t)b * T + (t - 1)) * 3;
-        const float* rq = a.root_rot + ((size_t)b * T + (t - 1)) * 4;
-        pos = v3(rp[0], rp[1], rp[2]);
-        q.w = rq[0]; q.x = rq[1]; q.y = rq[2]; q.z = rq[3];
-        if (t + 1 < T) { const float* gp = a.gaze_pos + ((size_t)b * T + (t + 1)) * 3; gzp = v3(gp[0], gp[1], gp[2]); }
-      }
-      mbar_wait(&d_full[3], ph);
-      tc_fence_after_sync();
-      TCDBG(22);
-      {
-        uint8_t* xpn = tw.xpb[(t + 1) & 1];
-        float* xpf = w.XP + tn * actX;
-        float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f, r5 = 0.f;
-        for (int tile = 0; tile < n4t; ++tile) {
-          float y[16];
-          tmem_ld_cols<16>(tmem + R_MAIN + (uint32_t)(tile * na_side * 16), y);
-          for (int qa = 1; qa < na_side; ++qa) {
-            float u_[16];
-            tmem_ld_cols<16>(tmem + R_MAIN + (uint32_t)((tile * na_side + qa) * 16), u_);
+          for (int u = 0; u < U; ++u) w.H1[ts * actH + (size_t)(j0 + u) * 32 + b] = hv[u];
+          if (w.save) {
+            float* G = w.G1 + ((size_t)t * g.nbt) * 4 * H * 32;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) y[i] += u_[i];
-          }
-#pragma unroll
-          for (int r = 0; r < 16; ++r) {
-            const int lr = tile * 16 + r, n = c * g.rpc + lr;
-            if (lr < g.rpc && n < P_OUT) {
-              const float p = (y[r] + c_b2[lr]) * c_os[lr] + c_om[lr];
-              if (live) a.Y[((size_t)b * T + t) * P_OUT + n] = p;
-              if (t + 1 < T) {
-                const float xn = (p - c_im[lr]) / c_is[lr];
-                *reinterpret_cast<__nv_bfloat16*>(xpn + img_off(32, b, n)) = __float2bfloat16_rn(xn);
-                if (w.save) xpf[(size_t)n * 32 + b] = xn;
-              }
-              if (tile == 0) { if (r == 0) r0 = p; if (r == 1) r1 = p; if (r == 2) r2 = p; if (r == 3) r3 = p; if (r == 4) r4 = p; if (r == 5) r5 = p; }
-            }
-          }
-        }
-        if (c == 0 && live) {
-          V3 npos = quat_mul_vec(q, a.dt * v3(r0, r1, r2)) + pos;
-          Q4 nq = quat_mul(quat_from_helical(quat_mul_vec(q, a.dt * v3(r3, r4, r5))), q);
-          float* op = a.root_pos + ((size_t)b * T + t) * 3;
-          float* oq = a.root_rot + ((size_t)b * T + t) * 4;
-          op[0] = npos.x; op[1] = npos.y; op[2] = npos.z;
-          oq[0] = nq.w; oq[1] = nq.x; oq[2] = nq.y; oq[3] = nq.z;
-          if (t + 1 < T) {
-            V3 gd = quat_mul_vec(quat_inv(nq), gzp - npos);
-            const float gx[3] = {gd.x, gd.y, gd.z};
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              const float xn = (gx[d] - c_gz[d]) / c_gz[3 + d];
-              *reinterpret_cast<__nv_bfloat16*>(xpn + img_off(32, b, P_OUT + d)) = __float2bfloat16_rn(xn);
-              if (w.save) xpf[(size_t)(P_OUT + d) * 32 + b] = xn;
+            for (int u = 0; u < U; ++u) {
+              const int j = j0 + u;
+              G[(size_t)(0 * H + j) * 32 + b] = rr[u]; G[(size_t)(1 * H + j) * 32 + b] = zz[u];
+              G[(size_t)(2 * H + j) * 32 + b] = nn[u]; G[(size_t)(3 * H + j) * 32 + b] = gn[u];
             }
           }
         }
       }
-      tc_fence_before_sync();
-      TCDBG(23);
-      if (t + 1 < T) grid_arrive(w.bar);
-      TCDBG(24);
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem, 512); }
+  if (csize > 1) cluster_sync_all();          // no member exits while a peer's multicast may still target it
+  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem, 512); }
+}
+
+// ------------------------------------------------------------------ after the recurrence: outputs + x_pose history
+// YC[(t,b)][n] = W2[n] . h1(t)[b] + b2[n]  (batched GEMM)  ->  Y[b][t][n] = YC * os + om  (modules.py:728; channels 0..5
+// take the values the in-kernel root integration used),  XP[t+1][n][b] = (Y - im) / is  (modules.py:713) and the gaze
+// rows of XP[t+1] from GZ (saved for the weight gradients).  One CTA per (t, 64-channel chunk).
+__global__ void __launch_bounds__(256) fold_finish_kernel(zeggs_decoder_fwd_args a, DecWs w, int nch) {
+  __shared__ float tile[32][65];
+  const int t = 1 + blockIdx.x, n0 = blockIdx.y * 64, T = a.T;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;       // 4 rows of 64 channels per pass
+  const int n = n0 + tx;
+  float os = 0.f, om = 0.f;
+  if (n < P_OUT) { os = a.out_std[n]; om = a.out_mean[n]; }
+  for (int b = ty; b < 32; b += 4) {
+    float p = 0.f;
+    if (n < P_OUT) {
+      p = w.YC[((size_t)(t - 1) * 32 + b) * P_OUT + n] * os + om;
+      if (n < 6) p = w.Y6[((size_t)t * 32 + b) * 8 + n];
+      if (b < a.B) a.Y[((size_t)b * T + t) * P_OUT + n] = p;
+    }
+    tile[b][tx] = p;
+  }
+  if (!w.save || t + 1 >= T) return;
+  __syncthreads();
+  float* xp = w.XP + (size_t)(t + 1) * K1P * 32;
+  const int b = threadIdx.x & 31;
+  for (int r = threadIdx.x >> 5; r < 64; r += 8) {
+    const int nn = n0 + r;
+    if (nn < P_OUT) xp[(size_t)nn * 32 + b] = (tile[b][r] - a.in_mean[nn]) / a.in_std[nn];
+  }
+  if (blockIdx.y == nch - 1 && threadIdx.x < 96) {
+    const int d = threadIdx.x >> 5;
+    xp[(size_t)(P_OUT + d) * 32 + b] = b < a.B ? w.GZ[((size_t)(t + 1) * 32 + b) * 4 + d] : 0.f;
+  }
 }
 
 // ------------------------------------------------------------------ host
 extern "C" size_t zeggs_decoder_packed_tc_bytes(int H, int S, int Z) {
-  if (H % 16 != 0 || pick_U(H) <= 0) return 0;
+  if (H % 64 != 0 || pick_U(H) <= 0 || H > 1024) return 0;
   DecGeom g = make_geom(1, H, S, Z);
-  return (size_t)g.G * make_tcgeom(g).cta_bytes;
+  return make_tcgeom(g).total_bytes;
 }
 extern "C" size_t zeggs_decoder_tc_workspace_bytes(int H, int S, int Z) {
-  if (H % 16 != 0 || pick_U(H) <= 0) return 0;
+  if (H % 64 != 0 || pick_U(H) <= 0 || H > 1024) return 0;
   DecGeom g = make_geom(1, H, S, Z);
   return make_tcws(nullptr, g).bytes;
 }
 extern "C" int zeggs_decoder_pack_weights_tc(const zeggs_decoder_fwd_args* a, void* packed, void* stream_) {
-  ZCHECK_ARG(a && packed && a->H % 16 == 0 && pick_U(a->H) > 0, "decoder tc pack: bad arguments");
+  ZCHECK_ARG(a && packed && a->H % 64 == 0 && pick_U(a->H) > 0 && a->H <= 1024, "decoder tc pack: bad arguments");
+  ZCHECK_ARG(a->in_mean && a->in_std && a->out_mean && a->out_std, "decoder tc pack: normalisation statistics missing");
+  cudaStream_t stream = (cudaStream_t)stream_;
   DecGeom g = make_geom(a->B, a->H, a->S, a->Z);
   TcGeom tg = make_tcgeom(g);
-  ZCHECK_ARG(tg.n4t <= 4, "decoder tc: hidden size %d too small for the tensor-core engine", a->H);
-  pack_decoder_tc_kernel<<<592, 256, 0, (cudaStream_t)stream_>>>(g, tg, a->W0, a->W_ih0, a->W_hh0, a->W_ih1, a->W_hh1, a->W2, (uint8_t*)packed);
+  const int H = a->H;
+  uint8_t* base = (uint8_t*)packed;
+  float* mfold = (float*)(base + tg.off_mfold);
+  float* wxdt = (float*)(base + tg.off_wxdt);
+  float* cfold = (float*)(base + tg.off_cfold);
+  float* bfold = (float*)(base + tg.off_bfold);
+  __nv_bfloat16* w2b = (__nv_bfloat16*)(base + tg.off_w2b);
+  fold_wxdt_kernel<<<dim3(ceil_div(P_OUT, 32), ceil_div(4 * H, 32)), dim3(32, 8), 0, stream>>>(H, g.A, a->W0, a->W_ih0, a->out_std, a->in_std, wxdt);
   count_launch();
+  fold_const_kernel<<<ceil_div(4 * H, 8), 256, 0, stream>>>(H, g.A, a->W0, a->W_ih0, a->b0, a->b_ih0, a->b2, a->out_std, a->out_mean,
+                                                            a->in_mean, a->in_std, cfold, bfold);
+  count_launch();
+  ZCHECK_LAUNCH();
+  // Mfold[4H][H] = WxDt^T [4H x 1131] . W2 [1131 x H]     (fp32-grade: split-bf16 tcgen05 GEMM when a scratch buffer is set)
+  int rc = gemm_f32_auto(1, 4 * H, H, P_OUT, wxdt, 4 * H, a->W2, H, nullptr, mfold, H, 0, 0, stream); if (rc) return rc;
+  pack_decoder_tc_kernel<<<592, 256, 0, stream>>>(g, tg, mfold, a->W_ih0, a->W_hh0, a->W_ih1, a->W_hh1, a->W2, base);
+  count_launch();
+  ZCHECK_CUDA(cudaMemsetAsync(w2b, 0, (size_t)round_up(P_OUT, 128) * H * 2, stream));
+  rc = zeggs_split_bf16(a->W2, P_OUT, H, H, w2b, nullptr, H, stream_); if (rc) return rc;
   ZCHECK_LAUNCH();
   return ZEGGS_OK;
 }
 
+// measured on B200: the activation broadcast is bound by bytes delivered per SM (~31 B/clk), not by L2 reads, so
+// multicast clusters bring nothing (cluster 4: 32.4k cycles/step, none: 31.5k); kept as a development switch, default off
+static int g_tc_cluster = 1, g_tc_cluster_used = 0;
+extern "C" void zeggs_debug_set_tc_cluster(int n) { g_tc_cluster = n < 1 ? 1 : n; }
+extern "C" int zeggs_debug_get_tc_cluster() { return g_tc_cluster_used; }
+
 template <int U>
 static int launch_tc(const zeggs_decoder_fwd_args& a, const DecGeom& g, const TcGeom& tg, const DecWs& w, const TcWs& tw,
                      const uint8_t* packed, cudaStream_t stream) {
-  const size_t smem = 1024 + (size_t)TC_XKB * 4096 + (size_t)tg.kbH * 4096 + TC_RING * TC_SLOT_BYTES + 12288 + 512 +
-                      (size_t)(9 * U + 5 * tg.n4t * 16 + 8) * sizeof(float);
+  const size_t smem = 1024 + (size_t)2 * tg.kbH * 4096 + (size_t)TC_RING * tg.slot_bytes + 4096 + 512 +
+                      (size_t)(12 * U + 16 * U + 18 + 8) * sizeof(float);
   ZCHECK_CUDA(cudaFuncSetAttribute(decoder_fwd_tc_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, nsm = 0, occ = 0;
   ZCHECK_CUDA(cudaGetDevice(&dev));
   ZCHECK_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  ZCHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decoder_fwd_tc_kernel<U>, 128, smem));
+  ZCHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decoder_fwd_tc_kernel<U>, 160, smem));
   ZCHECK_ARG(occ * nsm >= g.G, "decoder tc: cooperative grid of %d CTAs does not fit", g.G);
-  void* args[] = {(void*)&a, (void*)&g, (void*)&tg, (void*)&w, (void*)&tw, (void*)&packed};
-  ZCHECK_CUDA(cudaLaunchCooperativeKernel((void*)decoder_fwd_tc_kernel<U>, dim3(g.G), dim3(128), args, smem, stream));
+  // largest cluster size (8, 4, 2) whose clusters can ALL be co-resident (the kernel spins on grid barriers); else no clusters
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(g.G); cfg.blockDim = dim3(160); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  int cl = g_tc_cluster;
+  for (; cl > 1; cl >>= 1) {
+    if (g.G % cl != 0) continue;                 // (a 4 KB k-block splits into >= 512-byte parts for cl <= 8)
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, (void*)decoder_fwd_tc_kernel<U>, &cfg) == cudaSuccess && ncl * cl >= g.G) break;
+    (void)cudaGetLastError();
+  }
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = 2;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, decoder_fwd_tc_kernel<U>, a, g, tg, w, tw, packed);
+  if (e != cudaSuccess && cl > 1) {            // cooperative + cluster refused: co-residency was checked above
+    (void)cudaGetLastError();
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, decoder_fwd_tc_kernel<U>, a, g, tg, w, tw, packed);
+  }
+  ZCHECK_CUDA(e);
+  g_tc_cluster_used = cl;
   count_launch();
   return ZEGGS_OK;
 }
 
 static long long* g_tc_dbg = nullptr;
-static int g_tc_nacc = 0;
-extern "C" void zeggs_debug_set_tc_nacc(int n) { g_tc_nacc = n; }
+extern "C" void zeggs_debug_set_tc_nacc(int) {}
 long long* tc_debug_buffer() { return g_tc_dbg; }
 extern "C" void zeggs_debug_set_tc_trace(void* p) { g_tc_dbg = (long long*)p; }
 
-// called by zeggs_decoder_window_fwd after the prologue / CellStateEncoder / cond pre-pass when engine == 1
+// hoisted terms of the tc engine: S01[(t,b)][4H] = cond rows . [W0[:, 1134:] ; W_ih0[:, H+1134:]]^T + bfold, then the first
+// step's pose contribution (called by zeggs_decoder_window_fwd after the prologue / CellStateEncoder)
+int decoder_fwd_tc_hoist(const zeggs_decoder_fwd_args& a, const DecGeom& g, const DecWs& w, cudaStream_t stream) {
+  TcGeom tg = make_tcgeom(g);
+  ZCHECK_ARG(a.packed_tc, "decoder tc: packed_tc missing");
+  const uint8_t* base = (const uint8_t*)a.packed_tc;
+  const float* cfold = (const float*)(base + tg.off_cfold);
+  const float* bfold = (const float*)(base + tg.off_bfold);
+  const int C = a.S + a.Z, H = a.H;
+  int rc = gemm_f32_auto(0, a.T * 32, H, C, w.CONDR, C, a.W0 + P_IN, g.A, bfold, w.S01, 4 * H, 0, 0, stream); if (rc) return rc;
+  rc = gemm_f32_auto(0, a.T * 32, 3 * H, C, w.CONDR, C, a.W_ih0 + H + P_IN, g.A + H, bfold + H, w.S01 + H, 4 * H, 0, 0, stream); if (rc) return rc;
+  fold_first_step_kernel<<<ceil_div(4 * H, 8), 256, 0, stream>>>(H, g.A, a.W0, a.W_ih0, w.XP + (size_t)K1P * 32, cfold, w.S01 + (size_t)32 * 4 * H);
+  count_launch();
+  ZCHECK_LAUNCH();
+  return ZEGGS_OK;
+}
+
+// called by zeggs_decoder_window_fwd after the prologue / CellStateEncoder / hoisted terms when engine == 1
 int decoder_fwd_tc_run(const zeggs_decoder_fwd_args& a, const DecGeom& g, const DecWs& w, cudaStream_t stream) {
   TcGeom tg = make_tcgeom(g);
   ZCHECK_ARG(g.nbt == 1, "decoder tc engine handles one 32-sample batch tile (B <= 32); got B=%d", a.B);
   ZCHECK_ARG(a.packed_tc && a.workspace_tc, "decoder tc: packed_tc / workspace_tc missing");
-  ZCHECK_ARG(tg.n4t <= 4 && tg.kbH <= 16, "decoder tc: unsupported hidden size %d", a.H);
-  if (g_tc_nacc > 0) tg.nacc = g_tc_nacc;
+  ZCHECK_ARG(a.H % 64 == 0 && tg.kbH <= 4 * TC_XCH, "decoder tc: unsupported hidden size %d", a.H);
   TcWs tw = make_tcws(a.workspace_tc, g);
   tw.dbg = g_tc_dbg;
-  const size_t xb = (size_t)tg.kbX * 4096, hb = (size_t)tg.kbH * 4096;
-  ZCHECK_CUDA(cudaMemsetAsync(tw.xpb[0], 0, xb, stream));
-  ZCHECK_CUDA(cudaMemsetAsync(tw.xpb[1], 0, xb, stream));
-  // images of x_pose(1), h0(0), h1(0) from the fp32 k-major buffers the prologue / CellStateEncoder wrote
-  image_from_kmajor_kernel<<<64, 256, 0, stream>>>(w.XP + (size_t)1 * g.nbt * K1P * 32, K1P, tg.kbX, tw.xpb[1]); count_launch();
+  // images of h0(0), h1(0) from the fp32 k-major buffers the CellStateEncoder wrote
   image_from_kmajor_kernel<<<64, 256, 0, stream>>>(w.H0, a.H, tg.kbH, tw.h0b[0]); count_launch();
   image_from_kmajor_kernel<<<64, 256, 0, stream>>>(w.H1, a.H, tg.kbH, tw.h1b[0]); count_launch();
   ZCHECK_LAUNCH();
-  (void)hb;
   ScopedTimer tm("decoder_fwd", stream);
-  return g.U == 4 ? launch_tc<4>(a, g, tg, w, tw, (const uint8_t*)a.packed_tc, stream)
-                  : launch_tc<8>(a, g, tg, w, tw, (const uint8_t*)a.packed_tc, stream);
+  int rc = g.U == 4 ? launch_tc<4>(a, g, tg, w, tw, (const uint8_t*)a.packed_tc, stream)
+                    : launch_tc<8>(a, g, tg, w, tw, (const uint8_t*)a.packed_tc, stream);
+  if (rc) return rc;
+  // layer2 for every step at once: YC[(t,b)][:] = h1(t) W2^T + b2 over the bf16 history (rows t = 1..T-1)
+  const __nv_bfloat16* h1b = reinterpret_cast<const __nv_bfloat16*>(w.H1B) + (size_t)32 * a.H;
+  const __nv_bfloat16* w2b = reinterpret_cast<const __nv_bfloat16*>((const uint8_t*)a.packed_tc + tg.off_w2b);
+  rc = tc_gemm_launch((a.T - 1) * 32, P_OUT, a.H, h1b, nullptr, a.H, w2b, nullptr, a.H, a.b2, w.YC, P_OUT, 0, 0, stream); if (rc) return rc;
+  const int nch = ceil_div(P_OUT, 64);
+  fold_finish_kernel<<<dim3(a.T - 1, nch), 256, 0, stream>>>(a, w, nch);
+  count_launch();
+  ZCHECK_LAUNCH();
+  return ZEGGS_OK;
 }
 
 }  // namespace zeggs

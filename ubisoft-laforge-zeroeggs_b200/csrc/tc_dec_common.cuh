@@ -16,6 +16,19 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+
+// ---- thread-block clusters: rank / size, cluster barrier, multicast bulk copy (one L2 read feeds every CTA of the cluster)
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;\n" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// the copy lands at the same shared-memory offset in every CTA of `mask` and completes `bytes` on each one's mbarrier
+__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 
 template <int NC>
@@ -57,6 +70,29 @@ __device__ __forceinline__ void tmem_ld_cols<4>(uint32_t taddr, float (&v)[4]) {
   tmem_ld_wait();
 #pragma unroll
   for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+
+// issue-only TMEM loads (no wait) and the 4-accumulator sum built on them: four loads in flight, ONE wait
+template <int NC> __device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&r)[NC]);
+template <> __device__ __forceinline__ void tmem_ld_issue<8>(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+}
+template <> __device__ __forceinline__ void tmem_ld_issue<4>(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+// v = acc0 + acc1 + acc2 + acc3 (accumulators `stride` columns apart), NC columns starting at taddr
+template <int NC>
+__device__ __forceinline__ void tmem_ld4_sum(uint32_t taddr, uint32_t stride, float (&v)[NC]) {
+  uint32_t r0[NC], r1[NC], r2[NC], r3[NC];
+  tmem_ld_issue<NC>(taddr, r0); tmem_ld_issue<NC>(taddr + stride, r1);
+  tmem_ld_issue<NC>(taddr + 2 * stride, r2); tmem_ld_issue<NC>(taddr + 3 * stride, r3);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < NC; ++i)
+    v[i] = ((__uint_as_float(r0[i]) + __uint_as_float(r1[i])) + __uint_as_float(r2[i])) + __uint_as_float(r3[i]);
 }
 
 // bf16-engine gate math: exp via the SFU (relative error ~1e-6, far below the bf16 operand rounding)
