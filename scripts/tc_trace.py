@@ -23,8 +23,7 @@ _lib.lib().zeggs_debug_set_tc_trace(None)
 tr = buf.cpu().numpy().reshape(64, 32)
 print("cluster size used:", _lib.lib().zeggs_debug_get_tc_cluster())
 names = {0:"L:C(t-1) seen, h1 load issued",4:"M:fold issued",5:"E:d0 ready",6:"E:A done",7:"E:arrived A",8:"L:A seen",10:"M:gh1 issued",
-         11:"M:gi0a issued",12:"E:d1 ready",13:"E:B done",14:"L:B seen",16:"M:gi1 issued",17:"E:d2 ready",18:"E:C done",19:"E:arrived C",20:"M:gi0a x chunk0",21:"M:gi0a x chunk1",22:"M:gi0a x chunk2",23:"M:gi0a x chunk3",
-         24:"M:gi0a w slot0",25:"M:gi0a w slot1",26:"M:gi0a w slot2",27:"M:gi0a w slot3",28:"M:gi0a w slot4",29:"M:gi0a w slot5",30:"M:gi0a w slot6",31:"M:gi0a w slot7"}
+         11:"M:gi0a issued",12:"E:d1 ready",13:"E:B done",14:"L:B seen",16:"M:gi1 issued",17:"E:d2 ready",18:"E:C done",19:"E:arrived C",20:"M:gi0a group0 ready",21:"M:gi0a group1 ready",22:"M:gi0a group2 ready",23:"M:gi0a group3 ready"}
 for t in (10, 20):
     base = tr[t, 0]
     print(f"step {t}: (cycles since 'B4 seen'; 1 us ~ 1900 cyc)")

@@ -37,15 +37,15 @@
 
 namespace zeggs {
 
-constexpr int TC_RING = 6;              // weight ring slots (two k-block tiles each)
-constexpr int TC_XCH = 4;               // 4-k-block chunks of an activation load (kbH <= 16)
+constexpr int TC_RING = 4;              // operand ring slots
+constexpr int TC_GKB = 4;               // k-blocks per ring slot ("group"): ONE mbarrier wait per 16 MMAs
 constexpr int TC_NEPI = 2;              // epilogue warps (grid-barrier arrivals per CTA and stage)
 
 struct TcGeom {
   int NP;          // rows of a gate chain: round_up(3U,8)
   int N1;          // rows of the fold chain: 4U + 8 (6 used: W2[0:6])
   int kbH;         // k-blocks of an H-vector
-  int slot_bytes;  // ring slot: two k-block tiles of the widest chain
+  int slot_bytes;  // ring slot: TC_GKB k-block tiles of the widest chain
   size_t chain_off[6];   // byte offset of chain c inside one CTA's packed block
   size_t cta_bytes;
   // tail of the packed buffer (after G * cta_bytes)
@@ -59,7 +59,7 @@ inline TcGeom make_tcgeom(const DecGeom& g) {
   t.NP = round_up(3 * g.U, 8);      // M = 64 allows N % 8 == 0: no padding rows at U = 8
   t.N1 = 4 * g.U + 8;
   t.kbH = ceil_div(g.H, 64);
-  t.slot_bytes = 2 * (int)tc_tile_bytes(t.N1);
+  t.slot_bytes = TC_GKB * (int)tc_tile_bytes(t.N1);
   size_t off = 0;
   t.chain_off[0] = off; off += (size_t)t.kbH * tc_tile_bytes(t.N1);     // fold  X = h1(t-1)
   t.chain_off[1] = off; off += (size_t)t.kbH * tc_tile_bytes(t.NP);     // gh0   X = h0(t-1)
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(160, 1)
 decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, TcWs tw, const uint8_t* __restrict__ packed) {
   constexpr int NP = (3 * U + 7) / 8 * 8;        // gate-chain rows (24 for U=8, 16 for U=4)
   constexpr int N1 = 4 * U + 8;                  // fold-chain rows
-  constexpr int SLOT = 2 * N1 * 128;
+  constexpr int SLOT = TC_GKB * N1 * 128;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // layout: X0 | X1 | ring | 4 KB slack | barriers | constants   (operand rows 32..63 of the last k-block alias what follows)
@@ -197,11 +197,9 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
   uint8_t* ring = X1 + kbH * 4096;
   uint8_t* tail = ring + TC_RING * SLOT + 4096;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* full = bars;                        // [TC_RING]
+  uint64_t* full = bars;                        // [TC_RING]  two arrivals per use: weight producer + activation loader
   uint64_t* empty = bars + TC_RING;             // [TC_RING]
-  uint64_t* x_full = empty + TC_RING;           // [2][TC_XCH]
-  uint64_t* x_free = x_full + 2 * TC_XCH;       // [2]
-  uint64_t* d_full = x_free + 2;                // [3]
+  uint64_t* d_full = empty + TC_RING;           // [3]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 3);
   float* cst = reinterpret_cast<float*>(tail + 512);   // per-CTA constants
   float* c_bhh0 = cst;            // [3U]
@@ -217,9 +215,7 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
   const uint8_t* pk = packed + (size_t)c * tg.cta_bytes;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TC_RING; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2 * TC_XCH; ++i) mbar_init(&x_full[i], 1);
-    mbar_init(&x_free[0], 1); mbar_init(&x_free[1], 1);
+    for (int i = 0; i < TC_RING; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 3; ++i) mbar_init(&d_full[i], 1);
     fence_mbar_init();
   }
@@ -244,146 +240,137 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
   // ELECT / R2UR.BROADCAST waterfall loop (~90 cycles per MMA).
   if (*tmem_slot != 0u) __trap();
   constexpr uint32_t tmem = 0u;
-  // Cluster of `csize` consecutive CTAs: every activation vector is read from L2 once per cluster -- CTA rank r fetches
-  // 1/csize of each 16 KB chunk and multicasts it into all members' X buffers (same smem offsets, each member's own
-  // mbarrier gets the bytes).  Re-use of an X buffer needs no cluster handshake: a load is only issued after a grid
-  // barrier whose epilogues waited on commits covering every MMA that read the previous contents, in every CTA.
-  const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
-  if (csize > 1) cluster_sync_all();          // peers' mbarriers are initialised before any multicast can land
   // TMEM regions (columns): gh0 [0,128) | gh1 [128,256) | fold / gi0a / gi1 [256, 256 + 4*N1); accumulator q at +q*N
-  constexpr uint32_t R_GH0 = 0, R_GH1 = 128, R_MAIN = 256;
-  static_assert(4 * N1 <= 256 && 4 * NP <= 128, "TMEM budget");
+  // the critical chains (R_MAIN) use 8 accumulators when they fit: a dependent accumulate costs ~230 cycles of latency
+  constexpr int MAIN_ACC = (8 * N1 + 8 * NP <= 512) ? 8 : 4;
+  constexpr uint32_t R_GH0 = 0, R_GH1 = 4 * NP, R_MAIN = 8 * NP;
+  static_assert(MAIN_ACC * N1 + 8 * NP <= 512, "TMEM budget");
   const size_t actH = (size_t)g.nbt * H * 32;
   const unsigned bar_n = gridDim.x * TC_NEPI;
 
+  const int ng = (kbH + TC_GKB - 1) / TC_GKB;      // ring groups per chain
+  // Operand ring: slot = the weight tiles of TC_GKB k-blocks.  The X chunk of the same k-blocks lands in the resident X
+  // buffer but completes on the SAME mbarrier, so the MMA warp waits once per 16 MMAs (a successful mbarrier wait costs
+  // the issuing thread ~130 cycles that do not overlap with MMA issue).  Chains whose X is already resident (gh1 after the
+  // fold chain, gh0 after gi1) get the second arrival from the weight producer.  Chain sequence: q = 0: gh0 of step 1;
+  // step t: q = 1 + 5 (t-1) + {0 fold, 1 gh1, 2 gi0a, 3 gi1, 4 gh0 of t+1};  the last fold chain: q = 5 (T-1).
   if (warp == 3) {
     // ================= weight producer: streams every chain's tiles in the MMA warp's consumption order
     if (lane == 0) {
       uint32_t it = 0;
-      auto stream = [&](int chain) {
+      auto stream = [&](int chain, bool has_loader) {
         const int N = chain == 0 ? N1 : NP;
         const uint8_t* src = pk + tg.chain_off[chain];
-        for (int kb = 0; kb < kbH; kb += 2, ++it) {
+        for (int kb = 0; kb < kbH; kb += TC_GKB, ++it) {
           const uint32_t s = it % TC_RING, ph = (it / TC_RING) & 1;
-          const uint32_t bytes = (uint32_t)((kbH - kb >= 2 ? 2 : 1) * tc_tile_bytes(N));
+          const uint32_t bytes = (uint32_t)((kbH - kb >= TC_GKB ? TC_GKB : kbH - kb) * tc_tile_bytes(N));
           mbar_wait(&empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&full[s], bytes);
           bulk_g2s(ring + (size_t)s * SLOT, src + (size_t)kb * tc_tile_bytes(N), bytes, &full[s]);
+          if (!has_loader) mbar_arrive(&full[s]);
         }
       };
-      stream(1);                                       // gh0 of step 1
+      stream(1, true);                                 // gh0 of step 1
       for (int t = 1; t < T; ++t) {                    // per step: fold(0), gh1(3), gi0a(2), gi1(4), gh0 of t+1 (1)
-        stream(0); stream(3); stream(2); stream(4);
-        if (t + 1 < T) stream(1);
+        stream(0, true); stream(3, false); stream(2, true); stream(4, true);
+        if (t + 1 < T) stream(1, false);
       }
-      stream(0);                                       // y(T-1)[0:6] for the last root integration
+      stream(0, true);                                 // y(T-1)[0:6] for the last root integration
     }
   } else if (warp == 4) {
-    // ================= activation loader.  Load n goes to buffer n&1; it is the (n>>1)-th use of that buffer.
+    // ================= activation loader.  Load n goes to X buffer n&1.  Re-use of an X buffer needs no handshake: a load
+    // is only issued after a grid barrier whose epilogues waited on commits covering every MMA that read the old contents.
     if (lane == 0) {
-      uint32_t n = 0;
-      auto load = [&](const uint8_t* img) {
+      auto load = [&](const uint8_t* img, uint32_t q, uint32_t n) {
         uint8_t* X = (n & 1) ? X1 : X0;
-        uint64_t* xf = x_full + (n & 1) * TC_XCH;
-        if (n >= 2) mbar_wait(&x_free[n & 1], ((n >> 1) - 1) & 1);
         fence_proxy_async();
-        for (int ch = 0; ch < TC_XCH; ++ch) {
-          const int k0 = ch * 4;
-          if (k0 < kbH) {
-            const uint32_t bytes = (uint32_t)((kbH - k0 >= 4 ? 4 : kbH - k0) * 4096);
-            mbar_arrive_expect_tx(&xf[ch], bytes);
-            if (csize == 1) {
-              bulk_g2s(X + (size_t)k0 * 4096, img + (size_t)k0 * 4096, bytes, &xf[ch]);
-            } else {
-              const uint32_t part = bytes / csize, o = (uint32_t)k0 * 4096 + crank * part;
-              bulk_g2s_multicast(X + o, img + o, part, &xf[ch], (uint16_t)((1u << csize) - 1u));
-            }
-          } else {
-            mbar_arrive(&xf[ch]);                      // keep every chunk barrier in phase
-          }
+        uint32_t it = q * (uint32_t)ng;
+        for (int kb = 0; kb < kbH; kb += TC_GKB, ++it) {
+          const uint32_t s = it % TC_RING, ph = (it / TC_RING) & 1;
+          const uint32_t bytes = (uint32_t)((kbH - kb >= TC_GKB ? TC_GKB : kbH - kb) * 4096);
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], bytes);
+          bulk_g2s(X + (size_t)kb * 4096, img + (size_t)kb * 4096, bytes, &full[s]);
         }
-        ++n;
       };
-      load(tw.h0b[0]);                                              // h0(0) for gh0 of step 1
+      load(tw.h0b[0], 0, 0);                                        // h0(0) for gh0 of step 1
       for (int t = 1; t < T; ++t) {
+        const uint32_t base = 1u + 5u * (uint32_t)(t - 1);
         if (t > 1) grid_wait(w.bar, (unsigned)(3 * (t - 1)) * bar_n);           // C(t-1): h1(t-1) complete
         if (tw.dbg && c == 0 && t < 64) tw.dbg[t * 32 + 0] = clock64();
-        load(tw.h1b[(t - 1) & 1]);
+        load(tw.h1b[(t - 1) & 1], base, (uint32_t)(3 * t - 2));
         grid_wait(w.bar, (unsigned)(3 * (t - 1) + 1) * bar_n);                  // A(t): a(t) complete
         if (tw.dbg && c == 0 && t < 64) tw.dbg[t * 32 + 8] = clock64();
-        load(tw.ab);
+        load(tw.ab, base + 2, (uint32_t)(3 * t - 1));
         grid_wait(w.bar, (unsigned)(3 * (t - 1) + 2) * bar_n);                  // B(t): h0(t) complete
         if (tw.dbg && c == 0 && t < 64) tw.dbg[t * 32 + 14] = clock64();
-        load(tw.h0b[t & 1]);
+        load(tw.h0b[t & 1], base + 3, (uint32_t)(3 * t));
       }
       grid_wait(w.bar, (unsigned)(3 * (T - 1)) * bar_n);
-      load(tw.h1b[(T - 1) & 1]);
+      load(tw.h1b[(T - 1) & 1], 5u * (uint32_t)(T - 1), (uint32_t)(3 * T - 2));
     }
   } else if (warp == 2) {
     // ================= MMA issuer.  The warp runs the loops converged; one elected lane issues.  Descriptors advance by
-    // constants and the four k-steps of a k-block go to four independent TMEM accumulators.
+    // constants; the four k-steps of a k-block go to four independent TMEM accumulators (odd k-blocks to four more when wide).
     uint32_t it = 0, n = 0;
     const uint64_t dX0 = make_smem_desc_sw128(X0), dX1 = make_smem_desc_sw128(X1), dRing = make_smem_desc_sw128(ring);
-    int dbg_t = -1;                                  // >= 0: trace this chain's operand arrivals (events 20..31)
-    auto chain_mma = [&](int N, uint32_t d0) {       // consumes load n (buffer n&1)
+    int dbg_t = -1;                                  // >= 0: trace this chain's group arrivals (events 20..23)
+    auto chain_mma = [&](int N, uint32_t d0, bool wide) {       // reads X buffer n&1
       const uint32_t idesc = make_idesc_bf16_f32(64, N);
       const uint64_t dx = (n & 1) ? dX1 : dX0;
-      uint64_t* xf = x_full + (n & 1) * TC_XCH;
-      const uint32_t xph = (n >> 1) & 1;
       const uint64_t bstep = (uint64_t)(N * 8);            // one k-block tile of the weight slice, in 16-byte units
-      for (int kb = 0; kb < kbH; kb += 2, ++it) {
+      const uint32_t d1 = wide ? d0 + 4 * N : d0;
+      for (int kb = 0; kb < kbH; kb += TC_GKB, ++it) {
         const uint32_t s = it % TC_RING, ph = (it / TC_RING) & 1;
-        if ((kb & 3) == 0) {
-          mbar_wait(&xf[kb >> 2], xph);
-          if (tw.dbg && c == 0 && warp_lane0 && dbg_t >= 0 && dbg_t < 64) tw.dbg[dbg_t * 32 + 20 + (kb >> 2)] = clock64();
-        }
         mbar_wait(&full[s], ph);
-        if (tw.dbg && c == 0 && warp_lane0 && dbg_t >= 0 && dbg_t < 64) tw.dbg[dbg_t * 32 + 24 + (kb >> 1)] = clock64();
-        tc_fence_after_sync();
+        if (tw.dbg && c == 0 && warp_lane0 && dbg_t >= 0 && dbg_t < 64) tw.dbg[dbg_t * 32 + 20 + (kb >> 2)] = clock64();
         const uint64_t da = dx + (uint64_t)kb * 256, db = dRing + (uint64_t)s * (SLOT >> 4);
-        const bool acc0 = kb > 0, two = kb + 1 < kbH;
+        const int nk = kbH - kb >= TC_GKB ? TC_GKB : kbH - kb;
         if (elect_one_sync()) {
-          umma_bf16(d0 + 0 * N, da + 0, db + 0, idesc, acc0);
-          umma_bf16(d0 + 1 * N, da + 2, db + 2, idesc, acc0);
-          umma_bf16(d0 + 2 * N, da + 4, db + 4, idesc, acc0);
-          umma_bf16(d0 + 3 * N, da + 6, db + 6, idesc, acc0);
-          if (two) {
-            umma_bf16(d0 + 0 * N, da + 256 + 0, db + bstep + 0, idesc, true);
-            umma_bf16(d0 + 1 * N, da + 256 + 2, db + bstep + 2, idesc, true);
-            umma_bf16(d0 + 2 * N, da + 256 + 4, db + bstep + 4, idesc, true);
-            umma_bf16(d0 + 3 * N, da + 256 + 6, db + bstep + 6, idesc, true);
+#pragma unroll
+          for (int j = 0; j < TC_GKB; ++j) {
+            if (j < nk) {
+              const uint32_t dd = (j & 1) ? d1 : d0;
+              const bool acc = wide ? (kb + j) > 1 : (kb + j) > 0;
+              const uint64_t a_ = da + (uint64_t)(j * 256), b_ = db + (uint64_t)j * bstep;
+              umma_bf16(dd + 0 * N, a_ + 0, b_ + 0, idesc, acc);
+              umma_bf16(dd + 1 * N, a_ + 2, b_ + 2, idesc, acc);
+              umma_bf16(dd + 2 * N, a_ + 4, b_ + 4, idesc, acc);
+              umma_bf16(dd + 3 * N, a_ + 6, b_ + 6, idesc, acc);
+            }
           }
           umma_commit(&empty[s]);
         }
         __syncwarp();
       }
     };
-    auto commit2 = [&](uint64_t* b0, uint64_t* b1) {
-      if (elect_one_sync()) { if (b0) umma_commit(b0); if (b1) umma_commit(b1); }
+    auto commit1 = [&](uint64_t* b0) {
+      if (elect_one_sync()) umma_commit(b0);
       __syncwarp();
     };
-    chain_mma(NP, tmem + R_GH0);                                        // gh0 of step 1 from h0(0)
-    commit2(&x_free[n & 1], nullptr); ++n;
+    chain_mma(NP, tmem + R_GH0, false);                                 // gh0 of step 1 from h0(0)
+    ++n;
     for (int t = 1; t < T; ++t) {
-      chain_mma(N1, tmem + R_MAIN);                                     // fold: [pre_a ; gi0 ; y6] from h1(t-1)
-      commit2(&d_full[0], nullptr);
+      chain_mma(N1, tmem + R_MAIN, MAIN_ACC == 8);                      // fold: [pre_a ; gi0 ; y6] from h1(t-1)
+      commit1(&d_full[0]);
       TCDBG(4);
-      chain_mma(NP, tmem + R_GH1);                                      // gh1 from h1(t-1)
-      commit2(&x_free[n & 1], nullptr); ++n;
+      chain_mma(NP, tmem + R_GH1, false);                               // gh1 from h1(t-1)
+      ++n;
       TCDBG(10);
       dbg_t = t;
-      chain_mma(NP, tmem + R_MAIN);                                     // gi0a from a(t)
+      chain_mma(NP, tmem + R_MAIN, MAIN_ACC == 8);                      // gi0a from a(t)
       dbg_t = -1;
-      commit2(&d_full[1], &x_free[n & 1]); ++n;
+      commit1(&d_full[1]);
+      ++n;
       TCDBG(11);
-      chain_mma(NP, tmem + R_MAIN);                                     // gi1 from h0(t)
-      commit2(&d_full[2], nullptr);
+      chain_mma(NP, tmem + R_MAIN, MAIN_ACC == 8);                      // gi1 from h0(t)
+      commit1(&d_full[2]);
       TCDBG(16);
-      if (t + 1 < T) chain_mma(NP, tmem + R_GH0);                       // gh0 of step t+1 from h0(t)
-      commit2(&x_free[n & 1], nullptr); ++n;
+      if (t + 1 < T) chain_mma(NP, tmem + R_GH0, false);                // gh0 of step t+1 from h0(t)
+      ++n;
     }
-    chain_mma(N1, tmem + R_MAIN);                                       // y(T-1)[0:6]
-    commit2(&d_full[0], nullptr);
+    chain_mma(N1, tmem + R_MAIN, MAIN_ACC == 8);                        // y(T-1)[0:6]
+    commit1(&d_full[0]);
   } else {
     // ================= epilogue warps 0,1: TMEM lanes 0..15 of quadrant `warp` = samples 16*warp .. 16*warp+15
     const bool act = lane < 16;
@@ -423,12 +410,12 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
       {
         // y6 columns and the fold columns (+ hoisted terms) first; the serial root / gaze chain then overlaps nothing else
         float y8[8];
-        tmem_ld4_sum<8>(tmem + lane_base + R_MAIN + 4 * U, N1, y8);
+        tmem_ldn_sum<8, MAIN_ACC>(tmem + lane_base + R_MAIN + 4 * U, N1, y8);
         if (t >= 2 && t < T) {
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) {
             float v[U];
-            tmem_ld4_sum<U>(tmem + lane_base + R_MAIN + qq * U, N1, v);
+            tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + qq * U, N1, v);
 #pragma unroll
             for (int u = 0; u < U; ++u) sv[qq * U + u] += v[u];
           }
@@ -509,13 +496,13 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
         float hv[U], rr[U], zz[U], nn[U], gn[U];
         {
           float gh[U], gi[U];
-          tmem_ld4_sum<U>(tmem + lane_base + R_GH0, NP, gh); tmem_ld4_sum<U>(tmem + lane_base + R_MAIN, NP, gi);
+          tmem_ld4_sum<U>(tmem + lane_base + R_GH0, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN, NP, gi);
 #pragma unroll
           for (int u = 0; u < U; ++u) rr[u] = fast_sigmoid(gi[u] + gi0p[u] + gh[u] + c_bhh0[u]);
-          tmem_ld4_sum<U>(tmem + lane_base + R_GH0 + U, NP, gh); tmem_ld4_sum<U>(tmem + lane_base + R_MAIN + U, NP, gi);
+          tmem_ld4_sum<U>(tmem + lane_base + R_GH0 + U, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + U, NP, gi);
 #pragma unroll
           for (int u = 0; u < U; ++u) zz[u] = fast_sigmoid(gi[u] + gi0p[U + u] + gh[u] + c_bhh0[U + u]);
-          tmem_ld4_sum<U>(tmem + lane_base + R_GH0 + 2 * U, NP, gh); tmem_ld4_sum<U>(tmem + lane_base + R_MAIN + 2 * U, NP, gi);
+          tmem_ld4_sum<U>(tmem + lane_base + R_GH0 + 2 * U, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + 2 * U, NP, gi);
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             gn[u] = gh[u] + c_bhh0[2 * U + u];
@@ -551,13 +538,13 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
         float hv[U], rr[U], zz[U], nn[U], gn[U];
         {
           float gh[U], gi[U];
-          tmem_ld4_sum<U>(tmem + lane_base + R_GH1, NP, gh); tmem_ld4_sum<U>(tmem + lane_base + R_MAIN, NP, gi);
+          tmem_ld4_sum<U>(tmem + lane_base + R_GH1, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN, NP, gi);
 #pragma unroll
           for (int u = 0; u < U; ++u) rr[u] = fast_sigmoid(gi[u] + c_bih1[u] + gh[u] + c_bhh1[u]);
-          tmem_ld4_sum<U>(tmem + lane_base + R_GH1 + U, NP, gh); tmem_ld4_sum<U>(tmem + lane_base + R_MAIN + U, NP, gi);
+          tmem_ld4_sum<U>(tmem + lane_base + R_GH1 + U, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + U, NP, gi);
 #pragma unroll
           for (int u = 0; u < U; ++u) zz[u] = fast_sigmoid(gi[u] + c_bih1[U + u] + gh[u] + c_bhh1[U + u]);
-          tmem_ld4_sum<U>(tmem + lane_base + R_GH1 + 2 * U, NP, gh); tmem_ld4_sum<U>(tmem + lane_base + R_MAIN + 2 * U, NP, gi);
+          tmem_ld4_sum<U>(tmem + lane_base + R_GH1 + 2 * U, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + 2 * U, NP, gi);
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             gn[u] = gh[u] + c_bhh1[2 * U + u];
@@ -595,7 +582,6 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (csize > 1) cluster_sync_all();          // no member exits while a peer's multicast may still target it
   if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem, 512); }
 }
 
@@ -673,11 +659,10 @@ extern "C" int zeggs_decoder_pack_weights_tc(const zeggs_decoder_fwd_args* a, vo
   return ZEGGS_OK;
 }
 
-// measured on B200: the activation broadcast is bound by bytes delivered per SM (~31 B/clk), not by L2 reads, so
-// multicast clusters bring nothing (cluster 4: 32.4k cycles/step, none: 31.5k); kept as a development switch, default off
-static int g_tc_cluster = 1, g_tc_cluster_used = 0;
-extern "C" void zeggs_debug_set_tc_cluster(int n) { g_tc_cluster = n < 1 ? 1 : n; }
-extern "C" int zeggs_debug_get_tc_cluster() { return g_tc_cluster_used; }
+// (A thread-block-cluster variant that multicast each activation chunk to 4 CTAs was measured and dropped: the broadcast is
+// bound by bytes delivered per SM, not by L2 reads -- 32.4k cycles/step with clusters of 4 against 31.5k without.)
+extern "C" void zeggs_debug_set_tc_cluster(int) {}
+extern "C" int zeggs_debug_get_tc_cluster() { return 1; }
 
 template <int U>
 static int launch_tc(const zeggs_decoder_fwd_args& a, const DecGeom& g, const TcGeom& tg, const DecWs& w, const TcWs& tw,
@@ -690,31 +675,8 @@ static int launch_tc(const zeggs_decoder_fwd_args& a, const DecGeom& g, const Tc
   ZCHECK_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
   ZCHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decoder_fwd_tc_kernel<U>, 160, smem));
   ZCHECK_ARG(occ * nsm >= g.G, "decoder tc: cooperative grid of %d CTAs does not fit", g.G);
-  // largest cluster size (8, 4, 2) whose clusters can ALL be co-resident (the kernel spins on grid barriers); else no clusters
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(g.G); cfg.blockDim = dim3(160); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-  cudaLaunchAttribute at[2];
-  int cl = g_tc_cluster;
-  for (; cl > 1; cl >>= 1) {
-    if (g.G % cl != 0) continue;                 // (a 4 KB k-block splits into >= 512-byte parts for cl <= 8)
-    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    int ncl = 0;
-    if (cudaOccupancyMaxActiveClusters(&ncl, (void*)decoder_fwd_tc_kernel<U>, &cfg) == cudaSuccess && ncl * cl >= g.G) break;
-    (void)cudaGetLastError();
-  }
-  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
-  cfg.attrs = at; cfg.numAttrs = 2;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, decoder_fwd_tc_kernel<U>, a, g, tg, w, tw, packed);
-  if (e != cudaSuccess && cl > 1) {            // cooperative + cluster refused: co-residency was checked above
-    (void)cudaGetLastError();
-    cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, decoder_fwd_tc_kernel<U>, a, g, tg, w, tw, packed);
-  }
-  ZCHECK_CUDA(e);
-  g_tc_cluster_used = cl;
+  void* args[] = {(void*)&a, (void*)&g, (void*)&tg, (void*)&w, (void*)&tw, (void*)&packed};
+  ZCHECK_CUDA(cudaLaunchCooperativeKernel((void*)decoder_fwd_tc_kernel<U>, dim3(g.G), dim3(160), args, smem, stream));
   count_launch();
   return ZEGGS_OK;
 }
@@ -746,7 +708,7 @@ int decoder_fwd_tc_run(const zeggs_decoder_fwd_args& a, const DecGeom& g, const 
   TcGeom tg = make_tcgeom(g);
   ZCHECK_ARG(g.nbt == 1, "decoder tc engine handles one 32-sample batch tile (B <= 32); got B=%d", a.B);
   ZCHECK_ARG(a.packed_tc && a.workspace_tc, "decoder tc: packed_tc / workspace_tc missing");
-  ZCHECK_ARG(a.H % 64 == 0 && tg.kbH <= 4 * TC_XCH, "decoder tc: unsupported hidden size %d", a.H);
+  ZCHECK_ARG(a.H % 64 == 0 && tg.kbH <= 16, "decoder tc: unsupported hidden size %d", a.H);
   TcWs tw = make_tcws(a.workspace_tc, g);
   tw.dbg = g_tc_dbg;
   // images of h0(0), h1(0) from the fp32 k-major buffers the CellStateEncoder wrote

@@ -95,6 +95,18 @@ __device__ __forceinline__ void tmem_ld4_sum(uint32_t taddr, uint32_t stride, fl
     v[i] = ((__uint_as_float(r0[i]) + __uint_as_float(r1[i])) + __uint_as_float(r2[i])) + __uint_as_float(r3[i]);
 }
 
+// same with NA (4 or 8) accumulators
+template <int NC, int NA>
+__device__ __forceinline__ void tmem_ldn_sum(uint32_t taddr, uint32_t stride, float (&v)[NC]) {
+  tmem_ld4_sum<NC>(taddr, stride, v);
+  if (NA == 8) {
+    float u_[NC];
+    tmem_ld4_sum<NC>(taddr + 4 * stride, stride, u_);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) v[i] += u_[i];
+  }
+}
+
 // bf16-engine gate math: exp via the SFU (relative error ~1e-6, far below the bf16 operand rounding)
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
