@@ -69,6 +69,7 @@ typedef struct {
   const float* fb_w;
   float* mel_out;
   float* feat_out;
+  int fb_total;          /* number of weights in fb_w (<= 4096: staged in shared memory; 0: read from global memory) */
 } zeggs_mel_args;
 int zeggs_mel_num_frames(int n_samples, int n_fft, int hop);
 int zeggs_mel_forward(const zeggs_mel_args* a, void* stream);

@@ -15,7 +15,7 @@ class MelArgs(C.Structure):
                 ("frames_per_anim", C.c_double),
                 ("wav", C.c_void_p), ("window", C.c_void_p), ("twiddle", C.c_void_p),
                 ("fb_start", C.c_void_p), ("fb_len", C.c_void_p), ("fb_off", C.c_void_p), ("fb_w", C.c_void_p),
-                ("mel_out", C.c_void_p), ("feat_out", C.c_void_p)]
+                ("mel_out", C.c_void_p), ("feat_out", C.c_void_p), ("fb_total", C.c_int)]
 
 
 class DecoderFwdArgs(C.Structure):

@@ -95,7 +95,7 @@ class MelFrontEnd:
                          anim_length=int(anim_length or 0), min_amp=self.min_amp, frames_per_anim=float(fpa),
                          wav=_lib.ptr(wav), window=_lib.ptr(self.window), twiddle=_lib.ptr(self.twiddle),
                          fb_start=_lib.ptr(self.fb_start), fb_len=_lib.ptr(self.fb_len), fb_off=_lib.ptr(self.fb_off),
-                         fb_w=_lib.ptr(self.fb_w), mel_out=_lib.ptr(mel), feat_out=_lib.ptr(feat))
+                         fb_w=_lib.ptr(self.fb_w), mel_out=_lib.ptr(mel), feat_out=_lib.ptr(feat), fb_total=int(self.fb_w.numel()))
         _lib.check(_lib.lib().zeggs_mel_forward(a, _lib.stream_ptr()), "zeggs_mel_forward")
         return mel, feat
 
