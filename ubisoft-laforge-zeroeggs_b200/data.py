@@ -59,6 +59,10 @@ class WindowDataset:
         return vec
 
     def sample_batch(self, batchsize, device):
+        return {k: v.to(device, non_blocking=True) for k, v in self.sample_host_batch(batchsize).items()}
+
+    def sample_host_batch(self, batchsize):
+        """Same draw as sample_batch, left in pinned host memory (for DevicePrefetcher.upload)."""
         idx = self.rs.randint(0, len(self.starts), size=batchsize)
         rows = torch.as_tensor(self.starts[idx][:, None] + np.arange(self.window)[None, :])
         out = {"audio": self.X[rows]}
@@ -70,4 +74,29 @@ class WindowDataset:
             out["style"] = lab
         else:
             out["style"] = torch.stack([self._example(int(self.starts[i]), int(self.rng_idx[i])) for i in idx])
-        return {k: v.pin_memory().to(device, non_blocking=True) for k, v in out.items()}
+        return {k: v.pin_memory() for k, v in out.items()}
+
+
+class DevicePrefetcher:
+    """Double-buffered host->device input pipeline: `upload` enqueues the copies of the NEXT step's batch on a side stream
+    so they overlap the current step's kernels; `acquire` makes the compute stream wait for them.  (The reference copies
+    its 11 batch tensors synchronously at the top of every iteration, train.py:215-225.)"""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+
+    def upload(self, host_batch):
+        with torch.cuda.stream(self.stream):
+            dev = {k: v.to(self.device, non_blocking=True) for k, v in host_batch.items()}
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return dev, ev
+
+    def acquire(self, token):
+        dev, ev = token
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for v in dev.values():
+            v.record_stream(cur)
+        return dev

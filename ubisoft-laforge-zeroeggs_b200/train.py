@@ -104,7 +104,7 @@ def build_networks(network_options, dimensions, style_encoding_type, nlabels, de
 def train(models_dir, logs_dir, path_processed_data, path_data_definition, train_options, network_options):
     """Drop-in for ZEGGS/train.py:29 (same arguments, same artefacts in models_dir).  Data-parallel when launched under
     torchrun (RANK/WORLD_SIZE set): each rank draws its own windows, one gradient all-reduce per step."""
-    from .data import WindowDataset
+    from .data import DevicePrefetcher, WindowDataset
     np.random.seed(train_options["seed"])
     torch.manual_seed(train_options["seed"])
     if not (train_options["use_gpu"] and torch.cuda.is_available()):
@@ -138,9 +138,12 @@ def train(models_dir, logs_dir, path_processed_data, path_data_definition, train
     batchsize = train_options["batchsize"]
     ex_len = network_options["style_encoder"]["example_length"]
     start = datetime.datetime.now()
+    prefetch = DevicePrefetcher(device)
+    token = prefetch.upload(ds.sample_host_batch(batchsize))
     while stepper.iteration < total:
-        batch = ds.sample_batch(batchsize, device)
+        batch = prefetch.acquire(token)
         ds.example_window_length = 2 * random.randint(ex_len // 2, ex_len)          # train.py:228-229
+        token = prefetch.upload(ds.sample_host_batch(batchsize))                    # next step's windows copy under this step
         loss = stepper.step(batch)
         it = stepper.iteration
         if it % 1000 == 0:
