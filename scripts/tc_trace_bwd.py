@@ -22,8 +22,8 @@ _lib.lib().zeggs_debug_set_tc_trace(buf.data_ptr())
 loss.backward(); torch.cuda.synchronize()
 _lib.lib().zeggs_debug_set_tc_trace(None)
 tr = buf.cpu().numpy().reshape(64, 32)
-names = {21:"cta1 d3 ready",22:"cta1 R done",0:"L:R seen",1:"L:DY issued",2:"L:B1 seen",3:"L:G1 issued",4:"L:B2 seen",5:"L:G0 issued",6:"L:B3 seen",7:"L:DPA issued",8:"M:c1 done",9:"M:c2 done",10:"M:c3 done",11:"M:c4 done",
-         12:"E:d0 ready",13:"E:epi1 done",14:"E:d1 ready",16:"E:epi2 done",17:"E:d2 ready",18:"E:epi3 done",19:"E:d3 ready",20:"E:R done"}
+names = {0:"L:B4/R seen (G1 image ready)",3:"L:G1 issued",2:"L:B2 seen",5:"L:G0 issued",4:"L:B3 seen",7:"L:DPA issued",9:"M:B2 chain done",10:"M:B3 chain done",11:"M:B4 chain done",
+         14:"E:d(B2) ready",16:"E:epi B2 done",17:"E:d(B3) ready",18:"E:epi B3 done",19:"E:d(B4) ready",20:"E:R done"}
 for s_ in (10,):
     base = tr[s_, 0]
     for ev in sorted(names, key=lambda e: tr[s_, e]):

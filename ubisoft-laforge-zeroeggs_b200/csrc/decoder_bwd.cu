@@ -397,6 +397,36 @@ __global__ void colsum_kernel(const float* __restrict__ x, int rows, int cols, f
   out[c] = s;
 }
 
+// tc engine (folded recurrence): rebuild the layer-2 / x_pose gradient history the weight gradients read.
+//   DY[t][n][b] = out_std[n] (dY_ext[b][t][n] + DXP[(t+1,b)][n] / in_std[n] + [n < 6] DCH[t][b][n]),  t = 1..T-1
+// One CTA per (t, 64-channel chunk); DXP rows (t,b) are transposed through shared memory into the k-major history.
+__global__ void __launch_bounds__(256) dy_combine_kernel(zeggs_decoder_fwd_args a, const float* __restrict__ dYext, const float* __restrict__ dxp,
+                                                         const float* __restrict__ dch, float* __restrict__ DY) {
+  __shared__ float tile[32][65];
+  const int t = 1 + blockIdx.x, n0 = blockIdx.y * 64, T = a.T;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int n = n0 + tx;
+  float os = 0.f, ris = 0.f;
+  if (n < P_OUT) { os = a.out_std[n]; ris = 1.0f / a.in_std[n]; }
+  for (int b = ty; b < 32; b += 4) {
+    float v = 0.f;
+    if (n < P_OUT && b < a.B) {
+      v = dYext ? dYext[((size_t)b * T + t) * P_OUT + n] : 0.f;
+      if (t + 1 < T) v += dxp[((size_t)(t + 1) * 32 + b) * P_OUT + n] * ris;
+      if (n < 6) v += dch[((size_t)t * 32 + b) * 8 + n];
+      v *= os;
+    }
+    tile[b][tx] = v;
+  }
+  __syncthreads();
+  float* dst = DY + (size_t)t * K1P * 32;
+  const int b = threadIdx.x & 31;
+  for (int r = threadIdx.x >> 5; r < 64; r += 8) {
+    const int nn = n0 + r;
+    if (nn < P_OUT) dst[(size_t)nn * 32 + b] = tile[b][r];
+  }
+}
+
 // ------------------------------------------------------------------ host
 extern "C" size_t zeggs_decoder_packed_bwd_bytes(int H, int S, int Z) {
   if (H % 16 != 0 || pick_U(H) <= 0) return 0;
@@ -497,20 +527,50 @@ extern "C" int zeggs_decoder_window_bwd(const zeggs_decoder_fwd_args* ap, const 
       {w.XP, sX, P_IN, nullptr, nullptr, nullptr}, {bw.COND, sC, C, nullptr, nullptr, nullptr}};
     size_t need = 0;
     for (auto& h : hs) need += (size_t)h.rows * ld * 2 * (want_lo ? 2 : 1);
-    if (need <= scratch_bytes()) {
+    // tc engine: the dpre_a / dgi0 histories are also needed transposed ([(t,b)][row], bf16) -- for the hoisted cond terms and
+    // for the x_pose gradient of the folded recurrence -- plus the transposed weight blocks and the DXP result
+    const bool fold = use_tc && nbt == 1 && H % 64 == 0;
+    const size_t extra = fold ? (ld * H * 2 + ld * 3 * H * 2 + (size_t)C * 4 * H * 2 + (size_t)P_OUT * 4 * H * 2 + ld * P_OUT * 4 + 4096) : 0;
+    if (need + extra <= scratch_bytes()) {
       // all hi parts first, then all lo parts: (ld * 2) bytes per row, 16 B aligned, so consecutive histories stack into ONE
       // row-contiguous operand ([a | x_pose | cond] is the input of layer0 / GRU0 in the weights' own column order)
       for (auto& h : hs) { h.hi = (__nv_bfloat16*)p; p += (size_t)h.rows * ld * 2; }
       if (want_lo) for (auto& h : hs) { h.lo = (__nv_bfloat16*)p; p += (size_t)h.rows * ld * 2; }
-      for (auto& h : hs) {
+      auto takeq = [&](size_t bytes) { char* r = (char*)(((uintptr_t)p + 255) & ~(uintptr_t)255); p = r + bytes; return r; };
+      __nv_bfloat16 *paT = nullptr, *giT = nullptr, *w0T = nullptr, *wiT = nullptr, *w0xT = nullptr, *wixT = nullptr;
+      float* dxp = nullptr;
+      if (fold) {
+        paT = (__nv_bfloat16*)takeq(ld * H * 2); giT = (__nv_bfloat16*)takeq(ld * 3 * H * 2);
+        w0T = (__nv_bfloat16*)takeq((size_t)C * H * 2); wiT = (__nv_bfloat16*)takeq((size_t)C * 3 * H * 2);
+        w0xT = (__nv_bfloat16*)takeq((size_t)P_OUT * H * 2); wixT = (__nv_bfloat16*)takeq((size_t)P_OUT * 3 * H * 2);
+        dxp = (float*)takeq(ld * P_OUT * 4);
+      }
+      const int cur = nbt * 32;                  // column offset of slot t = 1
+      const int Kc = nT * nbt * 32;
+      for (int hi_ = fold ? 1 : 0; hi_ < 11; ++hi_) {
+        Hist& h = hs[hi_];
         // per-slot stride of the fp32 history is (stride / nbt) floats: slots (t,bt) are contiguous
         // gradient histories: the same pass returns the bias gradient (sum over slots t >= 1, i.e. s >= nbt)
         rc = split_hist_launch(h.src, h.stride / nbt, S, h.rows, h.hi, h.lo, stream, h.db, nbt); if (rc) return rc;
       }
+      if (fold) {
+        // transposes of the dpre_a / dgi0 histories, then the x_pose gradient of every step at once:
+        //   DXP[(t,b)][n] = dpre_a(t)^T W0[:, n] + dgi0(t)^T W_ih0[:, H + n]      (n < 1131; modules.py:172-175 adjoint)
+        // and the layer-2 / x_pose gradient history the weight gradients read (modules.py:713, :728 adjoints):
+        //   DY[t][n][b] = out_std[n] (dY_ext[b][t][n] + DXP[(t+1,b)][n] / in_std[n] + [n < 6] dch(t)[b][n])
+        if ((rc = transpose_bf16_launch(hs[5].hi, H, (int)ld, ld, paT, H, stream))) return rc;
+        if ((rc = transpose_bf16_launch(hs[3].hi, 3 * H, (int)ld, ld, giT, 3 * H, stream))) return rc;
+        if ((rc = split_t_launch(a.W0, H, P_OUT, A, w0xT, nullptr, H, stream))) return rc;
+        if ((rc = split_t_launch(a.W_ih0 + H, 3 * H, P_OUT, A + H, wixT, nullptr, 3 * H, stream))) return rc;
+        if ((rc = tc_gemm_launch(Kc, P_OUT, H, paT + (size_t)cur * H, nullptr, H, w0xT, nullptr, H, nullptr, dxp + (size_t)cur * P_OUT, P_OUT, 0, 0, stream))) return rc;
+        if ((rc = tc_gemm_launch(Kc, P_OUT, 3 * H, giT + (size_t)cur * 3 * H, nullptr, 3 * H, wixT, nullptr, 3 * H, nullptr, dxp + (size_t)cur * P_OUT, P_OUT, 0, 1, stream))) return rc;
+        dy_combine_kernel<<<dim3(T - 1, ceil_div(P_OUT, 64)), 256, 0, stream>>>(a, b.dY, dxp, bw.DCH, bw.DY);
+        count_launch();
+        ZCHECK_LAUNCH();
+        rc = split_hist_launch(hs[0].src, hs[0].stride / nbt, S, hs[0].rows, hs[0].hi, hs[0].lo, stream, hs[0].db, nbt); if (rc) return rc;
+      }
       char* ws_p = (char*)(((uintptr_t)p + 255) & ~(uintptr_t)255);             // split-K partials behind the histories
       const size_t ws_bytes = (size_t)(scratch_base() + scratch_bytes() - ws_p);
-      const int Kc = nT * nbt * 32;
-      const int cur = nbt * 32;                  // column offset of slot t = 1
       auto G = [&](const Hist& ga, int ga_off, int N, const Hist& xb, int xb_off, int K, float* dW, int ldw) {
         return tc_gemm_launch(N, K, Kc, ga.hi + ga_off, want_lo ? ga.lo + ga_off : nullptr, (int)ld,
                               xb.hi + xb_off, want_lo ? xb.lo + xb_off : nullptr, (int)ld, nullptr, dW, ldw, 0, 0, stream,
@@ -525,25 +585,21 @@ extern "C" int zeggs_decoder_window_bwd(const zeggs_decoder_fwd_args* ap, const 
       if ((rc = G(hGH0, cur, 3 * H, hH0, 0, H, b.dW_hh0, H))) return rc;
       if ((rc = G(hPA, cur, H, hXP, cur, P_IN + C, b.dW0, A))) return rc;                    // [x_pose | cond] stacked
       tc_done = true;
-      // ---- d cond on tcgen05 (single-pass bf16, tc engine): transpose the dpa / dgi0 histories to [(t,b)][row] and contract
-      // them with the transposed cond columns of W0 / W_ih0:  DCOND[(t,b)][c] = dpa^T W0[:, 1134+c] + dgi0^T W_ih0[:, H+1134+c]
-      if (!want_lo && nbt == 1 && H % 64 == 0) {
-        char* q = ws_p;
-        auto takeq = [&](size_t bytes) { char* r = q; q += (bytes + 255) / 256 * 256; return (__nv_bfloat16*)r; };
-        __nv_bfloat16* paT = takeq(ld * H * 2); __nv_bfloat16* giT = takeq(ld * 3 * H * 2);
-        __nv_bfloat16* w0T = takeq((size_t)C * H * 2); __nv_bfloat16* wiT = takeq((size_t)C * 3 * H * 2);
-        if ((size_t)(q - scratch_base()) <= scratch_bytes()) {
-          if ((rc = transpose_bf16_launch(hPA.hi, H, (int)ld, ld, paT, H, stream))) return rc;
-          if ((rc = transpose_bf16_launch(hGI0.hi, 3 * H, (int)ld, ld, giT, 3 * H, stream))) return rc;
-          if ((rc = split_t_launch(a.W0 + P_IN, H, C, A, w0T, nullptr, H, stream))) return rc;
-          if ((rc = split_t_launch(a.W_ih0 + H + P_IN, 3 * H, C, A + H, wiT, nullptr, 3 * H, stream))) return rc;
-          float* out = bw.DCOND + (size_t)cur * C;
-          if ((rc = tc_gemm_launch(Kc, C, H, paT + (size_t)cur * H, nullptr, H, w0T, nullptr, H, nullptr, out, C, 0, 0, stream))) return rc;
-          if ((rc = tc_gemm_launch(Kc, C, 3 * H, giT + (size_t)cur * 3 * H, nullptr, 3 * H, wiT, nullptr, 3 * H, nullptr, out, C, 0, 1, stream))) return rc;
-          dcond_rows = true;
-        }
+      // ---- d cond on tcgen05 (single-pass bf16, tc engine): contract the transposed dpa / dgi0 histories with the transposed
+      // cond columns of W0 / W_ih0:  DCOND[(t,b)][c] = dpa^T W0[:, 1134+c] + dgi0^T W_ih0[:, H+1134+c]
+      if (fold) {
+        if ((rc = split_t_launch(a.W0 + P_IN, H, C, A, w0T, nullptr, H, stream))) return rc;
+        if ((rc = split_t_launch(a.W_ih0 + H + P_IN, 3 * H, C, A + H, wiT, nullptr, 3 * H, stream))) return rc;
+        float* out = bw.DCOND + (size_t)cur * C;
+        if ((rc = tc_gemm_launch(Kc, C, H, paT + (size_t)cur * H, nullptr, H, w0T, nullptr, H, nullptr, out, C, 0, 0, stream))) return rc;
+        if ((rc = tc_gemm_launch(Kc, C, 3 * H, giT + (size_t)cur * 3 * H, nullptr, 3 * H, wiT, nullptr, 3 * H, nullptr, out, C, 0, 1, stream))) return rc;
+        dcond_rows = true;
       }
+    } else {
+      ZCHECK_ARG(!use_tc, "decoder bwd tc: scratch buffer too small for the batched gradient GEMMs (%zu bytes needed)", need + extra);
     }
+  } else {
+    ZCHECK_ARG(!use_tc, "decoder bwd tc: needs the tcgen05 GEMM front end (zeggs_set_scratch, gemm mode 1 or 2)");
   }
 #define WG(...) do { if (!tc_done) { rc = wgrad(__VA_ARGS__); if (rc) return rc; } } while (0)
 #define RS(...) do { if (!tc_done) { rc = rowsum(__VA_ARGS__); if (rc) return rc; } } while (0)

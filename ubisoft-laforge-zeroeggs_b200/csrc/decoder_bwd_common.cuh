@@ -34,6 +34,7 @@ struct BwdWs {
   unsigned* bar;
   float *DY, *DGI1, *DGH1, *DGI0, *DGH0, *DPA, *DH0, *DH1, *COND, *DCOND;
   float *cse_dout, *cse_d2, *cse_d1, *cse_din;
+  float* DCH;   // tc engine: [T][32][8] d loss / d y(t)[0:6] through the root-integration chain
   size_t bytes;
 };
 
@@ -56,6 +57,7 @@ inline BwdWs make_bws(void* base, const DecGeom& g, int T) {
   w.COND = take(S * C * 32); w.DCOND = take(S * C * 32);
   w.cse_dout = take((size_t)g.B * 2 * g.H); w.cse_d2 = take((size_t)g.B * g.H); w.cse_d1 = take((size_t)g.B * g.H);
   w.cse_din = take((size_t)g.B * (P_IN + g.Z));
+  w.DCH = take((size_t)T * 32 * 8);
   w.bytes = off;
   return w;
 }

@@ -681,6 +681,12 @@ static int launch_tc(const zeggs_decoder_fwd_args& a, const DecGeom& g, const Tc
   return ZEGGS_OK;
 }
 
+const float* decoder_tc_mfold(const zeggs_decoder_fwd_args& a) {
+  if (!a.packed_tc) return nullptr;
+  DecGeom g = make_geom(a.B, a.H, a.S, a.Z);
+  return reinterpret_cast<const float*>((const uint8_t*)a.packed_tc + make_tcgeom(g).off_mfold);
+}
+
 static long long* g_tc_dbg = nullptr;
 extern "C" void zeggs_debug_set_tc_nacc(int) {}
 long long* tc_debug_buffer() { return g_tc_dbg; }
