@@ -50,7 +50,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -158,6 +158,12 @@ def run_ours(args):
         sampler = ClockSampler(lrank)
         if rank == 0 and timing:
             sampler.start()
+        if timing:
+            # nvidia-smi needs ~0.1-0.3 s to start reporting: every rank keeps its GPU under the same load meanwhile (untimed)
+            for _ in range(16):
+                stepper.step(dbatch)
+            barrier()
+            lib.zeggs_timing_reset()
         n0 = lib.zeggs_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -61,38 +61,44 @@ inline BtGeom make_btgeom(const DecGeom& g, const BwdGeom&) {
 
 // B3's extra 48 rows = three 16-row groups (gates r, z, n of d gi0): rows 0..U-1 = Mfold[(1+g)H + k][j] (this CTA's units j),
 // rows 8..10 = W_ih0[gH + k][H + 1131 + d] (gaze columns); B4's 16 rows: the same with the pre_a block / W0.
+// One thread per 16-byte image chunk, rows fastest: for a fixed k the 8 units of a row group are contiguous in the source
+// (the weights are read transposed), so a warp reads full 32-byte segments.
 __global__ void pack_decoder_bwd_tc_kernel(DecGeom g, BtGeom tg, const float* __restrict__ Mfold, const float* __restrict__ W0,
                                            const float* __restrict__ Wih0, const float* __restrict__ Whh0,
                                            const float* __restrict__ Wih1, const float* __restrict__ Whh1, uint8_t* __restrict__ out) {
   const int H = g.H, U = g.U, A = g.A;
-  const size_t per = tg.cta_bytes / 2, total = (size_t)g.G * per;
+  const size_t per = tg.cta_bytes / 16, total = (size_t)g.G * per;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i / per);
-    size_t b = (i % per) * 2;
+    size_t ci = i % per;                                // chunk index inside the CTA block, re-ordered (kb, logical chunk, row)
     int chain = 2;
-    for (int q = 0; q < 2; ++q) if (b < tg.off[q + 1]) { chain = q; break; }
-    b -= tg.off[chain];
+    for (int q = 0; q < 2; ++q) if (ci < tg.off[q + 1] / 16) { chain = q; break; }
+    ci -= tg.off[chain] / 16;
     const int N = chain == 0 ? tg.N2 : chain == 1 ? tg.N3 : tg.N4;
-    const int kb = (int)(b / ((size_t)N * 128)), rb = (int)(b % ((size_t)N * 128));
-    const int row = rb / 128, cp = (rb % 128) / 16, e = (rb % 16) / 2;
-    const int k = kb * 64 + ((cp ^ (row & 7)) << 3) + e;
-    float v = 0.f;
-    if (k < H) {
-      if (chain <= 1 && row < 6 * U) {           // gate-row transposes
+    const int row = (int)(ci % N), cl = (int)((ci / N) % 8), kb = (int)(ci / ((size_t)8 * N));
+    const int k0 = kb * 64 + cl * 8;
+    const float* src = nullptr; size_t stride = 0;      // element e of the chunk = src[e * stride]
+    if (k0 < H) {
+      if (chain <= 1 && row < 6 * U) {                  // gate-row transposes
         const int wsel = row / U, u = row % U, gq = wsel % 3, j = c * U + u;
-        const size_t r = (size_t)(gq * H + k);
-        if (chain == 0) v = wsel < 3 ? Wih1[r * H + j] : Whh1[r * H + j];
-        else            v = wsel < 3 ? Wih0[r * (A + H) + j] : Whh0[r * H + j];
+        const size_t r = (size_t)(gq * H + k0);
+        if (chain == 0) { src = (wsel < 3 ? Wih1 : Whh1) + r * H + j; stride = H; }
+        else if (wsel < 3) { src = Wih0 + r * (A + H) + j; stride = A + H; }
+        else { src = Whh0 + r * H + j; stride = H; }
       } else if (chain == 1 && row >= tg.P6) {
         const int rr = row - tg.P6, gq = rr / 16, lr = rr % 16;
-        if (lr < U) v = Mfold[((size_t)(1 + gq) * H + k) * H + c * U + lr];
-        else if (lr >= 8 && lr < 11) v = Wih0[(size_t)(gq * H + k) * (A + H) + H + P_OUT + (lr - 8)];
+        if (lr < U) { src = Mfold + ((size_t)(1 + gq) * H + k0) * H + c * U + lr; stride = H; }
+        else if (lr >= 8 && lr < 11) { src = Wih0 + (size_t)(gq * H + k0) * (A + H) + H + P_OUT + (lr - 8); stride = A + H; }
       } else if (chain == 2) {
-        if (row < U) v = Mfold[(size_t)k * H + c * U + row];
-        else if (row >= 8 && row < 11) v = W0[(size_t)k * A + P_OUT + (row - 8)];
+        if (row < U) { src = Mfold + (size_t)k0 * H + c * U + row; stride = H; }
+        else if (row >= 8 && row < 11) { src = W0 + (size_t)k0 * A + P_OUT + (row - 8); stride = A; }
       }
     }
-    reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+    __nv_bfloat16 t[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) t[e] = __float2bfloat16_rn(src ? __ldg(src + (size_t)e * stride) : 0.f);
+    uint8_t* dst = out + (size_t)c * tg.cta_bytes + tg.off[chain] + (size_t)kb * N * 128 + (size_t)row * 128 + (size_t)((cl ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(t);
   }
 }
 

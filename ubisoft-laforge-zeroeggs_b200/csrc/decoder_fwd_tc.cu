@@ -124,34 +124,46 @@ __global__ void fold_first_step_kernel(int H, int A, const float* __restrict__ W
 }
 
 // ------------------------------------------------------------------ packing (bf16 images of the weight slices)
+// One thread per 16-byte image chunk: 8 consecutive k of one weight row (two 16-byte reads, one 16-byte write).
 __global__ void pack_decoder_tc_kernel(DecGeom g, TcGeom tg, const float* __restrict__ Mfold, const float* __restrict__ Wih0,
                                        const float* __restrict__ Whh0, const float* __restrict__ Wih1,
                                        const float* __restrict__ Whh1, const float* __restrict__ W2, uint8_t* __restrict__ out) {
   const int H = g.H, U = g.U, A = g.A;
-  const size_t total_elems = (size_t)g.G * tg.cta_bytes / 2;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_elems; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i / (tg.cta_bytes / 2));
-    size_t b = (i % (tg.cta_bytes / 2)) * 2;           // byte offset inside the CTA block
+  const size_t per = tg.cta_bytes / 16, total = (size_t)g.G * per;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i / per);
+    size_t b = (i % per) * 16;                          // byte offset inside the CTA block
     int chain = 4;
     for (int q = 0; q < 4; ++q) if (b < tg.chain_off[q + 1]) { chain = q; break; }
     b -= tg.chain_off[chain];
     const int N = chain == 0 ? tg.N1 : tg.NP;
     const int kb = (int)(b / tc_tile_bytes(N));
     const int rb = (int)(b % tc_tile_bytes(N));
-    const int row = rb / 128, chunk_phys = (rb % 128) / 16, e = (rb % 16) / 2;
-    const int k = kb * 64 + ((chunk_phys ^ (row & 7)) << 3) + e;
-    float v = 0.f;
-    if (k < H) {
+    const int row = rb / 128, chunk_phys = (rb % 128) / 16;
+    const int k0 = kb * 64 + ((chunk_phys ^ (row & 7)) << 3);
+    const float* src = nullptr;
+    if (k0 < H) {
       if (chain == 0) {
-        if (row < 4 * U) { const int gi = row / U, j = c * U + row % U; v = Mfold[(size_t)(gi * H + j) * H + k]; }
-        else if (row < 4 * U + 6) v = W2[(size_t)(row - 4 * U) * H + k];
+        if (row < 4 * U) { const int gi = row / U, j = c * U + row % U; src = Mfold + (size_t)(gi * H + j) * H + k0; }
+        else if (row < 4 * U + 6) src = W2 + (size_t)(row - 4 * U) * H + k0;
       } else if (row < 3 * U) {
         const int gi = row / U, j = c * U + row % U;
         const size_t r = (size_t)(gi * H + j);
-        v = chain == 1 ? Whh0[r * H + k] : chain == 2 ? Wih0[r * (A + H) + k] : chain == 3 ? Whh1[r * H + k] : Wih1[r * H + k];
+        src = chain == 1 ? Whh0 + r * H + k0 : chain == 2 ? Wih0 + r * (A + H) + k0 : chain == 3 ? Whh1 + r * H + k0 : Wih1 + r * H + k0;
       }
     }
-    reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+    __nv_bfloat16 t[8];
+    if (src) {
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) {                  // rows are 8-byte aligned (H and A + H are even), k0 % 8 == 0
+        const float2 v = __ldg(reinterpret_cast<const float2*>(src + e));
+        t[e] = __float2bfloat16_rn(v.x); t[e + 1] = __float2bfloat16_rn(v.y);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t[e] = __float2bfloat16_rn(0.f);
+    }
+    *reinterpret_cast<uint4*>(out + i * 16) = *reinterpret_cast<const uint4*>(t);
   }
 }
 
