@@ -160,6 +160,14 @@ def decoder_window(dec, root_pos0, root_rot0, pose0, gaze_pos, speech, style,
                    in_mean, in_std, out_mean, out_std, dt):
     if speech.device.type != "cuda":
         raise _lib.ZeggsError("zeggs_b200.Decoder runs on CUDA tensors only (no CPU fallback)")
+    B = speech.shape[0]
+    if (DECODER_ENGINE == "tc" and B > 32 and dec.hidden_size >= 288 and
+            _lib.lib().zeggs_decoder_packed_tc_bytes(dec.hidden_size, dec.speech_encoding_size, dec.style_encoding_size) > 0):
+        # the tensor-core recurrence works on one 32-sample batch tile: independent windows -> run the tiles back to back
+        outs = [decoder_window(dec, root_pos0[i:i + 32], root_rot0[i:i + 32], pose0[i:i + 32], gaze_pos[i:i + 32],
+                               speech[i:i + 32], style[i:i + 32], in_mean, in_std, out_mean, out_std, dt)
+                for i in range(0, B, 32)]
+        return tuple(torch.cat(o, 0) for o in zip(*outs))
     needs_grad = torch.is_grad_enabled() and (
         any(p.requires_grad for p in dec.parameters()) or speech.requires_grad or style.requires_grad)
     if needs_grad:
