@@ -142,7 +142,7 @@ class TrainLossFn(torch.autograd.Function):
     """loss = train.py:277-421 evaluated (and differentiated) by zeggs_loss_fwd_bwd in the forward call."""
 
     @staticmethod
-    def forward(ctx, Y, rp, rq, WY, Wrp, Wrq, gaze, parents_i32, dt, mu, logvar, kl_weight, terms_out):
+    def forward(ctx, Y, rp, rq, WY, Wrp, Wrq, gaze, parents_i32, dt, mu, logvar, kl_weight, terms_out, unit_grad=False):
         l = _lib.lib()
         dev = Y.device
         B, T = Y.shape[0], Y.shape[1]
@@ -165,11 +165,12 @@ class TrainLossFn(torch.autograd.Function):
         a.workspace, a.workspace_bytes = ws.data_ptr(), wsb
         _lib.check(l.zeggs_loss_fwd_bwd(a, _lib.stream_ptr()), "zeggs_loss_fwd_bwd")
         ctx.grads = (dY, dRp, dRq, dmu, dlv)
+        ctx.unit_grad = bool(unit_grad)     # the caller promises loss.backward() with the implicit gradient 1 (TrainStep)
         return losses[0]
 
     @staticmethod
     def backward(ctx, g):
         dY, dRp, dRq, dmu, dlv = ctx.grads
         ctx.grads = None
-        s = lambda t: None if t is None else t * g
-        return (s(dY), s(dRp), s(dRq), None, None, None, None, None, None, s(dmu), s(dlv), None, None)
+        s = (lambda t: t) if ctx.unit_grad else (lambda t: None if t is None else t * g)
+        return (s(dY), s(dRp), s(dRq), None, None, None, None, None, None, s(dmu), s(dlv), None, None, None)

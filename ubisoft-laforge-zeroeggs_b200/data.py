@@ -80,23 +80,44 @@ class WindowDataset:
 class DevicePrefetcher:
     """Double-buffered host->device input pipeline: `upload` enqueues the copies of the NEXT step's batch on a side stream
     so they overlap the current step's kernels; `acquire` makes the compute stream wait for them.  (The reference copies
-    its 11 batch tensors synchronously at the top of every iteration, train.py:215-225.)"""
+    its 11 batch tensors synchronously at the top of every iteration, train.py:215-225.)  The device buffers are allocated
+    once (grow-only, per tensor name) and re-used, so the steady state performs no allocation; a buffer is overwritten
+    only after the step that read it has been enqueued two acquires ago (event-ordered, no host synchronisation)."""
 
-    def __init__(self, device):
+    def __init__(self, device, nbuf=2):
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(self.device)
+        self.flat = [dict() for _ in range(nbuf)]       # name -> 1-D device buffer (capacity)
+        self.free_ev = [None] * nbuf                     # recorded on the compute stream when the buffer may be overwritten
+        self.n = 0
+        self.last = None
 
     def upload(self, host_batch):
+        k = self.n % len(self.flat)
+        self.n += 1
+        views = {}
+        for name, v in host_batch.items():
+            buf = self.flat[k].get(name)
+            if buf is None or buf.numel() < v.numel() or buf.dtype != v.dtype:
+                buf = torch.empty(max(v.numel(), 1), dtype=v.dtype, device=self.device)
+                self.flat[k][name] = buf
+            views[name] = buf[:v.numel()].view(v.shape)
         with torch.cuda.stream(self.stream):
-            dev = {k: v.to(self.device, non_blocking=True) for k, v in host_batch.items()}
+            if self.free_ev[k] is not None:
+                self.stream.wait_event(self.free_ev[k])
+            for name, v in host_batch.items():
+                views[name].copy_(v, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        return dev, ev
+        return k, views, ev
 
     def acquire(self, token):
-        dev, ev = token
+        k, views, ev = token
         cur = torch.cuda.current_stream(self.device)
+        if self.last is not None:                        # everything that read the previous buffer is enqueued by now
+            fe = torch.cuda.Event()
+            fe.record(cur)
+            self.free_ev[self.last] = fe
         cur.wait_event(ev)
-        for v in dev.values():
-            v.record_stream(cur)
-        return dev
+        self.last = k
+        return views

@@ -96,6 +96,13 @@ class Decoder(nn.Module):
             anim_input_mean, anim_input_std, anim_output_mean, anim_output_std, float(dt))
         return ops.split_pose(Y, root_pos, root_rot)
 
+    def forward_packed(self, root_pos0, root_rot0, pose0, gaze_pos, speech_encoding, style_encoding,
+                       anim_input_mean, anim_input_std, anim_output_mean, anim_output_std, dt: float):
+        """Same window with the pose channels left packed ([B,T,1131] in the order of modules.py:731-736): what the fused
+        loss consumes -- the trainer skips the split into 8 views and the re-concatenation (and their autograd)."""
+        return ops.decoder_window(self, root_pos0, root_rot0, pose0, gaze_pos, speech_encoding, style_encoding,
+                                  anim_input_mean, anim_input_std, anim_output_mean, anim_output_std, float(dt))
+
 
 # ===============================================================================================
 #                                  Small torch-side helpers kept for API parity

@@ -67,12 +67,12 @@ class TrainStep:
             z = batch["style"]
         T = speech.shape[1]
         W = [batch[k] for k in POSE_KEYS]
-        out = self.dec(*[w[:, 0] for w in W], batch["gaze_pos"], speech, z.unsqueeze(1).repeat((1, T, 1)),
-                       None, self.in_mean, self.in_std, self.out_mean, self.out_std, self.dt)
-        Y = pack_pose(*out[2:])
-        WY = pack_pose(*W[2:])
-        loss = TrainLossFn.apply(Y, out[0], out[1], WY, W[0], W[1], batch["gaze_pos"], self.parents, self.dt, mu, logvar,
-                                 kl_weight(self.iteration) if mu is not None else 0.0, self.terms)
+        WY = pack_pose(*W[2:])                                   # ground-truth window, packed once
+        Y, rp, rq = self.dec.forward_packed(W[0][:, 0], W[1][:, 0], WY[:, 0], batch["gaze_pos"], speech,
+                                            z.unsqueeze(1).expand(-1, T, -1), self.in_mean, self.in_std,
+                                            self.out_mean, self.out_std, self.dt)
+        loss = TrainLossFn.apply(Y, rp, rq, WY, W[0], W[1], batch["gaze_pos"], self.parents, self.dt, mu, logvar,
+                                 kl_weight(self.iteration) if mu is not None else 0.0, self.terms, True)
         loss.backward()
         return loss
 
