@@ -116,6 +116,8 @@ def train(models_dir, logs_dir, path_processed_data, path_data_definition, train
     torch.cuda.set_device(device)
     if world > 1 and not torch.distributed.is_initialized():
         torch.distributed.init_process_group("nccl")
+    # additive option: recurrence engine ("tc": tcgen05 bf16 operands / fp32 state, the fast path; "fp32": SIMT parity-grade path)
+    ops.set_decoder_engine(train_options.get("decoder_engine", "tc"))
     models_dir, logs_dir = Path(models_dir), Path(logs_dir)
     with open(path_data_definition, "r") as f:
         details = json.load(f)
