@@ -233,6 +233,9 @@ int zeggs_loss_fwd_bwd(const zeggs_loss_args* a, void* stream);
  * degenerated_to_sgd).  `step` is the 1-based step count; gradients are multiplied by grad_scale first. */
 int zeggs_radam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
                      float eps, int step, float grad_scale, void* stream);
+/* Dropout mask (u >= p) / (1 - p) with a counter-based generator: one pass instead of torch's rand / compare / cast / scale
+ * (the Bernoulli draw of nn.Dropout, modules.py:263-270, :383-388, :551, :606).  Reproducible for a given seed. */
+int zeggs_dropout_mask(float* out, size_t n, float p, unsigned long long seed, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Generic fp32 GEMM used for the batched (non-recurrent) linear layers:

@@ -601,3 +601,21 @@ def test_full_size_train_step_engines_agree(dev, decoder_engine):
     assert np.isfinite(l1) and abs(l1 - l0) <= 1e-2 * abs(l0)
     bad = [(k, res["tc"][1][k], v) for k, v in res["fp32"][1].items() if not abs(res["tc"][1][k] - v) <= 6e-2 * max(v, 1e-7)]
     assert not bad, bad
+
+
+def test_dropout_mask_kernel(dev):
+    """zeggs_dropout_mask: values are 0 or 1/(1-p), keep fraction = 1-p within 4 sigma, reproducible under torch.manual_seed,
+    different for consecutive draws."""
+    from zeggs_b200 import ops
+    for p in (0.1, 0.2):
+        torch.manual_seed(5)
+        a = ops._drop_mask((64, 257, 33), p, dev)
+        b = ops._drop_mask((64, 257, 33), p, dev)
+        torch.manual_seed(5)
+        a2 = ops._drop_mask((64, 257, 33), p, dev)
+        n = a.numel()
+        keep = float((a > 0).float().mean())
+        assert torch.equal(a, a2) and not torch.equal(a, b)
+        vals = torch.unique(a).cpu().numpy()
+        assert len(vals) == 2 and vals[0] == 0.0 and abs(vals[1] - 1.0 / (1.0 - p)) <= 1e-6
+        assert abs(keep - (1.0 - p)) <= 4.0 * np.sqrt(p * (1.0 - p) / n)

@@ -44,3 +44,31 @@ extern "C" int zeggs_radam_step(float* p, const float* g, float* m, float* v, si
 }
 
 }  // namespace zeggs
+
+// ---------------------------------------------------------------------------------------------- dropout masks
+// mask[i] = (u_i >= p) / (1 - p), u_i ~ U[0,1) from a counter-based generator (the Bernoulli draw + rescale of
+// nn.Dropout / F.dropout, modules.py:263-270, :383-388, :551, :606) in ONE pass instead of rand / compare / cast / scale.
+// splitmix64 of (seed, index): independent of the launch shape, reproducible for a given seed.
+namespace zeggs {
+__device__ __forceinline__ uint32_t mix_u32(uint64_t seed, uint64_t i) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (i + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z = z ^ (z >> 31);
+  return (uint32_t)(z >> 32);
+}
+__global__ void dropout_mask_kernel(float* __restrict__ out, size_t n, float p, float keep_scale, uint64_t seed) {
+  const uint32_t thr = (uint32_t)fminf(4294967040.0f, p * 4294967296.0f);     // P(u32 < thr) = p
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = mix_u32(seed, i) >= thr ? keep_scale : 0.0f;
+}
+extern "C" int zeggs_dropout_mask(float* out, size_t n, float p, unsigned long long seed, void* stream) {
+  ZCHECK_ARG(out && p >= 0.0f && p < 1.0f, "dropout mask: bad arguments");
+  if (n == 0) return ZEGGS_OK;
+  const size_t blocks = (n + 1023) / 1024;
+  dropout_mask_kernel<<<(unsigned)(blocks > 2368 ? 2368 : blocks), 256, 0, (cudaStream_t)stream>>>(out, n, p, 1.0f / (1.0f - p), seed);
+  count_launch();
+  ZCHECK_LAUNCH();
+  return ZEGGS_OK;
+}
+}  // namespace zeggs

@@ -222,7 +222,12 @@ def tc_gemm(A_hi, B_hi, A_lo=None, B_lo=None, K=None, bias=None, act=0, out=None
 
 # ---------------------------------------------------------------------------------------------- encoders
 def _drop_mask(shape, p, device):
-    return (torch.rand(shape, device=device) >= p).float().mul_(1.0 / (1.0 - p))
+    """Dropout mask (u >= p) / (1 - p) in one kernel; the seed comes from torch's CPU generator, so torch.manual_seed()
+    makes training runs reproducible (and no device synchronisation is involved)."""
+    out = torch.empty(shape, dtype=torch.float32, device=device)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    _lib.check(_lib.lib().zeggs_dropout_mask(out.data_ptr(), out.numel(), float(p), seed, _lib.stream_ptr()), "zeggs_dropout_mask")
+    return out
 
 
 def speech_enc_args(enc, x, masks, y, ws):
