@@ -261,6 +261,9 @@ int zeggs_tc_gemm_bf16(int M, int N, int K, const void* A_hi, const void* A_lo, 
  * fp32 SIMT kernel.  zeggs_set_gemm_mode: 0 = fp32 SIMT only, 1 = tcgen05 split-bf16 x3 (default), 2 = tcgen05 bf16. */
 int zeggs_set_scratch(void* device_ptr, size_t bytes);
 int zeggs_set_gemm_mode(int mode);
+/* 1: weight-gradient products of the encoders (contraction over samples/frames) use ONE bf16 pass instead of the split-bf16
+ * three -- the accuracy class of the tensor-core recurrence engine's own weight gradients; set by zeggs_b200.ops.set_decoder_engine. */
+int zeggs_set_fast_wgrad(int on);
 int zeggs_gemm_f32(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* bias,
                    float* C, int ldc, int act, int accumulate, void* stream);
 int zeggs_split_bf16(const float* x, int rows, int cols, int ld_in, void* hi, void* lo, int ld_out, void* stream);

@@ -25,6 +25,7 @@ int sgemm_batched_launch(int mode, int M, int N, int K, const float* A, int lda,
 int gemm_f32_auto(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* bias,
                   float* C, int ldc, int act, int accumulate, cudaStream_t stream);
 int gemm_mode();
+int set_fast_wgrad_internal(int on);   // returns the previous setting
 char* scratch_base();
 size_t scratch_bytes();
 int split_hist_launch(const float* x, long long slot_stride, int S, int R, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t stream,

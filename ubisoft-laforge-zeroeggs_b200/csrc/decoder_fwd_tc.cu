@@ -662,7 +662,10 @@ extern "C" int zeggs_decoder_pack_weights_tc(const zeggs_decoder_fwd_args* a, vo
   count_launch();
   ZCHECK_LAUNCH();
   // Mfold[4H][H] = WxDt^T [4H x 1131] . W2 [1131 x H]     (fp32-grade: split-bf16 tcgen05 GEMM when a scratch buffer is set)
-  int rc = gemm_f32_auto(1, 4 * H, H, P_OUT, wxdt, 4 * H, a->W2, H, nullptr, mfold, H, 0, 0, stream); if (rc) return rc;
+  const int fw = set_fast_wgrad_internal(0);       // the fold matrix is a weight product: always the fp32-grade 3-pass GEMM
+  int rc = gemm_f32_auto(1, 4 * H, H, P_OUT, wxdt, 4 * H, a->W2, H, nullptr, mfold, H, 0, 0, stream);
+  set_fast_wgrad_internal(fw);
+  if (rc) return rc;
   pack_decoder_tc_kernel<<<592, 256, 0, stream>>>(g, tg, mfold, a->W_ih0, a->W_hh0, a->W_ih1, a->W_hh1, a->W2, base);
   count_launch();
   ZCHECK_CUDA(cudaMemsetAsync(w2b, 0, (size_t)round_up(P_OUT, 128) * H * 2, stream));

@@ -315,12 +315,16 @@ int split_t_launch(const float* x, int rows, int cols, int ld_in, __nv_bfloat16*
 static char* g_scratch = nullptr;
 static size_t g_scratch_bytes = 0;
 static int g_gemm_mode = 1;   // 0: fp32 SIMT everywhere, 1: tcgen05 split-bf16 (x3, ~fp32 accuracy), 2: tcgen05 plain bf16
+static int g_fast_wgrad = 0;  // 1: weight-gradient products (mode 1, contraction over samples/frames) run as ONE bf16 pass -- set together
+                              //    with the tensor-core recurrence engine, whose own weight gradients are single-pass bf16 already
 
 extern "C" int zeggs_set_scratch(void* p, size_t bytes) { g_scratch = (char*)p; g_scratch_bytes = bytes; return ZEGGS_OK; }
 extern "C" int zeggs_set_gemm_mode(int mode) {
   ZCHECK_ARG(mode >= 0 && mode <= 2, "gemm mode must be 0 (fp32 SIMT), 1 (tcgen05 bf16x3) or 2 (tcgen05 bf16)");
   g_gemm_mode = mode; return ZEGGS_OK;
 }
+extern "C" int zeggs_set_fast_wgrad(int on) { g_fast_wgrad = on ? 1 : 0; return ZEGGS_OK; }
+int set_fast_wgrad_internal(int on) { const int old = g_fast_wgrad; g_fast_wgrad = on; return old; }
 int gemm_mode() { return g_gemm_mode; }
 char* scratch_base() { return g_scratch; }
 size_t scratch_bytes() { return g_scratch_bytes; }
@@ -340,7 +344,7 @@ int gemm_f32_auto(int mode, int M, int N, int K, const float* A, int lda, const 
                   float* C, int ldc, int act, int accumulate, cudaStream_t stream) {
   const int Kp = round_up(K, 8);
   const size_t elems = (size_t)(M + N) * Kp;
-  const bool want_lo = g_gemm_mode == 1;
+  const bool want_lo = g_gemm_mode == 1 && !(mode == 1 && g_fast_wgrad);
   const size_t need = elems * 2 * (want_lo ? 2 : 1) + 1024;
   if (g_gemm_mode == 0 || g_scratch == nullptr || need > g_scratch_bytes || (double)M * N * K < 4.0e6)
     return sgemm_launch(mode, M, N, K, A, lda, B, ldb, bias, C, ldc, act, accumulate, stream);

@@ -60,6 +60,8 @@ def set_decoder_engine(name):
     if name not in ("fp32", "tc"):
         raise _lib.ZeggsError("decoder engine must be 'fp32' or 'tc'")
     DECODER_ENGINE = name
+    # the tensor-core engine's weight gradients are single-pass bf16: the encoders' weight-gradient GEMMs follow it
+    _lib.check(_lib.lib().zeggs_set_fast_wgrad(1 if name == "tc" else 0), "zeggs_set_fast_wgrad")
 
 
 def bump_weights_epoch():
