@@ -578,12 +578,16 @@ template <int U>
 static int launch_bt(const zeggs_decoder_fwd_args& a, const DecGeom& g, const BwdGeom& bg, const BtGeom& tg, const DecWs& w,
                      const BwdWs& bw, const BtWs& iw, const BwdArgsDev& d, const uint8_t* packed, cudaStream_t stream) {
   const size_t smem = 1024 + (size_t)BT_RING * tg.slot_bytes + 512 + (size_t)(4 * 32 * (2 * U + 16) + 6 * U + 16) * sizeof(float);
-  ZCHECK_CUDA(cudaFuncSetAttribute(decoder_bwd_tc_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int dev = 0, nsm = 0, occ = 0;
-  ZCHECK_CUDA(cudaGetDevice(&dev));
-  ZCHECK_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  ZCHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decoder_bwd_tc_kernel<U>, 224, smem));
-  ZCHECK_ARG(occ * nsm >= g.G, "decoder bwd tc: cooperative grid of %d CTAs does not fit", g.G);
+  static size_t checked_smem = 0;     // attribute + co-residency check once per shared-memory size (one device per process)
+  if (checked_smem != smem) {
+    ZCHECK_CUDA(cudaFuncSetAttribute(decoder_bwd_tc_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, nsm = 0, occ = 0;
+    ZCHECK_CUDA(cudaGetDevice(&dev));
+    ZCHECK_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    ZCHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decoder_bwd_tc_kernel<U>, 224, smem));
+    ZCHECK_ARG(occ * nsm >= g.G, "decoder bwd tc: cooperative grid of %d CTAs does not fit", g.G);
+    checked_smem = smem;
+  }
   void* args[] = {(void*)&a, (void*)&g, (void*)&bg, (void*)&tg, (void*)&w, (void*)&bw, (void*)&iw, (void*)&d, (void*)&packed};
   ZCHECK_CUDA(cudaLaunchCooperativeKernel((void*)decoder_bwd_tc_kernel<U>, dim3(g.G), dim3(224), args, smem, stream));
   count_launch();

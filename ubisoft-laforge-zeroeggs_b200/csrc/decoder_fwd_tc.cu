@@ -684,12 +684,16 @@ static int launch_tc(const zeggs_decoder_fwd_args& a, const DecGeom& g, const Tc
                      const uint8_t* packed, cudaStream_t stream) {
   const size_t smem = 1024 + (size_t)2 * tg.kbH * 4096 + (size_t)TC_RING * tg.slot_bytes + 4096 + 512 +
                       (size_t)(12 * U + 16 * U + 18 + 8) * sizeof(float);
-  ZCHECK_CUDA(cudaFuncSetAttribute(decoder_fwd_tc_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int dev = 0, nsm = 0, occ = 0;
-  ZCHECK_CUDA(cudaGetDevice(&dev));
-  ZCHECK_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  ZCHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decoder_fwd_tc_kernel<U>, 160, smem));
-  ZCHECK_ARG(occ * nsm >= g.G, "decoder tc: cooperative grid of %d CTAs does not fit", g.G);
+  static size_t checked_smem = 0;     // attribute + co-residency check once per shared-memory size (one device per process)
+  if (checked_smem != smem) {
+    ZCHECK_CUDA(cudaFuncSetAttribute(decoder_fwd_tc_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, nsm = 0, occ = 0;
+    ZCHECK_CUDA(cudaGetDevice(&dev));
+    ZCHECK_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    ZCHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decoder_fwd_tc_kernel<U>, 160, smem));
+    ZCHECK_ARG(occ * nsm >= g.G, "decoder tc: cooperative grid of %d CTAs does not fit", g.G);
+    checked_smem = smem;
+  }
   void* args[] = {(void*)&a, (void*)&g, (void*)&tg, (void*)&w, (void*)&tw, (void*)&packed};
   ZCHECK_CUDA(cudaLaunchCooperativeKernel((void*)decoder_fwd_tc_kernel<U>, dim3(g.G), dim3(160), args, smem, stream));
   count_launch();

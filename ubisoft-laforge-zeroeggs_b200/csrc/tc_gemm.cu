@@ -276,7 +276,8 @@ int tc_gemm_launch(int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bf
     if ((rc = encode_map(&maps.b[1], B_lo, N, K, ldb, TG_BN))) return rc;
   }
   const size_t smem = 1024 + TG_STAGES * (TG_A_BYTES + TG_B_BYTES) + (2 * TG_STAGES + 1) * 8 + 16;
-  ZCHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool attr_set = false;     // one device per process (one rank per GPU): set once, not on every launch
+  if (!attr_set) { ZCHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
   dim3 grid(ceil_div(N, TG_BN), ceil_div(M, TG_BM));
   // split-K when the output has too few tiles to fill the 148 SMs and the contraction is long
   const int tiles = (int)(grid.x * grid.y), kblocks = ceil_div(K, TG_BK);
