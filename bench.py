@@ -182,6 +182,8 @@ def run_ours(args):
         ms = max_over_ranks(e0.elapsed_time(e1))
         launches = int(lib.zeggs_launch_count() - n0)
         clocks = sampler.stop() if (rank == 0 and timing) else None
+        if clocks is not None:
+            clocks["note"] = "nvidia-smi every 200 ms from the start of 24 untimed warm steps of the same loop through the timed region"
         spans = {}
         if timing:
             lib.zeggs_timing_enable(0)

@@ -7,6 +7,7 @@
 // lo = bf16(x - hi); passes (A_hi,B_hi), (A_lo,B_hi), (A_hi,B_lo) accumulate into the same TMEM tile,
 // recovering ~fp32 product accuracy at 3x the tensor work.
 #include <cuda.h>
+#include <mutex>
 #include "decoder_common.cuh"
 #include "tc_common.cuh"
 
@@ -245,7 +246,7 @@ int transpose_bf16_launch(const __nv_bfloat16* in, int R, int Ncols, size_t ld_i
 // transposing split of a weight sub-block: x[rows][cols] (ld_in) -> hi [cols][ld_out] bf16
 int split_t_launch(const float* x, int rows, int cols, int ld_in, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_out, cudaStream_t stream);
 
-static int encode_map(CUtensorMap* m, const void* base, int rows, int K, int ld_elems, int box_rows) {
+static int encode_map_uncached(CUtensorMap* m, const void* base, int rows, int K, int ld_elems, int box_rows) {
   PFN_encodeTiled fn = get_encode_fn();
   ZCHECK_ARG(fn != nullptr, "tc_gemm: cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -256,6 +257,25 @@ static int encode_map(CUtensorMap* m, const void* base, int rows, int K, int ld_
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   ZCHECK_ARG(r == CUDA_SUCCESS, "tc_gemm: cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%d", (int)r, rows, K, ld_elems);
+  return ZEGGS_OK;
+}
+
+// A tensor map describes geometry only (base, extents, strides, box), and a training step presents the same few hundred
+// operand geometries every iteration (caller-owned buffers come back at the same addresses): a small direct-mapped cache
+// takes the ~250 driver encodes per step off the launch path.
+static int encode_map(CUtensorMap* m, const void* base, int rows, int K, int ld_elems, int box_rows) {
+  struct Entry { const void* base; int rows, K, ld, box; bool valid; CUtensorMap map; };
+  constexpr int NE = 1024;
+  static Entry* cache = nullptr;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!cache) cache = new Entry[NE]();
+  uint64_t hsh = (uint64_t)(uintptr_t)base * 0x9E3779B97F4A7C15ULL ^ ((uint64_t)rows << 40) ^ ((uint64_t)K << 20) ^ ((uint64_t)ld_elems << 4) ^ (uint64_t)box_rows;
+  Entry& e = cache[(hsh >> 20) % NE];
+  if (e.valid && e.base == base && e.rows == rows && e.K == K && e.ld == ld_elems && e.box == box_rows) { *m = e.map; return ZEGGS_OK; }
+  int rc = encode_map_uncached(m, base, rows, K, ld_elems, box_rows);
+  if (rc) return rc;
+  e.base = base; e.rows = rows; e.K = K; e.ld = ld_elems; e.box = box_rows; e.map = *m; e.valid = true;
   return ZEGGS_OK;
 }
 
