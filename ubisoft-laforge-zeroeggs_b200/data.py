@@ -74,7 +74,8 @@ class WindowDataset:
             out["style"] = lab
         else:
             out["style"] = torch.stack([self._example(int(self.starts[i]), int(self.rng_idx[i])) for i in idx])
-        return {k: v.pin_memory() for k, v in out.items()}
+        pin = torch.cuda.is_available()
+        return {k: (v.pin_memory() if pin else v.contiguous()) for k, v in out.items()}
 
 
 class DevicePrefetcher:
