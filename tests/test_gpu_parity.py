@@ -619,3 +619,34 @@ def test_dropout_mask_kernel(dev):
         vals = torch.unique(a).cpu().numpy()
         assert len(vals) == 2 and vals[0] == 0.0 and abs(vals[1] - 1.0 / (1.0 - p)) <= 1e-6
         assert abs(keep - (1.0 - p)) <= 4.0 * np.sqrt(p * (1.0 - p) / n)
+
+
+def test_label_style_z9_engines_agree(dev, decoder_engine):
+    """configs_v2 geometry (one-hot label style, Z = 9 -> odd W_ih0 row stride A + H): the tensor-core engine against the fp32
+    SIMT engine, window outputs <= 2e-2 * max(1, |ref|), parameter / speech gradient norms within 2e-2 relative."""
+    from zeggs_b200 import modules, synth
+    H, B, T, Z = 512, 4, 6, 9
+    st = stats_tensors()
+    torch.manual_seed(3)
+    dec = modules.Decoder(1134, 1131, 64, Z, H, 2).to(dev)
+    win = tt(synth.make_pose_windows(B, T, seed=3))
+    speech = (torch.randn(B, T, 64) * 0.5).to(dev).requires_grad_(True)
+    style = torch.zeros(B, T, Z)
+    style[:, :, 2] = 1.0
+    res = {}
+    for eng in ("fp32", "tc"):
+        decoder_engine(eng)
+        for p in dec.parameters():
+            p.grad = None
+        speech.grad = None
+        out = dec(*[win[n][:, 0].to(dev) for n in NAMES], win["gaze_pos"].to(dev), speech, style.to(dev), st["parents"],
+                  *[st[k].to(dev) for k in ("anim_input_mean", "anim_input_std", "anim_output_mean", "anim_output_std")], st["dt"])
+        sum((o * o).sum() for o in out).backward()
+        torch.cuda.synchronize()
+        res[eng] = ([o.detach().clone() for o in out], float(torch.cat([p.grad.flatten() for p in dec.parameters()]).norm()),
+                    float(speech.grad.norm()))
+    for n, a, b in zip(NAMES, res["tc"][0], res["fp32"][0]):
+        err, sc = report(f"z9 tc vs fp32 {n}", a, b)
+        assert err <= 2e-2 * max(1.0, sc), n
+    assert abs(res["tc"][1] - res["fp32"][1]) <= 2e-2 * res["fp32"][1]
+    assert abs(res["tc"][2] - res["fp32"][2]) <= 2e-2 * res["fp32"][2]

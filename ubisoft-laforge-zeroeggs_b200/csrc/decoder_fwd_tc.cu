@@ -153,12 +153,15 @@ __global__ void pack_decoder_tc_kernel(DecGeom g, TcGeom tg, const float* __rest
       }
     }
     __nv_bfloat16 t[8];
-    if (src) {
+    if (src && (reinterpret_cast<uintptr_t>(src) & 7) == 0) {
 #pragma unroll
-      for (int e = 0; e < 8; e += 2) {                  // rows are 8-byte aligned (H and A + H are even), k0 % 8 == 0
+      for (int e = 0; e < 8; e += 2) {                  // 8-byte aligned row segment (always for even row strides)
         const float2 v = __ldg(reinterpret_cast<const float2*>(src + e));
         t[e] = __float2bfloat16_rn(v.x); t[e + 1] = __float2bfloat16_rn(v.y);
       }
+    } else if (src) {                                   // odd row stride (e.g. W_ih0 with the 9-label style code, A + H = 2231)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t[e] = __float2bfloat16_rn(__ldg(src + e));
     } else {
 #pragma unroll
       for (int e = 0; e < 8; ++e) t[e] = __float2bfloat16_rn(0.f);
