@@ -225,6 +225,7 @@ typedef struct {
   float *dY, *dRootPos, *dRootRot, *dmu, *dlogvar;
   void* workspace;
   size_t workspace_bytes;
+  const float* kl_weight_dev; /* optional DEVICE scalar overriding kl_weight (updated by the host between CUDA-graph replays) */
 } zeggs_loss_args;
 size_t zeggs_loss_workspace_bytes(int B, int T);
 int zeggs_loss_fwd_bwd(const zeggs_loss_args* a, void* stream);
@@ -233,9 +234,17 @@ int zeggs_loss_fwd_bwd(const zeggs_loss_args* a, void* stream);
  * degenerated_to_sgd).  `step` is the 1-based step count; gradients are multiplied by grad_scale first. */
 int zeggs_radam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
                      float eps, int step, float grad_scale, void* stream);
+/* The same step with every step-dependent scalar in DEVICE memory, so that a captured CUDA graph can be replayed:
+ * hyper[0..4] = lr, beta1, beta2, eps, grad_scale (inputs; the host rewrites them between replays when they change),
+ * hyper[5..7] = scratch written by the call; *step_count is the number of steps taken so far and is incremented by the call
+ * (the rectification terms of optimizers.py:66-78 are evaluated on the device in double from *step_count + 1). */
+int zeggs_radam_step_dev(float* p, const float* g, float* m, float* v, size_t n, float* hyper, int* step_count, void* stream);
 /* Dropout mask (u >= p) / (1 - p) with a counter-based generator: one pass instead of torch's rand / compare / cast / scale
  * (the Bernoulli draw of nn.Dropout, modules.py:263-270, :383-388, :551, :606).  Reproducible for a given seed. */
 int zeggs_dropout_mask(float* out, size_t n, float p, unsigned long long seed, void* stream);
+/* Same, seeded from DEVICE memory: effective seed = hash(*seed_dev, salt) (CUDA-graph replays draw fresh masks when the
+ * caller advances *seed_dev between replays; `salt` separates the masks of one step). */
+int zeggs_dropout_mask_dev(float* out, size_t n, float p, const unsigned long long* seed_dev, unsigned long long salt, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Generic fp32 GEMM used for the batched (non-recurrent) linear layers:

@@ -497,7 +497,7 @@ def decoder_engine():
     ops.set_decoder_engine("fp32")
 
 
-@pytest.mark.parametrize("H,B,T", [(128, 4, 9), (512, 16, 40), (1024, 32, 24), (1024, 7, 64), (512, 40, 10), (1024, 3, 2)])
+@pytest.mark.parametrize("H,B,T", [(320, 4, 9), (512, 16, 40), (1024, 32, 24), (1024, 7, 64), (512, 40, 10), (1024, 3, 2)])
 def test_decoder_forward_tc_engine_vs_oracle(dev, decoder_engine, H, B, T):
     """tcgen05 recurrence (bf16 MMA operands, fp32 accumulate/state): free-running per-pose-channel max-abs
     <= 2e-2 * max(1, max|ref|) in de-normalised units (bf16 operand rounding, 2^-9 relative, compounds over the window)."""
@@ -650,3 +650,200 @@ def test_label_style_z9_engines_agree(dev, decoder_engine):
         assert err <= 2e-2 * max(1.0, sc), n
     assert abs(res["tc"][1] - res["fp32"][1]) <= 2e-2 * res["fp32"][1]
     assert abs(res["tc"][2] - res["fp32"][2]) <= 2e-2 * res["fp32"][2]
+
+
+# ---------------------------------------------------------------------------------------------- round 2: the benchmarked engine pinned to the oracle / reference
+def test_tc_engine_request_is_strict(dev, decoder_engine):
+    """An explicit 'tc' request on an ineligible hidden size raises (it never silently runs the fp32 engine); 'auto' falls back."""
+    from zeggs_b200 import _lib
+    decoder_engine("tc")
+    with pytest.raises(_lib.ZeggsError):
+        _decoder_case(dev, 128, 2, 4, seed=1)
+    decoder_engine("auto")
+    out, ref = _decoder_case(dev, 128, 2, 4, seed=1)
+    for n, o, r in zip(NAMES, out, ref):
+        err, sc = report(f"auto->fp32 H128 {n}", o, r)
+        assert err <= 2e-4 * max(1.0, sc)
+
+
+def _channel_table(tag, out, ref, frames=None):
+    """Per-pose-channel-group max-abs error table (de-normalised units), optionally per frame range; returns {name: (err, scale)}."""
+    res = {}
+    for n, o, r in zip(NAMES, out, ref):
+        o, r = o.detach().float().cpu(), r.detach().float().cpu()
+        if frames is not None:
+            o, r = o[:, frames[0]:frames[1]], r[:, frames[0]:frames[1]]
+        res[n] = (float((o - r).abs().max()), float(r.abs().max()))
+        print(f"  [{tag}] {n:9s} max-abs err {res[n][0]:.3e}  ref max {res[n][1]:.3e}  rel-to-max(1,ref) {res[n][0] / max(1.0, res[n][1]):.3e}")
+    return res
+
+
+# tolerances of the tensor-core (bf16 operand) recurrence against the fp32 CPU oracle, as fractions of max(1, max|ref|) per pose-channel
+# group, free running (errors feed back through the pose): stated in DESIGN.md 2 with the measured values
+TC_TOL_WINDOW = 5e-2        # B=32, T=256 training window
+TC_TOL_LONG = 2.5e-1        # T=3600 (60 s) generation
+
+
+def test_full_size_tc_forward_vs_oracle(dev, decoder_engine):
+    """BASELINE config 2, reference-actual size (B=32, T=256, H=1024): the tcgen05 engine against the CPU oracle's forward
+    (oracle/model_oracle.decoder_forward, modules.py:47-162), per-pose-channel table printed and asserted."""
+    decoder_engine("tc")
+    out, ref = _decoder_case(dev, 1024, 32, 256, seed=2024)
+    res = _channel_table("full-size tc vs ORACLE", out, ref)
+    _channel_table("full-size tc vs ORACLE, frames 0..64", out, ref, frames=(0, 64))
+    for n, (err, sc) in res.items():
+        assert err <= TC_TOL_WINDOW * max(1.0, sc), n
+    decoder_engine("fp32")
+    out32, _ = _decoder_case(dev, 1024, 32, 256, seed=2024)
+    res32 = _channel_table("full-size fp32 engine vs ORACLE", out32, ref)
+    for n, (err, sc) in res32.items():
+        assert err <= 2e-3 * max(1.0, sc), n
+
+
+@pytest.mark.parametrize("tag", ["h320", "h1024"])
+def test_train_step_tc_engine_vs_reference_golden(dev, golden_dir, decoder_engine, tag):
+    """The whole step body on the TENSOR-CORE engine (H >= 288: U=4/G=80 at H=320, U=8/G=128 -- the bench geometry -- at H=1024)
+    against the unmodified reference's loss, 18 terms and gradients (oracle/make_golden.py): loss within 5e-3 relative, terms
+    within 3e-2, gradient norms within 5e-2, stored gradient tensors rel-L2 <= 6e-2 (bf16 MMA operands; encoders' weight
+    gradients single-pass bf16)."""
+    decoder_engine("tc")
+    g = np.load(os.path.join(golden_dir, f"train_{tag}.npz"))
+    H, B, T, T_ex = int(g["H"]), int(g["B"]), int(g["T"]), int(g["T_ex"])
+    step, P = _make_step(dev, H, int(g["param_seed"]))
+    step.iteration = int(g["iteration"])
+    batch = _batch(dev, B, T, T_ex, int(g["input_seed"]))
+    step.optimizer.zero_grad()
+    loss = step.forward_backward(batch, eps=torch.from_numpy(g["eps"]).to(dev), train_mode=False)
+    torch.cuda.synchronize()
+    assert step.dec.__dict__.get("_zeggs_packed_tc") is not None, "the tensor-core engine did not run"
+    terms = step.terms.cpu().numpy()
+    rel = abs(loss.item() - float(g["loss"])) / abs(float(g["loss"]))
+    print(f"  [{tag} tc] loss {loss.item():.6f} vs reference golden {float(g['loss']):.6f}  rel {rel:.3e}")
+    names = ["root_pos", "root_rot", "root_vel", "root_vrt", "lpos", "lrot", "lvel", "lvrt", "cpos", "crot", "cvel", "cvrt",
+             "ldvl", "ldvt", "cdvl", "cdvt", "gaze", "kl_div"]
+    worst_t = 0.0
+    for i, n in enumerate(names):
+        ref = float(g["loss_" + n])
+        worst_t = max(worst_t, abs(terms[1 + i] - ref) / max(1e-3, abs(ref)))
+    worst_n, worst_e, bad = 0.0, 0.0, []
+    for prefix, net in (("speech_encoder.", step.se), ("decoder.", step.dec), ("style_encoder.", step.st)):
+        for k, p in net.named_parameters():
+            ref_n = float(g["gradnorm." + prefix + k])
+            got_n = float(p.grad.double().norm())
+            r = abs(got_n - ref_n) / max(ref_n, 1e-7)
+            worst_n = max(worst_n, r)
+            if r > 5e-2:
+                bad.append((prefix + k, "norm", got_n, ref_n))
+            if "grad." + prefix + k in g.files:
+                ref = g["grad." + prefix + k]
+                e = float(np.linalg.norm(p.grad.cpu().numpy() - ref)) / max(float(np.linalg.norm(ref)), 1e-9)
+                worst_e = max(worst_e, e)
+                if e > 6e-2:
+                    bad.append((prefix + k, "relL2", e))
+    print(f"  [{tag} tc] worst loss-term rel {worst_t:.3e}, worst grad-norm rel {worst_n:.3e}, worst stored-grad relL2 {worst_e:.3e}")
+    assert rel <= 5e-3
+    assert worst_t <= 3e-2
+    assert not bad, bad
+
+
+def test_long_clip_drift_T3600(dev, decoder_engine):
+    """BASELINE config 5 horizon (60 s = 3600 frames, H=1024): (a) tc engine vs the CPU oracle at B=2, (b) tc vs the fp32 engine at
+    B=64 (two 32-sample tiles).  Free running for 3599 bf16-operand steps; per-pose-channel max-abs over the whole clip and
+    over the first 600 frames printed; asserted against TC_TOL_LONG."""
+    decoder_engine("tc")
+    out, ref = _decoder_case(dev, 1024, 2, 3600, seed=3600)
+    _channel_table("T3600 B2 tc vs ORACLE, frames 0..600", out, ref, frames=(0, 600))
+    res = _channel_table("T3600 B2 tc vs ORACLE", out, ref)
+    for o in out:
+        assert torch.isfinite(o).all()
+    from zeggs_b200 import synth
+    st = stats_tensors()
+    H, B, T = 1024, 64, 3600
+    P = synth.make_params(H=H, seed=88, with_style=False)
+    win = tt(synth.make_pose_windows(B, 2, seed=88))
+    rs = np.random.RandomState(88)
+    speech = torch.from_numpy((rs.randn(B, T, 64) * 0.5).astype(np.float32)).to(dev)
+    style = torch.from_numpy(rs.randn(B, 1, 64).astype(np.float32)).repeat(1, T, 1).to(dev)
+    gaze = win["gaze_pos"][:, :1].repeat(1, T, 1).to(dev)
+    dec = make_decoder(P, H, device=dev)
+    args = [win[n][:, 0].to(dev) for n in NAMES] + [gaze, speech, style, st["parents"]] + \
+           [st[k].to(dev) for k in ("anim_input_mean", "anim_input_std", "anim_output_mean", "anim_output_std")] + [st["dt"]]
+    outs = {}
+    with torch.no_grad():
+        for eng in ("tc", "fp32"):
+            decoder_engine(eng)
+            outs[eng] = [o.clone() for o in dec(*args)]
+    torch.cuda.synchronize()
+    res64 = _channel_table("T3600 B64 tc vs fp32 engine", outs["tc"], outs["fp32"])
+    for n, (err, sc) in list(res.items()) + list(res64.items()):
+        assert err <= TC_TOL_LONG * max(1.0, sc), n
+
+
+def _v1_weights(golden_dir):
+    wpath = os.path.join(os.path.dirname(golden_dir), "_v1", "weights.npz")
+    if not os.path.exists(wpath):
+        pytest.skip("tests/_v1/weights.npz (the shipped v1 weights, git-ignored) is not present on this box")
+    return dict(np.load(wpath))
+
+
+def test_v1_pretrained_weights_vs_reference_golden(dev, golden_dir, decoder_engine):
+    """The shipped, TRAINED v1 weights (larger gates, saturating GRUs) through the CUDA path -- SpeechEncoder, StyleEncoder and the
+    decoder on both engines -- against outputs the unmodified reference produced from the pickles (tests/golden/v1_pretrained.npz)."""
+    import json
+    from zeggs_b200 import modules, synth
+    P = _v1_weights(golden_dir)
+    g = np.load(os.path.join(golden_dir, "v1_pretrained.npz"))
+    B, T, T_ex, seed, H = int(g["B"]), int(g["T"]), int(g["T_ex"]), int(g["input_seed"]), int(g["H"])
+    st = stats_tensors(dev)
+    se = _load(modules.SpeechEncoder(81, 64, 64), P, "speech_encoder.", dev).eval()
+    sty = _load(modules.StyleEncoder(1134, 512, 64, type="attn", use_vae=True), P, "style_encoder.", dev).eval()
+    de = _load(modules.Decoder(1134, 1131, 64, 64, H, 2), P, "decoder.", dev).eval()
+    win = tt(synth.make_pose_windows(B, T, seed=seed), dev)
+    audio = torch.from_numpy(synth.make_audio_features(B, T, seed=seed)).to(dev)
+    ex = torch.from_numpy(synth.make_style_example(B, T_ex, seed=seed)).to(dev)
+    record = {}
+    with torch.no_grad():
+        speech = se((audio - st["audio_input_mean"]) / st["audio_input_std"])
+        z, mu, logvar = sty((ex - st["anim_input_mean"]) / st["anim_input_std"], 1.0, eps=torch.zeros(B, 64, device=dev))
+        err_s, sc_s = report("v1 speech encoder", speech, torch.from_numpy(g["speech"]))
+        err_m, sc_m = report("v1 style mu", mu, torch.from_numpy(g["mu"]))
+        record["speech"] = [err_s, sc_s]; record["mu"] = [err_m, sc_m]
+        assert err_s <= 2e-4 * max(1.0, sc_s) and err_m <= 2e-4 * max(1.0, sc_m)
+        ref = [torch.from_numpy(g["O_" + n]) for n in NAMES]
+        sp_ref = torch.from_numpy(g["speech"]).to(dev)
+        sy_ref = torch.from_numpy(g["mu"]).to(dev).unsqueeze(1).repeat(1, T, 1)
+        for eng, tol in (("fp32", 1e-3), ("tc", TC_TOL_WINDOW)):
+            decoder_engine(eng)
+            out = de(*[win[n][:, 0] for n in NAMES], win["gaze_pos"], sp_ref, sy_ref, st["parents"], st["anim_input_mean"],
+                     st["anim_input_std"], st["anim_output_mean"], st["anim_output_std"], st["dt"])
+            res = _channel_table(f"v1 weights, {eng} engine vs REFERENCE", out, ref)
+            record[eng] = {n: list(v) for n, v in res.items()}
+            for n, (err, sc) in res.items():
+                assert err <= tol * max(1.0, sc), (eng, n)
+    os.makedirs(os.path.join(os.path.dirname(os.path.dirname(golden_dir)), "gpurun_out"), exist_ok=True)
+    with open(os.path.join(os.path.dirname(os.path.dirname(golden_dir)), "gpurun_out", "v1_pretrained_parity.json"), "w") as f:
+        json.dump(record, f, indent=1)
+
+
+def test_short_training_curve_tc_tracks_fp32(dev, decoder_engine):
+    """Convergence evidence for training on the tensor-core engine: 40 optimizer steps from the same initial weights, batches,
+    dropout masks and VAE noise (same torch seed) on both engines at H=320, lr=1e-3: the loss curves stay within 2 % of each other
+    at every step and both decrease."""
+    curves = {}
+    for eng in ("fp32", "tc"):
+        decoder_engine(eng)
+        step, P = _make_step(dev, 320, 4321)
+        for gr in step.optimizer.param_groups:
+            gr["lr"] = 1e-3
+        torch.manual_seed(7); torch.cuda.manual_seed(7)
+        losses = []
+        for it in range(40):
+            batch = _batch(dev, 8, 24, 32, 1000 + it % 4)
+            losses.append(float(step.step(batch).item()))
+        curves[eng] = losses
+        del step
+    a, b = np.array(curves["fp32"]), np.array(curves["tc"])
+    print("  fp32 curve", np.round(a[::5], 4)); print("  tc   curve", np.round(b[::5], 4))
+    assert np.all(np.isfinite(b))
+    assert np.max(np.abs(a - b) / np.abs(a)) <= 2e-2
+    assert a[-4:].mean() < a[:4].mean() and b[-4:].mean() < b[:4].mean()

@@ -59,7 +59,7 @@ def _run_oracle(g):
     return P, speech, (z, mu, logvar), O, loss, terms
 
 
-@pytest.mark.parametrize("tag", ["h64", "h128"])
+@pytest.mark.parametrize("tag", ["h64", "h128", "h320", "h1024"])
 def test_network_oracle_matches_reference_golden(golden_dir, tag):
     g = np.load(os.path.join(golden_dir, f"train_{tag}.npz"))
     P, speech, (z, mu, logvar), O, loss, terms = _run_oracle(g)
@@ -93,3 +93,29 @@ def test_radam_oracle_matches_reference_golden(golden_dir):
     for i in range(g["grads"].shape[0]):
         mo.radam_step(p, torch.from_numpy(g["grads"][i]), m, v, i + 1, lr=1e-4, eps=1e-5)
         assert np.max(np.abs(p.numpy() - g["traj"][i])) <= 1e-7, i
+
+
+def test_oracle_on_shipped_v1_weights_matches_reference_golden(golden_dir):
+    """The v1 pickles' weights (tests/_v1/weights.npz, git-ignored, written by oracle/make_golden.py) through the oracle against
+    the outputs the unmodified reference produced from the pickles themselves (tests/golden/v1_pretrained.npz)."""
+    wpath = os.path.join(os.path.dirname(golden_dir), "_v1", "weights.npz")
+    if not os.path.exists(wpath):
+        pytest.skip("tests/_v1/weights.npz not present (python -m oracle.make_golden v1)")
+    g = np.load(os.path.join(golden_dir, "v1_pretrained.npz"))
+    P = tt(dict(np.load(wpath)))
+    B, T, T_ex, seed = int(g["B"]), int(g["T"]), int(g["T_ex"]), int(g["input_seed"])
+    st = synth.load_stats()
+    f = lambda k: torch.as_tensor(st[k], dtype=torch.float32)
+    win = tt(synth.make_pose_windows(B, T, seed=seed))
+    audio = torch.from_numpy(synth.make_audio_features(B, T, seed=seed))
+    style_ex = torch.from_numpy(synth.make_style_example(B, T_ex, seed=seed))
+    with torch.no_grad():
+        speech = mo.speech_encoder(P, (audio - f("audio_input_mean")) / f("audio_input_std"))
+        z, mu, logvar = mo.style_encoder(P, (style_ex - f("anim_input_mean")) / f("anim_input_std"), eps=torch.zeros(B, 64))
+        O = mo.decoder_forward(P, *[win[n][:, 0] for n in NAMES], win["gaze_pos"], speech, mu.unsqueeze(1).repeat(1, T, 1),
+                               f("anim_input_mean"), f("anim_input_std"), f("anim_output_mean"), f("anim_output_std"), float(st["dt"]))
+    assert np.max(np.abs(speech.numpy() - g["speech"])) <= 1e-5
+    assert np.max(np.abs(mu.numpy() - g["mu"])) <= 2e-5
+    for n, o in zip(NAMES, O):
+        ref = g["O_" + n]
+        assert np.max(np.abs(o.numpy() - ref)) <= 1e-4 * max(1.0, float(np.max(np.abs(ref)))), n

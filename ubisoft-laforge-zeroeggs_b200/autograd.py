@@ -39,7 +39,9 @@ class DecoderWindowFn(torch.autograd.Function):
                 setattr(b, name, g.data_ptr())
         # transposed weight slices for the backward recurrence (cached on the module like the forward pack)
         ver = ops.weights_key(dec._weights())
-        use_tc = a.engine == 1 and l.zeggs_decoder_packed_bwd_tc_bytes(H, S, Z) > 0 and H >= 288
+        use_tc = a.engine == 1
+        if use_tc and l.zeggs_decoder_packed_bwd_tc_bytes(H, S, Z) == 0:
+            raise _lib.ZeggsError(f"tensor-core decoder backward unavailable for hidden size {H}")
         if not use_tc:
             cache = dec.__dict__.get("_zeggs_packed_bwd")
             if cache is None or cache[0] != ver or cache[1].device != dev:
@@ -142,7 +144,7 @@ class TrainLossFn(torch.autograd.Function):
     """loss = train.py:277-421 evaluated (and differentiated) by zeggs_loss_fwd_bwd in the forward call."""
 
     @staticmethod
-    def forward(ctx, Y, rp, rq, WY, Wrp, Wrq, gaze, parents_i32, dt, mu, logvar, kl_weight, terms_out, unit_grad=False):
+    def forward(ctx, Y, rp, rq, WY, Wrp, Wrq, gaze, parents_i32, dt, mu, logvar, kl_weight, terms_out, unit_grad=False, kl_weight_dev=None):
         l = _lib.lib()
         dev = Y.device
         B, T = Y.shape[0], Y.shape[1]
@@ -151,6 +153,8 @@ class TrainLossFn(torch.autograd.Function):
         losses = terms_out if terms_out is not None else torch.empty(19, dtype=torch.float32, device=dev)
         dY, dRp, dRq = torch.empty_like(Y), torch.empty_like(rp), torch.empty_like(rq)
         a = _lib.LossArgs(B=B, T=T, Z=(mu.shape[1] if mu is not None else 0), dt=dt, kl_weight=kl_weight)
+        if kl_weight_dev is not None:          # device scalar (graph-replayable): overrides the by-value weight
+            a.kl_weight_dev = kl_weight_dev.data_ptr()
         a.Y, a.root_pos, a.root_rot = Y.data_ptr(), rp.data_ptr(), rq.data_ptr()
         a.WY, a.W_root_pos, a.W_root_rot = WY.data_ptr(), Wrp.data_ptr(), Wrq.data_ptr()
         a.gaze_pos, a.parents, a.losses = gaze.data_ptr(), parents_i32.data_ptr(), losses.data_ptr()
@@ -173,4 +177,4 @@ class TrainLossFn(torch.autograd.Function):
         dY, dRp, dRq, dmu, dlv = ctx.grads
         ctx.grads = None
         s = (lambda t: t) if ctx.unit_grad else (lambda t: None if t is None else t * g)
-        return (s(dY), s(dRp), s(dRq), None, None, None, None, None, None, s(dmu), s(dlv), None, None, None)
+        return (s(dY), s(dRp), s(dRq), None, None, None, None, None, None, s(dmu), s(dlv), None, None, None, None)

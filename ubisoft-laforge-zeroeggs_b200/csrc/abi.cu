@@ -25,8 +25,8 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 // added); durations are resolved lazily by zeggs_timing_read() after the caller has synchronised.
 namespace zeggs {
 struct TimedSpan { int name; cudaEvent_t e0, e1; };
-static const char* kTimerNames[] = {"decoder_fwd", "decoder_bwd", "decoder_wgrad", "mel", "loss", "encoders_fwd", "encoders_bwd"};
-constexpr int kNumTimers = 7;
+static const char* kTimerNames[] = {"decoder_fwd", "decoder_bwd", "decoder_wgrad", "mel", "loss", "encoders_fwd", "encoders_bwd", "optimizer", "weight_pack"};
+constexpr int kNumTimers = 9;
 static bool g_timing = false;
 static std::vector<TimedSpan> g_spans;
 static std::vector<cudaEvent_t> g_pool;
@@ -40,18 +40,25 @@ static cudaEvent_t get_event() {
   if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
+// Under stream capture the record becomes an EXTERNAL event-record node (cudaEventRecordExternal): every replay of the
+// captured graph re-records the same event pair, and zeggs_timing_read() after a synchronised replay returns that replay's span.
+static void record_event(cudaEvent_t e, cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &st);
+  cudaEventRecordWithFlags(e, s, st == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
 void* timer_begin(int id, cudaStream_t s) {
   if (!g_timing || id < 0) return nullptr;
   std::lock_guard<std::mutex> lk(g_tmu);
   TimedSpan sp; sp.name = id; sp.e0 = get_event(); sp.e1 = get_event();
-  cudaEventRecord(sp.e0, s);
+  record_event(sp.e0, s);
   g_spans.push_back(sp);
   return (void*)(uintptr_t)g_spans.size();
 }
 void timer_end(void* h, cudaStream_t s) {
   if (!h) return;
   std::lock_guard<std::mutex> lk(g_tmu);
-  cudaEventRecord(g_spans[(size_t)(uintptr_t)h - 1].e1, s);
+  record_event(g_spans[(size_t)(uintptr_t)h - 1].e1, s);
 }
 }  // namespace zeggs
 

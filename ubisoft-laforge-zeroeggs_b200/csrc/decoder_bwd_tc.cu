@@ -568,6 +568,7 @@ extern "C" int zeggs_decoder_pack_weights_bwd_tc(const zeggs_decoder_fwd_args* a
   BwdGeom bg = make_bgeom(g);
   BtGeom tg = make_btgeom(g, bg);
   ZCHECK_ARG(g.U <= 8, "decoder bwd tc: unsupported units per CTA");
+  ScopedTimer tm_pack("weight_pack", (cudaStream_t)stream_);
   pack_decoder_bwd_tc_kernel<<<592, 256, 0, (cudaStream_t)stream_>>>(g, tg, mfold, a->W0, a->W_ih0, a->W_hh0, a->W_ih1, a->W_hh1, (uint8_t*)packed);
   count_launch();
   ZCHECK_LAUNCH();

@@ -649,6 +649,7 @@ extern "C" int zeggs_decoder_pack_weights_tc(const zeggs_decoder_fwd_args* a, vo
   ZCHECK_ARG(a && packed && a->H % 64 == 0 && pick_U(a->H) > 0 && a->H <= 1024, "decoder tc pack: bad arguments");
   ZCHECK_ARG(a->in_mean && a->in_std && a->out_mean && a->out_std, "decoder tc pack: normalisation statistics missing");
   cudaStream_t stream = (cudaStream_t)stream_;
+  ScopedTimer tm_pack("weight_pack", stream);
   DecGeom g = make_geom(a->B, a->H, a->S, a->Z);
   TcGeom tg = make_tcgeom(g);
   const int H = a->H;

@@ -115,8 +115,12 @@ __global__ void __launch_bounds__(256) loss_terms_kernel(LossDev d, float* __res
 // deterministic final reduction + KL (modules.py:764-789).  losses[0] = total, [1..17] = the 17 terms, [18] = kl term
 __global__ void __launch_bounds__(1024) loss_final_kernel(const float* __restrict__ partial, int nblk, int B, int T, float dt,
                                                           const float* __restrict__ mu, const float* __restrict__ logvar, int Z,
-                                                          float kl_weight, float* __restrict__ losses, float* __restrict__ dmu,
+                                                          float kl_weight_host, const float* __restrict__ kl_weight_dev,
+                                                          float* __restrict__ losses, float* __restrict__ dmu,
                                                           float* __restrict__ dlogvar) {
+  // the annealed KL weight (modules.py:745-761) either by value or from device memory (CUDA-graph replays: the host updates
+  // the scalar between replays without re-capturing)
+  const float kl_weight = kl_weight_dev ? *kl_weight_dev : kl_weight_host;
   __shared__ double wacc[32][N_TERMS + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane <= N_TERMS) wacc[warp][lane] = 0.0;
@@ -221,7 +225,7 @@ extern "C" int zeggs_loss_fwd_bwd(const zeggs_loss_args* ap, void* stream_) {
   d.gaze = a.gaze_pos; d.parents = a.parents; d.Q[0] = w.Q[0]; d.Q[1] = w.Q[1]; d.G = w.G; d.gYs = w.gYs; d.stride = w.stride;
   loss_fk_fwd_kernel<<<dim3(ceil_div(BT, 128), 2), 128, 0, s>>>(d); count_launch();
   loss_terms_kernel<<<dim3(w.nblk, Q_CH), 256, 0, s>>>(d, w.partial, w.nblk); count_launch();
-  loss_final_kernel<<<1, 1024, 0, s>>>(w.partial, w.nblk, a.B, a.T, a.dt, a.mu, a.logvar, a.Z, a.kl_weight, a.losses, a.dmu, a.dlogvar); count_launch();
+  loss_final_kernel<<<1, 1024, 0, s>>>(w.partial, w.nblk, a.B, a.T, a.dt, a.mu, a.logvar, a.Z, a.kl_weight, a.kl_weight_dev, a.losses, a.dmu, a.dlogvar); count_launch();
   ZCHECK_LAUNCH();
   if (a.dY) {
     ZCHECK_ARG(a.dRootPos && a.dRootRot, "loss: gradient outputs missing");

@@ -19,6 +19,53 @@ __global__ void radam_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+// device-resident variant (CUDA-graph replay): the step count lives in device memory; one thread evaluates the rectification
+// terms in double exactly as the host path does, the main kernel reads them back
+__global__ void radam_prep_kernel(float* __restrict__ hyper, int* __restrict__ step_count) {
+  const int step = *step_count + 1;
+  *step_count = step;
+  const double lr = hyper[0], beta1 = hyper[1], beta2 = hyper[2];
+  const double b2t = pow(beta2, (double)step);
+  const double n_max = 2.0 / (1.0 - beta2) - 1.0;
+  const double n_sma = n_max - 2.0 * step * b2t / (1.0 - b2t);            // optimizers.py:66-68
+  double step_size; float adaptive;
+  if (n_sma >= 5.0) {
+    step_size = sqrt((1.0 - b2t) * (n_sma - 4.0) / (n_max - 4.0) * (n_sma - 2.0) / n_sma * n_max / (n_max - 2.0)) /
+                (1.0 - pow(beta1, (double)step));                         // :72-76
+    adaptive = 1.f;
+  } else {
+    step_size = 1.0 / (1.0 - pow(beta1, (double)step));                   // :77-78
+    adaptive = 0.f;
+  }
+  hyper[5] = (float)(step_size * lr);
+  hyper[6] = adaptive;
+}
+__global__ void radam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                 size_t n, const float* __restrict__ hyper) {
+  const float beta1 = hyper[1], beta2 = hyper[2], eps = hyper[3], grad_scale = hyper[4], step_lr = hyper[5];
+  const bool adaptive = hyper[6] != 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float vi = v[i] * beta2 + (1.0f - beta2) * gi * gi;
+    const float mi = m[i] * beta1 + (1.0f - beta1) * gi;
+    v[i] = vi; m[i] = mi;
+    if (adaptive) p[i] = p[i] - step_lr * mi / (sqrtf(vi) + eps);
+    else p[i] = p[i] - step_lr * mi;
+  }
+}
+extern "C" int zeggs_radam_step_dev(float* p, const float* g, float* m, float* v, size_t n, float* hyper, int* step_count, void* stream) {
+  ZCHECK_ARG(p && g && m && v && hyper && step_count, "radam (device scalars): bad arguments");
+  if (n == 0) return ZEGGS_OK;
+  ScopedTimer tm("optimizer", (cudaStream_t)stream);
+  radam_prep_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper, step_count);
+  count_launch();
+  const size_t blocks = (n + 1023) / 1024;
+  radam_dev_kernel<<<(unsigned)(blocks > 1184 ? 1184 : blocks), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hyper);
+  count_launch();
+  ZCHECK_LAUNCH();
+  return ZEGGS_OK;
+}
+
 extern "C" int zeggs_radam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
                                 float eps, int step, float grad_scale, void* stream) {
   ZCHECK_ARG(p && g && m && v && step >= 1, "radam: bad arguments");
@@ -35,6 +82,7 @@ extern "C" int zeggs_radam_step(float* p, const float* g, float* m, float* v, si
     step_size = 1.0 / (1.0 - pow((double)beta1, (double)step));           // :77-78
     adaptive = 0;
   }
+  ScopedTimer tm("optimizer", (cudaStream_t)stream);
   const size_t blocks = (n + 1023) / 1024;
   radam_kernel<<<(unsigned)(blocks > 1184 ? 1184 : blocks), 256, 0, (cudaStream_t)stream>>>(
       p, g, m, v, n, beta1, beta2, eps, (float)(step_size * (double)lr), adaptive, grad_scale);
@@ -61,6 +109,26 @@ __global__ void dropout_mask_kernel(float* __restrict__ out, size_t n, float p, 
   const uint32_t thr = (uint32_t)fminf(4294967040.0f, p * 4294967296.0f);     // P(u32 < thr) = p
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = mix_u32(seed, i) >= thr ? keep_scale : 0.0f;
+}
+__global__ void dropout_mask_dev_kernel(float* __restrict__ out, size_t n, float p, float keep_scale,
+                                        const unsigned long long* __restrict__ seed_dev, unsigned long long salt) {
+  // effective seed: splitmix-style hash of (device seed, salt)
+  uint64_t z = *seed_dev * 0xD1342543DE82EF95ULL + (salt + 1) * 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  const uint64_t seed = z ^ (z >> 31);
+  const uint32_t thr = (uint32_t)fminf(4294967040.0f, p * 4294967296.0f);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = mix_u32(seed, i) >= thr ? keep_scale : 0.0f;
+}
+extern "C" int zeggs_dropout_mask_dev(float* out, size_t n, float p, const unsigned long long* seed_dev, unsigned long long salt, void* stream) {
+  ZCHECK_ARG(out && seed_dev && p >= 0.0f && p < 1.0f, "dropout mask (device seed): bad arguments");
+  if (n == 0) return ZEGGS_OK;
+  const size_t blocks = (n + 1023) / 1024;
+  dropout_mask_dev_kernel<<<(unsigned)(blocks > 2368 ? 2368 : blocks), 256, 0, (cudaStream_t)stream>>>(out, n, p, 1.0f / (1.0f - p), seed_dev, salt);
+  count_launch();
+  ZCHECK_LAUNCH();
+  return ZEGGS_OK;
 }
 extern "C" int zeggs_dropout_mask(float* out, size_t n, float p, unsigned long long seed, void* stream) {
   ZCHECK_ARG(out && p >= 0.0f && p < 1.0f, "dropout mask: bad arguments");

@@ -51,17 +51,36 @@ def ensure_scratch(dev):
 
 _weights_epoch = 0
 
-# decoder recurrence engine: "fp32" (SIMT, parity grade) or "tc" (tcgen05, bf16 operands / fp32 state; B <= 32)
+# decoder recurrence engine: "fp32" (SIMT, parity grade), "tc" (tcgen05, bf16 operands / fp32 state) or "auto" (tc where the
+# geometry is eligible, fp32 otherwise).  An explicit "tc" request on an ineligible geometry RAISES (it never silently
+# runs the other engine).
 DECODER_ENGINE = __import__("os").environ.get("ZEGGS_DECODER_ENGINE", "fp32")
+TC_MIN_HIDDEN = 288
+
+
+def tc_eligible(H, S, Z):
+    """The tensor-core recurrence covers H % 64 == 0, 288 <= H <= 1024 (zeggs_decoder_packed_tc_bytes reports 0 otherwise)."""
+    return H >= TC_MIN_HIDDEN and _lib.lib().zeggs_decoder_packed_tc_bytes(H, S, Z) > 0
 
 
 def set_decoder_engine(name):
     global DECODER_ENGINE
-    if name not in ("fp32", "tc"):
-        raise _lib.ZeggsError("decoder engine must be 'fp32' or 'tc'")
+    if name not in ("fp32", "tc", "auto"):
+        raise _lib.ZeggsError("decoder engine must be 'fp32', 'tc' or 'auto'")
     DECODER_ENGINE = name
     # the tensor-core engine's weight gradients are single-pass bf16: the encoders' weight-gradient GEMMs follow it
-    _lib.check(_lib.lib().zeggs_set_fast_wgrad(1 if name == "tc" else 0), "zeggs_set_fast_wgrad")
+    _lib.check(_lib.lib().zeggs_set_fast_wgrad(0 if name == "fp32" else 1), "zeggs_set_fast_wgrad")
+
+
+def resolve_engine(H, S, Z):
+    """-> True when the tensor-core engine runs this geometry under the current setting."""
+    if DECODER_ENGINE == "fp32":
+        return False
+    ok = tc_eligible(H, S, Z)
+    if DECODER_ENGINE == "tc" and not ok:
+        raise _lib.ZeggsError(f"decoder engine 'tc' requested but hidden size {H} is not eligible (needs H % 64 == 0 and "
+                              f"{TC_MIN_HIDDEN} <= H <= 1024); use 'fp32' or 'auto'")
+    return ok
 
 
 def bump_weights_epoch():
@@ -105,7 +124,9 @@ def _decoder_args(dec, B, T, dev, tensors, stats, dt, save):
         keep.append(t)
     # packed weights: re-packed whenever any parameter's version counter moved (each engine packs only its own slices)
     ver = weights_key(dec._weights())
-    use_tc = DECODER_ENGINE == "tc" and B <= 32 and l.zeggs_decoder_packed_tc_bytes(H, S, Z) > 0 and H >= 288
+    use_tc = resolve_engine(H, S, Z)
+    if use_tc and B > 32:
+        raise _lib.ZeggsError("tensor-core decoder engine: one call covers one 32-sample batch tile (decoder_window splits larger batches)")
     if not use_tc:
         cache = getattr(dec, "_zeggs_packed", None)
         if cache is None or cache[0] != ver or cache[1].device != dev:
@@ -163,8 +184,7 @@ def decoder_window(dec, root_pos0, root_rot0, pose0, gaze_pos, speech, style,
     if speech.device.type != "cuda":
         raise _lib.ZeggsError("zeggs_b200.Decoder runs on CUDA tensors only (no CPU fallback)")
     B = speech.shape[0]
-    if (DECODER_ENGINE == "tc" and B > 32 and dec.hidden_size >= 288 and
-            _lib.lib().zeggs_decoder_packed_tc_bytes(dec.hidden_size, dec.speech_encoding_size, dec.style_encoding_size) > 0):
+    if B > 32 and resolve_engine(dec.hidden_size, dec.speech_encoding_size, dec.style_encoding_size):
         # the tensor-core recurrence works on one 32-sample batch tile: independent windows -> run the tiles back to back
         outs = [decoder_window(dec, root_pos0[i:i + 32], root_rot0[i:i + 32], pose0[i:i + 32], gaze_pos[i:i + 32],
                                speech[i:i + 32], style[i:i + 32], in_mean, in_std, out_mean, out_std, dt)
@@ -223,10 +243,47 @@ def tc_gemm(A_hi, B_hi, A_lo=None, B_lo=None, K=None, bias=None, act=0, out=None
 
 
 # ---------------------------------------------------------------------------------------------- encoders
+class DeviceSeed:
+    """Dropout seed in DEVICE memory (zeggs_dropout_mask_dev): a captured CUDA graph of the train step draws fresh masks on every
+    replay because `advance()` -- one in-graph increment -- is part of the step.  `salt` separates the masks within a step."""
+
+    def __init__(self, device):
+        self.t = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).to(device)      # torch.manual_seed() -> reproducible runs
+        self.salt = 0
+
+    def advance(self):
+        self.t.add_(1)
+        self.salt = 0
+
+
+_dev_seed = None
+
+
+class device_seed:
+    """Context: dropout masks drawn inside it use `seed` (a DeviceSeed) instead of the host generator."""
+
+    def __init__(self, seed):
+        self.seed = seed
+
+    def __enter__(self):
+        global _dev_seed
+        self.prev, _dev_seed = _dev_seed, self.seed
+
+    def __exit__(self, *exc):
+        global _dev_seed
+        _dev_seed = self.prev
+
+
 def _drop_mask(shape, p, device):
     """Dropout mask (u >= p) / (1 - p) in one kernel; the seed comes from torch's CPU generator, so torch.manual_seed()
-    makes training runs reproducible (and no device synchronisation is involved)."""
+    makes training runs reproducible (and no device synchronisation is involved) -- or from a DeviceSeed inside a
+    `device_seed` context (graph-replayable)."""
     out = torch.empty(shape, dtype=torch.float32, device=device)
+    if _dev_seed is not None:
+        _dev_seed.salt += 1
+        _lib.check(_lib.lib().zeggs_dropout_mask_dev(out.data_ptr(), out.numel(), float(p), _dev_seed.t.data_ptr(), _dev_seed.salt,
+                                                    _lib.stream_ptr()), "zeggs_dropout_mask_dev")
+        return out
     seed = int(torch.randint(0, 2 ** 62, (1,)).item())
     _lib.check(_lib.lib().zeggs_dropout_mask(out.data_ptr(), out.numel(), float(p), seed, _lib.stream_ptr()), "zeggs_dropout_mask")
     return out

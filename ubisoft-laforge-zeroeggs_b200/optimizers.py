@@ -33,6 +33,20 @@ class RAdam(torch.optim.Optimizer):
             off += k
         self._step = 0
         self.grad_scale = 1.0
+        # step-dependent scalars live in DEVICE memory (zeggs_radam_step_dev) so a captured CUDA graph of the step can be replayed:
+        # hyper = [lr, beta1, beta2, eps, grad_scale, <scratch x3>], step_dev = steps taken so far (incremented by the kernel)
+        self.hyper = torch.zeros(8, dtype=torch.float32, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._hyper_host = None
+
+    def sync_hyper(self):
+        """Push lr / betas / eps / grad_scale to the device when they changed (call OUTSIDE graph capture; train() changes lr every
+        1000 iterations through param_groups like the reference's ExponentialLR, train.py:431-432)."""
+        g = self.param_groups[0]
+        h = (float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(self.grad_scale))
+        if h != self._hyper_host:
+            self.hyper[:5].copy_(torch.tensor(h, dtype=torch.float32))
+            self._hyper_host = h
 
     def zero_grad(self, set_to_none=False):
         self.flat_grad.zero_()
@@ -40,12 +54,13 @@ class RAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
-        g = self.param_groups[0]
-        self._step += 1
-        _lib.check(_lib.lib().zeggs_radam_step(
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            self.sync_hyper()
+            self._step += 1          # host mirror of step_dev (a graph replay wrapper keeps it in step, see train.GraphedStep)
+        _lib.check(_lib.lib().zeggs_radam_step_dev(
             self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-            self.flat_param.numel(), float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
-            int(self._step), float(self.grad_scale), _lib.stream_ptr()), "zeggs_radam_step")
+            self.flat_param.numel(), self.hyper.data_ptr(), self.step_dev.data_ptr(), _lib.stream_ptr()), "zeggs_radam_step_dev")
         ops.bump_weights_epoch()     # parameters changed behind autograd's back: invalidate packed-weight caches
         return loss
 
@@ -54,10 +69,21 @@ class RAdam(torch.optim.Optimizer):
         d["zeggs"] = dict(step=self._step, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq)
         return d
 
+    def _restore_groups(self, state_dict):
+        """lr / betas / eps of the checkpoint (the reference's optimizer.load_state_dict restores the DECAYED lr and its
+        ExponentialLR continues from it, train.py:165-175)."""
+        for g, sg in zip(self.param_groups, state_dict.get("param_groups", [])):
+            for k in ("lr", "betas", "eps"):
+                if k in sg:
+                    g[k] = tuple(sg[k]) if k == "betas" else sg[k]
+        self._hyper_host = None
+
     def load_state_dict(self, state_dict):
+        self._restore_groups(state_dict)
         z = state_dict.get("zeggs")
         if z is not None:
             self._step = int(z["step"])
+            self.step_dev.fill_(self._step)
             self.exp_avg.copy_(z["exp_avg"])
             self.exp_avg_sq.copy_(z["exp_avg_sq"])
             return
@@ -72,3 +98,4 @@ class RAdam(torch.optim.Optimizer):
                 self.exp_avg[off:off + k].copy_(st["exp_avg"].reshape(-1))
                 self.exp_avg_sq[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
             off += k
+        self.step_dev.fill_(self._step)

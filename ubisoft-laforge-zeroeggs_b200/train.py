@@ -13,7 +13,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
-from . import _lib, modules, ops
+from . import _lib, dp, modules, ops
 from .autograd import TrainLossFn
 from .optimizers import RAdam
 
@@ -32,10 +32,16 @@ def pack_pose(root_vel, root_vrt, lpos, ltxy, lvel, lvrt):
 
 
 class TrainStep:
-    """One optimisation step on one GPU (one rank).  Networks are zeggs_b200.modules.* instances."""
+    """One optimisation step on one GPU (one rank).  Networks are zeggs_b200.modules.* instances.
+
+    use_graph=True: the step body is captured ONCE per batch geometry into CUDA graphs (zero_grad + encoders + decoder window
+    fwd/BPTT + loss + weight packs [+ RAdam]) and replayed; every step-dependent scalar lives in device memory (RAdam step count
+    and hyper-parameters, KL weight, dropout seed), so replays need no host arithmetic: the host enqueues a handful of calls per
+    step instead of ~265 launches through Python/ctypes/autograd.  Data parallel: graph A (backward done) -> ONE eager NCCL
+    all-reduce of the flat gradient -> graph B (RAdam)."""
 
     def __init__(self, speech_encoder, decoder, style_encoder, stats, parents, dt, lr=1e-4, eps=1e-5,
-                 world_size=1, process_group=None):
+                 world_size=1, process_group=None, use_graph=False):
         self.se, self.dec, self.st = speech_encoder, decoder, style_encoder
         self.dev = next(decoder.parameters()).device
         f = lambda k: torch.as_tensor(stats[k], dtype=torch.float32, device=self.dev)
@@ -52,10 +58,26 @@ class TrainStep:
         self.optimizer.grad_scale = 1.0 / world_size
         self.iteration = 0
         self.terms = torch.zeros(19, dtype=torch.float32, device=self.dev)
+        self.klw = torch.zeros(1, dtype=torch.float32, device=self.dev)      # annealed KL weight, device scalar
+        self.use_graph = bool(use_graph)
+        self.seed = ops.DeviceSeed(self.dev) if self.use_graph else None
+        self._graphs, self._seen, self._pool = {}, {}, None
+        self.graph_launches = 0            # library launches captured per replay (gpu_launches accounting)
+        self.ar_events = None              # set to [] to record (start, end) CUDA events around every all-reduce
 
     def forward_backward(self, batch, eps=None, masks=None, train_mode=True):
         """batch: dict of DEVICE tensors: audio[B,T,81], the 8 pose tensors [B,T,...], gaze_pos[B,T,3], style (example
         [B,T_ex,1134] raw, or label [B,Z]).  Returns the loss tensor (device scalar); gradients land in optimizer.flat_grad."""
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            self.klw.fill_(kl_weight(self.iteration))
+        if self.seed is not None:
+            self.seed.advance()
+            with ops.device_seed(self.seed):
+                return self._forward_backward(batch, eps, masks, train_mode)
+        return self._forward_backward(batch, eps, masks, train_mode)
+
+    def _forward_backward(self, batch, eps, masks, train_mode):
         self.se.train(train_mode); self.dec.train(train_mode)
         speech = self.se((batch["audio"] - self.audio_mean) / self.audio_std, masks=None if masks is None else masks.get("speech"))
         mu = logvar = None
@@ -72,18 +94,119 @@ class TrainStep:
                                             z.unsqueeze(1).expand(-1, T, -1), self.in_mean, self.in_std,
                                             self.out_mean, self.out_std, self.dt)
         loss = TrainLossFn.apply(Y, rp, rq, WY, W[0], W[1], batch["gaze_pos"], self.parents, self.dt, mu, logvar,
-                                 kl_weight(self.iteration) if mu is not None else 0.0, self.terms, True)
+                                 kl_weight(self.iteration) if mu is not None else 0.0, self.terms, True,
+                                 self.klw if mu is not None else None)
         loss.backward()
         return loss
 
-    def step(self, batch, eps=None, masks=None):
+    def _allreduce(self):
+        if self.ar_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        dp.allreduce_sum_(self.optimizer.flat_grad, group=self.pg)                  # the one collective of the step
+        if self.ar_events is not None:
+            e1.record()
+            self.ar_events.append((e0, e1))
+
+    def _eager_step(self, batch, eps=None, masks=None):
         self.optimizer.zero_grad()
         loss = self.forward_backward(batch, eps, masks)
         if self.world_size > 1:
-            torch.distributed.all_reduce(self.optimizer.flat_grad, group=self.pg)   # the one collective of the step
+            self._allreduce()
         self.optimizer.step()
         self.iteration += 1
         return loss
+
+    def step(self, batch, eps=None, masks=None):
+        if self.use_graph and eps is None and masks is None:
+            return self._graph_step(batch)
+        return self._eager_step(batch, eps, masks)
+
+    # ---------------------------------------------------------------- CUDA-graph path
+    def _graph_step(self, batch):
+        key = tuple((k, tuple(v.shape), str(v.dtype)) for k, v in sorted(batch.items()))
+        ent = self._graphs.get(key)
+        if ent is None:
+            seen = self._seen.get(key, 0)
+            self._seen[key] = seen + 1
+            if seen < 1:        # first sight of a geometry: a real step, run eagerly (one-time initialisation, workspace growth)
+                return self._eager_step(batch)
+            ent = self._capture(key, batch)
+            if ent is None:
+                return self._eager_step(batch)
+        static, g1, g2 = ent
+        for k, v in batch.items():
+            static[k].copy_(v, non_blocking=True)
+        self.klw.fill_(kl_weight(self.iteration))
+        self.optimizer.sync_hyper()
+        g1.replay()
+        if g2 is not None:
+            self._allreduce()
+            g2.replay()
+        self.optimizer._step += 1
+        ops.bump_weights_epoch()          # the replay rewrote the parameters: cached weight packs of eager callers are stale
+        self.iteration += 1
+        return self.terms[0]
+
+    def _capture(self, key, batch):
+        import sys
+        static = {k: v.clone() for k, v in batch.items()}
+        self.optimizer.sync_hyper()
+        self.klw.fill_(kl_weight(self.iteration))
+        torch.cuda.synchronize()
+        n0 = _lib.lib().zeggs_launch_count()
+        try:
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1, **({} if self._pool is None else {"pool": self._pool})):
+                self.optimizer.zero_grad()
+                self.forward_backward(static)
+                if self.world_size == 1:
+                    self.optimizer.step()
+            if self._pool is None:
+                self._pool = g1.pool()
+            g2 = None
+            if self.world_size > 1:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, pool=self._pool):
+                    self.optimizer.step()
+        except Exception as e:       # capture refused (driver / library limitation): say so loudly and keep training eagerly
+            print(f"[zeggs_b200] CUDA-graph capture of the train step FAILED ({type(e).__name__}: {e}); continuing with eager launches",
+                  file=sys.stderr, flush=True)
+            self.use_graph = False
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
+            ops.bump_weights_epoch()          # nothing captured has run: packs recorded during the capture never happened
+            ops.WS.bufs.clear()
+            return None
+        self.graph_launches = int(_lib.lib().zeggs_launch_count() - n0)
+        ops.bump_weights_epoch()
+        self._graphs[key] = (static, g1, g2)
+        return self._graphs[key]
+
+
+def pin_to_gpu_numa(local_rank):
+    """Bind this process (the launch thread of one rank) to the CPUs of the NUMA node its GPU hangs off; returns the node or None.
+    Un-pinned ranks of GPUs 4-7 otherwise enqueue from the remote socket (measured in round 1: 8-GPU steps 22 ms vs 17 ms)."""
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
 
 
 def build_networks(network_options, dimensions, style_encoding_type, nlabels, device):
@@ -109,15 +232,16 @@ def train(models_dir, logs_dir, path_processed_data, path_data_definition, train
     torch.manual_seed(train_options["seed"])
     if not (train_options["use_gpu"] and torch.cuda.is_available()):
         raise _lib.ZeggsError("zeggs_b200.train needs a CUDA device (no CPU fallback)")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local_rank = dp.env_rank_world()
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
+    pin_to_gpu_numa(local_rank)
     if world > 1 and not torch.distributed.is_initialized():
         torch.distributed.init_process_group("nccl")
-    # additive option: recurrence engine ("tc": tcgen05 bf16 operands / fp32 state, the fast path; "fp32": SIMT parity-grade path)
-    ops.set_decoder_engine(train_options.get("decoder_engine", "tc"))
+    # additive option: recurrence engine ("auto": tcgen05 bf16 operands / fp32 state where the hidden size is eligible -- the fast
+    # path, pinned to the reference's loss/gradients by tests/golden/train_h320|h1024.npz and to the fp32 engine's loss curve by
+    # test_short_training_curve_tc_tracks_fp32; "tc": the same but raises when ineligible; "fp32": SIMT parity-grade path)
+    ops.set_decoder_engine(train_options.get("decoder_engine", "auto"))
     models_dir, logs_dir = Path(models_dir), Path(logs_dir)
     with open(path_data_definition, "r") as f:
         details = json.load(f)
@@ -130,7 +254,7 @@ def train(models_dir, logs_dir, path_processed_data, path_data_definition, train
             if net is not None:
                 net.load_state_dict(torch.load(models_dir / f"{name}.pt", weights_only=False).state_dict())
     stepper = TrainStep(se, de, st, ds.stats, details["parents"], details["dt"], lr=train_options["learning_rate"],
-                        eps=train_options["eps"], world_size=world)
+                        eps=train_options["eps"], world_size=world, use_graph=bool(train_options.get("cuda_graph", True)))
     if train_options["resume"] and (models_dir / "checkpoints.pt").exists():
         ck = torch.load(models_dir / "checkpoints.pt", weights_only=False)
         stepper.iteration = ck["iteration"]
