@@ -145,7 +145,7 @@ def run_ours(args):
     device = torch.device("cuda", lrank)
     torch.cuda.set_device(device)
     from zeggs_b200.train import pin_to_gpu_numa
-    numa = pin_to_gpu_numa(lrank)         # the launch thread next to its GPU (GPUs 4-7 hang off the second socket)
+    numa = pin_to_gpu_numa(lrank) if args.pin else None    # the launch thread next to its GPU (GPUs 4-7 hang off the second socket)
     try:
         os.nice(-10)                      # the launch thread competes with other tenants' all-core CPU jobs on a shared node
     except Exception:
@@ -475,6 +475,7 @@ if __name__ == "__main__":
     ap.add_argument("--alt", type=int, default=1, help="also time the BASELINE.json-worded sizes (reported under alt_config)")
     ap.add_argument("--extras", type=int, default=1, help="also time BASELINE configs 1, 3, 4, 5 (reported under other_configs)")
     ap.add_argument("--graph", type=int, default=1, help="replay the train step from CUDA graphs (0: eager launches)")
+    ap.add_argument("--pin", type=int, default=1, help="bind the launch thread to the CPUs of the GPU's NUMA node")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--engine", default="tc", choices=["tc", "fp32", "auto"], help="decoder recurrence engine: tcgen05 bf16 (default) or fp32 SIMT")
     a = ap.parse_args()

@@ -70,9 +70,38 @@ typedef struct {
   float* mel_out;
   float* feat_out;
   int fb_total;          /* number of weights in fb_w (<= 4096: staged in shared memory; 0: read from global memory) */
+  const float* gain;     /* optional [n_clips] per-clip gain applied to every sample at load (loudness normalisation, data_pipeline.py:34-39) */
+  const short* wav_i16;  /* optional int16 PCM input instead of `wav` (x / 32768, audio_files.py:211-236) */
 } zeggs_mel_args;
 int zeggs_mel_num_frames(int n_samples, int n_fft, int hop);
 int zeggs_mel_forward(const zeggs_mel_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Loudness normalisation ahead of the mel front end: replaces data_pipeline.py:34-39
+ * (pyloudnorm 0.1.0 Meter(rate).integrated_loudness + normalize.loudness(x, L, -20)).  Per clip:
+ * K-weighting (two biquads, coef = {b0,b1,b2,a1,a2} of the high shelf then of the high pass, a0-normalised, built on the
+ * host by zeggs_b200.audio in float64), gating-block energies, absolute/relative gates, integrated LUFS and
+ * gain_out[clip] = 10^((target - LUFS)/20).  The host also builds the block geometry with the package's own float64
+ * expressions: seg_bounds[n_seg+1] = sorted boundaries of all blocks, block j = segments [blk_seg_lo[j], blk_seg_hi[j]).
+ * The gain is consumed by zeggs_mel_forward (args.gain); the waveform is not rewritten.
+ */
+typedef struct {
+  int n_clips, n_samples, n_seg, n_blocks, warm;
+  double coef[10];
+  double inv_block_len;   /* 1 / (0.4 * rate) */
+  double target_lufs;
+  const float* wav;       /* [n_clips, n_samples] f32, or NULL with wav_i16 set */
+  const short* wav_i16;
+  const int* seg_bounds;  /* [n_seg + 1] */
+  const int* blk_seg_lo;  /* [n_blocks] */
+  const int* blk_seg_hi;  /* [n_blocks] */
+  float* gain_out;        /* [n_clips] */
+  float* lufs_out;        /* [n_clips] or NULL */
+  void* workspace;
+  size_t workspace_bytes;
+} zeggs_loudness_args;
+size_t zeggs_loudness_workspace_bytes(int n_clips, int n_seg);
+int zeggs_loudness_gain(const zeggs_loudness_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Decoder (modules.py:11-243, 677-742): CellStateEncoder + T-1 autoregressive steps of
@@ -230,6 +259,21 @@ typedef struct {
 size_t zeggs_loss_workspace_bytes(int B, int T);
 int zeggs_loss_fwd_bwd(const zeggs_loss_args* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Pose tensors -> the values the BVH writer prints (generate.py:389-406 + utils.py:47-87): per joint the rotation from the
+ * rotated x/y axes (txform.py:23-34 -> quat.py:166-206), the root re-based on its first frame and start_pos / start_rot
+ * (rebase != 0) and folded into joint 0, Euler angles in degrees in 'zyx' channel order (quat.py:111-119).
+ *   root_pos [N,T,3], root_rot [N,T,4] (w first), lpos [N,T,J,3], ltxy [N,T,J,2,3]
+ *   positions [N,T,J,3], euler_deg [N,T,J,3] (z, y, x angle per joint), lrot [N,T,J,4] or NULL
+ */
+typedef struct {
+  int N, T, J, rebase;
+  float start_pos[3], start_rot[4];
+  const float *root_pos, *root_rot, *lpos, *ltxy;
+  float *positions, *euler_deg, *lrot;
+} zeggs_pose_post_args;
+int zeggs_pose_to_bvh_channels(const zeggs_pose_post_args* a, void* stream);
+
 /* Fused RAdam step over a flat fp32 parameter buffer (optimizers.py:31-99; weight_decay 0,
  * degenerated_to_sgd).  `step` is the 1-based step count; gradients are multiplied by grad_scale first. */
 int zeggs_radam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
@@ -245,6 +289,8 @@ int zeggs_dropout_mask(float* out, size_t n, float p, unsigned long long seed, v
 /* Same, seeded from DEVICE memory: effective seed = hash(*seed_dev, salt) (CUDA-graph replays draw fresh masks when the
  * caller advances *seed_dev between replays; `salt` separates the masks of one step). */
 int zeggs_dropout_mask_dev(float* out, size_t n, float p, const unsigned long long* seed_dev, unsigned long long salt, void* stream);
+/* N(0,1) samples from the same device-seeded generator (the VAE noise of modules.py:299 inside a replayable graph). */
+int zeggs_randn_dev(float* out, size_t n, const unsigned long long* seed_dev, unsigned long long salt, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Generic fp32 GEMM used for the batched (non-recurrent) linear layers:

@@ -92,9 +92,9 @@ def ref_forward_train(se, st, de, win, audio, style_ex, eps, iteration):
 
 TRAIN_CASES = {   # tag: (H, B, T, T_ex)
     "h64": (64, 2, 6, 16), "h128": (128, 4, 9, 24),
-    # H >= 288 and H % 64 == 0: the tensor-core recurrence engine is eligible (U = 4 / G = 80 CTAs at H = 320; U = 8 / G = 128
+    # H % 128 == 0, H >= 384: the tensor-core recurrence engine is eligible (U = 4 / G = 96 CTAs at H = 384; U = 8 / G = 128
     # CTAs -- the bench geometry -- at H = 1024), so the same golden test runs tcgen05 against the REFERENCE's loss and gradients
-    "h320": (320, 4, 12, 24),   # (B, T != 3: the reference's dim-less torch.cross hazard)
+    "h384": (384, 4, 12, 24),   # (B, T != 3: the reference's dim-less torch.cross hazard)
     "h1024": (1024, 2, 8, 16),
 }
 
@@ -174,6 +174,10 @@ def main(only=None):
         for tag in only:
             if tag == "v1":
                 write_v1_golden()
+            elif tag == "generate":
+                write_generate_golden()
+            elif tag == "pose_post":
+                write_pose_post_golden()
             else:
                 write_train_golden(tag)
         return
@@ -201,6 +205,8 @@ def main(only=None):
     for tag in TRAIN_CASES:
         write_train_golden(tag)
     write_v1_golden()
+    write_pose_post_golden()
+    write_generate_golden()
 
     # ---- RAdam trajectory (optimizers.py), 8 steps crossing the N_sma>=5 switch (step 6)
     ref_shim.install()
@@ -217,6 +223,111 @@ def main(only=None):
         traj.append(p.detach().numpy().copy())
     np.savez_compressed(os.path.join(GOLD, "radam.npz"), p0=p0, grads=gs, traj=np.stack(traj))
     print("golden written to", GOLD)
+
+
+
+
+# ---------------------------------------------------------------------------------------------- generate_gesture end to end
+def _pyloudnorm_stub():
+    """`pyloudnorm` is not installed: a stub backed by oracle/loudness_oracle.py (the restated 0.1.0 algorithm, parity unpinned)
+    so that the reference's normalize_loudness=True code path (data_pipeline.py:34-39) can run for the golden."""
+    import sys
+    import types
+    from oracle import loudness_oracle as lo
+    m = types.ModuleType("pyloudnorm")
+
+    class Meter:
+        def __init__(self, rate):
+            self.rate = rate
+
+        def integrated_loudness(self, data):
+            return lo.integrated_loudness(data, self.rate)
+
+    m.Meter = Meter
+    m.normalize = types.SimpleNamespace(loudness=lambda data, inp, target: np.power(10.0, (target - inp) / 20.0) * data)
+    sys.modules["pyloudnorm"] = m
+
+
+def write_generate_golden(H=256):
+    """Run the UNMODIFIED reference generate_gesture (CPU) on the deterministic synthetic BVH + WAV of tests/_fixtures.py with
+    synth weights (whole-module pickles of the reference's own classes) and store what it wrote: the BVH channel values and the
+    returned style encoding, for three calls (one example style; two styles blended 'add'; two styles 'stitch'), with loudness
+    normalisation off (pure reference arithmetic) and on (through the oracle-backed pyloudnorm stub)."""
+    import json
+    import pathlib
+    import shutil
+    import tempfile
+    import torch
+    from tests import _fixtures as fx
+    ref_shim.install()
+    _pyloudnorm_stub()
+    import anim.bvh as rbvh
+    import generate as rgen                     # ZEGGS/generate.py
+    tmp = pathlib.Path(tempfile.mkdtemp())
+    P = synth.make_params(H=H, seed=41)
+    se, st, de = build_ref_nets(P, H)
+    net = tmp / "net"; net.mkdir()
+    torch.save(se, net / "speech_encoder.pt"); torch.save(de, net / "decoder.pt"); torch.save(st, net / "style_encoder.pt")
+    _orig_load = torch.load
+    torch.load = lambda *a, **k: _orig_load(*a, **{**k, "weights_only": False})       # generate.py:130-137 predates the new default
+    out = {}
+    try:
+        for loud in (False, True):
+            data = tmp / f"data{int(loud)}"; data.mkdir()
+            stats = synth.load_stats()
+            np.savez(data / "stats.npz", **{k: stats[k] for k in ("audio_input_mean", "audio_input_std", "anim_input_mean",
+                                                                 "anim_input_std", "anim_output_mean", "anim_output_std")})
+            pkg = os.path.join(os.path.dirname(GOLD), "..", "ubisoft-laforge-zeroeggs_b200", "data")
+            shutil.copy(os.path.join(pkg, "data_definition_v1.json"), data / "data_definition.json")
+            conf = json.load(open(os.path.join(pkg, "data_pipeline_conf_v1.json")))
+            conf["audio_conf"]["normalize_loudness"] = loud
+            json.dump(conf, open(data / "data_pipeline_conf.json", "w"))
+            bvh_path = pathlib.Path(fx.make_synthetic_bvh(str(tmp / "style.bvh")))
+            wav_path = pathlib.Path(fx.make_wav(str(tmp / "speech.wav")))
+            cases = dict(one=dict(styles=[(bvh_path, (10, 300))]),
+                         add=dict(styles=[(bvh_path, (10, 300)), (bvh_path, (150, 400))], blend_type="add", blend_ratio=[0.25, 0.75]),
+                         stitch=dict(styles=[(bvh_path, (10, 300)), (bvh_path, None)], blend_type="stitch", blend_ratio=[0.5, 0.5]))
+            for name, kw in cases.items():
+                res = tmp / f"res{int(loud)}_{name}"
+                enc = rgen.generate_gesture(wav_path, network_path=net, data_path=data, results_path=res, style_encoding_type="example",
+                                            file_name="out", first_pose=None, temperature=1e6, seed=1234, use_gpu=False, **kw)
+                b = rbvh.load(str(res / "out.bvh"))
+                tag = f"loud{int(loud)}_{name}"
+                out[tag + "_positions"] = b["positions"]; out[tag + "_rotations"] = b["rotations"]
+                out[tag + "_encoding"] = enc.detach().numpy()
+        # the embedding-only call (audio_file None) and a first_pose given as a path
+        out["embedding_only"] = rgen.generate_gesture(None, [(bvh_path, (10, 300))], net, tmp / "data0", None, temperature=1e6, use_gpu=False).numpy()
+    finally:
+        torch.load = _orig_load
+    out["H"] = H; out["param_seed"] = 41
+    np.savez_compressed(os.path.join(GOLD, "generate_e2e.npz"), **out)
+    print("generate_e2e golden:", {k: getattr(v, "shape", v) for k, v in out.items()})
+
+
+def write_pose_post_golden(T=40):
+    """generate.py:389-406 + utils.write_bvh through the reference's own functions: what bvh.save receives for a synthetic clip."""
+    ref_shim.install()
+    import anim.bvh as rbvh
+    import utils as rutils
+    from anim import quat
+    from anim.txform import xform_orthogonalize_from_xy
+    w = synth.make_pose_windows(2, T, seed=3)
+    rs = np.random.RandomState(0)
+    ltxy = (w["ltxy"] + 0.05 * rs.randn(*w["ltxy"].shape)).astype(np.float32)          # not exactly orthonormal, like network output
+    out = dict(root_pos=w["root_pos"], root_rot=w["root_rot"], lpos=w["lpos"], ltxy=ltxy)
+    cap = {}
+    orig = rbvh.save
+    rutils.bvh.save = lambda fn, d: cap.update(d)
+    try:
+        for n in range(2):
+            lrot = quat.from_xform(xform_orthogonalize_from_xy(torch.from_numpy(ltxy[n])).numpy())
+            rutils.write_bvh("unused", w["root_pos"][n], w["root_rot"][n], w["lpos"][n], lrot, parents=synth.load_stats()["parents"],
+                             names=None, order="zyx", dt=1 / 60, start_position=np.array([0, 0, 0]), start_rotation=np.array([1, 0, 0, 0]))
+            out[f"positions{n}"] = np.asarray(cap["positions"]); out[f"rotations{n}"] = np.asarray(cap["rotations"]); out[f"lrot{n}"] = lrot
+    finally:
+        rutils.bvh.save = orig
+    np.savez_compressed(os.path.join(GOLD, "pose_post.npz"), **out)
+    print("pose_post golden written")
 
 
 if __name__ == "__main__":

@@ -24,7 +24,7 @@ def main():
     from bench import build_stepper, synth_batch
     engine = os.environ.get("DP_ENGINE", "fp32")
     ops.set_decoder_engine(engine)
-    H, Bg, T, T_ex = 320, 8, 10, 16
+    H, Bg, T, T_ex = 384, 8, 10, 16
     full = synth_batch(Bg, T, T_ex, seed=7)
     eps = torch.from_numpy(np.random.RandomState(1).randn(Bg, 64).astype(np.float32))
     lo, hi = dp.shard_range(Bg, rank, world)

@@ -497,7 +497,7 @@ def decoder_engine():
     ops.set_decoder_engine("fp32")
 
 
-@pytest.mark.parametrize("H,B,T", [(320, 4, 9), (512, 16, 40), (1024, 32, 24), (1024, 7, 64), (512, 40, 10), (1024, 3, 2)])
+@pytest.mark.parametrize("H,B,T", [(384, 4, 9), (512, 16, 40), (1024, 32, 24), (1024, 7, 64), (512, 40, 10), (1024, 3, 2)])
 def test_decoder_forward_tc_engine_vs_oracle(dev, decoder_engine, H, B, T):
     """tcgen05 recurrence (bf16 MMA operands, fp32 accumulate/state): free-running per-pose-channel max-abs
     <= 2e-2 * max(1, max|ref|) in de-normalised units (bf16 operand rounding, 2^-9 relative, compounds over the window)."""
@@ -680,8 +680,8 @@ def _channel_table(tag, out, ref, frames=None):
 
 # tolerances of the tensor-core (bf16 operand) recurrence against the fp32 CPU oracle, as fractions of max(1, max|ref|) per pose-channel
 # group, free running (errors feed back through the pose): stated in DESIGN.md 2 with the measured values
-TC_TOL_WINDOW = 5e-2        # B=32, T=256 training window
-TC_TOL_LONG = 2.5e-1        # T=3600 (60 s) generation
+TC_TOL_WINDOW = 1e-2        # B=32, T=256 training window        (measured on B200: <= 3.0e-3 random init, <= 5.8e-3 shipped v1 weights)
+TC_TOL_LONG = 2e-2          # T=3600 (60 s) generation          (measured: <= 4.4e-3)
 
 
 def test_full_size_tc_forward_vs_oracle(dev, decoder_engine):
@@ -700,9 +700,9 @@ def test_full_size_tc_forward_vs_oracle(dev, decoder_engine):
         assert err <= 2e-3 * max(1.0, sc), n
 
 
-@pytest.mark.parametrize("tag", ["h320", "h1024"])
+@pytest.mark.parametrize("tag", ["h384", "h1024"])
 def test_train_step_tc_engine_vs_reference_golden(dev, golden_dir, decoder_engine, tag):
-    """The whole step body on the TENSOR-CORE engine (H >= 288: U=4/G=80 at H=320, U=8/G=128 -- the bench geometry -- at H=1024)
+    """The whole step body on the TENSOR-CORE engine (H >= 288: U=4/G=96 at H=384, U=8/G=128 -- the bench geometry -- at H=1024)
     against the unmodified reference's loss, 18 terms and gradients (oracle/make_golden.py): loss within 5e-3 relative, terms
     within 3e-2, gradient norms within 5e-2, stored gradient tensors rel-L2 <= 6e-2 (bf16 MMA operands; encoders' weight
     gradients single-pass bf16)."""
@@ -827,12 +827,12 @@ def test_v1_pretrained_weights_vs_reference_golden(dev, golden_dir, decoder_engi
 
 def test_short_training_curve_tc_tracks_fp32(dev, decoder_engine):
     """Convergence evidence for training on the tensor-core engine: 40 optimizer steps from the same initial weights, batches,
-    dropout masks and VAE noise (same torch seed) on both engines at H=320, lr=1e-3: the loss curves stay within 2 % of each other
+    dropout masks and VAE noise (same torch seed) on both engines at H=384, lr=1e-3: the loss curves stay within 2 % of each other
     at every step and both decrease."""
     curves = {}
     for eng in ("fp32", "tc"):
         decoder_engine(eng)
-        step, P = _make_step(dev, 320, 4321)
+        step, P = _make_step(dev, 384, 4321)
         for gr in step.optimizer.param_groups:
             gr["lr"] = 1e-3
         torch.manual_seed(7); torch.cuda.manual_seed(7)
@@ -847,3 +847,140 @@ def test_short_training_curve_tc_tracks_fp32(dev, decoder_engine):
     assert np.all(np.isfinite(b))
     assert np.max(np.abs(a - b) / np.abs(a)) <= 2e-2
     assert a[-4:].mean() < a[:4].mean() and b[-4:].mean() < b[:4].mean()
+
+
+def test_graph_replayed_train_steps_match_eager_launches(dev, decoder_engine):
+    """TrainStep(use_graph=True): step 1 eager, step 2 captured + replayed, steps 3-5 replayed -- against the same steps launched
+    eagerly (same device-side dropout/VAE seeds, same RAdam device counters): losses and parameters after 5 steps identical."""
+    from zeggs_b200 import modules, synth
+    from zeggs_b200.train import TrainStep
+    decoder_engine("tc")
+    res = {}
+    for mode in ("graph", "eager"):
+        torch.manual_seed(123)
+        P = synth.make_params(H=384, seed=77)
+        se = _load(modules.SpeechEncoder(81, 64, 64), P, "speech_encoder.", dev)
+        st = _load(modules.StyleEncoder(1134, 512, 64, type="attn", use_vae=True), P, "style_encoder.", dev)
+        de = _load(modules.Decoder(1134, 1131, 64, 64, 384, 2), P, "decoder.", dev)
+        stats = synth.load_stats()
+        step = TrainStep(se, de, st, stats, stats["parents"], float(stats["dt"]), lr=1e-3, use_graph=True)
+        if mode == "eager":
+            step.graph_min_seen = 10 ** 9
+        losses = []
+        for it in range(5):
+            losses.append(float(step.step(_batch(dev, 4, 16, 24, 50 + it)).item()))
+        torch.cuda.synchronize()
+        if mode == "graph":
+            assert step.use_graph and len(step._graphs) == 1, "the CUDA-graph path did not run"
+            assert step.graph_launches > 0
+        res[mode] = (losses, step.optimizer.flat_param.clone(), int(step.optimizer.step_dev.item()), step.optimizer._step)
+        del step
+    print("  graph losses", res["graph"][0]); print("  eager losses", res["eager"][0])
+    assert res["graph"][2] == 5 and res["graph"][3] == 5 and res["eager"][2] == 5
+    assert np.allclose(res["graph"][0], res["eager"][0], rtol=1e-6, atol=0)
+    assert float((res["graph"][1] - res["eager"][1]).abs().max()) <= 1e-7
+
+
+# ---------------------------------------------------------------------------------------------- loudness normalisation + int16 decode (SURVEY 8f row 4)
+def test_loudness_gain_and_normalised_features_vs_oracle(dev):
+    """zeggs_loudness_gain (BS.1770 K-weighting + gating on the device) against oracle/loudness_oracle.py (restated pyloudnorm 0.1.0,
+    parity unpinned): integrated loudness within 1e-3 LU, gain within 2e-4 relative; preprocess_audio(normalize_loudness=True) and
+    int16 PCM input against the oracle chain (gain * wav -> mel), abs <= 3e-4 on the features."""
+    from oracle import loudness_oracle as lo, mel_oracle
+    from oracle.make_golden import audio_params
+    from zeggs_b200 import audio, synth
+    wav = synth.make_waveforms(4, 160000, seed=12)
+    wav[1] *= 0.05                       # a quiet clip: gain > 1
+    wav[2, 30000:110000] = 0.0           # a long silent stretch: blocks below the absolute gate
+    wav[3] = np.clip(wav[3] * 3.0, -1, 1)
+    meter = audio.LoudnessMeter(dev, 16000)
+    gain, lufs = meter.gain(torch.from_numpy(wav).to(dev), want_lufs=True)
+    for i in range(4):
+        ref_l = lo.integrated_loudness(wav[i], 16000)
+        ref_g = lo.loudness_gain(wav[i], 16000)
+        print(f"  clip {i}: LUFS {float(lufs[i]):.5f} vs oracle {ref_l:.5f}; gain {float(gain[i]):.6f} vs {ref_g:.6f}")
+        assert abs(float(lufs[i]) - ref_l) <= 1e-3
+        assert abs(float(gain[i]) - ref_g) <= 2e-4 * ref_g
+    # ragged length (27 gating blocks, last block clamped) through the drop-in surface, float and int16 input
+    x = wav[0, :48123]
+    n60 = int(round(60.0 * len(x) / 16000))
+    p = audio_params(200); p.normalize_loudness = True
+    ref = mel_oracle.preprocess_audio((lo.normalize_loudness(x, 16000)).astype(np.float64), 60, n60)
+    got = audio.preprocess_audio(x, 60, n60, p, ["mel_spec", "energy"])
+    err = float(np.abs(got - ref).max()); print(f"  normalised features max-abs err {err:.3e}")
+    assert err <= 3e-4
+    x16 = np.round(x * 32767.0).astype(np.int16)
+    xf = (x16 / 32768.0).astype(np.float32)                                   # audio_files.py:211-236
+    ref16 = mel_oracle.preprocess_audio((lo.normalize_loudness(xf, 16000)).astype(np.float64), 60, n60)
+    got16 = audio.preprocess_audio(x16, 60, n60, p, ["mel_spec", "energy"])
+    err = float(np.abs(got16 - ref16).max()); print(f"  int16 PCM normalised features max-abs err {err:.3e}")
+    assert err <= 3e-4
+
+
+# ---------------------------------------------------------------------------------------------- pose -> BVH channels (8f row 3) and generate_gesture end to end
+def test_pose_to_bvh_channels_vs_reference_golden(dev, golden_dir):
+    """zeggs_pose_to_bvh_channels against what the reference's generate.py:389-406 + utils.write_bvh hand to bvh.save
+    (tests/golden/pose_post.npz): positions <= 2e-5 * max(1,|ref|), Euler angles <= 5e-3 degrees, local quaternions <= 1e-5."""
+    from zeggs_b200 import ops
+    g = np.load(os.path.join(golden_dir, "pose_post.npz"))
+    t = lambda k: torch.from_numpy(g[k]).to(dev)
+    pos, eul, lrot = ops.pose_to_bvh_channels(t("root_pos"), t("root_rot"), t("lpos"), t("ltxy"), want_lrot=True)
+    for n in range(2):
+        e, sc = report(f"bvh positions clip{n}", pos[n], torch.from_numpy(g[f"positions{n}"]))
+        assert e <= 2e-5 * max(1.0, sc)
+        e, _ = report(f"bvh euler deg clip{n}", eul[n], torch.from_numpy(g[f"rotations{n}"]))
+        assert e <= 5e-3
+        q_ref = torch.from_numpy(g[f"lrot{n}"])
+        e, _ = report(f"lrot clip{n} (joints 1..)", lrot[n, :, 1:], q_ref[:, 1:])
+        assert e <= 1e-5
+
+
+@pytest.mark.parametrize("loud", [0, 1])
+def test_generate_gesture_end_to_end_vs_reference_golden(dev, golden_dir, tmp_path, loud):
+    """generate_gesture() -- the reference's call surface -- on the synthetic BVH + int16 WAV of tests/_fixtures.py against the BVH
+    the UNMODIFIED reference wrote for the same files and weights (tests/golden/generate_e2e.npz, CPU run in the dev container):
+    one example style, two styles blended 'add', two styles 'stitch'; with loudness normalisation off (pure reference arithmetic)
+    and on (reference + oracle-backed pyloudnorm stub; that third-party step is parity-unpinned).  fp32 recurrence engine,
+    240 free-running frames: BVH positions <= 1e-3 * max(1,|ref|), Euler angles <= 0.05 degrees, style encodings <= 1e-4."""
+    import json
+    import shutil
+    from pathlib import Path
+    from tests import _fixtures as fx
+    from zeggs_b200 import animation, generate, modules, synth
+    g = np.load(os.path.join(golden_dir, "generate_e2e.npz"))
+    H = int(g["H"])
+    P = synth.make_params(H=H, seed=int(g["param_seed"]))
+    net = tmp_path / "net"; net.mkdir()
+    torch.save(_load(modules.SpeechEncoder(81, 64, 64), P, "speech_encoder.", "cpu"), net / "speech_encoder.pt")
+    torch.save(_load(modules.StyleEncoder(1134, 512, 64, type="attn", use_vae=True), P, "style_encoder.", "cpu"), net / "style_encoder.pt")
+    torch.save(_load(modules.Decoder(1134, 1131, 64, 64, H, 2), P, "decoder.", "cpu"), net / "decoder.pt")
+    data = tmp_path / "data"; data.mkdir()
+    stats = synth.load_stats()
+    np.savez(data / "stats.npz", **{k: stats[k] for k in ("audio_input_mean", "audio_input_std", "anim_input_mean", "anim_input_std",
+                                                         "anim_output_mean", "anim_output_std")})
+    shutil.copy(os.path.join(fx.DATA, "data_definition_v1.json"), data / "data_definition.json")
+    conf = json.load(open(os.path.join(fx.DATA, "data_pipeline_conf_v1.json")))
+    conf["audio_conf"]["normalize_loudness"] = bool(loud)
+    json.dump(conf, open(data / "data_pipeline_conf.json", "w"))
+    bvh_path = Path(fx.make_synthetic_bvh(str(tmp_path / "style.bvh")))
+    wav_path = Path(fx.make_wav(str(tmp_path / "speech.wav")))
+    cases = dict(one=dict(styles=[(bvh_path, (10, 300))]),
+                 add=dict(styles=[(bvh_path, (10, 300)), (bvh_path, (150, 400))], blend_type="add", blend_ratio=[0.25, 0.75]),
+                 stitch=dict(styles=[(bvh_path, (10, 300)), (bvh_path, None)], blend_type="stitch", blend_ratio=[0.5, 0.5]))
+    for name, kw in cases.items():
+        res = tmp_path / f"res_{name}"
+        enc = generate.generate_gesture(wav_path, network_path=net, data_path=data, results_path=res, style_encoding_type="example",
+                                        file_name="out", first_pose=None, temperature=1e6, seed=1234, use_gpu=True, **kw)
+        assert (res / "out.wav").exists()
+        b = animation.load_bvh(str(res / "out.bvh"))
+        tag = f"loud{loud}_{name}"
+        e, sc = report(f"{tag} encoding", enc, torch.from_numpy(g[tag + "_encoding"]))
+        assert tuple(enc.shape) == tuple(g[tag + "_encoding"].shape) and e <= 1e-4 * max(1.0, sc)
+        e, sc = report(f"{tag} BVH positions", torch.from_numpy(b["positions"]), torch.from_numpy(g[tag + "_positions"]))
+        assert e <= 1e-3 * max(1.0, sc)
+        e, _ = report(f"{tag} BVH euler degrees", torch.from_numpy(b["rotations"]), torch.from_numpy(g[tag + "_rotations"]))
+        assert e <= 5e-2
+    if not loud:
+        enc = generate.generate_gesture(None, [(bvh_path, (10, 300))], net, data, None, temperature=1e6)
+        e, sc = report("embedding-only call", enc, torch.from_numpy(g["embedding_only"]))
+        assert tuple(enc.shape) == (1, 64) and e <= 1e-4 * max(1.0, sc)

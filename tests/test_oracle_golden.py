@@ -59,7 +59,7 @@ def _run_oracle(g):
     return P, speech, (z, mu, logvar), O, loss, terms
 
 
-@pytest.mark.parametrize("tag", ["h64", "h128", "h320", "h1024"])
+@pytest.mark.parametrize("tag", ["h64", "h128", "h384", "h1024"])
 def test_network_oracle_matches_reference_golden(golden_dir, tag):
     g = np.load(os.path.join(golden_dir, f"train_{tag}.npz"))
     P, speech, (z, mu, logvar), O, loss, terms = _run_oracle(g)

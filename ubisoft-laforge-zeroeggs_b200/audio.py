@@ -78,11 +78,13 @@ class MelFrontEnd:
     def num_frames(self, n_samples):
         return _lib.lib().zeggs_mel_num_frames(int(n_samples), self.n_fft, self.hop)
 
-    def forward(self, wav, anim_fs=None, anim_length=None, want_mel=False, want_feat=True):
-        """wav [N, n_samples] f32 CUDA -> (mel [N, n_mels, L] or None, feat [N, anim_length, n_mels+1] or None)."""
+    def forward(self, wav, anim_fs=None, anim_length=None, want_mel=False, want_feat=True, gain=None):
+        """wav [N, n_samples] f32 (or int16 PCM) CUDA -> (mel [N, n_mels, L] or None, feat [N, anim_length, n_mels+1] or None).
+        gain: optional [N] f32 per-clip factor applied to the samples at load (LoudnessMeter.gain)."""
         if wav.dim() == 1:
             wav = wav[None]
-        wav = wav.contiguous().float()
+        pcm16 = wav.dtype == torch.int16
+        wav = wav.contiguous() if pcm16 else wav.contiguous().float()
         N, ns = wav.shape
         L = self.num_frames(ns)
         mel = torch.empty((N, self.n_mels, L), dtype=torch.float32, device=wav.device) if want_mel else None
@@ -93,14 +95,95 @@ class MelFrontEnd:
             feat = torch.empty((N, anim_length, self.n_mels + 1), dtype=torch.float32, device=wav.device)
         a = _lib.MelArgs(n_clips=N, n_samples=ns, n_fft=self.n_fft, hop=self.hop, n_mels=self.n_mels,
                          anim_length=int(anim_length or 0), min_amp=self.min_amp, frames_per_anim=float(fpa),
-                         wav=_lib.ptr(wav), window=_lib.ptr(self.window), twiddle=_lib.ptr(self.twiddle),
+                         wav=None if pcm16 else _lib.ptr(wav), wav_i16=_lib.ptr(wav) if pcm16 else None,
+                         gain=None if gain is None else _lib.ptr(gain.contiguous().float()),
+                         window=_lib.ptr(self.window), twiddle=_lib.ptr(self.twiddle),
                          fb_start=_lib.ptr(self.fb_start), fb_len=_lib.ptr(self.fb_len), fb_off=_lib.ptr(self.fb_off),
                          fb_w=_lib.ptr(self.fb_w), mel_out=_lib.ptr(mel), feat_out=_lib.ptr(feat), fb_total=int(self.fb_w.numel()))
         _lib.check(_lib.lib().zeggs_mel_forward(a, _lib.stream_ptr()), "zeggs_mel_forward")
         return mel, feat
 
 
+class LoudnessMeter:
+    """BS.1770 integrated loudness and the gain to `target` LUFS per clip, on the device (zeggs_loudness_gain) -- what
+    data_pipeline.py:34-39 does with pyloudnorm.  Filter coefficients and gating-block geometry are built here on the host
+    in float64 with the package's own expressions (pyloudnorm 0.1.0 IIRfilter.generate_coefficients / integrated_loudness)."""
+    T_G, OVERLAP = 0.4, 0.75
+
+    def __init__(self, device, rate=16000, target=-20.0):
+        self.device, self.rate, self.target = torch.device(device), int(rate), float(target)
+        self.coef = self._k_weighting(self.rate)
+        self._geom = {}
+
+    @staticmethod
+    def _biquad(G, Q, fc, rate, kind):
+        A = 10 ** (G / 40.0)
+        w0 = 2.0 * np.pi * (fc / rate)
+        alpha = np.sin(w0) / (2.0 * Q)
+        c = np.cos(w0)
+        if kind == "high_shelf":
+            b = [A * ((A + 1) + (A - 1) * c + 2 * np.sqrt(A) * alpha), -2 * A * ((A - 1) + (A + 1) * c),
+                 A * ((A + 1) + (A - 1) * c - 2 * np.sqrt(A) * alpha)]
+            a = [(A + 1) - (A - 1) * c + 2 * np.sqrt(A) * alpha, 2 * ((A - 1) - (A + 1) * c), (A + 1) - (A - 1) * c - 2 * np.sqrt(A) * alpha]
+        else:
+            b = [(1 + c) / 2, -(1 + c), (1 + c) / 2]
+            a = [1 + alpha, -2 * c, 1 - alpha]
+        return [b[0] / a[0], b[1] / a[0], b[2] / a[0], a[1] / a[0], a[2] / a[0]]
+
+    @classmethod
+    def _k_weighting(cls, rate):
+        return cls._biquad(4.0, 1.0 / np.sqrt(2.0), 1500.0, rate, "high_shelf") + cls._biquad(0.0, 0.5, 38.0, rate, "high_pass")
+
+    def _geometry(self, n_samples):
+        g = self._geom.get(n_samples)
+        if g is None:
+            if n_samples < self.T_G * self.rate:
+                raise _lib.ZeggsError("Audio must have length greater than the block size.")          # pyloudnorm util.valid_audio
+            step = 1.0 - self.OVERLAP
+            T = n_samples / self.rate
+            nb = int(np.round(((T - self.T_G) / (self.T_G * step))) + 1)
+            lo = [int(self.T_G * (j * step) * self.rate) for j in range(nb)]
+            hi = [min(int(self.T_G * (j * step + 1) * self.rate), n_samples) for j in range(nb)]     # numpy slicing clamps at the end
+            bounds = sorted(set(lo) | set(hi))
+            index = {b: i for i, b in enumerate(bounds)}
+            mk = lambda v: torch.tensor(v, dtype=torch.int32, device=self.device)
+            g = dict(n_seg=len(bounds) - 1, n_blocks=nb, bounds=mk(bounds), lo=mk([index[x] for x in lo]), hi=mk([index[x] for x in hi]))
+            self._geom[n_samples] = g
+        return g
+
+    def gain(self, wav, want_lufs=False):
+        """wav [N, n_samples] f32 / int16 CUDA -> gain [N] f32 (and the integrated loudness in LUFS)."""
+        if wav.dim() == 1:
+            wav = wav[None]
+        pcm16 = wav.dtype == torch.int16
+        wav = wav.contiguous() if pcm16 else wav.contiguous().float()
+        N, ns = wav.shape
+        g = self._geometry(ns)
+        l = _lib.lib()
+        wsb = l.zeggs_loudness_workspace_bytes(N, g["n_seg"])
+        ws = torch.empty(wsb, dtype=torch.uint8, device=wav.device)
+        gain = torch.empty(N, dtype=torch.float32, device=wav.device)
+        lufs = torch.empty(N, dtype=torch.float32, device=wav.device)
+        a = _lib.LoudnessArgs(n_clips=N, n_samples=ns, n_seg=g["n_seg"], n_blocks=g["n_blocks"], warm=int(0.3 * self.rate),
+                              inv_block_len=1.0 / (self.T_G * self.rate), target_lufs=self.target,
+                              wav=None if pcm16 else wav.data_ptr(), wav_i16=wav.data_ptr() if pcm16 else None,
+                              seg_bounds=g["bounds"].data_ptr(), blk_seg_lo=g["lo"].data_ptr(), blk_seg_hi=g["hi"].data_ptr(),
+                              gain_out=gain.data_ptr(), lufs_out=lufs.data_ptr(), workspace=ws.data_ptr(), workspace_bytes=wsb)
+        for i, c in enumerate(self.coef):
+            a.coef[i] = float(c)
+        _lib.check(l.zeggs_loudness_gain(a, _lib.stream_ptr()), "zeggs_loudness_gain")
+        return (gain, lufs) if want_lufs else gain
+
+
 _cache = {}
+_meters = {}
+
+
+def _meter(device, rate):
+    key = (str(device), int(rate))
+    if key not in _meters:
+        _meters[key] = LoudnessMeter(device, rate)
+    return _meters[key]
 
 
 def _front_end(device, **kw):
@@ -124,19 +207,22 @@ def _conf_kwargs(params):
 
 def preprocess_audio(audio_data, anim_fs, anim_length, params, feature_type, device="cuda"):
     """Drop-in for data_pipeline.preprocess_audio (data_pipeline.py:33-84): numpy/torch [T] (or [N,T]) in,
-    float32 [anim_length, 81] (numpy for numpy input, CUDA tensor for tensor input) out.
-    Loudness normalisation (pyloudnorm, :34-39) is a scalar gain outside this path: apply it before."""
+    float32 [anim_length, 81] (numpy for numpy input, CUDA tensor for tensor input) out.  int16 PCM input is decoded on the
+    device (x / 32768).  params.normalize_loudness (:34-39): BS.1770 integrated loudness -> gain to -20 LUFS, measured by
+    zeggs_loudness_gain and folded into the mel kernel's sample load."""
     nl = params["normalize_loudness"] if isinstance(params, dict) else getattr(params, "normalize_loudness", False)
-    if nl:
-        raise _lib.ZeggsError("normalize_loudness=True: apply the BS.1770 gain before calling (not on this path)")
     if list(feature_type) != ["mel_spec", "energy"]:
         raise _lib.ZeggsError("feature_type must be ['mel_spec', 'energy'] (the shipped audio_feature_type)")
     as_numpy = isinstance(audio_data, np.ndarray)
-    wav = torch.as_tensor(audio_data, dtype=torch.float32)
+    wav = torch.as_tensor(audio_data)
+    if wav.dtype != torch.int16:
+        wav = wav.to(torch.float32)
     if not wav.is_cuda:
-        wav = wav.pin_memory().to(device, non_blocking=True) if as_numpy else wav.to(device)
-    fe = _front_end(wav.device, **_conf_kwargs(params))
-    _, feat = fe.forward(wav, anim_fs, anim_length, want_mel=False, want_feat=True)
+        wav = wav.pin_memory().to(device, non_blocking=True) if (as_numpy and torch.cuda.is_available()) else wav.to(device)
+    kw = _conf_kwargs(params)
+    fe = _front_end(wav.device, **kw)
+    gain = _meter(wav.device, kw["sampling_rate"]).gain(wav) if nl else None
+    _, feat = fe.forward(wav, anim_fs, anim_length, want_mel=False, want_feat=True, gain=gain)
     if wav.dim() == 1 or (as_numpy and np.ndim(audio_data) == 1):
         feat = feat[0]
     return feat.cpu().numpy() if as_numpy else feat

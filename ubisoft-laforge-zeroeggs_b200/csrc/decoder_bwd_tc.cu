@@ -552,9 +552,12 @@ __global__ void dy_scale_bf16_kernel(const float* __restrict__ dY, const float* 
 }
 
 extern "C" size_t zeggs_decoder_packed_bwd_tc_bytes(int H, int S, int Z) {
-  if (H % 64 != 0 || pick_U(H) <= 0 || H > 1024) return 0;
+  // the BPTT kernel pairs k-blocks (H % 128 == 0) and keeps 4 accumulators of N2 columns in TMEM
+  if (H % 128 != 0 || pick_U(H) <= 0 || H > 1024) return 0;
   DecGeom g = make_geom(1, H, S, Z);
-  return (size_t)g.G * make_btgeom(g, make_bgeom(g)).cta_bytes;
+  BtGeom tg = make_btgeom(g, make_bgeom(g));
+  if (4 * tg.N2 > 512 || (tg.kbH % 2) != 0) return 0;
+  return (size_t)g.G * tg.cta_bytes;
 }
 extern "C" size_t zeggs_decoder_bwd_tc_workspace_bytes(int H, int S, int Z) {
   if (H % 64 != 0 || pick_U(H) <= 0 || H > 1024) return 0;

@@ -38,24 +38,43 @@ __global__ void __launch_bounds__(MEL_WARPS * 32, 2) mel_kernel(zeggs_mel_args a
   const float* fbw = fbt ? fbw_s : a.fb_w;
   const int clip = blockIdx.y, f0 = blockIdx.x * MEL_FT;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* wav = a.wav + (size_t)clip * a.n_samples;
+  const float* wav = a.wav ? a.wav + (size_t)clip * a.n_samples : nullptr;
+  const short* wav16 = a.wav_i16 ? a.wav_i16 + (size_t)clip * a.n_samples : nullptr;
+  const float gain = a.gain ? __ldg(a.gain + clip) : 1.0f;        // loudness normalisation folded into the load
   const int Ts = a.n_samples, Te = Ts < n_fft ? n_fft : Ts;     // spectrograms.py:233-234 zero-extends short clips
   // ---- stage the tile's samples (reflect padding, spectrograms.py:237-239)
   {
     const int o0 = f0 * hop - n_fft / 2;
-    if (o0 >= 0 && o0 + nsamp_tile <= Ts && ((o0 & 3) == 0) && ((a.n_samples & 3) == 0) && ((nsamp_tile & 3) == 0)) {
+    if (wav && o0 >= 0 && o0 + nsamp_tile <= Ts && ((o0 & 3) == 0) && ((a.n_samples & 3) == 0) && ((nsamp_tile & 3) == 0)) {
       // interior tile: straight 16-byte copies
       const float4* src4 = reinterpret_cast<const float4*>(wav + o0);
       float4* dst4 = reinterpret_cast<float4*>(samp);
-      for (int i = tid; i < nsamp_tile / 4; i += blockDim.x) dst4[i] = __ldg(src4 + i);
+      for (int i = tid; i < nsamp_tile / 4; i += blockDim.x) {
+        float4 v = __ldg(src4 + i);
+        v.x *= gain; v.y *= gain; v.z *= gain; v.w *= gain;
+        dst4[i] = v;
+      }
+    } else if (wav16 && o0 >= 0 && o0 + nsamp_tile <= Ts && ((o0 & 7) == 0) && ((a.n_samples & 7) == 0) && ((nsamp_tile & 7) == 0)) {
+      // interior tile of int16 PCM: 16-byte loads of 8 samples, x / 32768 (audio_files.py:211-236)
+      const uint4* src8 = reinterpret_cast<const uint4*>(wav16 + o0);
+      const float sc = gain * (1.0f / 32768.0f);
+      for (int i = tid; i < nsamp_tile / 8; i += blockDim.x) {
+        const uint4 v = __ldg(src8 + i);
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          samp[8 * i + 2 * h] = (float)(short)(w[h] & 0xffffu) * sc;
+          samp[8 * i + 2 * h + 1] = (float)(short)(w[h] >> 16) * sc;
+        }
+      }
     } else {
       for (int i = tid; i < nsamp_tile; i += blockDim.x) {
         int o = o0 + i;
         if (o < 0) o = -o;
         if (o >= Te) o = 2 * (Te - 1) - o;
         float v = 0.f;
-        if (o >= 0 && o < Ts) v = __ldg(wav + o);
-        samp[i] = v;
+        if (o >= 0 && o < Ts) v = wav ? __ldg(wav + o) : (float)__ldg(wav16 + o) * (1.0f / 32768.0f);
+        samp[i] = v * gain;
       }
     }
   }
@@ -209,7 +228,8 @@ extern "C" int zeggs_mel_forward(const zeggs_mel_args* ap, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (a.n_fft != 2 * MEL_N2) { set_error("mel: n_fft=%d unsupported (this build transforms n_fft=800 only)", a.n_fft); return ZEGGS_ERR_UNSUPPORTED; }
   ZCHECK_ARG(a.n_clips >= 0 && a.n_samples >= 1 && a.hop >= 1 && a.hop <= 800 && a.n_mels >= 1 && a.n_mels <= 256, "mel: bad shape");
-  ZCHECK_ARG(a.wav && a.window && a.twiddle && a.fb_start && a.fb_len && a.fb_off && a.fb_w, "mel: null table/input pointer");
+  ZCHECK_ARG((a.wav != nullptr) != (a.wav_i16 != nullptr), "mel: exactly one of wav (f32) / wav_i16 (int16 PCM)");
+  ZCHECK_ARG(a.window && a.twiddle && a.fb_start && a.fb_len && a.fb_off && a.fb_w, "mel: null table/input pointer");
   ZCHECK_ARG(a.mel_out || a.feat_out, "mel: no output requested");
   ZCHECK_ARG(a.n_samples >= a.n_fft / 2 + 1, "mel: clip shorter than n_fft/2+1 samples cannot be reflect-padded");
   if (a.n_clips == 0) return ZEGGS_OK;

@@ -130,6 +130,32 @@ extern "C" int zeggs_dropout_mask_dev(float* out, size_t n, float p, const unsig
   ZCHECK_LAUNCH();
   return ZEGGS_OK;
 }
+// N(0,1) draws from the same counter-based generator (Box-Muller on two 32-bit words per pair): the VAE noise of
+// modules.py:299 (torch.randn_like) without torch's generator, so a captured graph draws fresh noise on every replay
+__global__ void randn_dev_kernel(float* __restrict__ out, size_t n, const unsigned long long* __restrict__ seed_dev, unsigned long long salt) {
+  uint64_t z = *seed_dev * 0xD1342543DE82EF95ULL + (salt + 1) * 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  const uint64_t seed = z ^ (z >> 31);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; 2 * i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float u1 = ((float)mix_u32(seed, 2 * i) + 1.0f) * (1.0f / 4294967296.0f);        // (0, 1]
+    const float u2 = (float)mix_u32(seed, 2 * i + 1) * (1.0f / 4294967296.0f);
+    const float r = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincosf(6.283185307179586f * u2, &sn, &cs);
+    out[2 * i] = r * cs;
+    if (2 * i + 1 < n) out[2 * i + 1] = r * sn;
+  }
+}
+extern "C" int zeggs_randn_dev(float* out, size_t n, const unsigned long long* seed_dev, unsigned long long salt, void* stream) {
+  ZCHECK_ARG(out && seed_dev, "randn (device seed): bad arguments");
+  if (n == 0) return ZEGGS_OK;
+  const size_t blocks = (n / 2 + 256) / 256;
+  randn_dev_kernel<<<(unsigned)(blocks > 1184 ? 1184 : blocks), 256, 0, (cudaStream_t)stream>>>(out, n, seed_dev, salt);
+  count_launch();
+  ZCHECK_LAUNCH();
+  return ZEGGS_OK;
+}
 extern "C" int zeggs_dropout_mask(float* out, size_t n, float p, unsigned long long seed, void* stream) {
   ZCHECK_ARG(out && p >= 0.0f && p < 1.0f, "dropout mask: bad arguments");
   if (n == 0) return ZEGGS_OK;

@@ -37,19 +37,20 @@ def load_networks(network_path, device, with_style=True):
 
 
 def read_wav(path):
-    """scipy read + the reference's int->float rescale (audio_files.py:211-236); 16 kHz mono expected (generate.py:161-168)."""
+    """scipy read + the reference's int->float rescale (audio_files.py:211-236); 16 kHz mono expected (generate.py:161-168).
+    16-bit PCM is returned as int16 (the rescale x / 32768 happens on the device), everything else as float32."""
     from scipy.io import wavfile
     fs, x = wavfile.read(str(path))
     if x.ndim > 1:
         x = x[:, 0]
+    if fs != 16000:
+        raise _lib.ZeggsError(f"{path}: expected 16 kHz audio, got {fs} Hz (resample first; the reference shells out to SoX)")
     if x.dtype == np.int16:
-        x = x / 32768.0
+        return np.ascontiguousarray(x)             # decoded (x / 32768) by the kernels that consume it
     elif x.dtype == np.int32:
         x = x / 2147483648.0
     elif x.dtype == np.uint8:
         x = ((x / 255.0) - 0.5) * 2
-    if fs != 16000:
-        raise _lib.ZeggsError(f"{path}: expected 16 kHz audio, got {fs} Hz (resample first; the reference shells out to SoX)")
     return x.astype(np.float32)
 
 
@@ -86,85 +87,121 @@ def generate_motion(nets, stats, audio_conf, audio_data, style, first_pose, gaze
                            f("anim_input_mean"), f("anim_input_std"), f("anim_output_mean"), f("anim_output_std"), float(dt)), z
 
 
-def _reference_io():
-    """The reference's own file-format helpers, if this process can import them (drop-in use inside the reference tree)."""
-    try:
-        from anim import bvh, quat                      # noqa: F401
-        from data_pipeline import preprocess_animation  # noqa: F401
-        from utils import write_bvh                     # noqa: F401
-        return dict(bvh=bvh, quat=quat, preprocess_animation=preprocess_animation, write_bvh=write_bvh)
-    except Exception:
-        return None
+def split_by_ratio(length, ratio):
+    """Frame ranges of the `stitch` blend (ZEGGS/helpers.py:27-38): consecutive [start, end) with the last one closed at `length`."""
+    assert sum(ratio) == 1.0
+    end, out = 0.0, []
+    for r in ratio:
+        s = int(end)
+        end = s + r * length
+        out.append([s, int(end)])
+    out[-1][-1] = length
+    return out
 
 
 def generate_gesture(audio_file, styles, network_path, data_path, results_path, style_encoding_type="example",
                      blend_type="add", blend_ratio=[0.5, 0.5], file_name=None, first_pose=None, temperature=1.0,
                      seed=1234, use_gpu=True, use_script=False):
-    """Drop-in for ZEGGS/generate.py:22.  Same arguments and return value (the final style encoding)."""
+    """Drop-in for ZEGGS/generate.py:22-411: same arguments, same artefacts (<results_path>/<file_name>.bvh + .wav), same return
+    value (the final style encoding: [1,Z] without audio, [1,T,Z] with audio -- generate.py:356-357 re-binds it before returning).
+    BVH parsing / feature extraction (zeggs_b200.animation), loudness normalisation + mel (device), the three networks (device),
+    the pose -> Euler post-step (device) and the BVH text writer (zeggs_b200.bvhio) are all this package's own."""
+    from . import animation, bvhio
     assert (audio_file is None) == (results_path is None)                                # generate.py:84
     if not (use_gpu and torch.cuda.is_available()):
         raise _lib.ZeggsError("zeggs_b200.generate_gesture needs a CUDA device (no CPU fallback)")
     np.random.seed(seed); torch.manual_seed(seed)
-    device = torch.device("cuda:0")
+    device = torch.device("cuda", torch.cuda.current_device())
     data_path, network_path = Path(data_path), Path(network_path)
-    conf = json.load(open(data_path / "data_pipeline_conf.json"))
-    details = json.load(open(data_path / "data_definition.json"))
+    with open(data_path / "data_pipeline_conf.json") as fh:
+        conf = json.load(fh)
+    with open(data_path / "data_definition.json") as fh:
+        details = json.load(fh)
     stats = dict(np.load(data_path / "stats.npz"))
     nets = load_networks(network_path, device, with_style=(style_encoding_type == "example"))
-    io = _reference_io()
     label_names, dt = details["label_names"], details["dt"]
     f = lambda k: torch.as_tensor(stats[k], dtype=torch.float32, device=device)
+    is_path = lambda x: isinstance(x, (pathlib.PurePath, str))
 
-    def animation(src):
-        if isinstance(src, dict):
-            return src
-        if io is None:
-            raise _lib.ZeggsError("BVH parsing / preprocess_animation are outside the accelerated path: run inside the reference "
-                                  "tree (its anim.bvh + data_pipeline are used) or pass pre-processed arrays")
-        keys = ["root_pos", "root_rot", "root_vel", "root_vrt", "lpos", "lrot", "ltxy", "lvel", "lvrt", "cpos", "crot", "ctxy",
-                "cvel", "cvrt", "gaze_pos", "gaze_dir"]
-        return dict(zip(keys, io["preprocess_animation"](io["bvh"].load(src) if not isinstance(src, dict) else src)))
+    def features(src, cut=None):
+        """path or raw bvh dict (bvh.load layout) -> pose features; the frame range is cut from the RAW animation first (:196-203)."""
+        raw = animation.load_bvh(src) if is_path(src) else dict(src)
+        if cut is None and is_path(src):
+            assert int(np.ceil(1 / raw["frametime"])) == 60                               # generate.py:205-206
+        return animation.preprocess_animation(animation.trim(raw, cut))
 
-    encs, last_anim = [], None
+    if results_path is not None:
+        results_path = Path(results_path)
+        results_path.mkdir(exist_ok=True)
+    encs, last_anim, anim_name = [], None, None
     with torch.no_grad():
+        speech = None
+        if audio_file is not None:
+            wav = read_wav(audio_file)                                                    # int16 PCM stays int16: decoded on the device
+            n_frames = int(round(60.0 * (len(wav) / 16000)))                              # generate.py:170
+            ac = conf["audio_conf"] if "audio_conf" in conf else conf
+            feats = audio.preprocess_audio(torch.from_numpy(wav), 60, n_frames, ac, conf.get("audio_feature_type", ["mel_spec", "energy"]), device=device)
+            speech = nets["speech_encoder"]((feats[None] - f("audio_input_mean")) / f("audio_input_std"))
         for style in styles:
-            if style_encoding_type == "label":
-                e = torch.zeros((1, len(label_names)), device=device); e[0, label_names.index(style)] = 1.0
-            elif isinstance(style[0], np.ndarray):
-                e = torch.as_tensor(style[0], dtype=torch.float32, device=device)[None]
+            if style_encoding_type == "example":
+                if isinstance(style[0], np.ndarray):
+                    anim_name = style[1]
+                    encs.append(torch.as_tensor(style[0], dtype=torch.float32, device=device)[None])
+                else:
+                    anim_name = Path(style[0]).stem if is_path(style[0]) else "example"
+                    a = features(style[0], style[1]); last_anim = a
+                    n = len(a["root_vel"])
+                    vec = np.concatenate([a[k].reshape(n, -1) for k in ("root_vel", "root_vrt", "lpos", "ltxy", "lvel", "lvrt")]
+                                         + [np.zeros((n, 3), np.float32)], axis=1)        # gaze slot zero (generate.py:240-251)
+                    ex = (torch.as_tensor(vec, dtype=torch.float32, device=device) - f("anim_input_mean")) / f("anim_input_std")
+                    e, _, _ = nets["style_encoder"](ex[None], temperature)
+                    encs.append(e)
+            elif style_encoding_type == "label":
+                e = torch.zeros((1, len(label_names)), dtype=torch.float32, device=device)
+                e[0, label_names.index(style)] = 1.0
+                encs.append(e)
+                anim_name = style
+                assert first_pose is not None                                             # generate.py:270
             else:
-                a = animation(style[0]); last_anim = a
-                sl = slice(*style[1]) if style[1] is not None else slice(None)
-                n = len(a["root_vel"][sl])
-                vec = np.concatenate([a[k][sl].reshape(n, -1) for k in ("root_vel", "root_vrt", "lpos", "ltxy", "lvel", "lvrt")]
-                                     + [np.zeros((n, 3), np.float32)], axis=1)                # gaze slot zero (generate.py:240-251)
-                ex = (torch.as_tensor(vec, dtype=torch.float32, device=device) - f("anim_input_mean")) / f("anim_input_std")
-                e, _, _ = nets["style_encoder"](ex[None], temperature)
-            encs.append(e)
-        if len(encs) > 1 and blend_type == "add":
-            final = torch.matmul(torch.stack(encs, dim=1).transpose(2, 1), torch.tensor(blend_ratio, device=device))
+                raise ValueError("Unknown style encoding type")
+        if blend_type == "stitch":                                                        # generate.py:280-298
+            if len(encs) > 1:
+                if audio_file is None:
+                    final = encs
+                else:
+                    assert len(styles) == len(blend_ratio)
+                    se = split_by_ratio(n_frames, blend_ratio)
+                    final = torch.cat([e.unsqueeze(1).repeat((1, se[i][-1] - se[i][0], 1)) for i, e in enumerate(encs)], dim=1)
+            else:
+                final = encs[0]
+        elif blend_type == "add":                                                         # generate.py:299-309
+            if len(encs) > 1:
+                assert len(encs) == len(blend_ratio)
+                final = torch.matmul(torch.stack(encs, dim=1).transpose(2, 1), torch.tensor(blend_ratio, device=device))
+            else:
+                final = encs[0]
         else:
-            final = encs[0]
+            raise ValueError(f"unknown blend_type {blend_type!r}")
         if audio_file is None:
             return final
-        a = animation(first_pose) if first_pose is not None else last_anim
+        a = features(first_pose) if first_pose is not None else last_anim                # generate.py:313-354
         if a is None:
             raise _lib.ZeggsError("first_pose is required when no style example provides one (generate.py:313-354)")
-        fp = {k: np.asarray(a[k][0]) for k in POSE_KEYS}
-        wav = read_wav(audio_file)
-        ac = conf["audio_conf"] if "audio_conf" in conf else conf
-        ac = dict(ac, normalize_loudness=False)    # the BS.1770 gain (pyloudnorm) is outside the accelerated path
-        out, _ = generate_motion(nets, stats, ac, wav, final[0], fp, np.asarray(a["gaze_pos"][0]), dt, temperature, device=device)
-    V = {k: v[0].cpu().numpy() for k, v in zip(POSE_KEYS, out)}
-    results_path = Path(results_path); results_path.mkdir(parents=True, exist_ok=True)
-    file_name = file_name or f"audio_{Path(audio_file).stem}"
-    if io is not None:
-        from anim.txform import xform_orthogonalize_from_xy
-        lrot = io["quat"].from_xform(xform_orthogonalize_from_xy(torch.as_tensor(V["ltxy"])).numpy())
-        io["write_bvh"](str(results_path / (file_name + ".bvh")), V["root_pos"], V["root_rot"], V["lpos"], lrot,
-                        parents=np.asarray(details["parents"]), names=details["bone_names"], order="zyx", dt=dt,
-                        start_position=np.array([0, 0, 0]), start_rotation=np.array([1, 0, 0, 0]))
-    else:
-        np.savez(results_path / (file_name + ".npz"), **V)
-    copyfile(audio_file, str(results_path / (file_name + ".wav")))
+        T = speech.shape[1]
+        if final.dim() == 2:
+            final = final.unsqueeze(1).repeat((1, T, 1))
+        g0 = torch.as_tensor(a["gaze_pos"][0], dtype=torch.float32, device=device)
+        fp = [torch.as_tensor(a[k][0], dtype=torch.float32, device=device)[None] for k in POSE_KEYS]
+        out = nets["decoder"](*fp, g0.reshape(1, 1, 3).repeat(1, T, 1), speech, final, None,
+                              f("anim_input_mean"), f("anim_input_std"), f("anim_output_mean"), f("anim_output_std"), float(dt))
+        V = dict(zip(POSE_KEYS, out))
+        pos, eul = ops.pose_to_bvh_channels(V["root_pos"], V["root_rot"], V["lpos"], V["ltxy"], (0.0, 0.0, 0.0), (1.0, 0.0, 0.0, 0.0))
+        pos, eul = pos[0].cpu().numpy(), eul[0].cpu().numpy()
+    if file_name is None:
+        file_name = f"audio_{Path(audio_file).stem}_label_{anim_name}"
+    try:
+        bvhio.save_bvh(str(results_path / (file_name + ".bvh")), pos, eul, details["parents"], details["bone_names"], "zyx", dt)
+        copyfile(audio_file, str(results_path / (file_name + ".wav")))
+    except (PermissionError, OSError) as e:                                               # generate.py:407-408
+        print(e)
     return final

@@ -59,8 +59,10 @@ TC_MIN_HIDDEN = 288
 
 
 def tc_eligible(H, S, Z):
-    """The tensor-core recurrence covers H % 64 == 0, 288 <= H <= 1024 (zeggs_decoder_packed_tc_bytes reports 0 otherwise)."""
-    return H >= TC_MIN_HIDDEN and _lib.lib().zeggs_decoder_packed_tc_bytes(H, S, Z) > 0
+    """The tensor-core recurrence (forward AND BPTT kernels) covers H % 128 == 0, 384 <= H <= 1024: the library's
+    zeggs_decoder_packed_tc_bytes / _bwd_tc_bytes report 0 for anything else."""
+    l = _lib.lib()
+    return H >= TC_MIN_HIDDEN and l.zeggs_decoder_packed_tc_bytes(H, S, Z) > 0 and l.zeggs_decoder_packed_bwd_tc_bytes(H, S, Z) > 0
 
 
 def set_decoder_engine(name):
@@ -78,8 +80,8 @@ def resolve_engine(H, S, Z):
         return False
     ok = tc_eligible(H, S, Z)
     if DECODER_ENGINE == "tc" and not ok:
-        raise _lib.ZeggsError(f"decoder engine 'tc' requested but hidden size {H} is not eligible (needs H % 64 == 0 and "
-                              f"{TC_MIN_HIDDEN} <= H <= 1024); use 'fp32' or 'auto'")
+        raise _lib.ZeggsError(f"decoder engine 'tc' requested but hidden size {H} is not eligible (needs H % 128 == 0 and "
+                              f"384 <= H <= 1024); use 'fp32' or 'auto'")
     return ok
 
 
@@ -177,6 +179,101 @@ def decoder_window_forward(dec, root_pos0, root_rot0, pose0, gaze_pos, speech, s
     a, keep, ws = _decoder_args(dec, B, T, dev, tensors, stats, dt, save)
     _lib.check(_lib.lib().zeggs_decoder_window_fwd(a, _lib.stream_ptr()), "zeggs_decoder_window_fwd")
     return Y, rp, rq, (a, keep, ws)
+
+
+_DEC_GRAD_NAMES = ["dW0", "db0", "dW_ih0", "db_ih0", "dW_hh0", "db_hh0", "dW_ih1", "db_ih1", "dW_hh1", "db_hh1",
+                   "dW2", "db2", "dWc0", "dbc0", "dWc1", "dbc1", "dWc2", "dbc2"]
+
+
+def _grad_targets(weights, grads_out):
+    """Gradient buffers for `weights`: fresh tensors, or the caller's (e.g. the views of the optimizer's flat gradient buffer:
+    the kernels then write every parameter gradient straight to its final place -- no autograd accumulation pass)."""
+    if grads_out is None:
+        return [torch.empty_like(w, dtype=torch.float32, memory_format=torch.contiguous_format) for w in weights]
+    for w, g in zip(weights, grads_out):
+        if g.shape != w.shape or not g.is_contiguous() or g.dtype != torch.float32:
+            raise _lib.ZeggsError("gradient target must be a contiguous fp32 tensor of the parameter's shape")
+    return list(grads_out)
+
+
+def decoder_window_backward(dec, state, dY, dRp, dRq, grads_out=None):
+    """BPTT of one decoder window (zeggs_decoder_window_bwd).  state = the 4th result of decoder_window_forward(save=True).
+    Returns (weight gradients in dec._weights() order, dSpeech [B,T,S], dStyle [B,T,Z])."""
+    l = _lib.lib()
+    a, keep, ws = state
+    dev = ws.device
+    B, T, H, S, Z = a.B, a.T, a.H, a.S, a.Z
+    b = _lib.DecoderBwdArgs()
+    hold = []
+    for name, g in (("dY", dY), ("dRootPos", dRp), ("dRootRot", dRq)):
+        if g is not None:
+            g = g.contiguous().float()
+            hold.append(g)
+            setattr(b, name, g.data_ptr())
+    # transposed weight slices for the backward recurrence (cached on the module like the forward pack)
+    ver = weights_key(dec._weights())
+    use_tc = a.engine == 1
+    if use_tc and l.zeggs_decoder_packed_bwd_tc_bytes(H, S, Z) == 0:
+        raise _lib.ZeggsError(f"tensor-core decoder backward unavailable for hidden size {H}")
+    if not use_tc:
+        cache = dec.__dict__.get("_zeggs_packed_bwd")
+        if cache is None or cache[0] != ver or cache[1].device != dev:
+            nb = l.zeggs_decoder_packed_bwd_bytes(H, S, Z)
+            packed = torch.empty(nb // 4, dtype=torch.float32, device=dev)
+            _lib.check(l.zeggs_decoder_pack_weights_bwd(a, packed.data_ptr(), _lib.stream_ptr()), "zeggs_decoder_pack_weights_bwd")
+            dec.__dict__["_zeggs_packed_bwd"] = (ver, packed)
+            cache = dec.__dict__["_zeggs_packed_bwd"]
+        b.packed_bwd = cache[1].data_ptr()
+        hold.append(cache[1])
+    else:
+        tcc = dec.__dict__.get("_zeggs_packed_bwd_tc")
+        if tcc is None or tcc[0] != ver or tcc[1].device != dev:
+            ptc = torch.empty(l.zeggs_decoder_packed_bwd_tc_bytes(H, S, Z), dtype=torch.uint8, device=dev)
+            _lib.check(l.zeggs_decoder_pack_weights_bwd_tc(a, ptc.data_ptr(), _lib.stream_ptr()), "zeggs_decoder_pack_weights_bwd_tc")
+            dec.__dict__["_zeggs_packed_bwd_tc"] = (ver, ptc)
+            tcc = dec.__dict__["_zeggs_packed_bwd_tc"]
+        wtc = WS.get("dec_bwd_tc", l.zeggs_decoder_bwd_tc_workspace_bytes(H, S, Z), dev)
+        b.packed_bwd_tc, b.workspace_tc = tcc[1].data_ptr(), wtc.data_ptr()
+        hold += [tcc[1], wtc]
+    grads = _grad_targets(dec._weights(), grads_out)
+    for n, g in zip(_DEC_GRAD_NAMES, grads):
+        setattr(b, n, g.data_ptr())
+    dSpeech = torch.empty((B, T, S), dtype=torch.float32, device=dev)
+    dStyle = torch.empty((B, T, Z), dtype=torch.float32, device=dev)
+    b.dSpeech, b.dStyle = dSpeech.data_ptr(), dStyle.data_ptr()
+    wsb = l.zeggs_decoder_bwd_workspace_bytes(B, T, H, S, Z)
+    bws = WS.get("dec_bwd", wsb, dev)
+    b.workspace, b.workspace_bytes = bws.data_ptr(), wsb
+    _lib.check(l.zeggs_decoder_window_bwd(a, b, _lib.stream_ptr()), "zeggs_decoder_window_bwd")
+    return grads, dSpeech, dStyle
+
+
+def loss_fwd_bwd(Y, rp, rq, WY, Wrp, Wrq, gaze, parents_i32, dt, mu, logvar, kl_weight, terms_out=None, kl_weight_dev=None):
+    """train.py:277-421 forward and gradient in one call (zeggs_loss_fwd_bwd) -> (loss = terms[0], (dY, dRp, dRq, dmu, dlogvar))."""
+    l = _lib.lib()
+    dev = Y.device
+    B, T = Y.shape[0], Y.shape[1]
+    f = _f32c
+    Y, rp, rq, WY, Wrp, Wrq, gaze = f(Y), f(rp), f(rq), f(WY), f(Wrp), f(Wrq), f(gaze)
+    losses = terms_out if terms_out is not None else torch.empty(19, dtype=torch.float32, device=dev)
+    dY, dRp, dRq = torch.empty_like(Y), torch.empty_like(rp), torch.empty_like(rq)
+    a = _lib.LossArgs(B=B, T=T, Z=(mu.shape[1] if mu is not None else 0), dt=dt, kl_weight=kl_weight)
+    if kl_weight_dev is not None:          # device scalar (graph-replayable): overrides the by-value weight
+        a.kl_weight_dev = kl_weight_dev.data_ptr()
+    a.Y, a.root_pos, a.root_rot = Y.data_ptr(), rp.data_ptr(), rq.data_ptr()
+    a.WY, a.W_root_pos, a.W_root_rot = WY.data_ptr(), Wrp.data_ptr(), Wrq.data_ptr()
+    a.gaze_pos, a.parents, a.losses = gaze.data_ptr(), parents_i32.data_ptr(), losses.data_ptr()
+    a.dY, a.dRootPos, a.dRootRot = dY.data_ptr(), dRp.data_ptr(), dRq.data_ptr()
+    dmu = dlv = None
+    if mu is not None:
+        mu, logvar = f(mu), f(logvar)
+        dmu, dlv = torch.empty_like(mu), torch.empty_like(logvar)
+        a.mu, a.logvar, a.dmu, a.dlogvar = mu.data_ptr(), logvar.data_ptr(), dmu.data_ptr(), dlv.data_ptr()
+    wsb = l.zeggs_loss_workspace_bytes(B, T)
+    ws = WS.get("loss", wsb, dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), wsb
+    _lib.check(l.zeggs_loss_fwd_bwd(a, _lib.stream_ptr()), "zeggs_loss_fwd_bwd")
+    return losses[0], (dY, dRp, dRq, dmu, dlv)
 
 
 def decoder_window(dec, root_pos0, root_rot0, pose0, gaze_pos, speech, style,
@@ -304,18 +401,50 @@ def speech_enc_args(enc, x, masks, y, ws):
     return a, w
 
 
-def speech_encoder(enc, x, masks=None):
-    if x.device.type != "cuda":
-        raise _lib.ZeggsError("zeggs_b200.SpeechEncoder runs on CUDA tensors only (no CPU fallback)")
-    from .autograd import SpeechEncoderFn
-    ensure_scratch(x.device)
+def speech_encoder_masks(enc, x, masks=None):
+    """Dropout multipliers of modules.py:263-270 (sampled in train mode unless injected)."""
     B, T = x.shape[0], x.shape[1]
     H, O = enc.layer0.weight.shape[0], enc.layer1.weight.shape[0]
     if masks is None and enc.training:
         masks = (_drop_mask((B, T, H), 0.2, x.device), _drop_mask((B, T, O), 0.2, x.device))
     if masks is not None:
         masks = tuple(_f32c(m, x.device) for m in masks)
-    return SpeechEncoderFn.apply(enc, x, masks, *enc._weights())
+    return masks
+
+
+def speech_encoder_fwd(enc, x, masks):
+    """zeggs_speech_enc_fwd -> (y [B,T,O], state for speech_encoder_bwd)."""
+    if x.device.type != "cuda":
+        raise _lib.ZeggsError("zeggs_b200.SpeechEncoder runs on CUDA tensors only (no CPU fallback)")
+    l = _lib.lib()
+    ensure_scratch(x.device)
+    x = _f32c(x)
+    weights = enc._weights()
+    B, T = x.shape[0], x.shape[1]
+    Cin, H, O = weights[0].shape[1], weights[0].shape[0], weights[2].shape[0]
+    y = torch.empty((B, T, O), dtype=torch.float32, device=x.device)
+    ws = torch.empty(l.zeggs_speech_enc_workspace_bytes(B, T, Cin, H, O), dtype=torch.uint8, device=x.device)
+    a, keep = speech_enc_args(enc, x, masks, y, ws)
+    _lib.check(l.zeggs_speech_enc_fwd(a, _lib.stream_ptr()), "zeggs_speech_enc_fwd")
+    return y, (a, keep, x, masks, y, ws, weights)
+
+
+def speech_encoder_bwd(state, dy, grads_out=None):
+    a, keep, x, masks, y, ws, weights = state
+    dy = dy.contiguous().float()
+    grads = _grad_targets(weights, grads_out)
+    g = _lib.SpeechEncGrads(dy=dy.data_ptr())
+    for n, t in zip(("dW0", "db0", "dW1", "db1", "dW2", "db2"), grads):
+        setattr(g, n, t.data_ptr())
+    _lib.check(_lib.lib().zeggs_speech_enc_bwd(a, g, _lib.stream_ptr()), "zeggs_speech_enc_bwd")
+    return grads
+
+
+def speech_encoder(enc, x, masks=None):
+    if x.device.type != "cuda":
+        raise _lib.ZeggsError("zeggs_b200.SpeechEncoder runs on CUDA tensors only (no CPU fallback)")
+    from .autograd import SpeechEncoderFn
+    return SpeechEncoderFn.apply(enc, x, speech_encoder_masks(enc, x, masks), *enc._weights())
 
 
 _pe_cache = {}
@@ -345,10 +474,39 @@ def style_enc_args(enc, x, eps, masks, temperature, outs, ws):
     return a, w + [pe]
 
 
-def style_encoder(enc, x, temperature=1.0, eps=None, masks=None):
-    if x.device.type != "cuda":
-        raise _lib.ZeggsError("zeggs_b200.StyleEncoder runs on CUDA tensors only (no CPU fallback)")
-    from .autograd import StyleEncoderFn
+def style_encoder_fwd(enc, x, eps, masks, temperature):
+    """zeggs_style_enc_fwd -> ([z, mu, logvar], state for style_encoder_bwd)."""
+    l = _lib.lib()
+    x = _f32c(x)
+    weights = enc._weights()
+    B, T, Cin = x.shape
+    Hs, E = weights[0].shape[0], weights[4].shape[0]
+    nh = enc.encoder.blocks[0].attention.multi_head_attention.num_heads
+    outs = [torch.empty((B, E // 2), dtype=torch.float32, device=x.device) for _ in range(3)]
+    ws = torch.empty(l.zeggs_style_enc_workspace_bytes(B, T, Cin, Hs, E, nh), dtype=torch.uint8, device=x.device)
+    a, keep = style_enc_args(enc, x, eps, masks, temperature, outs, ws)
+    _lib.check(l.zeggs_style_enc_fwd(a, _lib.stream_ptr()), "zeggs_style_enc_fwd")
+    return outs, (a, keep, x, eps, masks, outs, ws, weights)
+
+
+def style_encoder_bwd(state, dz, dmu, dlv, grads_out=None):
+    a, keep, x, eps, masks, outs, ws, weights = state
+    g = _lib.StyleEncGrads()
+    hold = []
+    for n, t in (("dz", dz), ("dmu", dmu), ("dlogvar", dlv)):
+        if t is not None:
+            t = t.contiguous().float()
+            hold.append(t)
+            setattr(g, n, t.data_ptr())
+    grads = _grad_targets(weights, grads_out)
+    for n, t in zip(_lib.STYLE_W, grads):
+        setattr(g, "d" + n, t.data_ptr())
+    _lib.check(_lib.lib().zeggs_style_enc_bwd(a, g, _lib.stream_ptr()), "zeggs_style_enc_bwd")
+    return grads
+
+
+def style_encoder_prepare(enc, x, eps=None, masks=None):
+    """VAE noise (modules.py:299) and dropout multipliers (sampled in train mode unless injected) -> (eps, masks)."""
     dev = x.device
     ensure_scratch(dev)
     B, T = x.shape[0], x.shape[1]
@@ -356,11 +514,51 @@ def style_encoder(enc, x, temperature=1.0, eps=None, masks=None):
     E = enc.encoder.convs[4].conv.weight.shape[0]
     nh = enc.encoder.blocks[0].attention.multi_head_attention.num_heads
     if eps is None:
-        eps = torch.randn((B, E // 2), device=dev)          # modules.py:299
+        if _dev_seed is not None:                           # device-seeded draw (replayable graph), else torch's generator
+            eps = torch.empty((B, E // 2), dtype=torch.float32, device=dev)
+            _dev_seed.salt += 1
+            _lib.check(_lib.lib().zeggs_randn_dev(eps.data_ptr(), eps.numel(), _dev_seed.t.data_ptr(), _dev_seed.salt, _lib.stream_ptr()),
+                       "zeggs_randn_dev")
+        else:
+            eps = torch.randn((B, E // 2), device=dev)      # modules.py:299
     if masks is None and enc.training:
         masks = dict(c1=_drop_mask((B, T, Hs), 0.2, dev), c2=_drop_mask((B, T, E), 0.2, dev),
                      attn=_drop_mask((B, nh, T, T), 0.1, dev), ao=_drop_mask((B, T, E), 0.1, dev),
                      ff=_drop_mask((B, T, E), 0.1, dev))
     if masks is not None:
         masks = {k: _f32c(v, dev) for k, v in masks.items()}
-    return StyleEncoderFn.apply(enc, x, _f32c(eps, dev), masks, temperature, *enc._weights())
+    return _f32c(eps, dev), masks
+
+
+def style_encoder(enc, x, temperature=1.0, eps=None, masks=None):
+    if x.device.type != "cuda":
+        raise _lib.ZeggsError("zeggs_b200.StyleEncoder runs on CUDA tensors only (no CPU fallback)")
+    from .autograd import StyleEncoderFn
+    eps, masks = style_encoder_prepare(enc, x, eps, masks)
+    return StyleEncoderFn.apply(enc, x, eps, masks, temperature, *enc._weights())
+
+
+# ---------------------------------------------------------------------------------------------- pose -> BVH channel values
+def pose_to_bvh_channels(root_pos, root_rot, lpos, ltxy, start_position=(0.0, 0.0, 0.0), start_rotation=(1.0, 0.0, 0.0, 0.0),
+                         rebase=True, want_lrot=False):
+    """Device post-step of generate.py:389-406 / utils.py:47-87: [N,T,...] pose tensors -> (positions [N,T,J,3], euler degrees
+    [N,T,J,3] in 'zyx' channel order[, local rotations [N,T,J,4]]).  rebase: move the root's first frame to start_position /
+    start_rotation, as write_bvh does when both are given."""
+    if root_pos.device.type != "cuda":
+        raise _lib.ZeggsError("pose_to_bvh_channels runs on CUDA tensors only (no CPU fallback)")
+    rp, rq, lp, xy = _f32c(root_pos), _f32c(root_rot), _f32c(lpos), _f32c(ltxy)
+    if rp.dim() == 2:
+        rp, rq, lp, xy = rp[None], rq[None], lp[None], xy[None]
+    N, T, J = lp.shape[0], lp.shape[1], lp.shape[2]
+    pos = torch.empty((N, T, J, 3), dtype=torch.float32, device=lp.device)
+    eul = torch.empty((N, T, J, 3), dtype=torch.float32, device=lp.device)
+    lrot = torch.empty((N, T, J, 4), dtype=torch.float32, device=lp.device) if want_lrot else None
+    a = _lib.PosePostArgs(N=N, T=T, J=J, rebase=int(bool(rebase)), root_pos=rp.data_ptr(), root_rot=rq.data_ptr(), lpos=lp.data_ptr(),
+                          ltxy=xy.data_ptr(), positions=pos.data_ptr(), euler_deg=eul.data_ptr(),
+                          lrot=lrot.data_ptr() if want_lrot else None)
+    for i in range(3):
+        a.start_pos[i] = float(start_position[i])
+    for i in range(4):
+        a.start_rot[i] = float(start_rotation[i])
+    _lib.check(_lib.lib().zeggs_pose_to_bvh_channels(a, _lib.stream_ptr()), "zeggs_pose_to_bvh_channels")
+    return (pos, eul, lrot) if want_lrot else (pos, eul)

@@ -14,7 +14,6 @@ import numpy as np
 import torch
 
 from . import _lib, dp, modules, ops
-from .autograd import TrainLossFn
 from .optimizers import RAdam
 
 POSE_KEYS = ["root_pos", "root_rot", "root_vel", "root_vrt", "lpos", "ltxy", "lvel", "lvrt"]
@@ -62,6 +61,7 @@ class TrainStep:
         self.use_graph = bool(use_graph)
         self.seed = ops.DeviceSeed(self.dev) if self.use_graph else None
         self._graphs, self._seen, self._pool = {}, {}, None
+        self.graph_min_seen = 1            # eager steps on a new batch geometry before it is captured
         self.graph_launches = 0            # library launches captured per replay (gpu_launches accounting)
         self.ar_events = None              # set to [] to record (start, end) CUDA events around every all-reduce
 
@@ -78,25 +78,34 @@ class TrainStep:
         return self._forward_backward(batch, eps, masks, train_mode)
 
     def _forward_backward(self, batch, eps, masks, train_mode):
-        self.se.train(train_mode); self.dec.train(train_mode)
-        speech = self.se((batch["audio"] - self.audio_mean) / self.audio_std, masks=None if masks is None else masks.get("speech"))
-        mu = logvar = None
-        if self.st is not None:
-            self.st.train(train_mode)
-            z, mu, logvar = self.st((batch["style"] - self.in_mean) / self.in_std, 1.0, eps=eps,
-                                    masks=None if masks is None else masks.get("style"))
+        """Explicit forward + backward through the C ABI (no autograd engine on the step): every kernel writes its parameter
+        gradients straight into the optimizer's flat gradient buffer (the views RAdam installed as p.grad)."""
+        se, dec, st = self.se, self.dec, self.st
+        se.train(train_mode); dec.train(train_mode)
+        gv = lambda m: [p.grad for p in m._weights()]
+        xa = (batch["audio"] - self.audio_mean) / self.audio_std
+        speech, se_state = ops.speech_encoder_fwd(se, xa, ops.speech_encoder_masks(se, xa, None if masks is None else masks.get("speech")))
+        mu = logvar = st_state = None
+        if st is not None:
+            st.train(train_mode)
+            xs = (batch["style"] - self.in_mean) / self.in_std
+            eps_, smasks = ops.style_encoder_prepare(st, xs, eps, None if masks is None else masks.get("style"))
+            (z, mu, logvar), st_state = ops.style_encoder_fwd(st, xs, eps_, smasks, 1.0)
         else:
             z = batch["style"]
         T = speech.shape[1]
         W = [batch[k] for k in POSE_KEYS]
         WY = pack_pose(*W[2:])                                   # ground-truth window, packed once
-        Y, rp, rq = self.dec.forward_packed(W[0][:, 0], W[1][:, 0], WY[:, 0], batch["gaze_pos"], speech,
-                                            z.unsqueeze(1).expand(-1, T, -1), self.in_mean, self.in_std,
-                                            self.out_mean, self.out_std, self.dt)
-        loss = TrainLossFn.apply(Y, rp, rq, WY, W[0], W[1], batch["gaze_pos"], self.parents, self.dt, mu, logvar,
-                                 kl_weight(self.iteration) if mu is not None else 0.0, self.terms, True,
-                                 self.klw if mu is not None else None)
-        loss.backward()
+        Y, rp, rq, dstate = ops.decoder_window_forward(dec, W[0][:, 0], W[1][:, 0], WY[:, 0], batch["gaze_pos"], speech,
+                                                       z.unsqueeze(1).expand(-1, T, -1),
+                                                       (self.in_mean, self.in_std, self.out_mean, self.out_std), self.dt, save=True)
+        loss, (dY, dRp, dRq, dmu, dlv) = ops.loss_fwd_bwd(Y, rp, rq, WY, W[0], W[1], batch["gaze_pos"], self.parents, self.dt, mu, logvar,
+                                                          kl_weight(self.iteration) if mu is not None else 0.0, self.terms,
+                                                          self.klw if mu is not None else None)
+        _, dSpeech, dStyle = ops.decoder_window_backward(dec, dstate, dY, dRp, dRq, grads_out=gv(dec))
+        ops.speech_encoder_bwd(se_state, dSpeech, grads_out=gv(se))
+        if st is not None:
+            ops.style_encoder_bwd(st_state, dStyle.sum(dim=1), dmu, dlv, grads_out=gv(st))     # z was broadcast over the window
         return loss
 
     def _allreduce(self):
@@ -129,7 +138,7 @@ class TrainStep:
         if ent is None:
             seen = self._seen.get(key, 0)
             self._seen[key] = seen + 1
-            if seen < 1:        # first sight of a geometry: a real step, run eagerly (one-time initialisation, workspace growth)
+            if seen < self.graph_min_seen:        # first sight of a geometry: a real step, run eagerly (one-time initialisation, workspace growth)
                 return self._eager_step(batch)
             ent = self._capture(key, batch)
             if ent is None:
@@ -239,7 +248,7 @@ def train(models_dir, logs_dir, path_processed_data, path_data_definition, train
     if world > 1 and not torch.distributed.is_initialized():
         torch.distributed.init_process_group("nccl")
     # additive option: recurrence engine ("auto": tcgen05 bf16 operands / fp32 state where the hidden size is eligible -- the fast
-    # path, pinned to the reference's loss/gradients by tests/golden/train_h320|h1024.npz and to the fp32 engine's loss curve by
+    # path, pinned to the reference's loss/gradients by tests/golden/train_h384|h1024.npz and to the fp32 engine's loss curve by
     # test_short_training_curve_tc_tracks_fp32; "tc": the same but raises when ineligible; "fp32": SIMT parity-grade path)
     ops.set_decoder_engine(train_options.get("decoder_engine", "auto"))
     models_dir, logs_dir = Path(models_dir), Path(logs_dir)
