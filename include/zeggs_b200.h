@@ -274,6 +274,29 @@ typedef struct {
 } zeggs_pose_post_args;
 int zeggs_pose_to_bvh_channels(const zeggs_pose_post_args* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Device-resident window supplier: one launch gathers a training batch out of the processed arrays kept in HBM
+ * (dataset.py:110-153 windows, :176-204 style-example windows, train.py:215-225 copies).
+ *   src[k] [n_frames, width[k]] f32 (X_audio_features, Y_root_pos, ...), dst[k] [B, T, width[k]]:  dst[k][b][t] = src[k][start[b] + t]
+ *   ex_out [B, L, ex_width]: the arrays ex_src[0..n_ex) side by side (root_vel, root_vrt, lpos, ltxy, lvel, lvrt), remaining columns
+ *   zero; rows l >= ex_n[b] repeat the example's last L - ex_n[b] rows (dataset.py:201-203).  start / ex_start / ex_n: int32 [B] on
+ *   the device (drawn on the host by the same generator as the reference's sampler).
+ */
+#define ZEGGS_GATHER_MAX 12
+typedef struct {
+  int B, T, n_arrays;
+  const float* src[ZEGGS_GATHER_MAX];
+  float* dst[ZEGGS_GATHER_MAX];
+  int width[ZEGGS_GATHER_MAX];
+  const int* start;
+  float* ex_out;            /* NULL: no style example (label style) */
+  int L, ex_width, n_ex;
+  int ex_src[ZEGGS_GATHER_MAX];
+  const int* ex_start;
+  const int* ex_n;
+} zeggs_gather_args;
+int zeggs_window_gather(const zeggs_gather_args* a, void* stream);
+
 /* Fused RAdam step over a flat fp32 parameter buffer (optimizers.py:31-99; weight_decay 0,
  * degenerated_to_sgd).  `step` is the 1-based step count; gradients are multiplied by grad_scale first. */
 int zeggs_radam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,

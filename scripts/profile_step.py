@@ -7,8 +7,8 @@ from zeggs_b200 import ops
 ops.set_decoder_engine(os.environ.get("PROF_ENGINE", "tc"))
 T = int(os.environ.get("PROF_T", "32")); steps = int(os.environ.get("PROF_STEPS", "2"))
 dev = torch.device("cuda:0")
-stepper, P, stats = bench.build_stepper(1024, dev, 1)
-batch = bench.synth_batch(32, T, 384, seed=1, device=dev)
+stepper, P, stats = bench.build_stepper(1024, dev, 1, use_graph=False)      # eager launches: ncu lists every kernel
+batch = bench.synth_batch(32, T, int(os.environ.get("PROF_TEX", "384")), seed=1, device=dev)
 for _ in range(steps):
     stepper.step(batch)
 torch.cuda.synchronize()

@@ -941,7 +941,8 @@ def test_generate_gesture_end_to_end_vs_reference_golden(dev, golden_dir, tmp_pa
     the UNMODIFIED reference wrote for the same files and weights (tests/golden/generate_e2e.npz, CPU run in the dev container):
     one example style, two styles blended 'add', two styles 'stitch'; with loudness normalisation off (pure reference arithmetic)
     and on (reference + oracle-backed pyloudnorm stub; that third-party step is parity-unpinned).  fp32 recurrence engine,
-    240 free-running frames: BVH positions <= 1e-3 * max(1,|ref|), Euler angles <= 0.05 degrees, style encodings <= 1e-4."""
+    240 free-running frames: BVH positions <= 1e-3 (absolute, cm; measured 6e-5), Euler angles <= 5e-3 degrees (measured 5e-4),
+    style encodings <= 1e-4 (measured 8e-6)."""
     import json
     import shutil
     from pathlib import Path
@@ -977,10 +978,51 @@ def test_generate_gesture_end_to_end_vs_reference_golden(dev, golden_dir, tmp_pa
         e, sc = report(f"{tag} encoding", enc, torch.from_numpy(g[tag + "_encoding"]))
         assert tuple(enc.shape) == tuple(g[tag + "_encoding"].shape) and e <= 1e-4 * max(1.0, sc)
         e, sc = report(f"{tag} BVH positions", torch.from_numpy(b["positions"]), torch.from_numpy(g[tag + "_positions"]))
-        assert e <= 1e-3 * max(1.0, sc)
+        assert e <= 1e-3
         e, _ = report(f"{tag} BVH euler degrees", torch.from_numpy(b["rotations"]), torch.from_numpy(g[tag + "_rotations"]))
-        assert e <= 5e-2
+        assert e <= 5e-3
     if not loud:
         enc = generate.generate_gesture(None, [(bvh_path, (10, 300))], net, data, None, temperature=1e6)
         e, sc = report("embedding-only call", enc, torch.from_numpy(g["embedding_only"]))
         assert tuple(enc.shape) == (1, 64) and e <= 1e-4 * max(1.0, sc)
+
+
+# ---------------------------------------------------------------------------------------------- device-resident window supplier (8f row 2)
+def _synthetic_processed_data(tmp_path):
+    import json
+    from zeggs_b200 import synth
+    from zeggs_b200.data import KEYS
+    st = synth.load_stats()
+    rs = np.random.RandomState(3)
+    N = 900
+    data = {"X_audio_features": rs.randn(N, 81).astype(np.float32)}
+    win = synth.make_pose_windows(1, N, seed=4)
+    for k in KEYS:
+        data["Y_" + k] = win[k][0]
+    ranges = np.array([[0, 300], [300, 420], [420, 900]], dtype=np.int64)       # a short range exercises the clamping / tail repeat
+    data.update(ranges_train=ranges, ranges_valid=ranges[:1], ranges_train_labels=np.array([0, 2, 1]), ranges_valid_labels=np.array([0]))
+    for k in ("audio_input_mean", "audio_input_std", "anim_input_mean", "anim_input_std", "anim_output_mean", "anim_output_std"):
+        data[k] = st[k]
+    np.savez(tmp_path / "processed_data.npz", **data)
+    with open(tmp_path / "data_definition.json", "w") as f:
+        json.dump(dict(bone_names=[f"b{i}" for i in range(75)], label_names=["Neutral", "Happy", "Sad"],
+                       parents=[int(p) for p in st["parents"]], dt=float(st["dt"])), f)
+    return tmp_path / "data_definition.json", tmp_path / "processed_data.npz"
+
+
+@pytest.mark.parametrize("window,ex_len,style", [(64, 128, "example"), (100, 256, "example"), (64, 64, "example"), (64, 128, "label")])
+def test_device_window_gather_is_bit_identical_to_host_supplier(dev, tmp_path, window, ex_len, style):
+    """zeggs_window_gather (data in HBM, one launch per batch) against WindowDataset.sample_host_batch -- itself checked against the
+    reference's SGDataset in tests/test_dataset_vs_reference.py -- for the same seed: every tensor of the batch bit-identical."""
+    from zeggs_b200.data import DeviceWindowDataset, WindowDataset
+    ddef, dproc = _synthetic_processed_data(tmp_path)
+    host = WindowDataset(ddef, dproc, window, style, ex_len, seed=9)
+    devd = DeviceWindowDataset(ddef, dproc, window, style, ex_len, seed=9, device=dev)
+    for _ in range(3):
+        hb = host.sample_host_batch(7)
+        db = devd.sample_batch(7)
+        torch.cuda.synchronize()
+        assert set(hb) == set(db)
+        for k in hb:
+            assert tuple(hb[k].shape) == tuple(db[k].shape), k
+            assert torch.equal(hb[k], db[k].cpu()), k

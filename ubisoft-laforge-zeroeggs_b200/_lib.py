@@ -19,6 +19,15 @@ class MelArgs(C.Structure):
                 ("gain", C.c_void_p), ("wav_i16", C.c_void_p)]
 
 
+GATHER_MAX = 12
+
+
+class GatherArgs(C.Structure):
+    _fields_ = [("B", C.c_int), ("T", C.c_int), ("n_arrays", C.c_int), ("src", C.c_void_p * GATHER_MAX), ("dst", C.c_void_p * GATHER_MAX),
+                ("width", C.c_int * GATHER_MAX), ("start", C.c_void_p), ("ex_out", C.c_void_p), ("L", C.c_int), ("ex_width", C.c_int),
+                ("n_ex", C.c_int), ("ex_src", C.c_int * GATHER_MAX), ("ex_start", C.c_void_p), ("ex_n", C.c_void_p)]
+
+
 class PosePostArgs(C.Structure):
     _fields_ = [("N", C.c_int), ("T", C.c_int), ("J", C.c_int), ("rebase", C.c_int), ("start_pos", C.c_float * 3),
                 ("start_rot", C.c_float * 4), ("root_pos", C.c_void_p), ("root_rot", C.c_void_p), ("lpos", C.c_void_p),
@@ -87,6 +96,7 @@ SYMBOLS = [
     ("zeggs_timing_read", C.c_int, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     ("zeggs_mel_num_frames", C.c_int, [C.c_int, C.c_int, C.c_int]),
     ("zeggs_mel_forward", C.c_int, [C.POINTER(MelArgs), C.c_void_p]),
+    ("zeggs_window_gather", C.c_int, [C.POINTER(GatherArgs), C.c_void_p]),
     ("zeggs_pose_to_bvh_channels", C.c_int, [C.POINTER(PosePostArgs), C.c_void_p]),
     ("zeggs_loudness_workspace_bytes", C.c_size_t, [C.c_int, C.c_int]),
     ("zeggs_loudness_gain", C.c_int, [C.POINTER(LoudnessArgs), C.c_void_p]),

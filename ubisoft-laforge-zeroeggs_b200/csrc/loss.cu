@@ -53,7 +53,12 @@ struct LossDev {
   size_t stride;
 };
 
-__global__ void __launch_bounds__(128) loss_fk_fwd_kernel(LossDev d) {
+constexpr int LOSS_TB = 64;      // frames per CTA: 8192 frames x 2 sides = 256 CTAs (the per-frame FK chain is latency bound: spread it over every SM)
+
+__global__ void __launch_bounds__(LOSS_TB) loss_fk_fwd_kernel(LossDev d) {
+  __shared__ int s_par[NJ];
+  for (int i = threadIdx.x; i < NJ; i += blockDim.x) s_par[i] = d.parents[i];
+  __syncthreads();
   const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   const int X = blockIdx.y;
   if (idx >= (size_t)d.B * d.T) return;
@@ -64,7 +69,7 @@ __global__ void __launch_bounds__(128) loss_fk_fwd_kernel(LossDev d) {
   if (t > 0) { qp.w = q4[-4]; qp.x = q4[-3]; qp.y = q4[-2]; qp.z = q4[-1]; }
   V3 pos = v3(d.rp[X][idx * 3], d.rp[X][idx * 3 + 1], d.rp[X][idx * 3 + 2]);
   V3 gz = v3(d.gaze[idx * 3], d.gaze[idx * 3 + 1], d.gaze[idx * 3 + 2]);
-  loss_frame_forward(d.Ys[X], d.stride, idx, q, qp, pos, gz, d.parents, d.Q[X]);
+  loss_frame_forward(d.Ys[X], d.stride, idx, q, qp, pos, gz, s_par, d.Q[X]);
 }
 
 // one block = 256 consecutive frames of one channel.  partial[(ch*nblk + blk)*2 + {0,1}] = sum |D|, sum |D[t+1]-D[t]|
@@ -112,8 +117,19 @@ __global__ void __launch_bounds__(256) loss_terms_kernel(LossDev d, float* __res
   }
 }
 
-// deterministic final reduction + KL (modules.py:764-789).  losses[0] = total, [1..17] = the 17 terms, [18] = kl term
-__global__ void __launch_bounds__(1024) loss_final_kernel(const float* __restrict__ partial, int nblk, int B, int T, float dt,
+// deterministic reduction, stage 1: one warp per channel sums that channel's per-CTA partials in a fixed order
+// chan[ch][0] = sum |D|, chan[ch][1] = sum |D[t+1] - D[t]| / dt
+__global__ void __launch_bounds__(256) loss_chan_kernel(const float* __restrict__ partial, int nblk, double* __restrict__ chan) {
+  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (ch >= Q_CH) return;
+  double l0 = 0.0, l1 = 0.0;
+  for (int i = lane; i < nblk; i += 32) { l0 += partial[((size_t)ch * nblk + i) * 2]; l1 += partial[((size_t)ch * nblk + i) * 2 + 1]; }
+  for (int o = 16; o > 0; o >>= 1) { l0 += __shfl_xor_sync(0xffffffffu, l0, o); l1 += __shfl_xor_sync(0xffffffffu, l1, o); }
+  if (lane == 0) { chan[2 * ch] = l0; chan[2 * ch + 1] = l1; }
+}
+
+// stage 2 + KL (modules.py:764-789).  losses[0] = total, [1..17] = the 17 terms, [18] = kl term
+__global__ void __launch_bounds__(1024) loss_final_kernel(const double* __restrict__ chan, int B, int T, float dt,
                                                           const float* __restrict__ mu, const float* __restrict__ logvar, int Z,
                                                           float kl_weight_host, const float* __restrict__ kl_weight_dev,
                                                           float* __restrict__ losses, float* __restrict__ dmu,
@@ -127,14 +143,11 @@ __global__ void __launch_bounds__(1024) loss_final_kernel(const float* __restric
   __syncwarp();
   const double BT = (double)B * T;
   // warp w owns channels ch = w, w+32, ...: fixed summation order -> bitwise reproducible
-  for (int ch = warp; ch < Q_CH; ch += 32) {
-    const TermMap m = term_of_channel(ch);
-    double l0 = 0.0, l1 = 0.0;
-    for (int i = lane; i < nblk; i += 32) { l0 += partial[((size_t)ch * nblk + i) * 2]; l1 += partial[((size_t)ch * nblk + i) * 2 + 1]; }
-    for (int o = 16; o > 0; o >>= 1) { l0 += __shfl_xor_sync(0xffffffffu, l0, o); l1 += __shfl_xor_sync(0xffffffffu, l1, o); }
-    if (lane == 0) {
-      wacc[warp][m.term] += l0 * ((double)m.w / (BT * m.nch));
-      if (m.dterm >= 0 && T > 1) wacc[warp][m.dterm] += l1 * ((double)m.dw / ((double)B * (T - 1) * m.nch));
+  if (lane == 0) {
+    for (int ch = warp; ch < Q_CH; ch += 32) {
+      const TermMap m = term_of_channel(ch);
+      wacc[warp][m.term] += chan[2 * ch] * ((double)m.w / (BT * m.nch));
+      if (m.dterm >= 0 && T > 1) wacc[warp][m.dterm] += chan[2 * ch + 1] * ((double)m.dw / ((double)B * (T - 1) * m.nch));
     }
   }
   double kl = 0.0;
@@ -163,7 +176,10 @@ __global__ void __launch_bounds__(1024) loss_final_kernel(const float* __restric
   }
 }
 
-__global__ void __launch_bounds__(128) loss_fk_bwd_kernel(LossDev d, float* __restrict__ dRootPos, float* __restrict__ dq_own, float* __restrict__ dq_prev) {
+__global__ void __launch_bounds__(LOSS_TB) loss_fk_bwd_kernel(LossDev d, float* __restrict__ dRootPos, float* __restrict__ dq_own, float* __restrict__ dq_prev) {
+  __shared__ int s_par[NJ];
+  for (int i = threadIdx.x; i < NJ; i += blockDim.x) s_par[i] = d.parents[i];
+  __syncthreads();
   const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (idx >= (size_t)d.B * d.T) return;
   const int t = (int)(idx % d.T);
@@ -174,7 +190,7 @@ __global__ void __launch_bounds__(128) loss_fk_bwd_kernel(LossDev d, float* __re
   V3 pos = v3(d.rp[0][idx * 3], d.rp[0][idx * 3 + 1], d.rp[0][idx * 3 + 2]);
   V3 gz = v3(d.gaze[idx * 3], d.gaze[idx * 3 + 1], d.gaze[idx * 3 + 2]);
   V3 dpos; Q4 dq, dqp;
-  loss_frame_backward(d.Ys[0], d.Q[0], d.G, d.stride, idx, q, qp, pos, gz, d.parents, d.gYs, &dpos, &dq, &dqp);
+  loss_frame_backward(d.Ys[0], d.Q[0], d.G, d.stride, idx, q, qp, pos, gz, s_par, d.gYs, &dpos, &dq, &dqp);
   if (t == 0) { dq.w += dqp.w; dq.x += dqp.x; dq.y += dqp.y; dq.z += dqp.z; dqp.w = dqp.x = dqp.y = dqp.z = 0.f; }
   dRootPos[idx * 3] = dpos.x; dRootPos[idx * 3 + 1] = dpos.y; dRootPos[idx * 3 + 2] = dpos.z;
   dq_own[idx * 4] = dq.w; dq_own[idx * 4 + 1] = dq.x; dq_own[idx * 4 + 2] = dq.y; dq_own[idx * 4 + 3] = dq.z;
@@ -189,7 +205,7 @@ __global__ void root_rot_combine_kernel(const float* __restrict__ own, const flo
   out[i] = own[i] + (t + 1 < T ? prev[i + 4] : 0.f);
 }
 
-struct LossWs { float *Ys[2], *Q[2], *G, *gYs, *partial, *dq_own, *dq_prev; size_t stride; int nblk; size_t bytes; };
+struct LossWs { float *Ys[2], *Q[2], *G, *gYs, *partial, *dq_own, *dq_prev; double* chan; size_t stride; int nblk; size_t bytes; };
 static LossWs loss_ws(void* base, int B, int T) {
   LossWs w; size_t off = 0;
   auto take = [&](size_t n) { float* p = base ? (float*)((char*)base + off) : nullptr; off += ((n * 4 + 255) / 256) * 256; return p; };
@@ -202,6 +218,7 @@ static LossWs loss_ws(void* base, int B, int T) {
   w.gYs = take((size_t)P_OUT * w.stride);
   w.partial = take((size_t)Q_CH * w.nblk * 2);
   w.dq_own = take(BT * 4); w.dq_prev = take(BT * 4);
+  w.chan = (double*)take((size_t)Q_CH * 4);
   w.bytes = off; return w;
 }
 extern "C" size_t zeggs_loss_workspace_bytes(int B, int T) { return (B < 1 || T < 1) ? 0 : loss_ws(nullptr, B, T).bytes; }
@@ -223,13 +240,14 @@ extern "C" int zeggs_loss_fwd_bwd(const zeggs_loss_args* ap, void* stream_) {
   d.B = a.B; d.T = a.T; d.dt = a.dt;
   d.Ys[0] = w.Ys[0]; d.Ys[1] = w.Ys[1]; d.rp[0] = a.root_pos; d.rp[1] = a.W_root_pos; d.rq[0] = a.root_rot; d.rq[1] = a.W_root_rot;
   d.gaze = a.gaze_pos; d.parents = a.parents; d.Q[0] = w.Q[0]; d.Q[1] = w.Q[1]; d.G = w.G; d.gYs = w.gYs; d.stride = w.stride;
-  loss_fk_fwd_kernel<<<dim3(ceil_div(BT, 128), 2), 128, 0, s>>>(d); count_launch();
+  loss_fk_fwd_kernel<<<dim3(ceil_div(BT, LOSS_TB), 2), LOSS_TB, 0, s>>>(d); count_launch();
   loss_terms_kernel<<<dim3(w.nblk, Q_CH), 256, 0, s>>>(d, w.partial, w.nblk); count_launch();
-  loss_final_kernel<<<1, 1024, 0, s>>>(w.partial, w.nblk, a.B, a.T, a.dt, a.mu, a.logvar, a.Z, a.kl_weight, a.kl_weight_dev, a.losses, a.dmu, a.dlogvar); count_launch();
+  loss_chan_kernel<<<ceil_div(Q_CH, 8), 256, 0, s>>>(w.partial, w.nblk, w.chan); count_launch();
+  loss_final_kernel<<<1, 1024, 0, s>>>(w.chan, a.B, a.T, a.dt, a.mu, a.logvar, a.Z, a.kl_weight, a.kl_weight_dev, a.losses, a.dmu, a.dlogvar); count_launch();
   ZCHECK_LAUNCH();
   if (a.dY) {
     ZCHECK_ARG(a.dRootPos && a.dRootRot, "loss: gradient outputs missing");
-    loss_fk_bwd_kernel<<<ceil_div(BT, 128), 128, 0, s>>>(d, a.dRootPos, w.dq_own, w.dq_prev); count_launch();
+    loss_fk_bwd_kernel<<<ceil_div(BT, LOSS_TB), LOSS_TB, 0, s>>>(d, a.dRootPos, w.dq_own, w.dq_prev); count_launch();
     root_rot_combine_kernel<<<ceil_div(BT * 4, 256), 256, 0, s>>>(w.dq_own, w.dq_prev, a.B, a.T, a.dRootRot); count_launch();
     transpose_kernel<<<dim3(ceil_div(BT, 32), ceil_div(P_OUT, 32)), tb, 0, s>>>(w.gYs, P_OUT, BT, (int)w.stride, a.dY, P_OUT); count_launch();
     ZCHECK_LAUNCH();

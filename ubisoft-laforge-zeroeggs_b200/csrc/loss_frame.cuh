@@ -34,19 +34,25 @@ __host__ __device__ inline V3 mtv(const M3& a, V3 v) {   // a^T v
 }
 __host__ __device__ inline M3 mm(const M3& a, const M3& b) {
   M3 r;
+#pragma unroll
   for (int i = 0; i < 3; ++i)
+#pragma unroll
     for (int j = 0; j < 3; ++j) r.m[i * 3 + j] = a.m[i * 3] * b.m[j] + a.m[i * 3 + 1] * b.m[3 + j] + a.m[i * 3 + 2] * b.m[6 + j];
   return r;
 }
 __host__ __device__ inline M3 mtm(const M3& a, const M3& b) {  // a^T b
   M3 r;
+#pragma unroll
   for (int i = 0; i < 3; ++i)
+#pragma unroll
     for (int j = 0; j < 3; ++j) r.m[i * 3 + j] = a.m[i] * b.m[j] + a.m[3 + i] * b.m[3 + j] + a.m[6 + i] * b.m[6 + j];
   return r;
 }
 __host__ __device__ inline M3 mmt(const M3& a, const M3& b) {  // a b^T
   M3 r;
+#pragma unroll
   for (int i = 0; i < 3; ++i)
+#pragma unroll
     for (int j = 0; j < 3; ++j) r.m[i * 3 + j] = a.m[i * 3] * b.m[j * 3] + a.m[i * 3 + 1] * b.m[j * 3 + 1] + a.m[i * 3 + 2] * b.m[j * 3 + 2];
   return r;
 }
@@ -114,18 +120,22 @@ __host__ __device__ inline void st3(float* p, size_t stride, size_t idx, int ch,
 }
 __host__ __device__ inline M3 ldm(const float* p, size_t stride, size_t idx, int ch) {
   M3 r;
+#pragma unroll
   for (int i = 0; i < 9; ++i) r.m[i] = p[(size_t)(ch + i) * stride + idx];
   return r;
 }
 __host__ __device__ inline void stm(float* p, size_t stride, size_t idx, int ch, const M3& v) {
+#pragma unroll
   for (int i = 0; i < 9; ++i) p[(size_t)(ch + i) * stride + idx] = v.m[i];
 }
 
 // ------------------------------------------------------------------ forward: world-space quantities of one frame
 // Ys: pose vector in SoA [1131][stride]; q / qp: root rotation of this frame / of the previous frame (= q for t = 0);
 // pos: root position; gaze: gaze target.  Writes Q[Q_CH][stride] at column idx.
-__host__ __device__ inline void loss_frame_forward(const float* Ys, size_t stride, size_t idx, Q4 q, Q4 qp, V3 pos, V3 gaze,
-                                                   const int* __restrict__ parents, float* Q) {
+// Ys / Q never alias (separate workspace buffers): __restrict__ lets the compiler batch a joint's 15 local loads with the
+// parent's 18 instead of ordering every load behind the previous joint's stores
+__host__ __device__ inline void loss_frame_forward(const float* __restrict__ Ys, size_t stride, size_t idx, Q4 q, Q4 qp, V3 pos, V3 gaze,
+                                                   const int* __restrict__ parents, float* __restrict__ Q) {
   st3(Q, stride, idx, Q_ROOT_POS, pos);
   const M3 R = quat_to_xform(q);
   stm(Q, stride, idx, Q_ROOT_MAT, R);
@@ -168,9 +178,10 @@ __host__ __device__ inline void loss_frame_forward(const float* Ys, size_t strid
 // Q: forward world-space values of this frame (the "O" side); G: dLoss/dQ on entry (FK channels are used as
 // accumulators and clobbered).  Outputs: gY[1131][stride] (pose-vector gradient, SoA), *dpos, *dq (this frame's root
 // rotation), *dqp (previous frame's root rotation).
-__host__ __device__ inline void loss_frame_backward(const float* Ys, const float* Q, float* G, size_t stride, size_t idx,
-                                                    Q4 q, Q4 qp, V3 pos, V3 gaze, const int* __restrict__ parents,
-                                                    float* gY, V3* dpos_out, Q4* dq_out, Q4* dqp_out) {
+__host__ __device__ inline void loss_frame_backward(const float* __restrict__ Ys, const float* __restrict__ Q, float* __restrict__ G,
+                                                    size_t stride, size_t idx, Q4 q, Q4 qp, V3 pos, V3 gaze,
+                                                    const int* __restrict__ parents, float* __restrict__ gY, V3* dpos_out, Q4* dq_out,
+                                                    Q4* dqp_out) {
   // reverse FK: children push into their parents' accumulators
   for (int i = NJ - 1; i >= 1; --i) {
     const int p = parents[i];
@@ -188,6 +199,7 @@ __host__ __device__ inline void loss_frame_backward(const float* Ys, const float
     add_outer(acc, dgt, lr);                               // gt[i]  = gt[p] + gr[p] lvrt
     add_outer(acc, drp, lp);                               // rp = gr[p] lpos
     M3 t = mmt(dgr, lm);                                   // gr[i] = gr[p] lmat
+#pragma unroll
     for (int k = 0; k < 9; ++k) acc.m[k] += t.m[k];
     stm(G, stride, idx, Q_CMAT + 9 * p, acc);
     st3(G, stride, idx, Q_CPOS + 3 * p, ld3(G, stride, idx, Q_CPOS + 3 * p) + dgp);
@@ -230,6 +242,7 @@ __host__ __device__ inline void loss_frame_backward(const float* Ys, const float
   // m0 = R lmat0
   M3 lm0 = orthogonalize_xy(x, yv);
   M3 t = mmt(dm0, lm0);
+#pragma unroll
   for (int k = 0; k < 9; ++k) dR.m[k] += t.m[k];
   V3 dx, dyv;
   orthogonalize_xy_bwd(x, yv, mtm(R, dm0), dx, dyv);

@@ -78,6 +78,73 @@ class WindowDataset:
         return {k: (v.pin_memory() if pin else v.contiguous()) for k, v in out.items()}
 
 
+class DeviceWindowDataset(WindowDataset):
+    """The same windows, drawn by the same generator, with the processed arrays RESIDENT IN HBM and every batch produced by ONE
+    gather launch (zeggs_window_gather) -- no per-sample host indexing, no host->device copies beyond three int32 vectors of length
+    B (window starts, example starts, example lengths).  SURVEY.md 8f row 2; replaces dataset.py:110-153, 176-204 and
+    train.py:215-225.  sample_batch() returns the dict TrainStep.step() takes; bit-identical to WindowDataset.sample_host_batch()
+    for the same seed (pure row copies)."""
+    _EX = ("root_vel", "root_vrt", "lpos", "ltxy", "lvel", "lvrt")
+
+    def __init__(self, *args, device="cuda", **kw):
+        super().__init__(*args, **kw)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            from . import _lib
+            raise _lib.ZeggsError("DeviceWindowDataset keeps the data in HBM: needs a CUDA device")
+        self.names = ["audio"] + KEYS
+        flat = [self.X] + [self.Y[k] for k in KEYS]
+        self.dev_arrays = [a.reshape(a.shape[0], -1).contiguous().to(self.device) for a in flat]
+        self.shapes = [tuple(a.shape[1:]) for a in flat]
+        self.widths = [a.shape[1] for a in self.dev_arrays]
+        self.n_frames = flat[0].shape[0]
+        self.ex_width = sum(self.widths[self.names.index(k)] for k in self._EX) + 3
+
+    def _example_range(self, start, ri):
+        """(first row, rows available) of the example window (dataset.py:176-198) -- the integer part of WindowDataset._example."""
+        L, W = self.example_window_length, self.window
+        s0, e0 = int(self.ranges[ri][0]), int(self.ranges[ri][1])
+        first, last = start, start + W - 1
+        ext = (L - W) // 2
+        ws, we = min(ext, first - s0), min(ext, e0 - last)
+        s_ext, w_ext = ws + ext - we, we + ext - ws
+        a = max(first - s_ext, s0)
+        b = min(min(last + w_ext, e0) + 1, self.n_frames)
+        return a, b - a
+
+    def sample_batch(self, batchsize, device=None):
+        from . import _lib
+        idx = self.rs.randint(0, len(self.starts), size=batchsize)
+        starts = self.starts[idx].astype(np.int32)
+        T = self.window
+        dev = self.device
+        out = {n: torch.empty((batchsize, T) + shp, dtype=torch.float32, device=dev) for n, shp in zip(self.names, self.shapes)}
+        a = _lib.GatherArgs(B=batchsize, T=T, n_arrays=len(self.names))
+        for k, n in enumerate(self.names):
+            a.src[k], a.dst[k], a.width[k] = self.dev_arrays[k].data_ptr(), out[n].data_ptr(), self.widths[k]
+        keep = [torch.from_numpy(starts).to(dev)]
+        a.start = keep[0].data_ptr()
+        if self.style_encoding_type == "label":
+            lab = torch.zeros(batchsize, self.nlabels)
+            lab[torch.arange(batchsize), torch.as_tensor(self.labels[self.rng_idx[idx]]).long()] = 1.0
+            out["style"] = lab.to(dev)
+        else:
+            L = self.example_window_length
+            rng = [self._example_range(int(self.starts[i]), int(self.rng_idx[i])) for i in idx]
+            for (_, n) in rng:
+                if 2 * n < L:
+                    raise _lib.ZeggsError("style example shorter than half the example window (dataset.py:201-203 cannot pad it)")
+            ex = torch.empty((batchsize, L, self.ex_width), dtype=torch.float32, device=dev)
+            keep += [torch.tensor([r[0] for r in rng], dtype=torch.int32).to(dev), torch.tensor([r[1] for r in rng], dtype=torch.int32).to(dev)]
+            a.ex_out, a.L, a.ex_width, a.n_ex = ex.data_ptr(), L, self.ex_width, len(self._EX)
+            for k, n in enumerate(self._EX):
+                a.ex_src[k] = self.names.index(n)
+            a.ex_start, a.ex_n = keep[1].data_ptr(), keep[2].data_ptr()
+            out["style"] = ex
+        _lib.check(_lib.lib().zeggs_window_gather(a, _lib.stream_ptr()), "zeggs_window_gather")
+        return out
+
+
 class DevicePrefetcher:
     """Double-buffered host->device input pipeline: `upload` enqueues the copies of the NEXT step's batch on a side stream
     so they overlap the current step's kernels; `acquire` makes the compute stream wait for them.  (The reference copies

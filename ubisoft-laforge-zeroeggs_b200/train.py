@@ -236,7 +236,7 @@ def build_networks(network_options, dimensions, style_encoding_type, nlabels, de
 def train(models_dir, logs_dir, path_processed_data, path_data_definition, train_options, network_options):
     """Drop-in for ZEGGS/train.py:29 (same arguments, same artefacts in models_dir).  Data-parallel when launched under
     torchrun (RANK/WORLD_SIZE set): each rank draws its own windows, one gradient all-reduce per step."""
-    from .data import DevicePrefetcher, WindowDataset
+    from .data import DevicePrefetcher, DeviceWindowDataset, WindowDataset
     np.random.seed(train_options["seed"])
     torch.manual_seed(train_options["seed"])
     if not (train_options["use_gpu"] and torch.cuda.is_available()):
@@ -255,8 +255,12 @@ def train(models_dir, logs_dir, path_processed_data, path_data_definition, train
     with open(path_data_definition, "r") as f:
         details = json.load(f)
     style_encoding_type = train_options["style_encoding_type"]
-    ds = WindowDataset(path_data_definition, path_processed_data, train_options["window"], style_encoding_type,
-                       network_options["style_encoder"]["example_length"], seed=train_options["seed"] + rank)
+    # additive option "device_dataset" (default on): the processed arrays live in HBM and every batch is one gather launch; off: the
+    # host supplier + double-buffered H2D prefetch
+    on_device = bool(train_options.get("device_dataset", True))
+    ds = (DeviceWindowDataset if on_device else WindowDataset)(
+        path_data_definition, path_processed_data, train_options["window"], style_encoding_type,
+        network_options["style_encoder"]["example_length"], seed=train_options["seed"] + rank, **({"device": device} if on_device else {}))
     se, de, st = build_networks(network_options, ds.get_shapes(), style_encoding_type, len(details["label_names"]), device)
     if train_options["resume"] and (models_dir / "checkpoints.pt").exists():
         for net, name in ((se, "speech_encoder"), (de, "decoder"), (st, "style_encoder")):
@@ -273,12 +277,16 @@ def train(models_dir, logs_dir, path_processed_data, path_data_definition, train
     batchsize = train_options["batchsize"]
     ex_len = network_options["style_encoder"]["example_length"]
     start = datetime.datetime.now()
-    prefetch = DevicePrefetcher(device)
-    token = prefetch.upload(ds.sample_host_batch(batchsize))
+    prefetch = None if on_device else DevicePrefetcher(device)
+    token = None if on_device else prefetch.upload(ds.sample_host_batch(batchsize))
     while stepper.iteration < total:
-        batch = prefetch.acquire(token)
-        ds.example_window_length = 2 * random.randint(ex_len // 2, ex_len)          # train.py:228-229
-        token = prefetch.upload(ds.sample_host_batch(batchsize))                    # next step's windows copy under this step
+        if on_device:
+            batch = ds.sample_batch(batchsize)                                        # one gather launch out of the HBM-resident arrays
+            ds.example_window_length = 2 * random.randint(ex_len // 2, ex_len)        # train.py:228-229 (applies to the next draw)
+        else:
+            batch = prefetch.acquire(token)
+            ds.example_window_length = 2 * random.randint(ex_len // 2, ex_len)        # train.py:228-229
+            token = prefetch.upload(ds.sample_host_batch(batchsize))                  # next step's windows copy under this step
         loss = stepper.step(batch)
         it = stepper.iteration
         if it % 1000 == 0:
@@ -296,9 +304,22 @@ def save_checkpoint(models_dir, se, de, st, stepper, loss):
     """train.py:477-509: whole-module pickles + optimizer state."""
     models_dir = Path(models_dir)
     models_dir.mkdir(parents=True, exist_ok=True)
-    torch.save(se, models_dir / "speech_encoder.pt")
-    torch.save(de, models_dir / "decoder.pt")
+
+    def clean(m):
+        """A standalone CPU copy of the module: parameters cloned out of the optimizer's shared flat buffer (each pickle would otherwise
+        drag the whole 100 MB storage along), cached weight packs (`_zeggs_*`) dropped."""
+        import copy
+        c = copy.copy(m)
+        c.__dict__ = {k: v for k, v in m.__dict__.items() if not k.startswith("_zeggs")}
+        c = copy.deepcopy(c)
+        for p in c.parameters():
+            p.data = p.data.detach().clone().cpu()
+            p.grad = None
+        return c.cpu()
+
+    torch.save(clean(se), models_dir / "speech_encoder.pt")
+    torch.save(clean(de), models_dir / "decoder.pt")
     if st is not None:
-        torch.save(st, models_dir / "style_encoder.pt")
+        torch.save(clean(st), models_dir / "style_encoder.pt")
     torch.save({"iteration": stepper.iteration, "epoch": 0, "loss": loss,
                 "optimizer_state_dict": stepper.optimizer.state_dict()}, models_dir / "checkpoints.pt")
