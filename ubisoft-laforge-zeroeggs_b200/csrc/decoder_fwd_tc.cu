@@ -197,7 +197,13 @@ inline TcWs make_tcws(void* base, const DecGeom& g) {
 
 #define TCDBG(ev) do { if (tw.dbg && c == 0 && warp_lane0 && t < 64) tw.dbg[t * 32 + (ev)] = clock64(); } while (0)
 
-template <int U>
+// MAIN_ACC / GH_ACC: TMEM accumulators a chain's MMAs rotate over (critical chains / the hidden-to-hidden chains); the epilogue sums
+// them.  ROT: every CTA walks the k-block groups of a chain starting at group (CTA index mod groups), so that the 128 CTAs -- which
+// all read the SAME activation image right after a grid barrier -- do not hit the same 16 KB of L2 lines at the same moment.
+// DEFER: the weight producer starts a chain's tiles only after the previous chain's MMAs have drained the ring (experiment:
+// keeps weight prefetch out of the activation delivery window; measured no gain -- the 64 KB image streams at ~5 cycles per 128-byte
+// line with or without concurrent weight traffic, profiles/r02_fwd_tc_variants.md).
+template <int U, int MAIN_ACC, int GH_ACC, bool ROT, bool DEFER>
 __global__ void __launch_bounds__(160, 1)
 decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, TcWs tw, const uint8_t* __restrict__ packed) {
   constexpr int NP = (3 * U + 7) / 8 * 8;        // gate-chain rows (24 for U=8, 16 for U=4)
@@ -255,15 +261,15 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
   // ELECT / R2UR.BROADCAST waterfall loop (~90 cycles per MMA).
   if (*tmem_slot != 0u) __trap();
   constexpr uint32_t tmem = 0u;
-  // TMEM regions (columns): gh0 [0,128) | gh1 [128,256) | fold / gi0a / gi1 [256, 256 + 4*N1); accumulator q at +q*N
-  // the critical chains (R_MAIN) use 8 accumulators when they fit: a dependent accumulate costs ~230 cycles of latency
-  constexpr int MAIN_ACC = (8 * N1 + 8 * NP <= 512) ? 8 : 4;
-  constexpr uint32_t R_GH0 = 0, R_GH1 = 4 * NP, R_MAIN = 8 * NP;
-  static_assert(MAIN_ACC * N1 + 8 * NP <= 512, "TMEM budget");
+  // TMEM regions (columns): gh0 | gh1 | fold / gi0a / gi1; accumulator q of a region at +q*N
+  constexpr uint32_t R_GH0 = 0, R_GH1 = GH_ACC * NP, R_MAIN = 2 * GH_ACC * NP;
+  static_assert(MAIN_ACC * N1 + 2 * GH_ACC * NP <= 512, "TMEM budget");
   const size_t actH = (size_t)g.nbt * H * 32;
   const unsigned bar_n = gridDim.x * TC_NEPI;
 
   const int ng = (kbH + TC_GKB - 1) / TC_GKB;      // ring groups per chain
+  const int rot = ROT ? c % ng : 0;                // first group this CTA touches (every role walks the groups in the same order)
+  auto group_kb = [&](int gi) { int g_ = gi + rot; if (g_ >= ng) g_ -= ng; return g_ * TC_GKB; };
   // Operand ring: slot = the weight tiles of TC_GKB k-blocks.  The X chunk of the same k-blocks lands in the resident X
   // buffer but completes on the SAME mbarrier, so the MMA warp waits once per 16 MMAs (a successful mbarrier wait costs
   // the issuing thread ~130 cycles that do not overlap with MMA issue).  Chains whose X is already resident (gh1 after the
@@ -276,7 +282,9 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
       auto stream = [&](int chain, bool has_loader) {
         const int N = chain == 0 ? N1 : NP;
         const uint8_t* src = pk + tg.chain_off[chain];
-        for (int kb = 0; kb < kbH; kb += TC_GKB, ++it) {
+        if (DEFER && it > 0) mbar_wait(&empty[(it - 1) % TC_RING], ((it - 1) / TC_RING) & 1);   // previous chain fully consumed
+        for (int gi = 0; gi < ng; ++gi, ++it) {
+          const int kb = group_kb(gi);
           const uint32_t s = it % TC_RING, ph = (it / TC_RING) & 1;
           const uint32_t bytes = (uint32_t)((kbH - kb >= TC_GKB ? TC_GKB : kbH - kb) * tc_tile_bytes(N));
           mbar_wait(&empty[s], ph ^ 1);
@@ -300,7 +308,8 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
         uint8_t* X = (n & 1) ? X1 : X0;
         fence_proxy_async();
         uint32_t it = q * (uint32_t)ng;
-        for (int kb = 0; kb < kbH; kb += TC_GKB, ++it) {
+        for (int gi = 0; gi < ng; ++gi, ++it) {
+          const int kb = group_kb(gi);
           const uint32_t s = it % TC_RING, ph = (it / TC_RING) & 1;
           const uint32_t bytes = (uint32_t)((kbH - kb >= TC_GKB ? TC_GKB : kbH - kb) * 4096);
           mbar_wait(&empty[s], ph ^ 1);
@@ -330,32 +339,32 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
     uint32_t it = 0, n = 0;
     const uint64_t dX0 = make_smem_desc_sw128(X0), dX1 = make_smem_desc_sw128(X1), dRing = make_smem_desc_sw128(ring);
     int dbg_t = -1;                                  // >= 0: trace this chain's group arrivals (events 20..23)
-    auto chain_mma = [&](int N, uint32_t d0, bool wide) {       // reads X buffer n&1
+    auto chain_mma = [&](int N, uint32_t d0, int nacc) {       // reads X buffer n&1; the MMAs rotate over `nacc` accumulators
       const uint32_t idesc = make_idesc_bf16_f32(64, N);
       const uint64_t dx = (n & 1) ? dX1 : dX0;
       const uint64_t bstep = (uint64_t)(N * 8);            // one k-block tile of the weight slice, in 16-byte units
-      const uint32_t d1 = wide ? d0 + 4 * N : d0;
-      for (int kb = 0; kb < kbH; kb += TC_GKB, ++it) {
+      uint32_t issued = 0;                                 // MMAs of this chain so far: accumulator = issued % nacc
+      for (int gi = 0; gi < ng; ++gi, ++it) {
+        const int kb = group_kb(gi);
         const uint32_t s = it % TC_RING, ph = (it / TC_RING) & 1;
         mbar_wait(&full[s], ph);
-        if (tw.dbg && c == 0 && warp_lane0 && dbg_t >= 0 && dbg_t < 64) tw.dbg[dbg_t * 32 + 20 + (kb >> 2)] = clock64();
+        if (tw.dbg && c == 0 && warp_lane0 && dbg_t >= 0 && dbg_t < 64) tw.dbg[dbg_t * 32 + 20 + gi] = clock64();
         const uint64_t da = dx + (uint64_t)kb * 256, db = dRing + (uint64_t)s * (SLOT >> 4);
         const int nk = kbH - kb >= TC_GKB ? TC_GKB : kbH - kb;
         if (elect_one_sync()) {
+          uint32_t m = issued;
 #pragma unroll
           for (int j = 0; j < TC_GKB; ++j) {
             if (j < nk) {
-              const uint32_t dd = (j & 1) ? d1 : d0;
-              const bool acc = wide ? (kb + j) > 1 : (kb + j) > 0;
               const uint64_t a_ = da + (uint64_t)(j * 256), b_ = db + (uint64_t)j * bstep;
-              umma_bf16(dd + 0 * N, a_ + 0, b_ + 0, idesc, acc);
-              umma_bf16(dd + 1 * N, a_ + 2, b_ + 2, idesc, acc);
-              umma_bf16(dd + 2 * N, a_ + 4, b_ + 4, idesc, acc);
-              umma_bf16(dd + 3 * N, a_ + 6, b_ + 6, idesc, acc);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks, ++m)
+                umma_bf16(d0 + (m & (uint32_t)(nacc - 1)) * (uint32_t)N, a_ + 2 * ks, b_ + 2 * ks, idesc, m >= (uint32_t)nacc);
             }
           }
           umma_commit(&empty[s]);
         }
+        issued += (uint32_t)(4 * nk);        // warp-uniform count of this chain's MMAs (nacc is a power of two)
         __syncwarp();
       }
     };
@@ -363,28 +372,28 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
       if (elect_one_sync()) umma_commit(b0);
       __syncwarp();
     };
-    chain_mma(NP, tmem + R_GH0, false);                                 // gh0 of step 1 from h0(0)
+    chain_mma(NP, tmem + R_GH0, GH_ACC);                                // gh0 of step 1 from h0(0)
     ++n;
     for (int t = 1; t < T; ++t) {
-      chain_mma(N1, tmem + R_MAIN, MAIN_ACC == 8);                      // fold: [pre_a ; gi0 ; y6] from h1(t-1)
+      chain_mma(N1, tmem + R_MAIN, MAIN_ACC);                           // fold: [pre_a ; gi0 ; y6] from h1(t-1)
       commit1(&d_full[0]);
       TCDBG(4);
-      chain_mma(NP, tmem + R_GH1, false);                               // gh1 from h1(t-1)
+      chain_mma(NP, tmem + R_GH1, GH_ACC);                              // gh1 from h1(t-1)
       ++n;
       TCDBG(10);
       dbg_t = t;
-      chain_mma(NP, tmem + R_MAIN, MAIN_ACC == 8);                      // gi0a from a(t)
+      chain_mma(NP, tmem + R_MAIN, MAIN_ACC);                           // gi0a from a(t)
       dbg_t = -1;
       commit1(&d_full[1]);
       ++n;
       TCDBG(11);
-      chain_mma(NP, tmem + R_MAIN, MAIN_ACC == 8);                      // gi1 from h0(t)
+      chain_mma(NP, tmem + R_MAIN, MAIN_ACC);                           // gi1 from h0(t)
       commit1(&d_full[2]);
       TCDBG(16);
-      if (t + 1 < T) chain_mma(NP, tmem + R_GH0, false);                // gh0 of step t+1 from h0(t)
+      if (t + 1 < T) chain_mma(NP, tmem + R_GH0, GH_ACC);               // gh0 of step t+1 from h0(t)
       ++n;
     }
-    chain_mma(N1, tmem + R_MAIN, MAIN_ACC == 8);                        // y(T-1)[0:6]
+    chain_mma(N1, tmem + R_MAIN, MAIN_ACC);                             // y(T-1)[0:6]
     commit1(&d_full[0]);
   } else {
     // ================= epilogue warps 0,1: TMEM lanes 0..15 of quadrant `warp` = samples 16*warp .. 16*warp+15
@@ -511,13 +520,13 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
         float hv[U], rr[U], zz[U], nn[U], gn[U];
         {
           float gh[U], gi[U];
-          tmem_ld4_sum<U>(tmem + lane_base + R_GH0, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN, NP, gi);
+          tmem_ldn_sum<U, GH_ACC>(tmem + lane_base + R_GH0, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN, NP, gi);
 #pragma unroll
           for (int u = 0; u < U; ++u) rr[u] = fast_sigmoid(gi[u] + gi0p[u] + gh[u] + c_bhh0[u]);
-          tmem_ld4_sum<U>(tmem + lane_base + R_GH0 + U, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + U, NP, gi);
+          tmem_ldn_sum<U, GH_ACC>(tmem + lane_base + R_GH0 + U, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + U, NP, gi);
 #pragma unroll
           for (int u = 0; u < U; ++u) zz[u] = fast_sigmoid(gi[u] + gi0p[U + u] + gh[u] + c_bhh0[U + u]);
-          tmem_ld4_sum<U>(tmem + lane_base + R_GH0 + 2 * U, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + 2 * U, NP, gi);
+          tmem_ldn_sum<U, GH_ACC>(tmem + lane_base + R_GH0 + 2 * U, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + 2 * U, NP, gi);
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             gn[u] = gh[u] + c_bhh0[2 * U + u];
@@ -553,13 +562,13 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
         float hv[U], rr[U], zz[U], nn[U], gn[U];
         {
           float gh[U], gi[U];
-          tmem_ld4_sum<U>(tmem + lane_base + R_GH1, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN, NP, gi);
+          tmem_ldn_sum<U, GH_ACC>(tmem + lane_base + R_GH1, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN, NP, gi);
 #pragma unroll
           for (int u = 0; u < U; ++u) rr[u] = fast_sigmoid(gi[u] + c_bih1[u] + gh[u] + c_bhh1[u]);
-          tmem_ld4_sum<U>(tmem + lane_base + R_GH1 + U, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + U, NP, gi);
+          tmem_ldn_sum<U, GH_ACC>(tmem + lane_base + R_GH1 + U, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + U, NP, gi);
 #pragma unroll
           for (int u = 0; u < U; ++u) zz[u] = fast_sigmoid(gi[u] + c_bih1[U + u] + gh[u] + c_bhh1[U + u]);
-          tmem_ld4_sum<U>(tmem + lane_base + R_GH1 + 2 * U, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + 2 * U, NP, gi);
+          tmem_ldn_sum<U, GH_ACC>(tmem + lane_base + R_GH1 + 2 * U, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + 2 * U, NP, gi);
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             gn[u] = gh[u] + c_bhh1[2 * U + u];
@@ -683,23 +692,23 @@ extern "C" int zeggs_decoder_pack_weights_tc(const zeggs_decoder_fwd_args* a, vo
 extern "C" void zeggs_debug_set_tc_cluster(int) {}
 extern "C" int zeggs_debug_get_tc_cluster() { return 1; }
 
-template <int U>
+template <int U, int MAIN_ACC, int GH_ACC, bool ROT, bool DEFER>
 static int launch_tc(const zeggs_decoder_fwd_args& a, const DecGeom& g, const TcGeom& tg, const DecWs& w, const TcWs& tw,
                      const uint8_t* packed, cudaStream_t stream) {
   const size_t smem = 1024 + (size_t)2 * tg.kbH * 4096 + (size_t)TC_RING * tg.slot_bytes + 4096 + 512 +
                       (size_t)(12 * U + 16 * U + 18 + 8) * sizeof(float);
   static size_t checked_smem = 0;     // attribute + co-residency check once per shared-memory size (one device per process)
   if (checked_smem != smem) {
-    ZCHECK_CUDA(cudaFuncSetAttribute(decoder_fwd_tc_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ZCHECK_CUDA(cudaFuncSetAttribute(decoder_fwd_tc_kernel<U, MAIN_ACC, GH_ACC, ROT, DEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, nsm = 0, occ = 0;
     ZCHECK_CUDA(cudaGetDevice(&dev));
     ZCHECK_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    ZCHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decoder_fwd_tc_kernel<U>, 160, smem));
+    ZCHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decoder_fwd_tc_kernel<U, MAIN_ACC, GH_ACC, ROT, DEFER>, 160, smem));
     ZCHECK_ARG(occ * nsm >= g.G, "decoder tc: cooperative grid of %d CTAs does not fit", g.G);
     checked_smem = smem;
   }
   void* args[] = {(void*)&a, (void*)&g, (void*)&tg, (void*)&w, (void*)&tw, (void*)&packed};
-  ZCHECK_CUDA(cudaLaunchCooperativeKernel((void*)decoder_fwd_tc_kernel<U>, dim3(g.G), dim3(160), args, smem, stream));
+  ZCHECK_CUDA(cudaLaunchCooperativeKernel((void*)decoder_fwd_tc_kernel<U, MAIN_ACC, GH_ACC, ROT, DEFER>, dim3(g.G), dim3(160), args, smem, stream));
   count_launch();
   return ZEGGS_OK;
 }
@@ -711,7 +720,9 @@ const float* decoder_tc_mfold(const zeggs_decoder_fwd_args& a) {
 }
 
 static long long* g_tc_dbg = nullptr;
-extern "C" void zeggs_debug_set_tc_nacc(int) {}
+// kernel variant (development knob, zeggs_debug_set_tc_nacc): 0 = the shipped configuration
+static int g_tc_variant = 0;
+extern "C" void zeggs_debug_set_tc_nacc(int v) { g_tc_variant = v; }
 long long* tc_debug_buffer() { return g_tc_dbg; }
 extern "C" void zeggs_debug_set_tc_trace(void* p) { g_tc_dbg = (long long*)p; }
 
@@ -745,8 +756,17 @@ int decoder_fwd_tc_run(const zeggs_decoder_fwd_args& a, const DecGeom& g, const 
   image_from_kmajor_kernel<<<64, 256, 0, stream>>>(w.H1, a.H, tg.kbH, tw.h1b[0]); count_launch();
   ZCHECK_LAUNCH();
   ScopedTimer tm("decoder_fwd", stream);
-  int rc = g.U == 4 ? launch_tc<4>(a, g, tg, w, tw, (const uint8_t*)a.packed_tc, stream)
-                    : launch_tc<8>(a, g, tg, w, tw, (const uint8_t*)a.packed_tc, stream);
+  int rc;
+  const uint8_t* pk = (const uint8_t*)a.packed_tc;
+#define ZTC(U_, M_, G_, R_, D_) launch_tc<U_, M_, G_, R_, D_>(a, g, tg, w, tw, pk, stream)
+  if (g.U == 4) rc = g_tc_variant == 1 ? ZTC(4, 8, 4, false, false) : ZTC(4, 1, 1, false, false);
+  else switch (g_tc_variant) {
+    case 1: rc = ZTC(8, 8, 4, false, false); break;     // round-1 configuration
+    case 2: rc = ZTC(8, 1, 1, false, true); break;      // single accumulators, deferred weight prefetch (measured: no gain)
+    case 3: rc = ZTC(8, 1, 1, true, false); break;      // single accumulators + per-CTA group rotation (measured: no gain)
+    default: rc = ZTC(8, 1, 1, false, false); break;    // shipped: single accumulators, eager weight prefetch
+  }
+#undef ZTC
   if (rc) return rc;
   // layer2 for every step at once: YC[(t,b)][:] = h1(t) W2^T + b2 over the bf16 history (rows t = 1..T-1)
   const __nv_bfloat16* h1b = reinterpret_cast<const __nv_bfloat16*>(w.H1B) + (size_t)32 * a.H;

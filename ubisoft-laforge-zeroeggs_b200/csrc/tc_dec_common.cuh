@@ -95,15 +95,29 @@ __device__ __forceinline__ void tmem_ld4_sum(uint32_t taddr, uint32_t stride, fl
     v[i] = ((__uint_as_float(r0[i]) + __uint_as_float(r1[i])) + __uint_as_float(r2[i])) + __uint_as_float(r3[i]);
 }
 
-// same with NA (4 or 8) accumulators
+// same with NA (1, 2, 4 or 8) accumulators
 template <int NC, int NA>
 __device__ __forceinline__ void tmem_ldn_sum(uint32_t taddr, uint32_t stride, float (&v)[NC]) {
-  tmem_ld4_sum<NC>(taddr, stride, v);
-  if (NA == 8) {
-    float u_[NC];
-    tmem_ld4_sum<NC>(taddr + 4 * stride, stride, u_);
+  if (NA == 1) {
+    uint32_t r0[NC];
+    tmem_ld_issue<NC>(taddr, r0);
+    tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < NC; ++i) v[i] += u_[i];
+    for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(r0[i]);
+  } else if (NA == 2) {
+    uint32_t r0[NC], r1[NC];
+    tmem_ld_issue<NC>(taddr, r0); tmem_ld_issue<NC>(taddr + stride, r1);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(r0[i]) + __uint_as_float(r1[i]);
+  } else {
+    tmem_ld4_sum<NC>(taddr, stride, v);
+    if (NA == 8) {
+      float u_[NC];
+      tmem_ld4_sum<NC>(taddr + 4 * stride, stride, u_);
+#pragma unroll
+      for (int i = 0; i < NC; ++i) v[i] += u_[i];
+    }
   }
 }
 
