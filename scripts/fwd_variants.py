@@ -20,7 +20,7 @@ lib = _lib.lib()
 import ctypes as C
 ref = None
 res = {}
-for v in [int(x) for x in os.environ.get("VARIANTS", "1,2,0,3").split(",")]:
+for v in [int(x) for x in os.environ.get("VARIANTS", "1,0,2").split(",")]:
     lib.zeggs_debug_set_tc_nacc(v)
     with torch.no_grad():
         out = dec(*args)

@@ -32,6 +32,7 @@ namespace zeggs {
 
 constexpr int BT_RING = 3;               // unified operand ring: each slot = 2 k-blocks of (A tile 16 KB | B tile)
 constexpr int BT_XPART = 32768;          // bytes of the A part of a slot
+constexpr int BT_NACC = 1;               // TMEM accumulators per chain
 
 struct BtGeom {
   int N2, N3, N4, P6;
@@ -229,7 +230,17 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
         tc_fence_after_sync();
         uint64_t da = dR + (uint64_t)s * sstep, db = da + (BT_XPART >> 4);
         if (elect_one_sync()) {
-          if (nacc == 4) {
+          if (nacc == 1) {
+            // one TMEM accumulator per chain: a dependent accumulate does not stall these MMAs and the epilogue issues a quarter of
+            // the tcgen05.ld's (measured on the forward kernel, profiles/r02_fwd_tc_variants.md)
+            for (int kk = 0; kk < nk; ++kk, da += astep, db += wstep) {
+              const bool acc = (kb + kk) > 0;
+              umma_bf16(tmem, da + 0, db + 0, idesc, acc);
+              umma_bf16(tmem, da + 2, db + 2, idesc, true);
+              umma_bf16(tmem, da + 4, db + 4, idesc, true);
+              umma_bf16(tmem, da + 6, db + 6, idesc, true);
+            }
+          } else if (nacc == 4) {
             for (int kk = 0; kk < nk; ++kk, da += astep, db += wstep) {
               const bool acc = (kb + kk) > 0;
               umma_bf16(tmem + 0 * N, da + 0, db + 0, idesc, acc);
@@ -253,9 +264,9 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
     };
     auto commit_d = [&](int i) { if (elect_one_sync()) umma_commit(&d_full[i]); __syncwarp(); };
     for (int t = T - 1; t >= 1; --t) {
-      chain_mma(kbH, tg.N2, 4, 2, 16384); commit_d(0); BTDBG(9);
-      chain_mma(kbH, tg.N3, tg.nacc3, 2, 16384); commit_d(1); BTDBG(10);
-      if (t > 1) { chain_mma(kbH, tg.N4, 4, 8, 4096); commit_d(2); BTDBG(11); }
+      chain_mma(kbH, tg.N2, BT_NACC, 2, 16384); commit_d(0); BTDBG(9);
+      chain_mma(kbH, tg.N3, BT_NACC, 2, 16384); commit_d(1); BTDBG(10);
+      if (t > 1) { chain_mma(kbH, tg.N4, BT_NACC, 8, 4096); commit_d(2); BTDBG(11); }
     }
   } else {
     // ================= epilogue warps 0..3 (TMEM lane quadrant = warp index)
@@ -435,8 +446,8 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
       if (q == 0) BTDBG(14);
       {
         float v0[U], v1[U];
-        if (q < 3) ld_units((uint32_t)(q * U), tg.N2, 4, v0);               // ih_g
-        if (q != 2) ld_units((uint32_t)((3 + (q == 3 ? 2 : q)) * U), tg.N2, 4, v1);   // hh_g (quadrant 3 = pnr pairs with hh_n)
+        if (q < 3) ld_units((uint32_t)(q * U), tg.N2, BT_NACC, v0);               // ih_g
+        if (q != 2) ld_units((uint32_t)((3 + (q == 3 ? 2 : q)) * U), tg.N2, BT_NACC, v1);   // hh_g (quadrant 3 = pnr pairs with hh_n)
 #pragma unroll
         for (int u = 0; u < U; ++u) { mypart[u * 32] = q < 3 ? v0[u] : 0.f; mypart[(U + u) * 32] = q != 2 ? v1[u] : 0.f; }
       }
@@ -481,8 +492,8 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
       if (q == 0) BTDBG(17);
       {
         float v0[U], v1[U], vx[16];
-        if (q < 3) { ld_units((uint32_t)(q * U), tg.N3, tg.nacc3, v0); ld16((uint32_t)(tg.P6 + q * 16), tg.N3, tg.nacc3, vx); }
-        if (q != 2) ld_units((uint32_t)((3 + (q == 3 ? 2 : q)) * U), tg.N3, tg.nacc3, v1);
+        if (q < 3) { ld_units((uint32_t)(q * U), tg.N3, BT_NACC, v0); ld16((uint32_t)(tg.P6 + q * 16), tg.N3, BT_NACC, vx); }
+        if (q != 2) ld_units((uint32_t)((3 + (q == 3 ? 2 : q)) * U), tg.N3, BT_NACC, v1);
 #pragma unroll
         for (int u = 0; u < U; ++u) { mypart[u * 32] = q < 3 ? v0[u] : 0.f; mypart[(U + u) * 32] = q != 2 ? v1[u] : 0.f; }
 #pragma unroll
@@ -522,7 +533,7 @@ decoder_bwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, BwdGeom bg, BtGeom tg
         tc_fence_after_sync();
         BTDBG(19);
         float tot[16];
-        ld16(0, tg.N4, 4, tot);
+        ld16(0, tg.N4, BT_NACC, tot);
 #pragma unroll
         for (int r = 0; r < 16; ++r) tot[r] += dsum[r];
         float fold[U], dgz[3], dch[6];

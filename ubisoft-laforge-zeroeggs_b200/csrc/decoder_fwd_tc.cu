@@ -195,16 +195,20 @@ inline TcWs make_tcws(void* base, const DecGeom& g) {
   w.bytes = off; return w;
 }
 
-#define TCDBG(ev) do { if (tw.dbg && c == 0 && warp_lane0 && t < 64) tw.dbg[t * 32 + (ev)] = clock64(); } while (0)
+// per-CTA phase timestamps (development trace): dbg[(cta * 64 + t) * 32 + event], SM-local clock64
+#define TCDBG(ev) do { if (tw.dbg && warp_lane0 && t < 64) tw.dbg[((size_t)c * 64 + t) * 32 + (ev)] = clock64(); } while (0)
 
 // MAIN_ACC / GH_ACC: TMEM accumulators a chain's MMAs rotate over (critical chains / the hidden-to-hidden chains); the epilogue sums
-// them.  ROT: every CTA walks the k-block groups of a chain starting at group (CTA index mod groups), so that the 128 CTAs -- which
-// all read the SAME activation image right after a grid barrier -- do not hit the same 16 KB of L2 lines at the same moment.
-// DEFER: the weight producer starts a chain's tiles only after the previous chain's MMAs have drained the ring (experiment:
-// keeps weight prefetch out of the activation delivery window; measured no gain -- the 64 KB image streams at ~5 cycles per 128-byte
-// line with or without concurrent weight traffic, profiles/r02_fwd_tc_variants.md).
-template <int U, int MAIN_ACC, int GH_ACC, bool ROT, bool DEFER>
-__global__ void __launch_bounds__(160, 1)
+// them (measured: 1 is best -- a dependent accumulate does not stall, every extra accumulator only adds tcgen05.ld's).
+// PAIR: one MMA covers TWO k-blocks.  At M = 64 the A operand's rows 32..63 are the next k-block's 32 sample rows (the image tiles
+// are contiguous), so with the B operand = the weight tiles of both k-blocks stacked (2N rows, also contiguous)
+//     D[0:32,  0:N ] += X_kb   W_kb^T          D[32:64, N:2N] += X_kb+1 W_kb+1^T
+// (the off-diagonal blocks are garbage and never read): half the MMAs and 36 % fewer shared-memory operand bytes per chain -- the
+// operand reads compete with the incoming TMA writes for the SM's shared-memory port (profiles/r02_fwd_tc_variants.md).  The upper
+// diagonal block lives in TMEM lane quadrants 2 and 3: two helper warps (warp index % 4 = 2, 3) read it and hand it to the two
+// epilogue warps through shared memory.
+template <int U, int MAIN_ACC, int GH_ACC, bool PAIR>
+__global__ void __launch_bounds__(PAIR ? 224 : 160, 1)
 decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, TcWs tw, const uint8_t* __restrict__ packed) {
   constexpr int NP = (3 * U + 7) / 8 * 8;        // gate-chain rows (24 for U=8, 16 for U=4)
   constexpr int N1 = 4 * U + 8;                  // fold-chain rows
@@ -229,11 +233,16 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
   float* c_wgz = cst + 12 * U;    // [4U][4]  gaze columns of Wx for this CTA's fold rows (16-byte rows)
   float* c_y6 = c_wgz + 16 * U;   // b2[0:6], out_std[0:6], out_mean[0:6]
   float* c_gz = c_y6 + 18;        // in_mean[1131:1134], 1 / in_std[1131:1134]
+  constexpr int XW = (N1 > 2 * NP) ? N1 : 2 * NP;      // PAIR: columns a helper warp hands over per stage
+  float* xch = c_gz + 8;          // PAIR: [2 warp pairs][XW columns][16 lanes] upper-diagonal-block partial sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool warp_lane0 = lane == 0;
   const int c = blockIdx.x, H = a.H, T = a.T;
   const uint8_t* pk = packed + (size_t)c * tg.cta_bytes;
+  // warp roles: 0,1 epilogue | (PAIR: 2,3 upper-block readers) | MMA issuer | weight producer | activation loader
+  constexpr int W_MMA = PAIR ? 4 : 2, W_PROD = PAIR ? 5 : 3, W_LOAD = PAIR ? 6 : 4;
+  constexpr int NCM = PAIR ? 2 : 1;              // column multiplier of a chain's TMEM / MMA N
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_RING; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
@@ -252,7 +261,7 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
     c_y6[threadIdx.x] = a.b2[threadIdx.x]; c_y6[6 + threadIdx.x] = a.out_std[threadIdx.x]; c_y6[12 + threadIdx.x] = a.out_mean[threadIdx.x];
   }
   if (threadIdx.x < 3) { c_gz[threadIdx.x] = a.in_mean[P_OUT + threadIdx.x]; c_gz[3 + threadIdx.x] = 1.0f / a.in_std[P_OUT + threadIdx.x]; }
-  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == W_MMA) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -262,27 +271,26 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
   if (*tmem_slot != 0u) __trap();
   constexpr uint32_t tmem = 0u;
   // TMEM regions (columns): gh0 | gh1 | fold / gi0a / gi1; accumulator q of a region at +q*N
-  constexpr uint32_t R_GH0 = 0, R_GH1 = GH_ACC * NP, R_MAIN = 2 * GH_ACC * NP;
-  static_assert(MAIN_ACC * N1 + 2 * GH_ACC * NP <= 512, "TMEM budget");
+  constexpr uint32_t R_GH0 = 0, R_GH1 = GH_ACC * NP * NCM, R_MAIN = 2 * GH_ACC * NP * NCM;
+  static_assert((MAIN_ACC * N1 + 2 * GH_ACC * NP) * NCM <= 512, "TMEM budget");
+  static_assert(!PAIR || (MAIN_ACC == 1 && GH_ACC == 1), "the paired form keeps one accumulator per chain");
   const size_t actH = (size_t)g.nbt * H * 32;
   const unsigned bar_n = gridDim.x * TC_NEPI;
 
   const int ng = (kbH + TC_GKB - 1) / TC_GKB;      // ring groups per chain
-  const int rot = ROT ? c % ng : 0;                // first group this CTA touches (every role walks the groups in the same order)
-  auto group_kb = [&](int gi) { int g_ = gi + rot; if (g_ >= ng) g_ -= ng; return g_ * TC_GKB; };
+  auto group_kb = [&](int gi) { return gi * TC_GKB; };
   // Operand ring: slot = the weight tiles of TC_GKB k-blocks.  The X chunk of the same k-blocks lands in the resident X
   // buffer but completes on the SAME mbarrier, so the MMA warp waits once per 16 MMAs (a successful mbarrier wait costs
   // the issuing thread ~130 cycles that do not overlap with MMA issue).  Chains whose X is already resident (gh1 after the
   // fold chain, gh0 after gi1) get the second arrival from the weight producer.  Chain sequence: q = 0: gh0 of step 1;
   // step t: q = 1 + 5 (t-1) + {0 fold, 1 gh1, 2 gi0a, 3 gi1, 4 gh0 of t+1};  the last fold chain: q = 5 (T-1).
-  if (warp == 3) {
+  if (warp == W_PROD) {
     // ================= weight producer: streams every chain's tiles in the MMA warp's consumption order
     if (lane == 0) {
       uint32_t it = 0;
       auto stream = [&](int chain, bool has_loader) {
         const int N = chain == 0 ? N1 : NP;
         const uint8_t* src = pk + tg.chain_off[chain];
-        if (DEFER && it > 0) mbar_wait(&empty[(it - 1) % TC_RING], ((it - 1) / TC_RING) & 1);   // previous chain fully consumed
         for (int gi = 0; gi < ng; ++gi, ++it) {
           const int kb = group_kb(gi);
           const uint32_t s = it % TC_RING, ph = (it / TC_RING) & 1;
@@ -300,7 +308,7 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
       }
       stream(0, true);                                 // y(T-1)[0:6] for the last root integration
     }
-  } else if (warp == 4) {
+  } else if (warp == W_LOAD) {
     // ================= activation loader.  Load n goes to X buffer n&1.  Re-use of an X buffer needs no handshake: a load
     // is only issued after a grid barrier whose epilogues waited on commits covering every MMA that read the old contents.
     if (lane == 0) {
@@ -321,26 +329,26 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
       for (int t = 1; t < T; ++t) {
         const uint32_t base = 1u + 5u * (uint32_t)(t - 1);
         if (t > 1) grid_wait(w.bar, (unsigned)(3 * (t - 1)) * bar_n);           // C(t-1): h1(t-1) complete
-        if (tw.dbg && c == 0 && t < 64) tw.dbg[t * 32 + 0] = clock64();
+        if (tw.dbg && t < 64) tw.dbg[((size_t)c * 64 + t) * 32 + 0] = clock64();
         load(tw.h1b[(t - 1) & 1], base, (uint32_t)(3 * t - 2));
         grid_wait(w.bar, (unsigned)(3 * (t - 1) + 1) * bar_n);                  // A(t): a(t) complete
-        if (tw.dbg && c == 0 && t < 64) tw.dbg[t * 32 + 8] = clock64();
+        if (tw.dbg && t < 64) tw.dbg[((size_t)c * 64 + t) * 32 + 8] = clock64();
         load(tw.ab, base + 2, (uint32_t)(3 * t - 1));
         grid_wait(w.bar, (unsigned)(3 * (t - 1) + 2) * bar_n);                  // B(t): h0(t) complete
-        if (tw.dbg && c == 0 && t < 64) tw.dbg[t * 32 + 14] = clock64();
+        if (tw.dbg && t < 64) tw.dbg[((size_t)c * 64 + t) * 32 + 14] = clock64();
         load(tw.h0b[t & 1], base + 3, (uint32_t)(3 * t));
       }
       grid_wait(w.bar, (unsigned)(3 * (T - 1)) * bar_n);
       load(tw.h1b[(T - 1) & 1], 5u * (uint32_t)(T - 1), (uint32_t)(3 * T - 2));
     }
-  } else if (warp == 2) {
+  } else if (warp == W_MMA) {
     // ================= MMA issuer.  The warp runs the loops converged; one elected lane issues.  Descriptors advance by
     // constants; the four k-steps of a k-block go to four independent TMEM accumulators (odd k-blocks to four more when wide).
     uint32_t it = 0, n = 0;
     const uint64_t dX0 = make_smem_desc_sw128(X0), dX1 = make_smem_desc_sw128(X1), dRing = make_smem_desc_sw128(ring);
     int dbg_t = -1;                                  // >= 0: trace this chain's group arrivals (events 20..23)
     auto chain_mma = [&](int N, uint32_t d0, int nacc) {       // reads X buffer n&1; the MMAs rotate over `nacc` accumulators
-      const uint32_t idesc = make_idesc_bf16_f32(64, N);
+      const uint32_t idesc = make_idesc_bf16_f32(64, N * NCM);
       const uint64_t dx = (n & 1) ? dX1 : dX0;
       const uint64_t bstep = (uint64_t)(N * 8);            // one k-block tile of the weight slice, in 16-byte units
       uint32_t issued = 0;                                 // MMAs of this chain so far: accumulator = issued % nacc
@@ -348,23 +356,23 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
         const int kb = group_kb(gi);
         const uint32_t s = it % TC_RING, ph = (it / TC_RING) & 1;
         mbar_wait(&full[s], ph);
-        if (tw.dbg && c == 0 && warp_lane0 && dbg_t >= 0 && dbg_t < 64) tw.dbg[dbg_t * 32 + 20 + gi] = clock64();
+        if (tw.dbg && warp_lane0 && dbg_t >= 0 && dbg_t < 64) tw.dbg[((size_t)c * 64 + dbg_t) * 32 + 20 + gi] = clock64();
         const uint64_t da = dx + (uint64_t)kb * 256, db = dRing + (uint64_t)s * (SLOT >> 4);
         const int nk = kbH - kb >= TC_GKB ? TC_GKB : kbH - kb;
         if (elect_one_sync()) {
           uint32_t m = issued;
 #pragma unroll
-          for (int j = 0; j < TC_GKB; ++j) {
+          for (int j = 0; j < TC_GKB; j += NCM) {          // PAIR: k-blocks (j, j+1) in one MMA (kbH is even)
             if (j < nk) {
               const uint64_t a_ = da + (uint64_t)(j * 256), b_ = db + (uint64_t)j * bstep;
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks, ++m)
-                umma_bf16(d0 + (m & (uint32_t)(nacc - 1)) * (uint32_t)N, a_ + 2 * ks, b_ + 2 * ks, idesc, m >= (uint32_t)nacc);
+                umma_bf16(d0 + (m & (uint32_t)(nacc - 1)) * (uint32_t)(N * NCM), a_ + 2 * ks, b_ + 2 * ks, idesc, m >= (uint32_t)nacc);
             }
           }
           umma_commit(&empty[s]);
         }
-        issued += (uint32_t)(4 * nk);        // warp-uniform count of this chain's MMAs (nacc is a power of two)
+        issued += (uint32_t)(4 * nk / NCM);  // warp-uniform count of this chain's MMAs (nacc is a power of two)
         __syncwarp();
       }
     };
@@ -395,8 +403,45 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
     }
     chain_mma(N1, tmem + R_MAIN, MAIN_ACC);                             // y(T-1)[0:6]
     commit1(&d_full[0]);
+  } else if (PAIR && warp >= 2) {
+    // ================= upper-block readers (warps 2,3 = TMEM lane quadrants 2,3): rows 32..63 of every accumulator hold the
+    // second k-block of each pair; lane l < 16 of warp 2+h carries sample 16h + l, exactly like lane l of epilogue warp h
+    const int h = warp - 2;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    float* my = xch + (size_t)h * XW * 16 + (lane & 15);
+    auto hand_over = [&](uint32_t col0, int ncols, int xcol0) {     // columns [col0, col0 + ncols) -> xch columns xcol0..
+      for (int c8 = 0; c8 < ncols; c8 += 8) {
+        float v[8];
+        tmem_ld_cols<8>(tmem + lane_base + col0 + (uint32_t)c8, v);
+        if (lane < 16) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) my[(size_t)(xcol0 + c8 + i) * 16] = v[i];
+        }
+      }
+    };
+    for (int t = 1; t <= T; ++t) {
+      const uint32_t ph = (t - 1) & 1;
+      mbar_wait(&d_full[0], ph);
+      tc_fence_after_sync();
+      hand_over(R_MAIN + N1, N1, 0);
+      tc_fence_before_sync();
+      asm volatile("bar.sync %0, 64;\n" ::"r"(1 + h) : "memory");
+      if (t == T) break;
+      mbar_wait(&d_full[1], ph);
+      tc_fence_after_sync();
+      hand_over(R_MAIN + NP, NP, 0); hand_over(R_GH0 + NP, NP, NP);
+      tc_fence_before_sync();
+      asm volatile("bar.sync %0, 64;\n" ::"r"(1 + h) : "memory");
+      mbar_wait(&d_full[2], ph);
+      tc_fence_after_sync();
+      hand_over(R_MAIN + NP, NP, 0); hand_over(R_GH1 + NP, NP, NP);
+      tc_fence_before_sync();
+      asm volatile("bar.sync %0, 64;\n" ::"r"(1 + h) : "memory");
+    }
   } else {
     // ================= epilogue warps 0,1: TMEM lanes 0..15 of quadrant `warp` = samples 16*warp .. 16*warp+15
+    const float* xs = xch + (size_t)warp * XW * 16 + (lane & 15);
+    auto pair_sync = [&]() { if (PAIR) asm volatile("bar.sync %0, 64;\n" ::"r"(1 + warp) : "memory"); };   // the helper's columns are in xch
     const bool act = lane < 16;
     const int b = warp * 16 + (lane & 15);
     const bool live = act && b < a.B;
@@ -434,14 +479,23 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
       {
         // y6 columns and the fold columns (+ hoisted terms) first; the serial root / gaze chain then overlaps nothing else
         float y8[8];
-        tmem_ldn_sum<8, MAIN_ACC>(tmem + lane_base + R_MAIN + 4 * U, N1, y8);
+        tmem_ldn_sum<8, MAIN_ACC>(tmem + lane_base + R_MAIN + 4 * U, N1 * NCM, y8);
         if (t >= 2 && t < T) {
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) {
             float v[U];
-            tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + qq * U, N1, v);
+            tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + qq * U, N1 * NCM, v);
 #pragma unroll
             for (int u = 0; u < U; ++u) sv[qq * U + u] += v[u];
+          }
+        }
+        pair_sync();
+        if (PAIR) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y8[i] += xs[(size_t)(4 * U + i) * 16];
+          if (t >= 2 && t < T) {
+#pragma unroll
+            for (int i = 0; i < 4 * U; ++i) sv[i] += xs[(size_t)i * 16];
           }
         }
         float p6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gzn[3] = {0.f, 0.f, 0.f};
@@ -520,13 +574,23 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
         float hv[U], rr[U], zz[U], nn[U], gn[U];
         {
           float gh[U], gi[U];
-          tmem_ldn_sum<U, GH_ACC>(tmem + lane_base + R_GH0, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN, NP, gi);
+          auto xadd = [&](int g_) {          // + the second k-block of every pair (handed over by the helper warp)
+            if (PAIR) {
+#pragma unroll
+              for (int u = 0; u < U; ++u) { gi[u] += xs[(size_t)(g_ * U + u) * 16]; gh[u] += xs[(size_t)(NP + g_ * U + u) * 16]; }
+            }
+          };
+          tmem_ldn_sum<U, GH_ACC>(tmem + lane_base + R_GH0, NP * NCM, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN, NP * NCM, gi);
+          pair_sync();
+          xadd(0);
 #pragma unroll
           for (int u = 0; u < U; ++u) rr[u] = fast_sigmoid(gi[u] + gi0p[u] + gh[u] + c_bhh0[u]);
-          tmem_ldn_sum<U, GH_ACC>(tmem + lane_base + R_GH0 + U, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + U, NP, gi);
+          tmem_ldn_sum<U, GH_ACC>(tmem + lane_base + R_GH0 + U, NP * NCM, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + U, NP * NCM, gi);
+          xadd(1);
 #pragma unroll
           for (int u = 0; u < U; ++u) zz[u] = fast_sigmoid(gi[u] + gi0p[U + u] + gh[u] + c_bhh0[U + u]);
-          tmem_ldn_sum<U, GH_ACC>(tmem + lane_base + R_GH0 + 2 * U, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + 2 * U, NP, gi);
+          tmem_ldn_sum<U, GH_ACC>(tmem + lane_base + R_GH0 + 2 * U, NP * NCM, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + 2 * U, NP * NCM, gi);
+          xadd(2);
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             gn[u] = gh[u] + c_bhh0[2 * U + u];
@@ -562,13 +626,23 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
         float hv[U], rr[U], zz[U], nn[U], gn[U];
         {
           float gh[U], gi[U];
-          tmem_ldn_sum<U, GH_ACC>(tmem + lane_base + R_GH1, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN, NP, gi);
+          auto xadd = [&](int g_) {
+            if (PAIR) {
+#pragma unroll
+              for (int u = 0; u < U; ++u) { gi[u] += xs[(size_t)(g_ * U + u) * 16]; gh[u] += xs[(size_t)(NP + g_ * U + u) * 16]; }
+            }
+          };
+          tmem_ldn_sum<U, GH_ACC>(tmem + lane_base + R_GH1, NP * NCM, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN, NP * NCM, gi);
+          pair_sync();
+          xadd(0);
 #pragma unroll
           for (int u = 0; u < U; ++u) rr[u] = fast_sigmoid(gi[u] + c_bih1[u] + gh[u] + c_bhh1[u]);
-          tmem_ldn_sum<U, GH_ACC>(tmem + lane_base + R_GH1 + U, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + U, NP, gi);
+          tmem_ldn_sum<U, GH_ACC>(tmem + lane_base + R_GH1 + U, NP * NCM, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + U, NP * NCM, gi);
+          xadd(1);
 #pragma unroll
           for (int u = 0; u < U; ++u) zz[u] = fast_sigmoid(gi[u] + c_bih1[U + u] + gh[u] + c_bhh1[U + u]);
-          tmem_ldn_sum<U, GH_ACC>(tmem + lane_base + R_GH1 + 2 * U, NP, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + 2 * U, NP, gi);
+          tmem_ldn_sum<U, GH_ACC>(tmem + lane_base + R_GH1 + 2 * U, NP * NCM, gh); tmem_ldn_sum<U, MAIN_ACC>(tmem + lane_base + R_MAIN + 2 * U, NP * NCM, gi);
+          xadd(2);
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             gn[u] = gh[u] + c_bhh1[2 * U + u];
@@ -606,7 +680,7 @@ decoder_fwd_tc_kernel(zeggs_decoder_fwd_args a, DecGeom g, TcGeom tg, DecWs w, T
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem, 512); }
+  if (warp == W_MMA) { tc_fence_after_sync(); tmem_dealloc(tmem, 512); }
 }
 
 // ------------------------------------------------------------------ after the recurrence: outputs + x_pose history
@@ -692,23 +766,24 @@ extern "C" int zeggs_decoder_pack_weights_tc(const zeggs_decoder_fwd_args* a, vo
 extern "C" void zeggs_debug_set_tc_cluster(int) {}
 extern "C" int zeggs_debug_get_tc_cluster() { return 1; }
 
-template <int U, int MAIN_ACC, int GH_ACC, bool ROT, bool DEFER>
+template <int U, int MAIN_ACC, int GH_ACC, bool PAIR>
 static int launch_tc(const zeggs_decoder_fwd_args& a, const DecGeom& g, const TcGeom& tg, const DecWs& w, const TcWs& tw,
                      const uint8_t* packed, cudaStream_t stream) {
   const size_t smem = 1024 + (size_t)2 * tg.kbH * 4096 + (size_t)TC_RING * tg.slot_bytes + 4096 + 512 +
-                      (size_t)(12 * U + 16 * U + 18 + 8) * sizeof(float);
+                      (size_t)(12 * U + 16 * U + 18 + 8 + 2 * 48 * 16) * sizeof(float);
+  constexpr int NT = PAIR ? 224 : 160;
   static size_t checked_smem = 0;     // attribute + co-residency check once per shared-memory size (one device per process)
   if (checked_smem != smem) {
-    ZCHECK_CUDA(cudaFuncSetAttribute(decoder_fwd_tc_kernel<U, MAIN_ACC, GH_ACC, ROT, DEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ZCHECK_CUDA(cudaFuncSetAttribute(decoder_fwd_tc_kernel<U, MAIN_ACC, GH_ACC, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, nsm = 0, occ = 0;
     ZCHECK_CUDA(cudaGetDevice(&dev));
     ZCHECK_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    ZCHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decoder_fwd_tc_kernel<U, MAIN_ACC, GH_ACC, ROT, DEFER>, 160, smem));
+    ZCHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decoder_fwd_tc_kernel<U, MAIN_ACC, GH_ACC, PAIR>, NT, smem));
     ZCHECK_ARG(occ * nsm >= g.G, "decoder tc: cooperative grid of %d CTAs does not fit", g.G);
     checked_smem = smem;
   }
   void* args[] = {(void*)&a, (void*)&g, (void*)&tg, (void*)&w, (void*)&tw, (void*)&packed};
-  ZCHECK_CUDA(cudaLaunchCooperativeKernel((void*)decoder_fwd_tc_kernel<U, MAIN_ACC, GH_ACC, ROT, DEFER>, dim3(g.G), dim3(160), args, smem, stream));
+  ZCHECK_CUDA(cudaLaunchCooperativeKernel((void*)decoder_fwd_tc_kernel<U, MAIN_ACC, GH_ACC, PAIR>, dim3(g.G), dim3(NT), args, smem, stream));
   count_launch();
   return ZEGGS_OK;
 }
@@ -758,13 +833,12 @@ int decoder_fwd_tc_run(const zeggs_decoder_fwd_args& a, const DecGeom& g, const 
   ScopedTimer tm("decoder_fwd", stream);
   int rc;
   const uint8_t* pk = (const uint8_t*)a.packed_tc;
-#define ZTC(U_, M_, G_, R_, D_) launch_tc<U_, M_, G_, R_, D_>(a, g, tg, w, tw, pk, stream)
-  if (g.U == 4) rc = g_tc_variant == 1 ? ZTC(4, 8, 4, false, false) : ZTC(4, 1, 1, false, false);
+#define ZTC(U_, M_, G_, P_) launch_tc<U_, M_, G_, P_>(a, g, tg, w, tw, pk, stream)
+  if (g.U == 4) rc = g_tc_variant == 2 ? ZTC(4, 1, 1, true) : ZTC(4, 1, 1, false);
   else switch (g_tc_variant) {
-    case 1: rc = ZTC(8, 8, 4, false, false); break;     // round-1 configuration
-    case 2: rc = ZTC(8, 1, 1, false, true); break;      // single accumulators, deferred weight prefetch (measured: no gain)
-    case 3: rc = ZTC(8, 1, 1, true, false); break;      // single accumulators + per-CTA group rotation (measured: no gain)
-    default: rc = ZTC(8, 1, 1, false, false); break;    // shipped: single accumulators, eager weight prefetch
+    case 1: rc = ZTC(8, 8, 4, false); break;      // round-1 configuration (8 / 4 accumulators)
+    case 2: rc = ZTC(8, 1, 1, true); break;       // single accumulators + paired k-blocks (two k-blocks per MMA)
+    default: rc = ZTC(8, 1, 1, false); break;     // single accumulators
   }
 #undef ZTC
   if (rc) return rc;
