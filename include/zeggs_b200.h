@@ -234,6 +234,24 @@ int zeggs_style_enc_fwd(const zeggs_style_enc_args* a, void* stream);
 int zeggs_style_enc_bwd(const zeggs_style_enc_args* a, const zeggs_style_enc_grads* g, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * One teacher-forced decoder step (RecurrentDecoderNormal.forward, modules.py:179-185), fp32 throughout:
+ *   pose [B,1134] (the normalised input vector of modules.py:699-713), speech [B,S], style [B,Z], h_in [2,B,H]
+ *   -> y [B,1131] (normalised output of layer2), h_out [2,B,H].
+ * The tight parity point (<= 1e-4 vs the reference per step) and the unit of streaming inference; windows go through
+ * zeggs_decoder_window_fwd.
+ */
+typedef struct {
+  int B, H, S, Z;
+  const float *W0, *b0, *W_ih0, *b_ih0, *W_hh0, *b_hh0, *W_ih1, *b_ih1, *W_hh1, *b_hh1, *W2, *b2;
+  const float *pose, *speech, *style, *h_in;
+  float *y, *h_out;
+  void* workspace;
+  size_t workspace_bytes;
+} zeggs_decoder_step_args;
+size_t zeggs_decoder_step_workspace_bytes(int B, int H, int S, int Z);
+int zeggs_decoder_step_fwd(const zeggs_decoder_step_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Training loss, forward and backward in one call (train.py:277-421): world-space transforms, 75-joint FK with
  * velocities for the output and the ground truth, 17 weighted L1 means + kl_weight * KL(mu, logvar), divided by 18.
  * (Y, root_pos, root_rot) are the decoder outputs; (WY, W_root_pos, W_root_rot) the ground-truth window in the

@@ -80,6 +80,10 @@ StyleEncArgs = _struct("StyleEncArgs", ints=("B", "T", "C_in", "H", "E", "nheads
 StyleEncGrads = _struct("StyleEncGrads", ptrs=("dz", "dmu", "dlogvar") + tuple("d" + n for n in STYLE_W))
 
 
+DecoderStepArgs = _struct("DecoderStepArgs", ints=("B", "H", "S", "Z"),
+                          ptrs=("W0", "b0", "W_ih0", "b_ih0", "W_hh0", "b_hh0", "W_ih1", "b_ih1", "W_hh1", "b_hh1", "W2", "b2",
+                                "pose", "speech", "style", "h_in", "y", "h_out", "workspace"),
+                          tail=[("workspace_bytes", C.c_size_t)])
 LossArgs = _struct("LossArgs", ints=("B", "T", "Z"), floats=("dt", "kl_weight"),
                    ptrs=("Y", "root_pos", "root_rot", "WY", "W_root_pos", "W_root_rot", "gaze_pos", "parents", "mu", "logvar",
                          "losses", "dY", "dRootPos", "dRootRot", "dmu", "dlogvar", "workspace"),
@@ -96,6 +100,8 @@ SYMBOLS = [
     ("zeggs_timing_read", C.c_int, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     ("zeggs_mel_num_frames", C.c_int, [C.c_int, C.c_int, C.c_int]),
     ("zeggs_mel_forward", C.c_int, [C.POINTER(MelArgs), C.c_void_p]),
+    ("zeggs_decoder_step_workspace_bytes", C.c_size_t, [C.c_int] * 4),
+    ("zeggs_decoder_step_fwd", C.c_int, [C.POINTER(DecoderStepArgs), C.c_void_p]),
     ("zeggs_window_gather", C.c_int, [C.POINTER(GatherArgs), C.c_void_p]),
     ("zeggs_pose_to_bvh_channels", C.c_int, [C.POINTER(PosePostArgs), C.c_void_p]),
     ("zeggs_loudness_workspace_bytes", C.c_size_t, [C.c_int, C.c_int]),

@@ -562,3 +562,26 @@ def pose_to_bvh_channels(root_pos, root_rot, lpos, ltxy, start_position=(0.0, 0.
         a.start_rot[i] = float(start_rotation[i])
     _lib.check(_lib.lib().zeggs_pose_to_bvh_channels(a, _lib.stream_ptr()), "zeggs_pose_to_bvh_channels")
     return (pos, eul, lrot) if want_lrot else (pos, eul)
+
+
+# ---------------------------------------------------------------------------------------------- single decoder step
+def decoder_step(dec, pose, speech, style, state):
+    """RecurrentDecoderNormal.forward (modules.py:179-185) for one frame, fp32: pose [B,1134] normalised input vector, speech [B,S],
+    style [B,Z], state [2,B,H] -> (y [B,1131] normalised, new state [2,B,H])."""
+    if pose.device.type != "cuda":
+        raise _lib.ZeggsError("decoder_step runs on CUDA tensors only (no CPU fallback)")
+    l = _lib.lib()
+    dev = pose.device
+    w = [_f32c(p, dev) for p in dec._weights()[:12]]
+    pose, speech, style, state = _f32c(pose), _f32c(speech), _f32c(style), _f32c(state)
+    B, H, S, Z = pose.shape[0], dec.hidden_size, speech.shape[1], style.shape[1]
+    y = torch.empty((B, P_OUT), dtype=torch.float32, device=dev)
+    h_out = torch.empty((2, B, H), dtype=torch.float32, device=dev)
+    wsb = l.zeggs_decoder_step_workspace_bytes(B, H, S, Z)
+    ws = WS.get("dec_step", wsb, dev)
+    a = _lib.DecoderStepArgs(B=B, H=H, S=S, Z=Z, pose=pose.data_ptr(), speech=speech.data_ptr(), style=style.data_ptr(),
+                             h_in=state.data_ptr(), y=y.data_ptr(), h_out=h_out.data_ptr(), workspace=ws.data_ptr(), workspace_bytes=wsb)
+    for n, t in zip(("W0", "b0", "W_ih0", "b_ih0", "W_hh0", "b_hh0", "W_ih1", "b_ih1", "W_hh1", "b_hh1", "W2", "b2"), w):
+        setattr(a, n, t.data_ptr())
+    _lib.check(l.zeggs_decoder_step_fwd(a, _lib.stream_ptr()), "zeggs_decoder_step_fwd")
+    return y, h_out
