@@ -45,6 +45,19 @@ void zeggs_timing_reset(void);
 int zeggs_timing_read(const char* name, double* total_ms, int* count);
 
 /* ------------------------------------------------------------------------------------------------
+ * Per-call context of the batched-GEMM front end (caller-owned, plain data; no library globals are needed when it is passed):
+ * every args struct below ends in `const zeggs_ctx* ctx`.  NULL selects the process-wide defaults of the legacy setters
+ * (zeggs_set_scratch / zeggs_set_gemm_mode / zeggs_set_fast_wgrad), kept for callers of the plain-argument entry points.
+ * Two host threads driving two streams with two contexts never share mutable library state.
+ */
+typedef struct {
+  void* scratch;          /* device scratch for the bf16 operand copies of the tcgen05 GEMMs (and split-K partials) */
+  size_t scratch_bytes;
+  int gemm_mode;          /* 0: fp32 SIMT everywhere, 1: tcgen05 split-bf16 (x3, ~fp32 accuracy), 2: tcgen05 plain bf16 */
+  int fast_wgrad;         /* 1: weight-gradient products run as ONE bf16 pass (set together with the tensor-core recurrence) */
+} zeggs_ctx;
+
+/* ------------------------------------------------------------------------------------------------
  * Mel front end.  Replaces audio/spectrograms.py:8-54 (extract_mel_spectrogram_for_tts, pre-emphasis
  * off), :216-269 (extract_spectrogram), :161-183 + :386-503 (Slaney filterbank), :57-131 (clip/dB/[0,1])
  * and, for `feat`, data_pipeline.py:62-82 (ln(10^(s/20)), 80->60 fps linear resample, energy channel).
@@ -136,6 +149,7 @@ typedef struct {
   int engine;            /* 0: fp32 SIMT recurrence (parity grade); 1: tcgen05 recurrence, bf16 operands / fp32 state (B <= 32) */
   const void* packed_tc; /* engine 1: zeggs_decoder_pack_weights_tc output */
   void* workspace_tc;    /* engine 1: zeggs_decoder_tc_workspace_bytes bytes (bf16 activation images) */
+  const zeggs_ctx* ctx;  /* GEMM context of this call (NULL: process defaults) */
 } zeggs_decoder_fwd_args;
 
 size_t zeggs_decoder_packed_bytes(int H, int S, int Z);
@@ -195,6 +209,7 @@ typedef struct {
   float* y;             /* [B,T,O] */
   void* workspace;
   size_t workspace_bytes;
+  const zeggs_ctx* ctx;
 } zeggs_speech_enc_args;
 typedef struct {
   const float* dy; /* [B,T,O] */
@@ -222,6 +237,7 @@ typedef struct {
   float *z, *mu, *logvar; /* [B, E/2] each */
   void* workspace;
   size_t workspace_bytes;
+  const zeggs_ctx* ctx;
 } zeggs_style_enc_args;
 typedef struct {
   const float *dz, *dmu, *dlogvar; /* [B,E/2], any may be NULL */
@@ -362,6 +378,9 @@ int zeggs_set_gemm_mode(int mode);
 int zeggs_set_fast_wgrad(int on);
 int zeggs_gemm_f32(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* bias,
                    float* C, int ldc, int act, int accumulate, void* stream);
+/* same with an explicit context instead of the process defaults */
+int zeggs_gemm_f32_ctx(const zeggs_ctx* ctx, int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                       const float* bias, float* C, int ldc, int act, int accumulate, void* stream);
 int zeggs_split_bf16(const float* x, int rows, int cols, int ld_in, void* hi, void* lo, int ld_out, void* stream);
 
 #ifdef __cplusplus

@@ -200,10 +200,10 @@ def _load(mod, P, prefix, dev):
 @pytest.fixture
 def gemm_mode(dev):
     """Select the GEMM engine for one test and restore the default (1 = tcgen05 split-bf16) afterwards."""
-    from zeggs_b200 import _lib
+    from zeggs_b200 import ops
 
     def set_mode(m):
-        _lib.check(_lib.lib().zeggs_set_gemm_mode(m), "zeggs_set_gemm_mode")
+        ops.set_gemm_mode(m)
     yield set_mode
     set_mode(1)
 
@@ -410,8 +410,8 @@ def test_gemm_f32_front_end_tcgen05(dev, mode, M, N, K):
         A, B = torch.randn(M, K, generator=g), torch.randn(K, N, generator=g); ref = A.double() @ B.double()
     Ad, Bd = A.to(dev), B.to(dev)
     out = torch.empty(M, N, device=dev)
-    _lib.check(_lib.lib().zeggs_gemm_f32(mode, M, N, K, Ad.data_ptr(), Ad.stride(0), Bd.data_ptr(), Bd.stride(0), None,
-                                         out.data_ptr(), N, 0, 0, _lib.stream_ptr()), "zeggs_gemm_f32")
+    _lib.check(_lib.lib().zeggs_gemm_f32_ctx(ops.ctx_ptr(dev), mode, M, N, K, Ad.data_ptr(), Ad.stride(0), Bd.data_ptr(), Bd.stride(0), None,
+                                             out.data_ptr(), N, 0, 0, _lib.stream_ptr()), "zeggs_gemm_f32_ctx")
     err, sc = report(f"gemm_f32 mode{mode} {M}x{N}x{K}", out, ref)
     assert err <= 4e-5 * sc
 
@@ -425,8 +425,8 @@ def test_gemm_f32_splitk_epilogue(dev):
     A, B, bias, C0 = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(N, generator=g), torch.randn(M, N, generator=g)
     ref = C0.double() + torch.nn.functional.elu(A.double() @ B.double().T + bias.double())
     Ad, Bd, bd, out = A.to(dev), B.to(dev), bias.to(dev), C0.to(dev).clone()
-    _lib.check(_lib.lib().zeggs_gemm_f32(0, M, N, K, Ad.data_ptr(), K, Bd.data_ptr(), K, bd.data_ptr(), out.data_ptr(), N, 1, 1,
-                                         _lib.stream_ptr()), "zeggs_gemm_f32")
+    _lib.check(_lib.lib().zeggs_gemm_f32_ctx(ops.ctx_ptr(dev), 0, M, N, K, Ad.data_ptr(), K, Bd.data_ptr(), K, bd.data_ptr(), out.data_ptr(), N, 1, 1,
+                                             _lib.stream_ptr()), "zeggs_gemm_f32_ctx")
     err, sc = report("gemm_f32 split-K bias+elu+accumulate", out, ref)
     assert err <= 4e-5 * sc
 
@@ -1050,3 +1050,29 @@ def test_decoder_single_step_teacher_forced_vs_oracle(dev, H, B):
         e1, _ = report(f"step{k} H{H} y", y_g, y_o)
         e2, _ = report(f"step{k} H{H} state", st_g, st_o)
         assert e1 <= 1e-4 and e2 <= 1e-4
+
+
+def test_two_contexts_do_not_share_state(dev):
+    """The GEMM front end takes its scratch buffer / mode from the caller's zeggs_ctx: two contexts with different modes used
+    alternately on two streams give each its own numerics (fp32 SIMT exact-ish vs plain bf16), with no library-global setter involved."""
+    import ctypes as C
+    from zeggs_b200 import _lib
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 256, 384, 512
+    A, B = torch.randn(M, K, generator=g).to(dev), torch.randn(N, K, generator=g).to(dev)
+    ref = A.double() @ B.double().T
+    bufs = [torch.empty(64 << 20, dtype=torch.uint8, device=dev) for _ in range(2)]
+    ctxs = [_lib.Ctx(scratch=bufs[0].data_ptr(), scratch_bytes=bufs[0].numel(), gemm_mode=0, fast_wgrad=0),
+            _lib.Ctx(scratch=bufs[1].data_ptr(), scratch_bytes=bufs[1].numel(), gemm_mode=2, fast_wgrad=0)]
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    outs = [torch.empty(M, N, device=dev) for _ in range(2)]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for i in (0, 1):
+            _lib.check(_lib.lib().zeggs_gemm_f32_ctx(C.addressof(ctxs[i]), 0, M, N, K, A.data_ptr(), K, B.data_ptr(), K, None, outs[i].data_ptr(), N,
+                                                     0, 0, streams[i].cuda_stream), "zeggs_gemm_f32_ctx")
+    torch.cuda.synchronize()
+    e0 = float((outs[0].double() - ref).abs().max() / ref.abs().max())
+    e1 = float((outs[1].double() - ref).abs().max() / ref.abs().max())
+    print(f"  ctx0 (fp32 SIMT) rel err {e0:.2e}; ctx1 (plain bf16 tcgen05) rel err {e1:.2e}")
+    assert e0 <= 2e-5 and 1e-4 <= e1 <= 2e-2

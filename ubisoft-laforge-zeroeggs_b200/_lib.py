@@ -42,6 +42,11 @@ class LoudnessArgs(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
+class Ctx(C.Structure):
+    """zeggs_ctx: per-call GEMM context (scratch buffer, GEMM mode, single-pass weight gradients)."""
+    _fields_ = [("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t), ("gemm_mode", C.c_int), ("fast_wgrad", C.c_int)]
+
+
 class DecoderFwdArgs(C.Structure):
     _fields_ = ([("B", C.c_int), ("T", C.c_int), ("H", C.c_int), ("S", C.c_int), ("Z", C.c_int), ("dt", C.c_float)] +
                 [(n, C.c_void_p) for n in (
@@ -51,7 +56,7 @@ class DecoderFwdArgs(C.Structure):
                     "root_pos0", "root_rot0", "pose0", "gaze_pos", "speech", "style",
                     "Y", "root_pos", "root_rot", "workspace")] +
                 [("workspace_bytes", C.c_size_t), ("save_for_backward", C.c_int), ("engine", C.c_int),
-                 ("packed_tc", C.c_void_p), ("workspace_tc", C.c_void_p)])
+                 ("packed_tc", C.c_void_p), ("workspace_tc", C.c_void_p), ("ctx", C.c_void_p)])
 
 
 class DecoderBwdArgs(C.Structure):
@@ -69,14 +74,14 @@ def _struct(name, ints=(), floats=(), ptrs=(), tail=()):
 
 SpeechEncArgs = _struct("SpeechEncArgs", ints=("B", "T", "C_in", "H", "O"),
                         ptrs=("W0", "b0", "W1", "b1", "W2", "b2", "x", "mask0", "mask1", "y", "workspace"),
-                        tail=[("workspace_bytes", C.c_size_t)])
+                        tail=[("workspace_bytes", C.c_size_t), ("ctx", C.c_void_p)])
 SpeechEncGrads = _struct("SpeechEncGrads", ptrs=("dy", "dW0", "db0", "dW1", "db1", "dW2", "db2"))
 STYLE_W = ("Wc1", "bc1", "ln1_g", "ln1_b", "Wc2", "bc2", "ln2_g", "ln2_b", "Win", "bin", "Wout", "bout", "ln3_g", "ln3_b",
            "Wf1", "bf1", "Wf2", "bf2", "ln4_g", "ln4_b")
 StyleEncArgs = _struct("StyleEncArgs", ints=("B", "T", "C_in", "H", "E", "nheads"), floats=("temperature",),
                        ptrs=STYLE_W + ("x", "eps", "pe", "mask_c1", "mask_c2", "mask_attn", "mask_ao", "mask_ff",
                                        "z", "mu", "logvar", "workspace"),
-                       tail=[("workspace_bytes", C.c_size_t)])
+                       tail=[("workspace_bytes", C.c_size_t), ("ctx", C.c_void_p)])
 StyleEncGrads = _struct("StyleEncGrads", ptrs=("dz", "dmu", "dlogvar") + tuple("d" + n for n in STYLE_W))
 
 
@@ -146,6 +151,8 @@ SYMBOLS = [
     ("zeggs_set_gemm_mode", C.c_int, [C.c_int]),
     ("zeggs_gemm_f32", C.c_int, [C.c_int] * 4 + [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("zeggs_gemm_f32_ctx", C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("zeggs_split_bf16", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
 ]
 

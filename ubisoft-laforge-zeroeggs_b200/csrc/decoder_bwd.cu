@@ -435,6 +435,7 @@ extern "C" size_t zeggs_decoder_packed_bwd_bytes(int H, int S, int Z) {
 }
 
 extern "C" int zeggs_decoder_pack_weights_bwd(const zeggs_decoder_fwd_args* a, float* packed, void* stream_) {
+  CtxScope ctx_scope(a ? a->ctx : nullptr);
   ZCHECK_ARG(a && packed && a->H % 16 == 0 && pick_U(a->H) > 0, "decoder bwd pack: bad arguments");
   DecGeom g = make_geom(a->B, a->H, a->S, a->Z);
   BwdGeom bg = make_bgeom(g);
@@ -481,6 +482,7 @@ static int rowsum(const float* GA, long long gaT, long long gaBT, int N, int nT,
 }
 
 extern "C" int zeggs_decoder_window_bwd(const zeggs_decoder_fwd_args* ap, const zeggs_decoder_bwd_args* bp, void* stream_) {
+  CtxScope ctx_scope(ap ? ap->ctx : nullptr);
   ZCHECK_ARG(ap && bp, "decoder bwd: null args");
   const zeggs_decoder_fwd_args& a = *ap;
   const zeggs_decoder_bwd_args& b = *bp;

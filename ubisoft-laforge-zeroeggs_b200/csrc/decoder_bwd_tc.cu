@@ -575,6 +575,7 @@ extern "C" size_t zeggs_decoder_bwd_tc_workspace_bytes(int H, int S, int Z) {
   return make_btws(nullptr, make_geom(1, H, S, Z)).bytes;
 }
 extern "C" int zeggs_decoder_pack_weights_bwd_tc(const zeggs_decoder_fwd_args* a, void* packed, void* stream_) {
+  CtxScope ctx_scope(a ? a->ctx : nullptr);
   ZCHECK_ARG(a && packed && a->H % 64 == 0 && pick_U(a->H) > 0, "decoder bwd tc pack: bad arguments");
   const float* mfold = decoder_tc_mfold(*a);
   ZCHECK_ARG(mfold != nullptr, "decoder bwd tc pack: the forward pack (zeggs_decoder_pack_weights_tc -> args.packed_tc) must run first");

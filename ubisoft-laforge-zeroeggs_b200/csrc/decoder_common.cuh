@@ -24,6 +24,13 @@ int sgemm_batched_launch(int mode, int M, int N, int K, const float* A, int lda,
                          long long sA, long long sB, long long sC, cudaStream_t stream);
 int gemm_f32_auto(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* bias,
                   float* C, int ldc, int act, int accumulate, cudaStream_t stream);
+const zeggs_ctx* swap_ctx(const zeggs_ctx* c);
+// RAII: the caller's context is the active one for the duration of one extern "C" entry point on this host thread
+struct CtxScope {
+  const zeggs_ctx* old; bool active;
+  explicit CtxScope(const zeggs_ctx* c) : old(nullptr), active(c != nullptr) { if (active) old = swap_ctx(c); }
+  ~CtxScope() { if (active) swap_ctx(old); }
+};
 int gemm_mode();
 int set_fast_wgrad_internal(int on);   // returns the previous setting
 char* scratch_base();

@@ -323,6 +323,7 @@ extern "C" size_t zeggs_decoder_packed_bytes(int H, int S, int Z) {
 }
 
 extern "C" int zeggs_decoder_pack_weights(const zeggs_decoder_fwd_args* a, float* packed, void* stream_) {
+  CtxScope ctx_scope(a ? a->ctx : nullptr);
   int rc = check_fwd_args(a); if (rc) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
   DecGeom g = make_geom(a->B, a->H, a->S, a->Z);
@@ -357,6 +358,7 @@ static int launch_fwd(const zeggs_decoder_fwd_args& a, const DecGeom& g, const D
 extern "C" int zeggs_decoder_window_fwd(const zeggs_decoder_fwd_args* ap, void* stream_) {
   int rc = check_fwd_args(ap); if (rc) return rc;
   const zeggs_decoder_fwd_args& a = *ap;
+  CtxScope ctx_scope(a.ctx);
   cudaStream_t stream = (cudaStream_t)stream_;
   DecGeom g = make_geom(a.B, a.H, a.S, a.Z);
   DecWs w = make_ws(a.workspace, g, a.T, a.save_for_backward);

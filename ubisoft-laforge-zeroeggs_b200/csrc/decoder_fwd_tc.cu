@@ -729,6 +729,7 @@ extern "C" size_t zeggs_decoder_tc_workspace_bytes(int H, int S, int Z) {
   return make_tcws(nullptr, g).bytes;
 }
 extern "C" int zeggs_decoder_pack_weights_tc(const zeggs_decoder_fwd_args* a, void* packed, void* stream_) {
+  CtxScope ctx_scope(a ? a->ctx : nullptr);
   ZCHECK_ARG(a && packed && a->H % 64 == 0 && pick_U(a->H) > 0 && a->H <= 1024, "decoder tc pack: bad arguments");
   ZCHECK_ARG(a->in_mean && a->in_std && a->out_mean && a->out_std, "decoder tc pack: normalisation statistics missing");
   cudaStream_t stream = (cudaStream_t)stream_;

@@ -229,7 +229,7 @@ static int ew_add(float* dst, const float* a, const float* b, size_t n, size_t p
   ew_add_kernel<<<GRID1(n), 256, 0, s>>>(dst, a, b, n, period); LAUNCH_OK(); return 0; }
 static int ln_fwd(const float* a, const float* res, const float* g, const float* b, int rows, int D, float* y, float* xh, float* rs, cudaStream_t s) {
   layernorm_fwd_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(a, res, g, b, rows, D, y, xh, rs); LAUNCH_OK(); return 0; }
-static float* g_redbuf = nullptr;   // [COLRED_RB][2][D <= 4096] scratch inside the calling module's workspace
+static thread_local float* g_redbuf = nullptr;   // [COLRED_RB][2][D <= 4096] scratch inside the calling module's workspace (per host thread: re-entrant)
 static int colred(const float* a, const float* b, int rows, int D, float* out0, float* out1, cudaStream_t s) {
   ZCHECK_ARG(g_redbuf != nullptr && D <= 4096, "column reduction: scratch missing or D=%d too wide", D);
   const int RB = rows < 8 * COLRED_RB ? ceil_div(rows, 8) : COLRED_RB;
@@ -265,6 +265,7 @@ extern "C" size_t zeggs_speech_enc_workspace_bytes(int B, int T, int Cin, int H,
   return speech_ws(nullptr, B, T, Cin, H, O, 31).bytes;
 }
 extern "C" int zeggs_speech_enc_fwd(const zeggs_speech_enc_args* ap, void* stream_) {
+  CtxScope ctx_scope(ap ? ap->ctx : nullptr);
   ZCHECK_ARG(ap, "speech_enc: null args");
   const zeggs_speech_enc_args& a = *ap; cudaStream_t s = (cudaStream_t)stream_;
   const int B = a.B, T = a.T, Cin = a.C_in, H = a.H, O = a.O, k = 31, M = B * T;
@@ -281,6 +282,7 @@ extern "C" int zeggs_speech_enc_fwd(const zeggs_speech_enc_args* ap, void* strea
   return ZEGGS_OK;
 }
 extern "C" int zeggs_speech_enc_bwd(const zeggs_speech_enc_args* ap, const zeggs_speech_enc_grads* gp, void* stream_) {
+  CtxScope ctx_scope(ap ? ap->ctx : nullptr);
   ZCHECK_ARG(ap && gp && gp->dy, "speech_enc bwd: null args");
   const zeggs_speech_enc_args& a = *ap; const zeggs_speech_enc_grads& g = *gp; cudaStream_t s = (cudaStream_t)stream_;
   const int B = a.B, T = a.T, Cin = a.C_in, H = a.H, O = a.O, k = 31, M = B * T;
@@ -326,6 +328,7 @@ extern "C" size_t zeggs_style_enc_workspace_bytes(int B, int T, int Cin, int Hs,
 }
 
 extern "C" int zeggs_style_enc_fwd(const zeggs_style_enc_args* ap, void* stream_) {
+  CtxScope ctx_scope(ap ? ap->ctx : nullptr);
   ZCHECK_ARG(ap, "style_enc: null args");
   const zeggs_style_enc_args& a = *ap; cudaStream_t s = (cudaStream_t)stream_;
   const int B = a.B, T = a.T, Cin = a.C_in, Hs = a.H, E = a.E, nh = a.nheads, M = B * T, d = E / nh;
@@ -369,6 +372,7 @@ extern "C" int zeggs_style_enc_fwd(const zeggs_style_enc_args* ap, void* stream_
 }
 
 extern "C" int zeggs_style_enc_bwd(const zeggs_style_enc_args* ap, const zeggs_style_enc_grads* gp, void* stream_) {
+  CtxScope ctx_scope(ap ? ap->ctx : nullptr);
   ZCHECK_ARG(ap && gp, "style_enc bwd: null args");
   const zeggs_style_enc_args& a = *ap; const zeggs_style_enc_grads& g = *gp; cudaStream_t s = (cudaStream_t)stream_;
   const int B = a.B, T = a.T, Cin = a.C_in, Hs = a.H, E = a.E, nh = a.nheads, M = B * T, d = E / nh;

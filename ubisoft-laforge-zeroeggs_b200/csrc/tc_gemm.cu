@@ -345,10 +345,16 @@ extern "C" int zeggs_set_gemm_mode(int mode) {
   g_gemm_mode = mode; return ZEGGS_OK;
 }
 extern "C" int zeggs_set_fast_wgrad(int on) { g_fast_wgrad = on ? 1 : 0; return ZEGGS_OK; }
-int set_fast_wgrad_internal(int on) { const int old = g_fast_wgrad; g_fast_wgrad = on; return old; }
-int gemm_mode() { return g_gemm_mode; }
-char* scratch_base() { return g_scratch; }
-size_t scratch_bytes() { return g_scratch_bytes; }
+// The context of the entry point currently executing on this host thread (CtxScope in decoder_common.cuh): per-call state passed
+// by the caller; the process-wide values above are only the defaults for calls that pass none.
+static thread_local const zeggs_ctx* tl_ctx = nullptr;
+static thread_local int tl_fast_wgrad_override = -1;
+const zeggs_ctx* swap_ctx(const zeggs_ctx* c) { const zeggs_ctx* old = tl_ctx; tl_ctx = c; return old; }
+static int fast_wgrad() { return tl_fast_wgrad_override >= 0 ? tl_fast_wgrad_override : (tl_ctx ? tl_ctx->fast_wgrad : g_fast_wgrad); }
+int set_fast_wgrad_internal(int on) { const int old = tl_fast_wgrad_override; tl_fast_wgrad_override = on; return old; }
+int gemm_mode() { return tl_ctx ? tl_ctx->gemm_mode : g_gemm_mode; }
+char* scratch_base() { return tl_ctx ? (char*)tl_ctx->scratch : g_scratch; }
+size_t scratch_bytes() { return tl_ctx ? tl_ctx->scratch_bytes : g_scratch_bytes; }
 
 int split_hist_launch(const float* x, long long slot_stride, int S, int R, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t stream,
                       float* rowsum, int s_begin) {
@@ -365,15 +371,18 @@ int gemm_f32_auto(int mode, int M, int N, int K, const float* A, int lda, const 
                   float* C, int ldc, int act, int accumulate, cudaStream_t stream) {
   const int Kp = round_up(K, 8);
   const size_t elems = (size_t)(M + N) * Kp;
-  const bool want_lo = g_gemm_mode == 1 && !(mode == 1 && g_fast_wgrad);
+  char* const sbase = scratch_base();
+  const size_t sbytes = scratch_bytes();
+  const int gmode = gemm_mode();
+  const bool want_lo = gmode == 1 && !(mode == 1 && fast_wgrad());
   const size_t need = elems * 2 * (want_lo ? 2 : 1) + 1024;
-  if (g_gemm_mode == 0 || g_scratch == nullptr || need > g_scratch_bytes || (double)M * N * K < 4.0e6)
+  if (gmode == 0 || sbase == nullptr || need > sbytes || (double)M * N * K < 4.0e6)
     return sgemm_launch(mode, M, N, K, A, lda, B, ldb, bias, C, ldc, act, accumulate, stream);
-  char* p = g_scratch;
+  char* p = sbase;
   auto take = [&](size_t n) { __nv_bfloat16* r = (__nv_bfloat16*)p; p += ((n * 2 + 255) / 256) * 256; return r; };
   __nv_bfloat16* Ah = take((size_t)M * Kp); __nv_bfloat16* Bh = take((size_t)N * Kp);
   __nv_bfloat16* Al = want_lo ? take((size_t)M * Kp) : nullptr; __nv_bfloat16* Bl = want_lo ? take((size_t)N * Kp) : nullptr;
-  if ((size_t)(p - g_scratch) > g_scratch_bytes)
+  if ((size_t)(p - sbase) > sbytes)
     return sgemm_launch(mode, M, N, K, A, lda, B, ldb, bias, C, ldc, act, accumulate, stream);
   const dim3 tb(32, 8);
   if (mode == 1) split_bf16_t_kernel<<<dim3(ceil_div(M, 32), ceil_div(Kp, 32)), tb, 0, stream>>>(A, K, M, lda, Ah, Al, Kp);
@@ -385,11 +394,16 @@ int gemm_f32_auto(int mode, int M, int N, int K, const float* A, int lda, const 
   ZCHECK_LAUNCH();
   p = (char*)(((uintptr_t)p + 255) & ~(uintptr_t)255);
   return tc_gemm_launch(M, N, K, Ah, Al, Kp, Bh, Bl, Kp, bias, C, ldc, act, accumulate, stream, (float*)p,
-                        (size_t)(g_scratch + g_scratch_bytes - p));
+                        (size_t)(sbase + sbytes - p));
 }
 
 extern "C" int zeggs_gemm_f32(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* bias,
                               float* C, int ldc, int act, int accumulate, void* stream) {
+  return gemm_f32_auto(mode, M, N, K, A, lda, B, ldb, bias, C, ldc, act, accumulate, (cudaStream_t)stream);
+}
+extern "C" int zeggs_gemm_f32_ctx(const zeggs_ctx* ctx, int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                                  const float* bias, float* C, int ldc, int act, int accumulate, void* stream) {
+  CtxScope scope(ctx);
   return gemm_f32_auto(mode, M, N, K, A, lda, B, ldb, bias, C, ldc, act, accumulate, (cudaStream_t)stream);
 }
 

@@ -35,18 +35,39 @@ class _Workspace:
 WS = _Workspace()
 
 _scratch = {}
+_ctx = {}
+GEMM_MODE = 1          # 0: fp32 SIMT everywhere, 1: tcgen05 split-bf16 (~fp32 accuracy), 2: tcgen05 plain bf16
+
+
+def set_gemm_mode(mode):
+    """GEMM engine of the batched (non-recurrent) products for subsequent calls from this process."""
+    global GEMM_MODE
+    if mode not in (0, 1, 2):
+        raise _lib.ZeggsError("gemm mode must be 0 (fp32 SIMT), 1 (tcgen05 bf16x3) or 2 (tcgen05 bf16)")
+    GEMM_MODE = mode
+    for c in _ctx.values():
+        c.gemm_mode = mode
 
 
 def ensure_scratch(dev):
-    """Caller-owned scratch for the tcgen05 GEMM front end (bf16 operand copies); ZEGGS_SCRATCH_MB overrides the size."""
+    """Caller-owned scratch for the tcgen05 GEMM front end (bf16 operand copies); ZEGGS_SCRATCH_MB overrides the size.  The buffer,
+    the GEMM mode and the weight-gradient mode travel to the library in a per-device zeggs_ctx passed with every call (ctx_ptr):
+    the library keeps no mutable global state for them."""
     import os
     key = str(dev)
     if key not in _scratch:
         mb = int(os.environ.get("ZEGGS_SCRATCH_MB", "1536"))
         buf = torch.empty(mb << 20, dtype=torch.uint8, device=dev)
-        _lib.check(_lib.lib().zeggs_set_scratch(buf.data_ptr(), buf.numel()), "zeggs_set_scratch")
         _scratch[key] = buf
+        _ctx[key] = _lib.Ctx(scratch=buf.data_ptr(), scratch_bytes=buf.numel(), gemm_mode=GEMM_MODE,
+                             fast_wgrad=0 if DECODER_ENGINE == "fp32" else 1)
     return _scratch[key]
+
+
+def ctx_ptr(dev):
+    """Address of this device's zeggs_ctx (for the `ctx` field of the args structs)."""
+    ensure_scratch(dev)
+    return C.addressof(_ctx[str(dev)])
 
 
 _weights_epoch = 0
@@ -71,7 +92,8 @@ def set_decoder_engine(name):
         raise _lib.ZeggsError("decoder engine must be 'fp32', 'tc' or 'auto'")
     DECODER_ENGINE = name
     # the tensor-core engine's weight gradients are single-pass bf16: the encoders' weight-gradient GEMMs follow it
-    _lib.check(_lib.lib().zeggs_set_fast_wgrad(0 if name == "fp32" else 1), "zeggs_set_fast_wgrad")
+    for c in _ctx.values():
+        c.fast_wgrad = 0 if name == "fp32" else 1
 
 
 def resolve_engine(H, S, Z):
@@ -113,7 +135,7 @@ def _decoder_args(dec, B, T, dev, tensors, stats, dt, save):
     w = [_f32c(p, dev) for p in dec._weights()]
     names = ["W0", "b0", "W_ih0", "b_ih0", "W_hh0", "b_hh0", "W_ih1", "b_ih1", "W_hh1", "b_hh1", "W2", "b2",
              "Wc0", "bc0", "Wc1", "bc1", "Wc2", "bc2"]
-    a = _lib.DecoderFwdArgs(B=B, T=T, H=H, S=S, Z=Z, dt=dt)
+    a = _lib.DecoderFwdArgs(B=B, T=T, H=H, S=S, Z=Z, dt=dt, ctx=ctx_ptr(dev))
     for n, t in zip(names, w):
         setattr(a, n, _lib.ptr(t))
     keep = list(w)
@@ -391,7 +413,7 @@ def speech_enc_args(enc, x, masks, y, ws):
     H, Cin = w[0].shape[0], w[0].shape[1]
     O = w[2].shape[0]
     B, T = x.shape[0], x.shape[1]
-    a = _lib.SpeechEncArgs(B=B, T=T, C_in=Cin, H=H, O=O)
+    a = _lib.SpeechEncArgs(B=B, T=T, C_in=Cin, H=H, O=O, ctx=ctx_ptr(x.device))
     for n, t in zip(("W0", "b0", "W1", "b1", "W2", "b2"), w):
         setattr(a, n, t.data_ptr())
     a.x, a.y = x.data_ptr(), y.data_ptr()
@@ -456,7 +478,7 @@ def style_enc_args(enc, x, eps, masks, temperature, outs, ws):
     B, T, Cin = x.shape
     Hs, E = w[0].shape[0], w[4].shape[0]
     nh = enc.encoder.blocks[0].attention.multi_head_attention.num_heads
-    a = _lib.StyleEncArgs(B=B, T=T, C_in=Cin, H=Hs, E=E, nheads=nh, temperature=temperature)
+    a = _lib.StyleEncArgs(B=B, T=T, C_in=Cin, H=Hs, E=E, nheads=nh, temperature=temperature, ctx=ctx_ptr(dev))
     for n, t in zip(_lib.STYLE_W, w):
         setattr(a, n, t.data_ptr())
     key = (T, E, str(dev))
