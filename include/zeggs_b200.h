@@ -162,7 +162,8 @@ size_t zeggs_decoder_tc_workspace_bytes(int H, int S, int Z);
 int zeggs_decoder_pack_weights_tc(const zeggs_decoder_fwd_args* a, void* packed, void* stream);
 /* development aid: device buffer [64][32] of int64 receiving CTA 0's per-step phase timestamps (NULL = off) */
 void zeggs_debug_set_tc_trace(void* device_buffer);
-void zeggs_debug_set_tc_nacc(int n); /* development aid (no-op since the folded engine) */
+void zeggs_debug_set_tc_nacc(int n); /* development aid: forward recurrence kernel variant (0 = shipped) */
+void zeggs_debug_set_loss_impl(int v); /* development aid: 1 = warp-per-frame loss kernels (default), 0 = round-1 thread-per-frame version */
 void zeggs_debug_set_tc_cluster(int n); /* development aid: cap the thread-block cluster size of the tc recurrences (1 = no clusters) */
 int zeggs_debug_get_tc_cluster(void);   /* cluster size the last tc forward launch used */
 int zeggs_decoder_window_fwd(const zeggs_decoder_fwd_args* a, void* stream);

@@ -1076,3 +1076,34 @@ def test_two_contexts_do_not_share_state(dev):
     e1 = float((outs[1].double() - ref).abs().max() / ref.abs().max())
     print(f"  ctx0 (fp32 SIMT) rel err {e0:.2e}; ctx1 (plain bf16 tcgen05) rel err {e1:.2e}")
     assert e0 <= 2e-5 and 1e-4 <= e1 <= 2e-2
+
+
+def test_loss_warp_per_frame_kernels_match_round1_version(dev):
+    """The warp-per-frame loss kernels (default) against the thread-per-frame SoA version of round 1 (zeggs_debug_set_loss_impl(0)) on a
+    B=6, T=40 batch: total, all 18 terms and every gradient (dY, root pos / rot, mu, logvar) to 2e-5 of the tensor max."""
+    from zeggs_b200 import _lib, ops, synth
+    from zeggs_b200.train import pack_pose
+    B, T = 6, 40
+    st = synth.load_stats()
+    O = tt(synth.make_pose_windows(B, T, seed=51), dev); W = tt(synth.make_pose_windows(B, T, seed=52), dev)
+    rs = np.random.RandomState(1)
+    mu = torch.from_numpy(rs.randn(B, 64).astype(np.float32)).to(dev); lv = torch.from_numpy((rs.randn(B, 64) * 0.3).astype(np.float32)).to(dev)
+    Y = pack_pose(*[O[k] for k in NAMES[2:]]); WY = pack_pose(*[W[k] for k in NAMES[2:]])
+    par = torch.as_tensor(st["parents"], dtype=torch.int32, device=dev)
+    res = {}
+    try:
+        for impl in (1, 0):
+            _lib.lib().zeggs_debug_set_loss_impl(impl)
+            terms = torch.zeros(19, device=dev)
+            loss, grads = ops.loss_fwd_bwd(Y, O["root_pos"], O["root_rot"], WY, W["root_pos"], W["root_rot"], W["gaze_pos"], par, float(st["dt"]),
+                                           mu, lv, 0.13, terms)
+            torch.cuda.synchronize()
+            res[impl] = (terms.clone(), [g.clone() for g in grads])
+    finally:
+        _lib.lib().zeggs_debug_set_loss_impl(1)
+    t1, t0 = res[1][0].cpu().numpy(), res[0][0].cpu().numpy()
+    print("  terms new", np.round(t1, 5)); print("  terms old", np.round(t0, 5))
+    assert np.all(np.abs(t1 - t0) <= 2e-5 * np.maximum(np.abs(t0), 1e-3))
+    for n, a_, b_ in zip(("dY", "dRootPos", "dRootRot", "dmu", "dlogvar"), res[1][1], res[0][1]):
+        err, sc = report(f"loss impl 1 vs 0 {n}", a_, b_)
+        assert err <= 2e-5 * max(sc, 1e-9), n

@@ -120,6 +120,7 @@ SYMBOLS = [
     ("zeggs_decoder_pack_weights_tc", C.c_int, [C.POINTER(DecoderFwdArgs), C.c_void_p, C.c_void_p]),
     ("zeggs_debug_set_tc_trace", None, [C.c_void_p]),
     ("zeggs_debug_set_tc_nacc", None, [C.c_int]),
+    ("zeggs_debug_set_loss_impl", None, [C.c_int]),
     ("zeggs_debug_set_tc_cluster", None, [C.c_int]),
     ("zeggs_debug_get_tc_cluster", C.c_int, []),
     ("zeggs_decoder_packed_bwd_bytes", C.c_size_t, [C.c_int, C.c_int, C.c_int]),

@@ -205,7 +205,407 @@ __global__ void root_rot_combine_kernel(const float* __restrict__ own, const flo
   out[i] = own[i] + (t + 1 < T ? prev[i + 4] : 0.f);
 }
 
-struct LossWs { float *Ys[2], *Q[2], *G, *gYs, *partial, *dq_own, *dq_prev; double* chan; size_t stride; int nblk; size_t bytes; };
+// ================================================================================================================
+// Warp-per-frame implementation (round 2; zeggs_loss_fwd_bwd's default).  One warp owns one frame; the joints of one tree level are
+// processed in parallel (the shipped skeleton: 13 levels, at most 12 joints wide), every world-space quantity lives in shared
+// memory, and the only global intermediates are the differences D of the four channel groups whose frame-to-frame terms need the
+// neighbouring frames (1575 floats per frame) plus 17 per-frame partial sums.  The SoA buffers of the thread-per-frame version
+// (245 MB per step, 74-deep dependent chains through L2: 5 % of the machine busy, profiles/r02_ncu_summary.md) are gone; results are
+// bitwise reproducible (fixed shuffle and frame orders).
+//   K1 loss_w_fwd_kernel   FK of the output (lanes 0..15) and of the target (lanes 16..31), D, direct |D| sums, D rows of the diff groups
+//   K2 loss_w_bwd_kernel   recomputes K1's shared-memory state, builds dLoss/dQ in place of the target-side records (direct terms +
+//                          the frame-difference terms from the neighbours' D rows), runs the adjoint FK level by level (children
+//                          publish their contribution, parents gather them in index order), writes the dY row + the root gradients
+//   K3 loss_w_final_kernel deterministic reduction over frames + KL
+// The frame-difference residual is evaluated as (D[t+1] - D[t]) / dt with D = Q_out - Q_target (train.py:356-393 computes
+// dQ_out/dt - dQ_target/dt: equal up to fp32 rounding).
+// ================================================================================================================
+struct TreeTables {           // built on the device from `parents` by loss_tree_kernel (one thread; 75 joints)
+  int order[NJ];              // joints sorted by level
+  int lvl_off[NJ + 1];        // level l = order[lvl_off[l] .. lvl_off[l+1])
+  int nlev;
+  int child_off[NJ + 1];      // children of joint i = child_idx[child_off[i] .. child_off[i+1]) in index order
+  int child_idx[NJ];
+  int parents[NJ];
+};
+__global__ void loss_tree_kernel(const int* __restrict__ parents, TreeTables* __restrict__ tt) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int lvl[NJ];
+  lvl[0] = 0; tt->parents[0] = -1;
+  int maxl = 0;
+  for (int i = 1; i < NJ; ++i) { const int p = parents[i]; tt->parents[i] = p; lvl[i] = lvl[p] + 1; if (lvl[i] > maxl) maxl = lvl[i]; }
+  int n = 0;
+  for (int l = 0; l <= maxl; ++l) { tt->lvl_off[l] = n; for (int i = 0; i < NJ; ++i) if (lvl[i] == l) tt->order[n++] = i; }
+  tt->lvl_off[maxl + 1] = n; tt->nlev = maxl + 1;
+  int m = 0;
+  for (int i = 0; i < NJ; ++i) { tt->child_off[i] = m; for (int c = 1; c < NJ; ++c) if (parents[c] == i) tt->child_idx[m++] = c; }
+  tt->child_off[NJ] = m;
+}
+
+constexpr int LW_WARPS = 4;                      // frames per CTA
+// per-joint record: the channel groups of one joint in the order the terms consume them
+constexpr int R_LPOS = 0, R_LTXY = 3, R_LVEL = 9, R_LVRT = 12, R_GP = 15, R_GR = 18, R_GV = 27, R_GT = 30, LW_REC = 33;
+constexpr int LW_Q = NJ * LW_REC;                // 2475 floats per side
+constexpr int LW_RT = 24;                        // root block: pos3 R9 velw3 vrtw3 gaze3
+constexpr int LW_PUSH = NJ * 18;                 // adjoint hand-over per joint: gr9 gp3 gt3 gv3
+constexpr int LW_GY = 1136;                      // dY row under construction
+constexpr int LW_DD = NJ * 21;                   // 1575: D rows of LPOS (225) | LTXY (450) | CPOS (225) | CMAT (675)
+constexpr int LW_FWD_FLOATS = 2 * LW_Q + 2 * LW_RT;
+constexpr int LW_BWD_FLOATS = LW_FWD_FLOATS + LW_PUSH + LW_GY;
+constexpr int LW_NP = 17;                        // partial sums per frame: terms 0..11, gaze, then the 4 frame-difference terms
+
+struct LossWArgs {
+  int B, T; float dt;
+  const float *Y[2], *rp[2], *rq[2];            // [0] output, [1] target; Y rows [frame][1131]
+  const float* gaze;
+  const TreeTables* tt;
+  float* Dd;                                     // [frames][LW_DD]
+  float* partial;                                // [frames][LW_NP]
+  float *dY, *dRootPos, *dq_own, *dq_prev;
+};
+
+__device__ __forceinline__ M3 ldm9(const float* p) { M3 r;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) r.m[i] = p[i];
+  return r; }
+__device__ __forceinline__ void stm9(float* p, const M3& v) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) p[i] = v.m[i]; }
+__device__ __forceinline__ V3 ldv(const float* p) { return v3(p[0], p[1], p[2]); }
+__device__ __forceinline__ void stv(float* p, V3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float sgnf(float d) { return (float)((d > 0.f) - (d < 0.f)); }
+// record element -> direct-term group (4 LPOS, 5 LTXY, 6 LVEL, 7 LVRT, 8 CPOS, 9 CMAT, 10 CVEL, 11 CVRT)
+__device__ __forceinline__ int rec_group(int e) { return e < 3 ? 4 : e < 9 ? 5 : e < 12 ? 6 : e < 15 ? 7 : e < 18 ? 8 : e < 27 ? 9 : e < 30 ? 10 : 11; }
+
+// static weights / channel counts of the 13 direct groups in partial order (terms 0..11, then gaze = term 16) and of the four
+// frame-difference terms (12..15: LPOS, LTXY, CPOS, CMAT); train.py:340-395
+__constant__ float c_lw_w[13] = {0.1f, 10.f, 0.1f, 5.f, 15.f, 15.f, 10.f, 7.f, 0.1f, 3.f, 0.06f, 1.25f, 10.f};
+__constant__ float c_lw_n[13] = {3.f, 9.f, 3.f, 3.f, NJ * 3.f, NJ * 6.f, NJ * 3.f, NJ * 3.f, NJ * 3.f, NJ * 9.f, NJ * 3.f, NJ * 3.f, 3.f};
+__constant__ float c_lw_dw[4] = {7.f, 8.f, 0.06f, 1.25f};
+__constant__ float c_lw_dn[4] = {NJ * 3.f, NJ * 6.f, NJ * 3.f, NJ * 9.f};
+
+// forward of both sides into shared memory (lanes 0..15: output side, 16..31: target side): q[side][joint][33], rt[side][21]
+__device__ __forceinline__ void lw_forward(const LossWArgs& a, const TreeTables& tt, size_t frame, int lane, float* const (&q)[2], float* const (&rt)[2]) {
+  const int side = lane >> 4, l16 = lane & 15;
+  const int t = (int)(frame % a.T);
+  const float* y = a.Y[side] + frame * P_OUT;
+  float* qs = q[side];
+  if (l16 == 0) {
+    const float* q4 = a.rq[side] + frame * 4;
+    Q4 qr; qr.w = q4[0]; qr.x = q4[1]; qr.y = q4[2]; qr.z = q4[3];
+    Q4 qp = qr;
+    if (t > 0) { qp.w = q4[-4]; qp.x = q4[-3]; qp.y = q4[-2]; qp.z = q4[-1]; }
+    const V3 pos = ldv(a.rp[side] + frame * 3), gz = ldv(a.gaze + frame * 3);
+    const M3 R = quat_to_xform(qr);
+    const V3 velw = quat_mul_vec(qp, ldv(y)), vrtw = quat_mul_vec(qp, ldv(y + 3));          // train.py:281-286
+    float* r = rt[side];
+    stv(r, pos); stm9(r + 3, R); stv(r + 12, velw); stv(r + 15, vrtw);
+    stv(r + 18, quat_mul_vec(quat_inv(qr), unit_eps(gz - pos, 1e-8f)));                     // train.py:336-337
+    const V3 lp = ldv(y + OFF_LPOS), lv = ldv(y + OFF_LVEL), lr = ldv(y + OFF_LVRT);
+    const V3 x = ldv(y + OFF_LTXY), yv = ldv(y + OFF_LTXY + 3);
+    const V3 rp0 = quat_mul_vec(qr, lp);
+    const V3 p0 = rp0 + pos, t0 = vrtw + quat_mul_vec(qr, lr), v0 = velw + quat_mul_vec(qr, lv) + cross(vrtw, rp0);
+    // joint 0 is compared in world space (train.py:296-305); its raw two-axis rotation stays local
+    stv(qs + R_LPOS, p0); stv(qs + R_LTXY, x); stv(qs + R_LTXY + 3, yv); stv(qs + R_LVEL, v0); stv(qs + R_LVRT, t0);
+    stv(qs + R_GP, p0); stm9(qs + R_GR, mm(R, orthogonalize_xy(x, yv))); stv(qs + R_GV, v0); stv(qs + R_GT, t0);
+  }
+  __syncwarp();
+  for (int l = 1; l < tt.nlev; ++l) {                       // txform.py:10-20, one tree level at a time
+    for (int k = tt.lvl_off[l] + l16; k < tt.lvl_off[l + 1]; k += 16) {
+      const int i = tt.order[k], p = tt.parents[i];
+      const float* cp = qs + p * LW_REC;
+      const M3 grp = ldm9(cp + R_GR);
+      const V3 gpp = ldv(cp + R_GP), gtp = ldv(cp + R_GT), gvp = ldv(cp + R_GV);
+      const V3 lp = ldv(y + OFF_LPOS + 3 * i), lv = ldv(y + OFF_LVEL + 3 * i), lr = ldv(y + OFF_LVRT + 3 * i);
+      const V3 x = ldv(y + OFF_LTXY + 6 * i), yv = ldv(y + OFF_LTXY + 6 * i + 3);
+      const V3 rp = mv(grp, lp);
+      float* ci = qs + i * LW_REC;
+      stv(ci + R_LPOS, lp); stv(ci + R_LTXY, x); stv(ci + R_LTXY + 3, yv); stv(ci + R_LVEL, lv); stv(ci + R_LVRT, lr);
+      stv(ci + R_GP, gpp + rp); stm9(ci + R_GR, mm(grp, orthogonalize_xy(x, yv))); stv(ci + R_GV, gvp + mv(grp, lv) + cross(gtp, rp));
+      stv(ci + R_GT, gtp + mv(grp, lr));
+    }
+    __syncwarp();
+  }
+}
+
+// position of record element (joint i, element e) inside a frame's D row, or -1 when the group has no frame-difference term
+__device__ __forceinline__ int dd_index(int i, int e) {
+  if (e < 3) return 3 * i + e;                                   // LPOS
+  if (e < 9) return NJ * 3 + 6 * i + (e - 3);                    // LTXY
+  if (e >= R_GP && e < R_GR) return NJ * 9 + 3 * i + (e - R_GP); // CPOS
+  if (e >= R_GR && e < R_GV) return NJ * 12 + 9 * i + (e - R_GR);// CMAT
+  return -1;
+}
+
+__global__ void __launch_bounds__(LW_WARPS * 32) loss_w_fwd_kernel(LossWArgs a) {
+  extern __shared__ float lw_sm[];
+  __shared__ TreeTables tt;
+  for (int i = threadIdx.x; i < (int)(sizeof(TreeTables) / 4); i += blockDim.x) reinterpret_cast<int*>(&tt)[i] = reinterpret_cast<const int*>(a.tt)[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t frame = (size_t)blockIdx.x * LW_WARPS + warp;
+  if (frame >= (size_t)a.B * a.T) return;
+  float* base = lw_sm + (size_t)warp * LW_FWD_FLOATS;
+  float* const q[2] = {base, base + LW_Q};
+  float* const rt[2] = {base + 2 * LW_Q, base + 2 * LW_Q + LW_RT};
+  lw_forward(a, tt, frame, lane, q, rt);
+  float sum[13];
+#pragma unroll
+  for (int g = 0; g < 13; ++g) sum[g] = 0.f;
+  float* dd = a.Dd + frame * LW_DD;
+  for (int i = lane; i < NJ; i += 32) {
+    const float* o = q[0] + i * LW_REC; const float* w = q[1] + i * LW_REC;
+#pragma unroll
+    for (int e = 0; e < LW_REC; ++e) {
+      const float D = o[e] - w[e];
+      sum[rec_group(e)] += fabsf(D);
+      const int x = dd_index(i, e);
+      if (x >= 0) dd[x] = D;
+    }
+  }
+  if (lane == 0) {
+    const float* o = rt[0]; const float* w = rt[1];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) sum[k < 3 ? 0 : k < 12 ? 1 : k < 15 ? 2 : k < 18 ? 3 : 12] += fabsf(o[k] - w[k]);
+  }
+#pragma unroll
+  for (int g = 0; g < 13; ++g) { const float v = warp_sum(sum[g]); if (lane == 0) a.partial[frame * LW_NP + g] = v; }
+}
+
+__global__ void __launch_bounds__(LW_WARPS * 32) loss_w_bwd_kernel(LossWArgs a) {
+  extern __shared__ float lw_sm[];
+  __shared__ TreeTables tt;
+  for (int i = threadIdx.x; i < (int)(sizeof(TreeTables) / 4); i += blockDim.x) reinterpret_cast<int*>(&tt)[i] = reinterpret_cast<const int*>(a.tt)[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t frame = (size_t)blockIdx.x * LW_WARPS + warp;
+  if (frame >= (size_t)a.B * a.T) return;
+  const int t = (int)(frame % a.T);
+  float* base = lw_sm + (size_t)warp * LW_BWD_FLOATS;
+  float* const q[2] = {base, base + LW_Q};
+  float* const rt[2] = {base + 2 * LW_Q, base + 2 * LW_Q + LW_RT};
+  float* push = base + LW_FWD_FLOATS;
+  float* gy = push + LW_PUSH;
+  lw_forward(a, tt, frame, lane, q, rt);
+  // ---- dLoss/dQ of the direct terms, in place of the target-side values
+  const float BT = (float)a.B * (float)a.T;
+  for (int i = lane; i < NJ; i += 32) {
+    const float* o = q[0] + i * LW_REC; float* w = q[1] + i * LW_REC;
+#pragma unroll
+    for (int e = 0; e < LW_REC; ++e) {
+      const int g = rec_group(e);
+      w[e] = c_lw_w[g] / (BT * c_lw_n[g]) * (1.0f / 18.0f) * sgnf(o[e] - w[e]);
+    }
+  }
+  if (lane == 0) {
+    const float* o = rt[0]; float* w = rt[1];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) {
+      const int g = k < 3 ? 0 : k < 12 ? 1 : k < 15 ? 2 : k < 18 ? 3 : 12;
+      w[k] = c_lw_w[g] / (BT * c_lw_n[g]) * (1.0f / 18.0f) * sgnf(o[k] - w[k]);
+    }
+  }
+  __syncwarp();
+  // ---- frame-difference terms (train.py:356-393): e_t = (D[t+1] - D[t]) / dt needs the neighbouring frames' D rows
+  float dsum[4] = {0.f, 0.f, 0.f, 0.f};
+  if (a.T > 1) {
+    const float inv_dt = 1.0f / a.dt;
+    const float* d0 = a.Dd + frame * LW_DD;
+    const bool has_p = t + 1 < a.T, has_m = t > 0;
+    for (int x = lane; x < LW_DD; x += 32) {
+      int g, i, e;
+      if (x < NJ * 3) { g = 0; i = x / 3; e = R_LPOS + x % 3; }
+      else if (x < NJ * 9) { const int y_ = x - NJ * 3; g = 1; i = y_ / 6; e = R_LTXY + y_ % 6; }
+      else if (x < NJ * 12) { const int y_ = x - NJ * 9; g = 2; i = y_ / 3; e = R_GP + y_ % 3; }
+      else { const int y_ = x - NJ * 12; g = 3; i = y_ / 9; e = R_GR + y_ % 9; }
+      const float D = d0[x];
+      float gd = 0.f;
+      if (has_p) { const float er = (d0[x + LW_DD] - D) * inv_dt; dsum[g] += fabsf(er); gd -= sgnf(er); }
+      if (has_m) { const float el = (D - d0[x - LW_DD]) * inv_dt; gd += sgnf(el); }
+      q[1][i * LW_REC + e] += c_lw_dw[g] * inv_dt * gd / ((float)a.B * (float)(a.T - 1) * c_lw_dn[g]) * (1.0f / 18.0f);
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) { const float v = warp_sum(dsum[g]); if (lane == 0) a.partial[frame * LW_NP + 13 + g] = v; }
+  __syncwarp();
+  // ---- adjoint FK, deepest level first.  G = q[1] (dLoss/d record), accumulated with the children's hand-overs.
+  float* G = q[1];
+  const float* Q = q[0];
+  for (int l = tt.nlev - 1; l >= 1; --l) {
+    for (int k = tt.lvl_off[l] + lane; k < tt.lvl_off[l + 1]; k += 32) {
+      const int i = tt.order[k], p = tt.parents[i];
+      float* gi = G + i * LW_REC;
+      for (int cc = tt.child_off[i]; cc < tt.child_off[i + 1]; ++cc) {       // children publish [gr9 gp3 gt3 gv3]
+        const float* ps = push + tt.child_idx[cc] * 18;
+#pragma unroll
+        for (int m = 0; m < 9; ++m) gi[R_GR + m] += ps[m];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) { gi[R_GP + m] += ps[9 + m]; gi[R_GT + m] += ps[12 + m]; gi[R_GV + m] += ps[15 + m]; }
+      }
+      const float* qi = Q + i * LW_REC; const float* qp = Q + p * LW_REC;
+      const V3 lp = ldv(qi + R_LPOS), lv = ldv(qi + R_LVEL), lr = ldv(qi + R_LVRT), x = ldv(qi + R_LTXY), yv = ldv(qi + R_LTXY + 3);
+      const M3 lm = orthogonalize_xy(x, yv);
+      const M3 grp = ldm9(qp + R_GR);
+      const V3 gtp = ldv(qp + R_GT);
+      const V3 rp = mv(grp, lp);
+      const V3 dgp = ldv(gi + R_GP), dgt = ldv(gi + R_GT), dgv = ldv(gi + R_GV);
+      const M3 dgr = ldm9(gi + R_GR);
+      const V3 drp = dgp + cross(dgv, gtp);                 // gp[i] = gp[p] + rp ;  gv[i] += gt[p] x rp
+      M3 acc = mmt(dgr, lm);                                // gr[i] = gr[p] lmat
+      add_outer(acc, dgv, lv);                              // gv[i] += gr[p] lvel
+      add_outer(acc, dgt, lr);                              // gt[i]  = gt[p] + gr[p] lvrt
+      add_outer(acc, drp, lp);                              // rp = gr[p] lpos
+      float* ps = push + i * 18;
+      stm9(ps, acc); stv(ps + 9, dgp); stv(ps + 12, dgt + cross(rp, dgv)); stv(ps + 15, dgv);
+      // local quantities of joint i: direct L1 terms + FK
+      stv(gy + OFF_LPOS + 3 * i, ldv(gi + R_LPOS) + mtv(grp, drp));
+      stv(gy + OFF_LVEL + 3 * i, ldv(gi + R_LVEL) + mtv(grp, dgv));
+      stv(gy + OFF_LVRT + 3 * i, ldv(gi + R_LVRT) + mtv(grp, dgt));
+      V3 dx, dyv;
+      orthogonalize_xy_bwd(x, yv, mtm(grp, dgr), dx, dyv);
+      stv(gy + OFF_LTXY + 6 * i, ldv(gi + R_LTXY) + dx);
+      stv(gy + OFF_LTXY + 6 * i + 3, ldv(gi + R_LTXY + 3) + dyv);
+    }
+    __syncwarp();
+  }
+  // ---- joint 0 + root terms (one lane; the serial tail of the chain)
+  if (lane == 0) {
+    float* g0 = G;
+    for (int cc = tt.child_off[0]; cc < tt.child_off[1]; ++cc) {
+      const float* ps = push + tt.child_idx[cc] * 18;
+#pragma unroll
+      for (int m = 0; m < 9; ++m) g0[R_GR + m] += ps[m];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) { g0[R_GP + m] += ps[9 + m]; g0[R_GT + m] += ps[12 + m]; g0[R_GV + m] += ps[15 + m]; }
+    }
+    const float* y = a.Y[0] + frame * P_OUT;
+    const float* q4 = a.rq[0] + frame * 4;
+    Q4 qr; qr.w = q4[0]; qr.x = q4[1]; qr.y = q4[2]; qr.z = q4[3];
+    Q4 qp = qr;
+    if (t > 0) { qp.w = q4[-4]; qp.x = q4[-3]; qp.y = q4[-2]; qp.z = q4[-1]; }
+    const V3 pos = ldv(a.rp[0] + frame * 3), gz = ldv(a.gaze + frame * 3);
+    const M3 R = quat_to_xform(qr);
+    const V3 lp = ldv(y + OFF_LPOS), lv = ldv(y + OFF_LVEL), lr = ldv(y + OFF_LVRT), x = ldv(y + OFF_LTXY), yv = ldv(y + OFF_LTXY + 3);
+    const V3 vel = ldv(y), vrt = ldv(y + 3);
+    const V3 vrtw = quat_mul_vec(qp, vrt);
+    const V3 rp0 = quat_mul_vec(qr, lp);
+    const float* gr_ = rt[1];                                  // dLoss/d(root block)
+    // joint 0 receives the local (world-space) and the FK-root gradients
+    const V3 dp0 = ldv(g0 + R_LPOS) + ldv(g0 + R_GP);
+    const V3 dv0 = ldv(g0 + R_LVEL) + ldv(g0 + R_GV);
+    const V3 dt0 = ldv(g0 + R_LVRT) + ldv(g0 + R_GT);
+    const M3 dm0 = ldm9(g0 + R_GR);
+    M3 dR = ldm9(gr_ + 3);
+    V3 dpos = ldv(gr_) + dp0;                                  // p0 = rp0 + pos
+    const V3 dvelw = ldv(gr_ + 12) + dv0;                      // v0 = velw + rot(q, lv) + vrtw x rp0
+    const V3 dvrtw = ldv(gr_ + 15) + dt0 + cross(rp0, dv0);    // t0 = vrtw + rot(q, lr)
+    const V3 drp0 = dp0 + cross(dv0, vrtw);
+    Q4 dq; dq.w = dq.x = dq.y = dq.z = 0.f;
+    Q4 gq; V3 gv_;
+    quat_mul_vec_bwd(qr, lp, drp0, gq, gv_); dq.w += gq.w; dq.x += gq.x; dq.y += gq.y; dq.z += gq.z;
+    stv(gy + OFF_LPOS, gv_);
+    quat_mul_vec_bwd(qr, lv, dv0, gq, gv_);  dq.w += gq.w; dq.x += gq.x; dq.y += gq.y; dq.z += gq.z;
+    stv(gy + OFF_LVEL, gv_);
+    quat_mul_vec_bwd(qr, lr, dt0, gq, gv_);  dq.w += gq.w; dq.x += gq.x; dq.y += gq.y; dq.z += gq.z;
+    stv(gy + OFF_LVRT, gv_);
+    const M3 lm0 = orthogonalize_xy(x, yv);                    // m0 = R lmat0
+    const M3 tm = mmt(dm0, lm0);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) dR.m[k] += tm.m[k];
+    V3 dx, dyv;
+    orthogonalize_xy_bwd(x, yv, mtm(R, dm0), dx, dyv);
+    stv(gy + OFF_LTXY, ldv(g0 + R_LTXY) + dx);
+    stv(gy + OFF_LTXY + 3, ldv(g0 + R_LTXY + 3) + dyv);
+    gq = quat_to_xform_bwd(qr, dR);          dq.w += gq.w; dq.x += gq.x; dq.y += gq.y; dq.z += gq.z;
+    const V3 u = gz - pos;                                     // gaze = rot(q^-1, unit(gaze - pos))
+    const V3 un = unit_eps(u, 1e-8f);
+    quat_mul_vec_bwd(quat_inv(qr), un, ldv(gr_ + 18), gq, gv_);
+    dq.w += gq.w; dq.x -= gq.x; dq.y -= gq.y; dq.z -= gq.z;
+    dpos = dpos - unit_eps_bwd(u, 1e-8f, gv_);
+    Q4 dqp; dqp.w = dqp.x = dqp.y = dqp.z = 0.f;              // the world root velocities use the PREVIOUS frame's rotation
+    quat_mul_vec_bwd(qp, vel, dvelw, gq, gv_); dqp.w += gq.w; dqp.x += gq.x; dqp.y += gq.y; dqp.z += gq.z;
+    stv(gy, gv_);
+    quat_mul_vec_bwd(qp, vrt, dvrtw, gq, gv_); dqp.w += gq.w; dqp.x += gq.x; dqp.y += gq.y; dqp.z += gq.z;
+    stv(gy + 3, gv_);
+    if (t == 0) { dq.w += dqp.w; dq.x += dqp.x; dq.y += dqp.y; dq.z += dqp.z; dqp.w = dqp.x = dqp.y = dqp.z = 0.f; }
+    stv(a.dRootPos + frame * 3, dpos);
+    float* o1 = a.dq_own + frame * 4; o1[0] = dq.w; o1[1] = dq.x; o1[2] = dq.y; o1[3] = dq.z;
+    float* o2 = a.dq_prev + frame * 4; o2[0] = dqp.w; o2[1] = dqp.x; o2[2] = dqp.y; o2[3] = dqp.z;
+  }
+  __syncwarp();
+  for (int i = lane; i < P_OUT; i += 32) a.dY[frame * P_OUT + i] = gy[i];
+}
+
+// forward-only calls (no gradient requested): the four frame-difference sums from the D rows, one warp per frame
+__global__ void __launch_bounds__(256) loss_w_diff_kernel(LossWArgs a) {
+  const int lane = threadIdx.x & 31;
+  const size_t frame = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (frame >= (size_t)a.B * a.T) return;
+  const int t = (int)(frame % a.T);
+  float dsum[4] = {0.f, 0.f, 0.f, 0.f};
+  if (t + 1 < a.T) {
+    const float inv_dt = 1.0f / a.dt;
+    const float* d0 = a.Dd + frame * LW_DD;
+    for (int x = lane; x < LW_DD; x += 32) {
+      const int g = x < NJ * 3 ? 0 : x < NJ * 9 ? 1 : x < NJ * 12 ? 2 : 3;
+      dsum[g] += fabsf((d0[x + LW_DD] - d0[x]) * inv_dt);
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) { const float v = warp_sum(dsum[g]); if (lane == 0) a.partial[frame * LW_NP + 13 + g] = v; }
+}
+
+// deterministic reduction over frames (warp g owns term g: lanes stride the frames, fixed shuffle tree, double) + KL
+__global__ void __launch_bounds__(LW_NP * 32) loss_w_final_kernel(const float* __restrict__ partial, int B, int T, const float* __restrict__ mu,
+                                                                  const float* __restrict__ logvar, int Z, float kl_weight_host,
+                                                                  const float* __restrict__ kl_weight_dev, float* __restrict__ losses,
+                                                                  float* __restrict__ dmu, float* __restrict__ dlogvar) {
+  const float kl_weight = kl_weight_dev ? *kl_weight_dev : kl_weight_host;
+  __shared__ double tsum[LW_NP + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int frames = B * T;
+  double s = 0.0;
+  for (int f = lane; f < frames; f += 32) s += partial[(size_t)f * LW_NP + warp];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    const double BT = (double)B * T;
+    if (warp < 13) tsum[warp] = s * ((double)c_lw_w[warp] / (BT * c_lw_n[warp]));
+    else tsum[warp] = T > 1 ? s * ((double)c_lw_dw[warp - 13] / ((double)B * (T - 1) * c_lw_dn[warp - 13])) : 0.0;
+  }
+  double kl = 0.0;
+  if (mu && logvar) {
+    for (int i = threadIdx.x; i < B * Z; i += blockDim.x) {
+      float m_ = mu[i], lv = logvar[i];
+      kl += -0.5 * (1.0 + lv - (double)m_ * m_ - exp((double)lv));
+      const float gscale = kl_weight / ((float)B * (float)Z) / 18.0f;
+      if (dmu) dmu[i] = gscale * m_;
+      if (dlogvar) dlogvar[i] = gscale * 0.5f * (expf(lv) - 1.0f);
+    }
+  }
+  __shared__ double klw[LW_NP];
+  for (int o = 16; o > 0; o >>= 1) kl += __shfl_xor_sync(0xffffffffu, kl, o);
+  if (lane == 0) klw[warp] = kl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double klt = 0.0;
+    for (int w = 0; w < LW_NP; ++w) klt += klw[w];
+    // losses[1..17]: train.py:397-416 order = terms 0..11, the four difference terms (12..15), gaze (16); [18] = weighted KL
+    double total = 0.0;
+    for (int k = 0; k < 12; ++k) { losses[1 + k] = (float)tsum[k]; total += tsum[k]; }
+    for (int k = 0; k < 4; ++k) { losses[13 + k] = (float)tsum[13 + k]; total += tsum[13 + k]; }
+    losses[17] = (float)tsum[12]; total += tsum[12];
+    const double klterm = (mu && logvar) ? kl_weight * klt / ((double)B * Z) : 0.0;
+    losses[18] = (float)klterm; total += klterm;
+    losses[0] = (float)(total / 18.0);
+  }
+}
+
+struct LossWs { float *Ys[2], *Q[2], *G, *gYs, *partial, *dq_own, *dq_prev; double* chan; float* Dd; float* fpartial; TreeTables* tt; size_t stride; int nblk; size_t bytes; };
 static LossWs loss_ws(void* base, int B, int T) {
   LossWs w; size_t off = 0;
   auto take = [&](size_t n) { float* p = base ? (float*)((char*)base + off) : nullptr; off += ((n * 4 + 255) / 256) * 256; return p; };
@@ -219,8 +619,12 @@ static LossWs loss_ws(void* base, int B, int T) {
   w.partial = take((size_t)Q_CH * w.nblk * 2);
   w.dq_own = take(BT * 4); w.dq_prev = take(BT * 4);
   w.chan = (double*)take((size_t)Q_CH * 4);
+  w.Dd = take(BT * LW_DD); w.fpartial = take(BT * LW_NP); w.tt = (TreeTables*)take(sizeof(TreeTables) / 4 + 1);
   w.bytes = off; return w;
 }
+// 1: warp-per-frame kernels (default), 0: the thread-per-frame SoA version of round 1 (kept as a cross-check)
+static int g_loss_impl = 1;
+extern "C" void zeggs_debug_set_loss_impl(int v) { g_loss_impl = v ? 1 : 0; }
 extern "C" size_t zeggs_loss_workspace_bytes(int B, int T) { return (B < 1 || T < 1) ? 0 : loss_ws(nullptr, B, T).bytes; }
 
 extern "C" int zeggs_loss_fwd_bwd(const zeggs_loss_args* ap, void* stream_) {
@@ -233,6 +637,34 @@ extern "C" int zeggs_loss_fwd_bwd(const zeggs_loss_args* ap, void* stream_) {
   const int BT = a.B * a.T;
   ZCHECK_ARG((long long)a.B * a.T < (1ll << 31), "loss: too many frames");
   ScopedTimer tm("loss", s);
+  if (g_loss_impl == 1) {
+    LossWArgs wa;
+    wa.B = a.B; wa.T = a.T; wa.dt = a.dt;
+    wa.Y[0] = a.Y; wa.Y[1] = a.WY; wa.rp[0] = a.root_pos; wa.rp[1] = a.W_root_pos; wa.rq[0] = a.root_rot; wa.rq[1] = a.W_root_rot;
+    wa.gaze = a.gaze_pos; wa.tt = w.tt; wa.Dd = w.Dd; wa.partial = w.fpartial;
+    wa.dY = a.dY; wa.dRootPos = a.dRootPos; wa.dq_own = w.dq_own; wa.dq_prev = w.dq_prev;
+    static bool attr = false;
+    if (!attr) {
+      ZCHECK_CUDA(cudaFuncSetAttribute(loss_w_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LW_WARPS * LW_FWD_FLOATS * sizeof(float))));
+      ZCHECK_CUDA(cudaFuncSetAttribute(loss_w_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LW_WARPS * LW_BWD_FLOATS * sizeof(float))));
+      attr = true;
+    }
+    loss_tree_kernel<<<1, 32, 0, s>>>(a.parents, w.tt); count_launch();
+    const int nb = ceil_div(BT, LW_WARPS);
+    loss_w_fwd_kernel<<<nb, LW_WARPS * 32, LW_WARPS * LW_FWD_FLOATS * sizeof(float), s>>>(wa); count_launch();
+    if (a.dY) {
+      ZCHECK_ARG(a.dRootPos && a.dRootRot, "loss: gradient outputs missing");
+      loss_w_bwd_kernel<<<nb, LW_WARPS * 32, LW_WARPS * LW_BWD_FLOATS * sizeof(float), s>>>(wa); count_launch();
+      root_rot_combine_kernel<<<ceil_div(BT * 4, 256), 256, 0, s>>>(w.dq_own, w.dq_prev, a.B, a.T, a.dRootRot); count_launch();
+    } else if (a.T > 1) {
+      wa.dY = nullptr;
+      loss_w_diff_kernel<<<ceil_div(BT, 8), 256, 0, s>>>(wa); count_launch();
+    }
+    loss_w_final_kernel<<<1, LW_NP * 32, 0, s>>>(w.fpartial, a.B, a.T, a.mu, a.logvar, a.Z, a.kl_weight, a.kl_weight_dev, a.losses, a.dmu, a.dlogvar);
+    count_launch();
+    ZCHECK_LAUNCH();
+    return ZEGGS_OK;
+  }
   dim3 tb(32, 8);
   transpose_kernel<<<dim3(ceil_div(P_OUT, 32), ceil_div(BT, 32)), tb, 0, s>>>(a.Y, BT, P_OUT, P_OUT, w.Ys[0], (int)w.stride); count_launch();
   transpose_kernel<<<dim3(ceil_div(P_OUT, 32), ceil_div(BT, 32)), tb, 0, s>>>(a.WY, BT, P_OUT, P_OUT, w.Ys[1], (int)w.stride); count_launch();
