@@ -213,9 +213,10 @@ __global__ void root_rot_combine_kernel(const float* __restrict__ own, const flo
 // (245 MB per step, 74-deep dependent chains through L2: 5 % of the machine busy, profiles/r02_ncu_summary.md) are gone; results are
 // bitwise reproducible (fixed shuffle and frame orders).
 //   K1 loss_w_fwd_kernel   FK of the output (lanes 0..15) and of the target (lanes 16..31), D, direct |D| sums, D rows of the diff groups
-//   K2 loss_w_bwd_kernel   recomputes K1's shared-memory state, builds dLoss/dQ in place of the target-side records (direct terms +
-//                          the frame-difference terms from the neighbours' D rows), runs the adjoint FK level by level (children
-//                          publish their contribution, parents gather them in index order), writes the dY row + the root gradients
+//                          + the signs of D (2 x 33 bits per joint) and the output-side FK rotations / angular velocities for K2
+//   K2 loss_w_bwd_kernel   two frames per warp, no forward recompute: builds dLoss/dQ from K1's signs (direct terms) and the
+//                          neighbours' D rows (frame-difference terms), runs the adjoint FK level by level (children publish their
+//                          contribution, parents gather them in index order), writes the dY row + the root gradients
 //   K3 loss_w_final_kernel deterministic reduction over frames + KL
 // The frame-difference residual is evaluated as (D[t+1] - D[t]) / dt with D = Q_out - Q_target (train.py:356-393 computes
 // dQ_out/dt - dQ_target/dt: equal up to fp32 rounding).
@@ -247,12 +248,10 @@ constexpr int LW_WARPS = 4;                      // frames per CTA
 constexpr int R_LPOS = 0, R_LTXY = 3, R_LVEL = 9, R_LVRT = 12, R_GP = 15, R_GR = 18, R_GV = 27, R_GT = 30, LW_REC = 33;
 constexpr int LW_Q = NJ * LW_REC;                // 2475 floats per side
 constexpr int LW_RT = 24;                        // root block: pos3 R9 velw3 vrtw3 gaze3
-constexpr int LW_PUSH = NJ * 18;                 // adjoint hand-over per joint: gr9 gp3 gt3 gv3
-constexpr int LW_GY = 1136;                      // dY row under construction
 constexpr int LW_DD = NJ * 21;                   // 1575: D rows of LPOS (225) | LTXY (450) | CPOS (225) | CMAT (675)
 constexpr int LW_FWD_FLOATS = 2 * LW_Q + 2 * LW_RT;
-constexpr int LW_BWD_FLOATS = LW_FWD_FLOATS + LW_PUSH + LW_GY;
-constexpr int LW_NP = 17;                        // partial sums per frame: terms 0..11, gaze, then the 4 frame-difference terms
+constexpr int LW_NP = 17;
+constexpr int LW_SW = NJ * 4 + 2;                // sign words per frame: joint i -> pos_lo, pos_hi, neg_lo, neg_hi (33 bits each); root pos, neg                        // partial sums per frame: terms 0..11, gaze, then the 4 frame-difference terms
 
 struct LossWArgs {
   int B, T; float dt;
@@ -261,6 +260,8 @@ struct LossWArgs {
   const TreeTables* tt;
   float* Dd;                                     // [frames][LW_DD]
   float* partial;                                // [frames][LW_NP]
+  float* F;                                      // [frames][NJ * 12]: output-side FK results the adjoint needs (gr9, gt3 per joint)
+  unsigned* S;                                   // [frames][LW_SW]: sign masks of D (per joint 2 x (pos, neg) words; root block last)
   float *dY, *dRootPos, *dq_own, *dq_prev;
 };
 
@@ -295,6 +296,13 @@ __device__ __forceinline__ void lw_forward(const LossWArgs& a, const TreeTables&
   const int t = (int)(frame % a.T);
   const float* y = a.Y[side] + frame * P_OUT;
   float* qs = q[side];
+  // local values of every joint: global -> records up front (independent loads: one memory latency instead of one per tree level)
+  for (int i = l16; i < NJ; i += 16) {
+    float* ci = qs + i * LW_REC;
+    stv(ci + R_LPOS, ldv(y + OFF_LPOS + 3 * i)); stv(ci + R_LTXY, ldv(y + OFF_LTXY + 6 * i)); stv(ci + R_LTXY + 3, ldv(y + OFF_LTXY + 6 * i + 3));
+    stv(ci + R_LVEL, ldv(y + OFF_LVEL + 3 * i)); stv(ci + R_LVRT, ldv(y + OFF_LVRT + 3 * i));
+  }
+  __syncwarp();
   if (l16 == 0) {
     const float* q4 = a.rq[side] + frame * 4;
     Q4 qr; qr.w = q4[0]; qr.x = q4[1]; qr.y = q4[2]; qr.z = q4[3];
@@ -306,12 +314,12 @@ __device__ __forceinline__ void lw_forward(const LossWArgs& a, const TreeTables&
     float* r = rt[side];
     stv(r, pos); stm9(r + 3, R); stv(r + 12, velw); stv(r + 15, vrtw);
     stv(r + 18, quat_mul_vec(quat_inv(qr), unit_eps(gz - pos, 1e-8f)));                     // train.py:336-337
-    const V3 lp = ldv(y + OFF_LPOS), lv = ldv(y + OFF_LVEL), lr = ldv(y + OFF_LVRT);
-    const V3 x = ldv(y + OFF_LTXY), yv = ldv(y + OFF_LTXY + 3);
+    const V3 lp = ldv(qs + R_LPOS), lv = ldv(qs + R_LVEL), lr = ldv(qs + R_LVRT);
+    const V3 x = ldv(qs + R_LTXY), yv = ldv(qs + R_LTXY + 3);
     const V3 rp0 = quat_mul_vec(qr, lp);
     const V3 p0 = rp0 + pos, t0 = vrtw + quat_mul_vec(qr, lr), v0 = velw + quat_mul_vec(qr, lv) + cross(vrtw, rp0);
     // joint 0 is compared in world space (train.py:296-305); its raw two-axis rotation stays local
-    stv(qs + R_LPOS, p0); stv(qs + R_LTXY, x); stv(qs + R_LTXY + 3, yv); stv(qs + R_LVEL, v0); stv(qs + R_LVRT, t0);
+    stv(qs + R_LPOS, p0); stv(qs + R_LVEL, v0); stv(qs + R_LVRT, t0);
     stv(qs + R_GP, p0); stm9(qs + R_GR, mm(R, orthogonalize_xy(x, yv))); stv(qs + R_GV, v0); stv(qs + R_GT, t0);
   }
   __syncwarp();
@@ -319,13 +327,12 @@ __device__ __forceinline__ void lw_forward(const LossWArgs& a, const TreeTables&
     for (int k = tt.lvl_off[l] + l16; k < tt.lvl_off[l + 1]; k += 16) {
       const int i = tt.order[k], p = tt.parents[i];
       const float* cp = qs + p * LW_REC;
+      float* ci = qs + i * LW_REC;
       const M3 grp = ldm9(cp + R_GR);
       const V3 gpp = ldv(cp + R_GP), gtp = ldv(cp + R_GT), gvp = ldv(cp + R_GV);
-      const V3 lp = ldv(y + OFF_LPOS + 3 * i), lv = ldv(y + OFF_LVEL + 3 * i), lr = ldv(y + OFF_LVRT + 3 * i);
-      const V3 x = ldv(y + OFF_LTXY + 6 * i), yv = ldv(y + OFF_LTXY + 6 * i + 3);
+      const V3 lp = ldv(ci + R_LPOS), lv = ldv(ci + R_LVEL), lr = ldv(ci + R_LVRT);
+      const V3 x = ldv(ci + R_LTXY), yv = ldv(ci + R_LTXY + 3);
       const V3 rp = mv(grp, lp);
-      float* ci = qs + i * LW_REC;
-      stv(ci + R_LPOS, lp); stv(ci + R_LTXY, x); stv(ci + R_LTXY + 3, yv); stv(ci + R_LVEL, lv); stv(ci + R_LVRT, lr);
       stv(ci + R_GP, gpp + rp); stm9(ci + R_GR, mm(grp, orthogonalize_xy(x, yv))); stv(ci + R_GV, gvp + mv(grp, lv) + cross(gtp, rp));
       stv(ci + R_GT, gtp + mv(grp, lr));
     }
@@ -358,100 +365,144 @@ __global__ void __launch_bounds__(LW_WARPS * 32) loss_w_fwd_kernel(LossWArgs a) 
 #pragma unroll
   for (int g = 0; g < 13; ++g) sum[g] = 0.f;
   float* dd = a.Dd + frame * LW_DD;
+  unsigned* sg = a.S + frame * LW_SW;
+  float* fk = a.F + frame * (NJ * 12);
   for (int i = lane; i < NJ; i += 32) {
     const float* o = q[0] + i * LW_REC; const float* w = q[1] + i * LW_REC;
+    unsigned long long pos = 0ull, neg = 0ull;
 #pragma unroll
     for (int e = 0; e < LW_REC; ++e) {
       const float D = o[e] - w[e];
       sum[rec_group(e)] += fabsf(D);
+      if (D > 0.f) pos |= 1ull << e;
+      if (D < 0.f) neg |= 1ull << e;
       const int x = dd_index(i, e);
       if (x >= 0) dd[x] = D;
     }
+    sg[4 * i] = (unsigned)pos; sg[4 * i + 1] = (unsigned)(pos >> 32); sg[4 * i + 2] = (unsigned)neg; sg[4 * i + 3] = (unsigned)(neg >> 32);
+#pragma unroll
+    for (int m = 0; m < 9; ++m) fk[12 * i + m] = o[R_GR + m];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) fk[12 * i + 9 + m] = o[R_GT + m];
   }
   if (lane == 0) {
     const float* o = rt[0]; const float* w = rt[1];
+    unsigned pos = 0u, neg = 0u;
 #pragma unroll
-    for (int k = 0; k < 21; ++k) sum[k < 3 ? 0 : k < 12 ? 1 : k < 15 ? 2 : k < 18 ? 3 : 12] += fabsf(o[k] - w[k]);
+    for (int k = 0; k < 21; ++k) {
+      const float D = o[k] - w[k];
+      sum[k < 3 ? 0 : k < 12 ? 1 : k < 15 ? 2 : k < 18 ? 3 : 12] += fabsf(D);
+      if (D > 0.f) pos |= 1u << k;
+      if (D < 0.f) neg |= 1u << k;
+    }
+    sg[NJ * 4] = pos; sg[NJ * 4 + 1] = neg;
   }
 #pragma unroll
   for (int g = 0; g < 13; ++g) { const float v = warp_sum(sum[g]); if (lane == 0) a.partial[frame * LW_NP + g] = v; }
 }
 
-__global__ void __launch_bounds__(LW_WARPS * 32) loss_w_bwd_kernel(LossWArgs a) {
+// K2: two frames per warp (lanes 0..15 / 16..31), no forward recompute: the output-side FK results and the signs of D come from K1.
+// Per frame in shared memory: O-records [joint][27] = locals (lpos3 ltxy6 lvel3 lvrt3) + gr9 + gt3 -- a processed joint's record is
+// re-used for its hand-over [gr9 gp3 gt3 gv3] -- and G-records [joint][33] = dLoss/d(record), plus the 21 root gradients.
+constexpr int LB_WARPS = 3;                      // 6 frames per CTA, 2 CTAs per SM
+constexpr int O_LPOS = 0, O_LTXY = 3, O_LVEL = 9, O_LVRT = 12, O_GR = 15, O_GT = 24, LB_OREC = 27;
+constexpr int LB_FRAME_FLOATS = NJ * LB_OREC + NJ * LW_REC + LW_RT;     // 4524
+
+__device__ __forceinline__ float half_sum(float v) {          // sum over the 16 lanes of a half warp
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(LB_WARPS * 32) loss_w_bwd_kernel(LossWArgs a) {
   extern __shared__ float lw_sm[];
   __shared__ TreeTables tt;
   for (int i = threadIdx.x; i < (int)(sizeof(TreeTables) / 4); i += blockDim.x) reinterpret_cast<int*>(&tt)[i] = reinterpret_cast<const int*>(a.tt)[i];
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t frame = (size_t)blockIdx.x * LW_WARPS + warp;
-  if (frame >= (size_t)a.B * a.T) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
+  const size_t nframes = (size_t)a.B * a.T;
+  const size_t frame_raw = ((size_t)blockIdx.x * LB_WARPS + warp) * 2 + half;
+  const bool live = frame_raw < nframes;
+  const size_t frame = live ? frame_raw : nframes - 1;          // a dead half mirrors the last frame (no stores), keeping the warp converged
   const int t = (int)(frame % a.T);
-  float* base = lw_sm + (size_t)warp * LW_BWD_FLOATS;
-  float* const q[2] = {base, base + LW_Q};
-  float* const rt[2] = {base + 2 * LW_Q, base + 2 * LW_Q + LW_RT};
-  float* push = base + LW_FWD_FLOATS;
-  float* gy = push + LW_PUSH;
-  lw_forward(a, tt, frame, lane, q, rt);
-  // ---- dLoss/dQ of the direct terms, in place of the target-side values
+  float* base = lw_sm + ((size_t)warp * 2 + half) * LB_FRAME_FLOATS;
+  float* Q = base;                                   // O-records
+  float* G = base + NJ * LB_OREC;                    // G-records
+  float* gr_ = G + NJ * LW_REC;                      // root gradients (21)
+  const float* y = a.Y[0] + frame * P_OUT;
+  const float* fk = a.F + frame * (NJ * 12);
+  const unsigned* sg = a.S + frame * LW_SW;
+  float* gy = a.dY + frame * P_OUT;
   const float BT = (float)a.B * (float)a.T;
-  for (int i = lane; i < NJ; i += 32) {
-    const float* o = q[0] + i * LW_REC; float* w = q[1] + i * LW_REC;
+  // ---- records: locals from the pose row, FK results and signs from K1; dLoss/dQ of the direct terms
+  for (int i = l16; i < NJ; i += 16) {
+    float* qi = Q + i * LB_OREC;
+    stv(qi + O_LPOS, ldv(y + OFF_LPOS + 3 * i)); stv(qi + O_LTXY, ldv(y + OFF_LTXY + 6 * i)); stv(qi + O_LTXY + 3, ldv(y + OFF_LTXY + 6 * i + 3));
+    stv(qi + O_LVEL, ldv(y + OFF_LVEL + 3 * i)); stv(qi + O_LVRT, ldv(y + OFF_LVRT + 3 * i));
+#pragma unroll
+    for (int m = 0; m < 12; ++m) qi[O_GR + m] = fk[12 * i + m];
+    const unsigned long long pos = (unsigned long long)sg[4 * i] | ((unsigned long long)sg[4 * i + 1] << 32);
+    const unsigned long long neg = (unsigned long long)sg[4 * i + 2] | ((unsigned long long)sg[4 * i + 3] << 32);
+    float* gi = G + i * LW_REC;
 #pragma unroll
     for (int e = 0; e < LW_REC; ++e) {
       const int g = rec_group(e);
-      w[e] = c_lw_w[g] / (BT * c_lw_n[g]) * (1.0f / 18.0f) * sgnf(o[e] - w[e]);
+      const float sc = c_lw_w[g] / (BT * c_lw_n[g]) * (1.0f / 18.0f);
+      gi[e] = ((pos >> e) & 1ull) ? sc : ((neg >> e) & 1ull) ? -sc : 0.f;
     }
   }
-  if (lane == 0) {
-    const float* o = rt[0]; float* w = rt[1];
+  if (l16 == 0) {
+    const unsigned pos = sg[NJ * 4], neg = sg[NJ * 4 + 1];
 #pragma unroll
     for (int k = 0; k < 21; ++k) {
       const int g = k < 3 ? 0 : k < 12 ? 1 : k < 15 ? 2 : k < 18 ? 3 : 12;
-      w[k] = c_lw_w[g] / (BT * c_lw_n[g]) * (1.0f / 18.0f) * sgnf(o[k] - w[k]);
+      const float sc = c_lw_w[g] / (BT * c_lw_n[g]) * (1.0f / 18.0f);
+      gr_[k] = ((pos >> k) & 1u) ? sc : ((neg >> k) & 1u) ? -sc : 0.f;
     }
   }
   __syncwarp();
-  // ---- frame-difference terms (train.py:356-393): e_t = (D[t+1] - D[t]) / dt needs the neighbouring frames' D rows
+  // ---- frame-difference terms (train.py:356-393): e_t = (D[t+1] - D[t]) / dt from the neighbouring frames' D rows, per joint
   float dsum[4] = {0.f, 0.f, 0.f, 0.f};
   if (a.T > 1) {
     const float inv_dt = 1.0f / a.dt;
     const float* d0 = a.Dd + frame * LW_DD;
     const bool has_p = t + 1 < a.T, has_m = t > 0;
-    for (int x = lane; x < LW_DD; x += 32) {
-      int g, i, e;
-      if (x < NJ * 3) { g = 0; i = x / 3; e = R_LPOS + x % 3; }
-      else if (x < NJ * 9) { const int y_ = x - NJ * 3; g = 1; i = y_ / 6; e = R_LTXY + y_ % 6; }
-      else if (x < NJ * 12) { const int y_ = x - NJ * 9; g = 2; i = y_ / 3; e = R_GP + y_ % 3; }
-      else { const int y_ = x - NJ * 12; g = 3; i = y_ / 9; e = R_GR + y_ % 9; }
-      const float D = d0[x];
-      float gd = 0.f;
-      if (has_p) { const float er = (d0[x + LW_DD] - D) * inv_dt; dsum[g] += fabsf(er); gd -= sgnf(er); }
-      if (has_m) { const float el = (D - d0[x - LW_DD]) * inv_dt; gd += sgnf(el); }
-      q[1][i * LW_REC + e] += c_lw_dw[g] * inv_dt * gd / ((float)a.B * (float)(a.T - 1) * c_lw_dn[g]) * (1.0f / 18.0f);
+    const float nd = (float)a.B * (float)(a.T - 1);
+    for (int i = l16; i < NJ; i += 16) {
+      float* gi = G + i * LW_REC;
+      auto run = [&](int x0, int n, int e0, int g) {        // n consecutive D-row entries starting at x0 <-> record elements e0..
+        const float sc = c_lw_dw[g] * inv_dt / (nd * c_lw_dn[g]) * (1.0f / 18.0f);
+        for (int k = 0; k < n; ++k) {
+          const float D = d0[x0 + k];
+          float gd = 0.f;
+          if (has_p) { const float er = (d0[x0 + k + LW_DD] - D) * inv_dt; dsum[g] += fabsf(er); gd -= sgnf(er); }
+          if (has_m) { const float el = (D - d0[x0 + k - LW_DD]) * inv_dt; gd += sgnf(el); }
+          gi[e0 + k] += sc * gd;
+        }
+      };
+      run(3 * i, 3, R_LPOS, 0); run(NJ * 3 + 6 * i, 6, R_LTXY, 1); run(NJ * 9 + 3 * i, 3, R_GP, 2); run(NJ * 12 + 9 * i, 9, R_GR, 3);
     }
   }
 #pragma unroll
-  for (int g = 0; g < 4; ++g) { const float v = warp_sum(dsum[g]); if (lane == 0) a.partial[frame * LW_NP + 13 + g] = v; }
+  for (int g = 0; g < 4; ++g) { const float v = half_sum(dsum[g]); if (l16 == 0 && live) a.partial[frame * LW_NP + 13 + g] = v; }
   __syncwarp();
-  // ---- adjoint FK, deepest level first.  G = q[1] (dLoss/d record), accumulated with the children's hand-overs.
-  float* G = q[1];
-  const float* Q = q[0];
+  // ---- adjoint FK, deepest level first: a joint gathers its children's hand-overs, then publishes its own in its (dead) O-record
   for (int l = tt.nlev - 1; l >= 1; --l) {
-    for (int k = tt.lvl_off[l] + lane; k < tt.lvl_off[l + 1]; k += 32) {
+    for (int k = tt.lvl_off[l] + l16; k < tt.lvl_off[l + 1]; k += 16) {
       const int i = tt.order[k], p = tt.parents[i];
       float* gi = G + i * LW_REC;
-      for (int cc = tt.child_off[i]; cc < tt.child_off[i + 1]; ++cc) {       // children publish [gr9 gp3 gt3 gv3]
-        const float* ps = push + tt.child_idx[cc] * 18;
+      for (int cc = tt.child_off[i]; cc < tt.child_off[i + 1]; ++cc) {
+        const float* ps = Q + tt.child_idx[cc] * LB_OREC;
 #pragma unroll
         for (int m = 0; m < 9; ++m) gi[R_GR + m] += ps[m];
 #pragma unroll
         for (int m = 0; m < 3; ++m) { gi[R_GP + m] += ps[9 + m]; gi[R_GT + m] += ps[12 + m]; gi[R_GV + m] += ps[15 + m]; }
       }
-      const float* qi = Q + i * LW_REC; const float* qp = Q + p * LW_REC;
-      const V3 lp = ldv(qi + R_LPOS), lv = ldv(qi + R_LVEL), lr = ldv(qi + R_LVRT), x = ldv(qi + R_LTXY), yv = ldv(qi + R_LTXY + 3);
+      float* qi = Q + i * LB_OREC; const float* qp = Q + p * LB_OREC;
+      const V3 lp = ldv(qi + O_LPOS), lv = ldv(qi + O_LVEL), lr = ldv(qi + O_LVRT), x = ldv(qi + O_LTXY), yv = ldv(qi + O_LTXY + 3);
       const M3 lm = orthogonalize_xy(x, yv);
-      const M3 grp = ldm9(qp + R_GR);
-      const V3 gtp = ldv(qp + R_GT);
+      const M3 grp = ldm9(qp + O_GR);
+      const V3 gtp = ldv(qp + O_GT);
       const V3 rp = mv(grp, lp);
       const V3 dgp = ldv(gi + R_GP), dgt = ldv(gi + R_GT), dgv = ldv(gi + R_GV);
       const M3 dgr = ldm9(gi + R_GR);
@@ -460,41 +511,39 @@ __global__ void __launch_bounds__(LW_WARPS * 32) loss_w_bwd_kernel(LossWArgs a) 
       add_outer(acc, dgv, lv);                              // gv[i] += gr[p] lvel
       add_outer(acc, dgt, lr);                              // gt[i]  = gt[p] + gr[p] lvrt
       add_outer(acc, drp, lp);                              // rp = gr[p] lpos
-      float* ps = push + i * 18;
-      stm9(ps, acc); stv(ps + 9, dgp); stv(ps + 12, dgt + cross(rp, dgv)); stv(ps + 15, dgv);
-      // local quantities of joint i: direct L1 terms + FK
-      stv(gy + OFF_LPOS + 3 * i, ldv(gi + R_LPOS) + mtv(grp, drp));
-      stv(gy + OFF_LVEL + 3 * i, ldv(gi + R_LVEL) + mtv(grp, dgv));
-      stv(gy + OFF_LVRT + 3 * i, ldv(gi + R_LVRT) + mtv(grp, dgt));
-      V3 dx, dyv;
-      orthogonalize_xy_bwd(x, yv, mtm(grp, dgr), dx, dyv);
-      stv(gy + OFF_LTXY + 6 * i, ldv(gi + R_LTXY) + dx);
-      stv(gy + OFF_LTXY + 6 * i + 3, ldv(gi + R_LTXY + 3) + dyv);
+      stm9(qi, acc); stv(qi + 9, dgp); stv(qi + 12, dgt + cross(rp, dgv)); stv(qi + 15, dgv);
+      if (live) {       // local quantities of joint i: direct L1 terms + FK
+        stv(gy + OFF_LPOS + 3 * i, ldv(gi + R_LPOS) + mtv(grp, drp));
+        stv(gy + OFF_LVEL + 3 * i, ldv(gi + R_LVEL) + mtv(grp, dgv));
+        stv(gy + OFF_LVRT + 3 * i, ldv(gi + R_LVRT) + mtv(grp, dgt));
+        V3 dx, dyv;
+        orthogonalize_xy_bwd(x, yv, mtm(grp, dgr), dx, dyv);
+        stv(gy + OFF_LTXY + 6 * i, ldv(gi + R_LTXY) + dx);
+        stv(gy + OFF_LTXY + 6 * i + 3, ldv(gi + R_LTXY + 3) + dyv);
+      }
     }
     __syncwarp();
   }
-  // ---- joint 0 + root terms (one lane; the serial tail of the chain)
-  if (lane == 0) {
+  // ---- joint 0 + root terms (one lane per frame; the serial tail of the chain)
+  if (l16 == 0 && live) {
     float* g0 = G;
     for (int cc = tt.child_off[0]; cc < tt.child_off[1]; ++cc) {
-      const float* ps = push + tt.child_idx[cc] * 18;
+      const float* ps = Q + tt.child_idx[cc] * LB_OREC;
 #pragma unroll
       for (int m = 0; m < 9; ++m) g0[R_GR + m] += ps[m];
 #pragma unroll
       for (int m = 0; m < 3; ++m) { g0[R_GP + m] += ps[9 + m]; g0[R_GT + m] += ps[12 + m]; g0[R_GV + m] += ps[15 + m]; }
     }
-    const float* y = a.Y[0] + frame * P_OUT;
     const float* q4 = a.rq[0] + frame * 4;
     Q4 qr; qr.w = q4[0]; qr.x = q4[1]; qr.y = q4[2]; qr.z = q4[3];
     Q4 qp = qr;
     if (t > 0) { qp.w = q4[-4]; qp.x = q4[-3]; qp.y = q4[-2]; qp.z = q4[-1]; }
     const V3 pos = ldv(a.rp[0] + frame * 3), gz = ldv(a.gaze + frame * 3);
     const M3 R = quat_to_xform(qr);
-    const V3 lp = ldv(y + OFF_LPOS), lv = ldv(y + OFF_LVEL), lr = ldv(y + OFF_LVRT), x = ldv(y + OFF_LTXY), yv = ldv(y + OFF_LTXY + 3);
+    const V3 lp = ldv(Q + O_LPOS), lv = ldv(Q + O_LVEL), lr = ldv(Q + O_LVRT), x = ldv(Q + O_LTXY), yv = ldv(Q + O_LTXY + 3);   // joint 0's raw locals
     const V3 vel = ldv(y), vrt = ldv(y + 3);
     const V3 vrtw = quat_mul_vec(qp, vrt);
     const V3 rp0 = quat_mul_vec(qr, lp);
-    const float* gr_ = rt[1];                                  // dLoss/d(root block)
     // joint 0 receives the local (world-space) and the FK-root gradients
     const V3 dp0 = ldv(g0 + R_LPOS) + ldv(g0 + R_GP);
     const V3 dv0 = ldv(g0 + R_LVEL) + ldv(g0 + R_GV);
@@ -537,8 +586,6 @@ __global__ void __launch_bounds__(LW_WARPS * 32) loss_w_bwd_kernel(LossWArgs a) 
     float* o1 = a.dq_own + frame * 4; o1[0] = dq.w; o1[1] = dq.x; o1[2] = dq.y; o1[3] = dq.z;
     float* o2 = a.dq_prev + frame * 4; o2[0] = dqp.w; o2[1] = dqp.x; o2[2] = dqp.y; o2[3] = dqp.z;
   }
-  __syncwarp();
-  for (int i = lane; i < P_OUT; i += 32) a.dY[frame * P_OUT + i] = gy[i];
 }
 
 // forward-only calls (no gradient requested): the four frame-difference sums from the D rows, one warp per frame
@@ -605,7 +652,7 @@ __global__ void __launch_bounds__(LW_NP * 32) loss_w_final_kernel(const float* _
   }
 }
 
-struct LossWs { float *Ys[2], *Q[2], *G, *gYs, *partial, *dq_own, *dq_prev; double* chan; float* Dd; float* fpartial; TreeTables* tt; size_t stride; int nblk; size_t bytes; };
+struct LossWs { float *Ys[2], *Q[2], *G, *gYs, *partial, *dq_own, *dq_prev; double* chan; float* Dd; float* fpartial; TreeTables* tt; float* F; unsigned* S; size_t stride; int nblk; size_t bytes; };
 static LossWs loss_ws(void* base, int B, int T) {
   LossWs w; size_t off = 0;
   auto take = [&](size_t n) { float* p = base ? (float*)((char*)base + off) : nullptr; off += ((n * 4 + 255) / 256) * 256; return p; };
@@ -620,6 +667,7 @@ static LossWs loss_ws(void* base, int B, int T) {
   w.dq_own = take(BT * 4); w.dq_prev = take(BT * 4);
   w.chan = (double*)take((size_t)Q_CH * 4);
   w.Dd = take(BT * LW_DD); w.fpartial = take(BT * LW_NP); w.tt = (TreeTables*)take(sizeof(TreeTables) / 4 + 1);
+  w.F = take(BT * NJ * 12); w.S = (unsigned*)take(BT * LW_SW);
   w.bytes = off; return w;
 }
 // 1: warp-per-frame kernels (default), 0: the thread-per-frame SoA version of round 1 (kept as a cross-check)
@@ -641,12 +689,12 @@ extern "C" int zeggs_loss_fwd_bwd(const zeggs_loss_args* ap, void* stream_) {
     LossWArgs wa;
     wa.B = a.B; wa.T = a.T; wa.dt = a.dt;
     wa.Y[0] = a.Y; wa.Y[1] = a.WY; wa.rp[0] = a.root_pos; wa.rp[1] = a.W_root_pos; wa.rq[0] = a.root_rot; wa.rq[1] = a.W_root_rot;
-    wa.gaze = a.gaze_pos; wa.tt = w.tt; wa.Dd = w.Dd; wa.partial = w.fpartial;
+    wa.gaze = a.gaze_pos; wa.tt = w.tt; wa.Dd = w.Dd; wa.partial = w.fpartial; wa.F = w.F; wa.S = w.S;
     wa.dY = a.dY; wa.dRootPos = a.dRootPos; wa.dq_own = w.dq_own; wa.dq_prev = w.dq_prev;
     static bool attr = false;
     if (!attr) {
       ZCHECK_CUDA(cudaFuncSetAttribute(loss_w_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LW_WARPS * LW_FWD_FLOATS * sizeof(float))));
-      ZCHECK_CUDA(cudaFuncSetAttribute(loss_w_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LW_WARPS * LW_BWD_FLOATS * sizeof(float))));
+      ZCHECK_CUDA(cudaFuncSetAttribute(loss_w_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LB_WARPS * 2 * LB_FRAME_FLOATS * sizeof(float))));
       attr = true;
     }
     loss_tree_kernel<<<1, 32, 0, s>>>(a.parents, w.tt); count_launch();
@@ -654,7 +702,7 @@ extern "C" int zeggs_loss_fwd_bwd(const zeggs_loss_args* ap, void* stream_) {
     loss_w_fwd_kernel<<<nb, LW_WARPS * 32, LW_WARPS * LW_FWD_FLOATS * sizeof(float), s>>>(wa); count_launch();
     if (a.dY) {
       ZCHECK_ARG(a.dRootPos && a.dRootRot, "loss: gradient outputs missing");
-      loss_w_bwd_kernel<<<nb, LW_WARPS * 32, LW_WARPS * LW_BWD_FLOATS * sizeof(float), s>>>(wa); count_launch();
+      loss_w_bwd_kernel<<<ceil_div(BT, LB_WARPS * 2), LB_WARPS * 32, LB_WARPS * 2 * LB_FRAME_FLOATS * sizeof(float), s>>>(wa); count_launch();
       root_rot_combine_kernel<<<ceil_div(BT * 4, 256), 256, 0, s>>>(w.dq_own, w.dq_prev, a.B, a.T, a.dRootRot); count_launch();
     } else if (a.T > 1) {
       wa.dY = nullptr;
