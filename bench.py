@@ -243,20 +243,29 @@ def run_ours(args):
         h2d = sum(v.numel() * v.element_size() for v in hbatch.values())
         # the public input pipeline (zeggs_b200.data.DevicePrefetcher, used by train()): every step's batch is copied from pinned
         # host memory inside the timed region, on a side stream, while the previous step's kernels run
-        from zeggs_b200.data import DevicePrefetcher
+        # ... and every step's loss is read back (4 bytes) through the package's LaggedScalarReader: the value of step i reaches the
+        # host while step i+1 runs (all K values are on the host before the clock stops)
+        from zeggs_b200.data import DevicePrefetcher, LaggedScalarReader
         pf = DevicePrefetcher(device)
         for _ in range(2):
             stepper.step(pf.acquire(pf.upload(hbatch))).item()
         barrier()
-        t0 = time.perf_counter()
+        rd = LaggedScalarReader(device, lag=int(os.environ.get("ZEGGS_BENCH_LOSS_LAG", "1")))
+        got = []
+        # steady state of the input pipeline: the batch of the first timed step is already in flight when the clock starts and the
+        # batch of step K+1 is uploaded during step K, so exactly K host->device copies (one per step) run inside the timed region
         tok = pf.upload(hbatch)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
         for i in range(K):
             db = pf.acquire(tok)
-            if i + 1 < K:
-                tok = pf.upload(hbatch)
-            float(stepper.step(db).item())
+            tok = pf.upload(hbatch)
+            got += rd.push(stepper.step(db))
+        got += rd.drain()
         torch.cuda.synchronize()
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        assert len(got) == K and all(np.isfinite(got)), got
         barrier()
         r = dict(ms=ms, e2e_ms=e2e_ms, launches=launches, clocks=clocks, spans=spans, span_src=span_src, h2d=h2d, loss=float(loss.item()),
                  P=P, stats=stats, graphed=graphed, host_enqueue_ms=host_enqueue_ms, ar_ms=ar_ms)

@@ -185,6 +185,10 @@ typedef struct {
   size_t workspace_bytes;
   const void* packed_bwd_tc; /* tensor-core engine (fwd args' engine == 1): zeggs_decoder_pack_weights_bwd_tc output, or NULL */
   void* workspace_tc;        /* zeggs_decoder_bwd_tc_workspace_bytes bytes (bf16 gradient images) */
+  int phase;                 /* 0: everything.  Tensor-core engine only: 1 = BPTT recurrence + CellStateEncoder gradients + dSpeech / dStyle
+                                (what the encoders' backward passes wait for), 2 = all remaining parameter gradients (same args, same
+                                stream or one ordered after phase 1; the ctx scratch must not be used by other calls in between).
+                                Other engines do all the work in phase 1 and return at once from phase 2. */
 } zeggs_decoder_bwd_args;
 size_t zeggs_decoder_packed_bwd_bytes(int H, int S, int Z);
 int zeggs_decoder_pack_weights_bwd(const zeggs_decoder_fwd_args* a, float* packed, void* stream);

@@ -102,11 +102,15 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
   const float m1 = s1 / D, m2 = s2 / D, rs = rstd[row];
   for (int i = lane; i < D; i += 32) dx[(size_t)row * D + i] = rs * (pd[i] * gamma[i] - m1 - px[i] * m2);
 }
-// Column reductions over many rows, two stages (deterministic): stage 1 grid (ceil(D/32), RB), block (32,8) writes
-// partial[rb][2][D]; stage 2 sums the RB partials.  mode 0: out0 = sum_r a[r][d];  mode 1: out0 = sum a*b, out1 = sum a.
+// Column reductions over many rows in ONE launch (deterministic): grid (ceil(D/32), RB), block (32,8); every block writes its
+// partial[rb][2][D] sums, the LAST block to arrive for a column group (device counter, reset by that block so the next launch finds
+// zeros) adds the RB partials in a fixed order.  mode 0: out0 = sum_r a[r][d];  mode 1: out0 = sum a*b, out1 = sum a.
 constexpr int COLRED_RB = 64;
-__global__ void colred_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, int rows, int D, float* __restrict__ partial) {
+constexpr int COLRED_MAXD = 4096;
+__global__ void colred_kernel(const float* __restrict__ a, const float* __restrict__ b, int rows, int D, float* partial, int* counters,
+                              float* __restrict__ out0, float* __restrict__ out1) {
   __shared__ float s0[8][33], s1[8][33];
+  __shared__ int last;
   const int d = blockIdx.x * 32 + threadIdx.x;
   const int per = (rows + gridDim.y - 1) / gridDim.y;
   const int r_lo = blockIdx.y * per, r_hi = min(rows, r_lo + per);
@@ -122,15 +126,30 @@ __global__ void colred_partial_kernel(const float* __restrict__ a, const float* 
     for (int r = 1; r < 8; ++r) { x += s0[r][threadIdx.x]; y += s1[r][threadIdx.x]; }
     partial[((size_t)blockIdx.y * 2) * D + d] = x;
     partial[((size_t)blockIdx.y * 2 + 1) * D + d] = y;
+    __threadfence();
   }
-}
-__global__ void colred_final_kernel(const float* __restrict__ partial, int RB, int D, float* __restrict__ out0, float* __restrict__ out1) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= D) return;
-  float x = 0.f, y = 0.f;
-  for (int rb = 0; rb < RB; ++rb) { x += partial[((size_t)rb * 2) * D + d]; y += partial[((size_t)rb * 2 + 1) * D + d]; }
-  out0[d] = x;
-  if (out1) out1[d] = y;
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    const int t = atomicAdd(&counters[blockIdx.x], 1);
+    last = (t == (int)gridDim.y - 1);
+    if (last) counters[blockIdx.x] = 0;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  x = 0.f; y = 0.f;
+  if (d < D)
+    for (int rb = threadIdx.y; rb < (int)gridDim.y; rb += 8) {
+      x += __ldcg(&partial[((size_t)rb * 2) * D + d]);
+      y += __ldcg(&partial[((size_t)rb * 2 + 1) * D + d]);
+    }
+  s0[threadIdx.y][threadIdx.x] = x; s1[threadIdx.y][threadIdx.x] = y;
+  __syncthreads();
+  if (threadIdx.y == 0 && d < D) {
+    for (int r = 1; r < 8; ++r) { x += s0[r][threadIdx.x]; y += s1[r][threadIdx.x]; }
+    out0[d] = x;
+    if (out1) out1[d] = y;
+  }
 }
 // row-wise softmax (+ dropout multiplier) over rows of length L:  P = softmax(S);  Pd = P * mask
 __global__ void softmax_rows_kernel(const float* __restrict__ S, const float* __restrict__ mask, size_t rows, int L,
@@ -231,10 +250,13 @@ static int ln_fwd(const float* a, const float* res, const float* g, const float*
   layernorm_fwd_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(a, res, g, b, rows, D, y, xh, rs); LAUNCH_OK(); return 0; }
 static thread_local float* g_redbuf = nullptr;   // [COLRED_RB][2][D <= 4096] scratch inside the calling module's workspace (per host thread: re-entrant)
 static int colred(const float* a, const float* b, int rows, int D, float* out0, float* out1, cudaStream_t s) {
-  ZCHECK_ARG(g_redbuf != nullptr && D <= 4096, "column reduction: scratch missing or D=%d too wide", D);
+  ZCHECK_ARG(g_redbuf != nullptr && D <= COLRED_MAXD, "column reduction: scratch missing or D=%d too wide", D);
   const int RB = rows < 8 * COLRED_RB ? ceil_div(rows, 8) : COLRED_RB;
-  colred_partial_kernel<<<dim3(ceil_div(D, 32), RB), dim3(32, 8), 0, s>>>(a, b, rows, D, g_redbuf); LAUNCH_OK();
-  colred_final_kernel<<<ceil_div(D, 256), 256, 0, s>>>(g_redbuf, RB, D, out0, out1); LAUNCH_OK(); return 0; }
+  int* counters = reinterpret_cast<int*>(g_redbuf + (size_t)COLRED_RB * 2 * COLRED_MAXD);
+  colred_kernel<<<dim3(ceil_div(D, 32), RB), dim3(32, 8), 0, s>>>(a, b, rows, D, g_redbuf, counters, out0, out1); LAUNCH_OK(); return 0; }
+// the arrival counters behind the partials must be zero before the first reduction of a call (the workspace is caller memory)
+static int colred_reset(cudaStream_t s) {
+  ZCHECK_CUDA(cudaMemsetAsync(g_redbuf + (size_t)COLRED_RB * 2 * COLRED_MAXD, 0, (COLRED_MAXD / 32) * sizeof(int), s)); return 0; }
 static int ln_bwd(const float* dy, const float* xh, const float* rs, const float* g, int rows, int D, float* dx, float* dg, float* db, cudaStream_t s) {
   layernorm_bwd_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(dy, xh, rs, g, rows, D, dx); LAUNCH_OK();
   return colred(dy, xh, rows, D, dg, db, s); }
@@ -257,7 +279,7 @@ static SpeechWs speech_ws(void* base, int B, int T, int Cin, int H, int O, int k
   SpeechWs w; const size_t R = (size_t)B * T;
   w.h0 = a.take(R * H); w.h0d = a.take(R * H); w.col1 = a.take(R * H * k); w.h1 = a.take(R * O); w.h1d = a.take(R * O);
   w.t0 = a.take(R * (H > O ? H : O)); w.t1 = a.take(R * (H > O ? H : O)); w.dcol = a.take(R * H * k);
-  w.red = a.take((size_t)COLRED_RB * 2 * 4096);
+  w.red = a.take((size_t)COLRED_RB * 2 * COLRED_MAXD + COLRED_MAXD / 32);
   w.bytes = a.off; return w;
 }
 extern "C" size_t zeggs_speech_enc_workspace_bytes(int B, int T, int Cin, int H, int O) {
@@ -288,6 +310,7 @@ extern "C" int zeggs_speech_enc_bwd(const zeggs_speech_enc_args* ap, const zeggs
   const int B = a.B, T = a.T, Cin = a.C_in, H = a.H, O = a.O, k = 31, M = B * T;
   SpeechWs w = speech_ws(a.workspace, B, T, Cin, H, O, k);
   g_redbuf = w.red;
+  RC(colred_reset(s));
   ScopedTimer tm("encoders_bwd", s);
   RC(ew_mul(w.t0, g.dy, nullptr, a.y, 1, (size_t)M * O, s));                        // dpre2 = dy * ELU'(y)
   RC(lin_bwd(w.t0, w.h1d, a.W2, g.dW2, g.db2, w.t1, M, O, O, s));                   // t1 = d h1d
@@ -319,7 +342,7 @@ static StyleWs style_ws(void* base, int B, int T, int Cin, int Hs, int E, int nh
   const size_t big = Hs > 3 * E ? Hs : 3 * E;
   w.g0 = a.take(R * big); w.g1 = a.take(R * big); w.g2 = a.take(R * big); w.gqkv = a.take(R * 3 * E);
   w.gcol = a.take(R * (size_t)(Hs * 3 > E * 3 ? Hs * 3 : E * 3));
-  w.red = a.take((size_t)COLRED_RB * 2 * 4096);
+  w.red = a.take((size_t)COLRED_RB * 2 * COLRED_MAXD + COLRED_MAXD / 32);
   w.bytes = a.off; return w;
 }
 extern "C" size_t zeggs_style_enc_workspace_bytes(int B, int T, int Cin, int Hs, int E, int nheads) {
@@ -380,6 +403,7 @@ extern "C" int zeggs_style_enc_bwd(const zeggs_style_enc_args* ap, const zeggs_s
   const long long TT = (long long)T * T;
   const size_t nE = (size_t)M * E;
   g_redbuf = w.red;
+  RC(colred_reset(s));
   ScopedTimer tm("encoders_bwd", s);
   // VAE sample + mean pool
   vae_sample_bwd_kernel<<<ceil_div(B * (E / 2), 256), 256, 0, s>>>(g.dz, g.dmu, g.dlogvar, a.eps, a.logvar, B, E / 2, 1.0f / a.temperature, w.pooled); LAUNCH_OK();

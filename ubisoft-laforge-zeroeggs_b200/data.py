@@ -189,3 +189,40 @@ class DevicePrefetcher:
         cur.wait_event(ev)
         self.last = k
         return views
+
+
+class LaggedScalarReader:
+    """Per-step device->host read of a scalar result (the loss) without draining the GPU: `push` enqueues a 4-byte copy into a
+    pinned ring behind the step that produced the value and returns the values of the steps whose copies have certainly landed
+    (those pushed `lag` calls ago); `drain` waits for the rest.  Every step's loss still reaches the host, one step late, so
+    the next step's launches are enqueued while the current one runs (train.py:424-431 reads `loss.item()` synchronously)."""
+
+    def __init__(self, device, lag=1, depth=8):
+        self.device = torch.device(device)
+        self.lag = lag
+        self.ring = torch.empty(depth, dtype=torch.float32).pin_memory()
+        self.pending = []                                 # (slot, event)
+        self.n = 0
+
+    def push(self, value):
+        slot = self.n % self.ring.numel()
+        self.n += 1
+        self.ring[slot:slot + 1].copy_(value.detach().reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.pending.append((slot, ev))
+        out = []
+        while len(self.pending) > self.lag:
+            s, e = self.pending.pop(0)
+            e.synchronize()
+            out.append(float(self.ring[s]))
+        return out
+
+    def drain(self):
+        out = []
+        while self.pending:
+            s, e = self.pending.pop(0)
+            e.synchronize()
+            out.append(float(self.ring[s]))
+        return out
+

@@ -37,6 +37,13 @@ WS = _Workspace()
 _scratch = {}
 _ctx = {}
 GEMM_MODE = 1          # 0: fp32 SIMT everywhere, 1: tcgen05 split-bf16 (~fp32 accuracy), 2: tcgen05 plain bf16
+# experiment knob: with the tensor-core recurrence engine selected, run the batched GEMMs (encoders, hoisted terms, fold matrix) as ONE
+# bf16 pass instead of the 3-pass split-bf16 scheme
+TC_GEMM_BF16 = __import__("os").environ.get("ZEGGS_TC_GEMM_BF16", "0") == "1"
+
+
+def _effective_gemm_mode():
+    return 2 if (TC_GEMM_BF16 and GEMM_MODE == 1 and DECODER_ENGINE != "fp32") else GEMM_MODE
 
 
 def set_gemm_mode(mode):
@@ -46,28 +53,53 @@ def set_gemm_mode(mode):
         raise _lib.ZeggsError("gemm mode must be 0 (fp32 SIMT), 1 (tcgen05 bf16x3) or 2 (tcgen05 bf16)")
     GEMM_MODE = mode
     for c in _ctx.values():
-        c.gemm_mode = mode
+        c.gemm_mode = _effective_gemm_mode()
+
+
+# Lanes: calls that run CONCURRENTLY on different CUDA streams (the two encoders next to each other, the encoders' backward next to the
+# decoder's weight-gradient GEMMs) must not share the GEMM front end's scratch buffer.  `with ops.lane("speech"):` makes every call issued
+# inside the block travel with that lane's own zeggs_ctx (own scratch); the default lane is "main".
+_lane_local = __import__("threading").local()
+
+
+def current_lane():
+    return getattr(_lane_local, "name", "main")
+
+
+class lane:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        self.prev = current_lane()
+        _lane_local.name = self.name
+        return self
+
+    def __exit__(self, *exc):
+        _lane_local.name = self.prev
+        return False
 
 
 def ensure_scratch(dev):
-    """Caller-owned scratch for the tcgen05 GEMM front end (bf16 operand copies); ZEGGS_SCRATCH_MB overrides the size.  The buffer,
-    the GEMM mode and the weight-gradient mode travel to the library in a per-device zeggs_ctx passed with every call (ctx_ptr):
-    the library keeps no mutable global state for them."""
+    """Caller-owned scratch for the tcgen05 GEMM front end (bf16 operand copies); ZEGGS_SCRATCH_MB (main lane) / ZEGGS_LANE_SCRATCH_MB
+    (side lanes) override the size.  The buffer, the GEMM mode and the weight-gradient mode travel to the library in a per-(device, lane)
+    zeggs_ctx passed with every call (ctx_ptr): the library keeps no mutable global state for them."""
     import os
-    key = str(dev)
+    ln = current_lane()
+    key = (str(dev), ln)
     if key not in _scratch:
-        mb = int(os.environ.get("ZEGGS_SCRATCH_MB", "1536"))
+        mb = int(os.environ.get("ZEGGS_SCRATCH_MB", "1536")) if ln == "main" else int(os.environ.get("ZEGGS_LANE_SCRATCH_MB", "768"))
         buf = torch.empty(mb << 20, dtype=torch.uint8, device=dev)
         _scratch[key] = buf
-        _ctx[key] = _lib.Ctx(scratch=buf.data_ptr(), scratch_bytes=buf.numel(), gemm_mode=GEMM_MODE,
+        _ctx[key] = _lib.Ctx(scratch=buf.data_ptr(), scratch_bytes=buf.numel(), gemm_mode=_effective_gemm_mode(),
                              fast_wgrad=0 if DECODER_ENGINE == "fp32" else 1)
     return _scratch[key]
 
 
 def ctx_ptr(dev):
-    """Address of this device's zeggs_ctx (for the `ctx` field of the args structs)."""
+    """Address of the current lane's zeggs_ctx on this device (for the `ctx` field of the args structs)."""
     ensure_scratch(dev)
-    return C.addressof(_ctx[str(dev)])
+    return C.addressof(_ctx[(str(dev), current_lane())])
 
 
 _weights_epoch = 0
@@ -94,6 +126,7 @@ def set_decoder_engine(name):
     # the tensor-core engine's weight gradients are single-pass bf16: the encoders' weight-gradient GEMMs follow it
     for c in _ctx.values():
         c.fast_wgrad = 0 if name == "fp32" else 1
+        c.gemm_mode = _effective_gemm_mode()
 
 
 def resolve_engine(H, S, Z):
@@ -218,9 +251,12 @@ def _grad_targets(weights, grads_out):
     return list(grads_out)
 
 
-def decoder_window_backward(dec, state, dY, dRp, dRq, grads_out=None):
+def decoder_window_backward(dec, state, dY, dRp, dRq, grads_out=None, split=False):
     """BPTT of one decoder window (zeggs_decoder_window_bwd).  state = the 4th result of decoder_window_forward(save=True).
-    Returns (weight gradients in dec._weights() order, dSpeech [B,T,S], dStyle [B,T,Z])."""
+    Returns (weight gradients in dec._weights() order, dSpeech [B,T,S], dStyle [B,T,Z]).
+    split=True: run phase 1 only (recurrence, CellStateEncoder gradients, dSpeech / dStyle) and return a 4th value `finish`;
+    calling it issues phase 2 (all remaining parameter gradients) on the then-current stream of the same lane -- the caller may run the
+    encoders' backward passes on other streams / lanes in between."""
     l = _lib.lib()
     a, keep, ws = state
     dev = ws.device
@@ -266,8 +302,17 @@ def decoder_window_backward(dec, state, dY, dRp, dRq, grads_out=None):
     wsb = l.zeggs_decoder_bwd_workspace_bytes(B, T, H, S, Z)
     bws = WS.get("dec_bwd", wsb, dev)
     b.workspace, b.workspace_bytes = bws.data_ptr(), wsb
-    _lib.check(l.zeggs_decoder_window_bwd(a, b, _lib.stream_ptr()), "zeggs_decoder_window_bwd")
-    return grads, dSpeech, dStyle
+    if not split:
+        _lib.check(l.zeggs_decoder_window_bwd(a, b, _lib.stream_ptr()), "zeggs_decoder_window_bwd")
+        return grads, dSpeech, dStyle
+    b.phase = 1
+    _lib.check(l.zeggs_decoder_window_bwd(a, b, _lib.stream_ptr()), "zeggs_decoder_window_bwd (phase 1)")
+
+    def finish():
+        b.phase = 2
+        _lib.check(l.zeggs_decoder_window_bwd(a, b, _lib.stream_ptr()), "zeggs_decoder_window_bwd (phase 2)")
+        return hold, bws, grads, state        # everything phase 2 reads stays referenced until it has been issued
+    return grads, dSpeech, dStyle, finish
 
 
 def loss_fwd_bwd(Y, rp, rq, WY, Wrp, Wrq, gaze, parents_i32, dt, mu, logvar, kl_weight, terms_out=None, kl_weight_dev=None):
@@ -453,6 +498,7 @@ def speech_encoder_fwd(enc, x, masks):
 
 def speech_encoder_bwd(state, dy, grads_out=None):
     a, keep, x, masks, y, ws, weights = state
+    a.ctx = ctx_ptr(x.device)              # the lane this call is issued from (may differ from the forward's)
     dy = dy.contiguous().float()
     grads = _grad_targets(weights, grads_out)
     g = _lib.SpeechEncGrads(dy=dy.data_ptr())
@@ -513,6 +559,7 @@ def style_encoder_fwd(enc, x, eps, masks, temperature):
 
 def style_encoder_bwd(state, dz, dmu, dlv, grads_out=None):
     a, keep, x, eps, masks, outs, ws, weights = state
+    a.ctx = ctx_ptr(x.device)              # the lane this call is issued from (may differ from the forward's)
     g = _lib.StyleEncGrads()
     hold = []
     for n, t in (("dz", dz), ("dmu", dmu), ("dlogvar", dlv)):

@@ -64,6 +64,15 @@ class TrainStep:
         self.graph_min_seen = 1            # eager steps on a new batch geometry before it is captured
         self.graph_launches = 0            # library launches captured per replay (gpu_launches accounting)
         self.ar_events = None              # set to [] to record (start, end) CUDA events around every all-reduce
+        # concurrent lanes: SpeechEncoder next to StyleEncoder in the forward; in the backward both encoders next to the decoder's
+        # weight-gradient GEMMs (the many small, latency-bound encoder kernels fill the tail waves of the large GEMMs).  Each lane
+        # has its own stream and its own GEMM scratch (ops.lane); fork/join by events, so the pattern captures into the graph as
+        # parallel branches.
+        import os
+        self.lanes = self.dev.type == "cuda" and os.environ.get("ZEGGS_LANES", "1") == "1"
+        # the side lanes carry the short latency-bound kernels: high priority, so their CTAs are placed ahead of the queued GEMM tiles
+        prio = -1 if os.environ.get("ZEGGS_LANE_PRIORITY", "1") == "1" else 0
+        self._lane_streams = [torch.cuda.Stream(self.dev, priority=prio), torch.cuda.Stream(self.dev, priority=prio)] if self.lanes else None
 
     def forward_backward(self, batch, eps=None, masks=None, train_mode=True):
         """batch: dict of DEVICE tensors: audio[B,T,81], the 8 pose tensors [B,T,...], gaze_pos[B,T,3], style (example
@@ -84,7 +93,14 @@ class TrainStep:
         se.train(train_mode); dec.train(train_mode)
         gv = lambda m: [p.grad for p in m._weights()]
         xa = (batch["audio"] - self.audio_mean) / self.audio_std
-        speech, se_state = ops.speech_encoder_fwd(se, xa, ops.speech_encoder_masks(se, xa, None if masks is None else masks.get("speech")))
+        cur = torch.cuda.current_stream(self.dev) if self.lanes else None
+        s1, s2 = self._lane_streams if self.lanes else (None, None)
+        if self.lanes:
+            s1.wait_stream(cur)
+            with torch.cuda.stream(s1), ops.lane("speech"):
+                speech, se_state = ops.speech_encoder_fwd(se, xa, ops.speech_encoder_masks(se, xa, None if masks is None else masks.get("speech")))
+        else:
+            speech, se_state = ops.speech_encoder_fwd(se, xa, ops.speech_encoder_masks(se, xa, None if masks is None else masks.get("speech")))
         mu = logvar = st_state = None
         if st is not None:
             st.train(train_mode)
@@ -93,6 +109,8 @@ class TrainStep:
             (z, mu, logvar), st_state = ops.style_encoder_fwd(st, xs, eps_, smasks, 1.0)
         else:
             z = batch["style"]
+        if self.lanes:
+            cur.wait_stream(s1)
         T = speech.shape[1]
         W = [batch[k] for k in POSE_KEYS]
         WY = pack_pose(*W[2:])                                   # ground-truth window, packed once
@@ -102,10 +120,26 @@ class TrainStep:
         loss, (dY, dRp, dRq, dmu, dlv) = ops.loss_fwd_bwd(Y, rp, rq, WY, W[0], W[1], batch["gaze_pos"], self.parents, self.dt, mu, logvar,
                                                           kl_weight(self.iteration) if mu is not None else 0.0, self.terms,
                                                           self.klw if mu is not None else None)
-        _, dSpeech, dStyle = ops.decoder_window_backward(dec, dstate, dY, dRp, dRq, grads_out=gv(dec))
-        ops.speech_encoder_bwd(se_state, dSpeech, grads_out=gv(se))
+        if not self.lanes:
+            _, dSpeech, dStyle = ops.decoder_window_backward(dec, dstate, dY, dRp, dRq, grads_out=gv(dec))
+            ops.speech_encoder_bwd(se_state, dSpeech, grads_out=gv(se))
+            if st is not None:
+                ops.style_encoder_bwd(st_state, dStyle.sum(dim=1), dmu, dlv, grads_out=gv(st))     # z was broadcast over the window
+            return loss
+        # phase 1 (recurrence + conditioning gradients) -> fork: encoders' backward on their lanes, phase 2 (weight gradients) here -> join
+        _, dSpeech, dStyle, finish = ops.decoder_window_backward(dec, dstate, dY, dRp, dRq, grads_out=gv(dec), split=True)
+        s1.wait_stream(cur)
+        with torch.cuda.stream(s1), ops.lane("speech"):
+            ops.speech_encoder_bwd(se_state, dSpeech, grads_out=gv(se))
         if st is not None:
-            ops.style_encoder_bwd(st_state, dStyle.sum(dim=1), dmu, dlv, grads_out=gv(st))     # z was broadcast over the window
+            s2.wait_stream(cur)
+            with torch.cuda.stream(s2), ops.lane("style"):
+                ops.style_encoder_bwd(st_state, dStyle.sum(dim=1), dmu, dlv, grads_out=gv(st))     # z was broadcast over the window
+        keep = finish()
+        cur.wait_stream(s1)
+        if st is not None:
+            cur.wait_stream(s2)
+        del keep
         return loss
 
     def _allreduce(self):
