@@ -273,6 +273,8 @@ def run_ours(args):
         torch.cuda.empty_cache()
         return r
 
+    if os.environ.get("ZEGGS_TC_GEMM_VARIANT"):          # experiment knob (profiles/r02_tc_gemm_variants.md)
+        lib.zeggs_debug_set_tc_gemm_variant(int(os.environ["ZEGGS_TC_GEMM_VARIANT"]))
     r = measure(B, T, H, T_ex, K, W, timing=True)
     frames = world * B * T
     value = frames / (r["ms"] / K) * 1e3
@@ -314,10 +316,15 @@ def run_ours(args):
                dtype=("bf16" if args.engine != "fp32" else "f32"), data="synthetic",
                config=dict(workload=wl["desc"], per_gpu_batch=B, global_batch=world * B, window=T, hidden=H, style_example_len=T_ex,
                            parallelism=f"dp{world}", decoder_engine=args.engine, cuda_graph=r["graphed"], numa_node=numa,
+                           lanes=(os.environ.get("ZEGGS_LANES", "1") == "1"),
                            l2="per-step working set ~1.4 GB of saved activations >> 126 MB L2 (no explicit flush)"),
                e2e=dict(value=round(frames / (r["e2e_ms"] / K) * 1e3, 1), unit="frames/s", h2d_bytes_per_step=r["h2d"], d2h_bytes_per_step=4),
                gpu_launches=r["launches"], host_enqueue_ms_per_step=round(r["host_enqueue_ms"], 3), clocks=r["clocks"], roofline=roofline,
-               kernel_ms_per_step=kms, loss=r["loss"])
+               kernel_ms_per_step=kms,
+               kernel_ms_note=("spans are per library call on the stream it was issued on; with lanes the two encoders (forward) and "
+                               "encoders_bwd / decoder_wgrad (backward) run concurrently on three streams, so those spans overlap in time "
+                               "and their sum exceeds the step"),
+               loss=r["loss"])
     if args.alt and args.workload == "train_v1":
         a = WORKLOADS["train_v1_stated"]
         ra = measure(a["B"], a["T"], a["H"], a["T_ex"], K, W)

@@ -36,6 +36,8 @@ extern "C" {
 
 const char* zeggs_last_error(void);
 int zeggs_version(void);
+/* sizeof of an args struct of this header by its C name, e.g. "zeggs_decoder_bwd_args" (0 = unknown name): bindings check their mirror. */
+size_t zeggs_struct_size(const char* name);
 /* number of kernels this library has launched since load (bench.py's gpu_launches claim) */
 long long zeggs_launch_count(void);
 /* Live device timing of the main kernel groups ("decoder_fwd", "decoder_bwd", "decoder_wgrad", "mel", "loss",
@@ -163,6 +165,7 @@ int zeggs_decoder_pack_weights_tc(const zeggs_decoder_fwd_args* a, void* packed,
 /* development aid: device buffer [64][32] of int64 receiving CTA 0's per-step phase timestamps (NULL = off) */
 void zeggs_debug_set_tc_trace(void* device_buffer);
 void zeggs_debug_set_tc_nacc(int n); /* development aid: forward recurrence kernel variant (0 = shipped) */
+int zeggs_debug_set_tc_gemm_variant(int v);  /* tcgen05 GEMM tile variant: -1 automatic (128x256 tiles for one-pass products with N >= 256, fused three-pass), 0 = 128x128 tiles with streamed passes */
 void zeggs_debug_set_loss_impl(int v); /* development aid: 1 = warp-per-frame loss kernels (default), 0 = round-1 thread-per-frame version */
 void zeggs_debug_set_tc_cluster(int n); /* development aid: cap the thread-block cluster size of the tc recurrences (1 = no clusters) */
 int zeggs_debug_get_tc_cluster(void);   /* cluster size the last tc forward launch used */

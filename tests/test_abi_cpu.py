@@ -27,6 +27,20 @@ def test_library_exports_every_header_symbol(built):
     assert l.zeggs_version() >= 100
 
 
+def test_ctypes_mirrors_have_the_library_struct_layout(built):
+    """Every args struct of the header is mirrored in _lib.py: same size as the compiled C struct (a drifted mirror would make the
+    library read garbage pointers), and every struct the header defines has a mirror."""
+    import ctypes
+    hdr = open(os.path.join(ROOT, "include", "zeggs_b200.h")).read()
+    defined = set(re.findall(r"^\}\s*(zeggs_[a-z0-9_]+);", hdr, flags=re.M))
+    mirrors = built.struct_mirrors()
+    assert defined == set(mirrors), (defined - set(mirrors), set(mirrors) - defined)
+    l = built.lib()
+    for name, cls in mirrors.items():
+        assert l.zeggs_struct_size(name.encode()) == ctypes.sizeof(cls), name
+    assert l.zeggs_struct_size(b"no_such_struct") == 0
+
+
 def test_mel_frame_count_rule(built):
     l = built.lib()
     from oracle import mel_oracle

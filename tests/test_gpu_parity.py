@@ -26,7 +26,7 @@ def dev():
 
 
 # ---------------------------------------------------------------------------------------------- GEMMs
-@pytest.mark.parametrize("M,N,K", [(7, 5, 3), (64, 64, 16), (130, 257, 1198), (32, 2048, 1024)])
+@pytest.mark.parametrize("M,N,K", [(7, 5, 3), (64, 64, 16), (130, 257, 1198), (32, 2048, 1024), (384, 32, 384), (200, 17, 100)])
 def test_sgemm(dev, M, N, K):
     from zeggs_b200 import ops
     g = torch.Generator().manual_seed(M * 1000 + N)
@@ -44,7 +44,7 @@ def test_sgemm(dev, M, N, K):
     assert err <= 2e-5 * max(sc, 1.0)
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 256), (256, 384, 512), (200, 300, 1136), (3072, 2286, 1024)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 256), (256, 384, 512), (200, 300, 1136), (3072, 2286, 1024), (1024, 1262, 4096), (130, 256, 192)])
 def test_tc_gemm_bf16(dev, M, N, K):
     from zeggs_b200 import ops
     g = torch.Generator().manual_seed(M + N + K)
@@ -879,6 +879,33 @@ def test_graph_replayed_train_steps_match_eager_launches(dev, decoder_engine):
     assert res["graph"][2] == 5 and res["graph"][3] == 5 and res["eager"][2] == 5
     assert np.allclose(res["graph"][0], res["eager"][0], rtol=1e-6, atol=0)
     assert float((res["graph"][1] - res["eager"][1]).abs().max()) <= 1e-7
+
+
+def test_concurrent_lanes_match_single_stream_step(dev, decoder_engine, monkeypatch):
+    """TrainStep with the concurrent lanes (encoders side by side; encoders' backward next to the decoder's phase-2 weight gradients,
+    each lane with its own stream and GEMM scratch) against the same steps issued on ONE stream with the one-call decoder backward:
+    every kernel is deterministic and the lanes only reorder independent work, so losses and parameters must be identical."""
+    from zeggs_b200 import modules, synth
+    from zeggs_b200.train import TrainStep
+    decoder_engine("tc")
+    res = {}
+    for lanes in ("1", "0"):
+        monkeypatch.setenv("ZEGGS_LANES", lanes)
+        torch.manual_seed(321)
+        P = synth.make_params(H=384, seed=78)
+        se = _load(modules.SpeechEncoder(81, 64, 64), P, "speech_encoder.", dev)
+        st = _load(modules.StyleEncoder(1134, 512, 64, type="attn", use_vae=True), P, "style_encoder.", dev)
+        de = _load(modules.Decoder(1134, 1131, 64, 64, 384, 2), P, "decoder.", dev)
+        stats = synth.load_stats()
+        step = TrainStep(se, de, st, stats, stats["parents"], float(stats["dt"]), lr=1e-3, use_graph=True)
+        assert step.lanes == (lanes == "1")
+        losses = [float(step.step(_batch(dev, 4, 16, 24, 70 + it)).item()) for it in range(4)]
+        torch.cuda.synchronize()
+        res[lanes] = (losses, step.optimizer.flat_param.clone())
+        del step
+    print("  lanes  losses", res["1"][0]); print("  serial losses", res["0"][0])
+    assert res["1"][0] == res["0"][0]
+    assert float((res["1"][1] - res["0"][1]).abs().max()) == 0.0
 
 
 # ---------------------------------------------------------------------------------------------- loudness normalisation + int16 decode (SURVEY 8f row 4)

@@ -96,9 +96,18 @@ LossArgs = _struct("LossArgs", ints=("B", "T", "Z"), floats=("dt", "kl_weight"),
 
 
 # every symbol include/zeggs_b200.h declares: (name, restype, argtypes)
+# C struct name -> ctypes mirror (checked against the library's sizeof at test time: tests/test_abi_cpu.py)
+def struct_mirrors():
+    return {"zeggs_ctx": Ctx, "zeggs_mel_args": MelArgs, "zeggs_loudness_args": LoudnessArgs, "zeggs_decoder_fwd_args": DecoderFwdArgs,
+            "zeggs_decoder_bwd_args": DecoderBwdArgs, "zeggs_speech_enc_args": SpeechEncArgs, "zeggs_speech_enc_grads": SpeechEncGrads,
+            "zeggs_style_enc_args": StyleEncArgs, "zeggs_style_enc_grads": StyleEncGrads, "zeggs_decoder_step_args": DecoderStepArgs,
+            "zeggs_loss_args": LossArgs, "zeggs_pose_post_args": PosePostArgs, "zeggs_gather_args": GatherArgs}
+
+
 SYMBOLS = [
     ("zeggs_last_error", C.c_char_p, []),
     ("zeggs_version", C.c_int, []),
+    ("zeggs_struct_size", C.c_size_t, [C.c_char_p]),
     ("zeggs_launch_count", C.c_longlong, []),
     ("zeggs_timing_enable", None, [C.c_int]),
     ("zeggs_timing_reset", None, []),
@@ -120,6 +129,7 @@ SYMBOLS = [
     ("zeggs_decoder_pack_weights_tc", C.c_int, [C.POINTER(DecoderFwdArgs), C.c_void_p, C.c_void_p]),
     ("zeggs_debug_set_tc_trace", None, [C.c_void_p]),
     ("zeggs_debug_set_tc_nacc", None, [C.c_int]),
+    ("zeggs_debug_set_tc_gemm_variant", C.c_int, [C.c_int]),
     ("zeggs_debug_set_loss_impl", None, [C.c_int]),
     ("zeggs_debug_set_tc_cluster", None, [C.c_int]),
     ("zeggs_debug_get_tc_cluster", C.c_int, []),

@@ -13,42 +13,53 @@
 
 namespace zeggs {
 
-constexpr int TG_BM = 128, TG_BN = 128, TG_BK = 64, TG_STAGES = 4;
-constexpr int TG_A_BYTES = TG_BM * TG_BK * 2, TG_B_BYTES = TG_BN * TG_BK * 2;
+constexpr int TG_BM = 128, TG_BK = 64;
+constexpr int TG_A_BYTES = TG_BM * TG_BK * 2;
 
 struct TcGemmMaps {
   CUtensorMap a[2];
   CUtensorMap b[2];
 };
 
+// Every operand byte comes from L2 through the chip-wide L2->SM path (~6.3 KB/clk over 148 SMs = ~43 B/clk per SM when all pull,
+// B300_MICROARCH.md "LTS throughput cap"; a 128x128x64 bf16 tile step needs 32 KB per 256 MMA cycles = 128 B/clk per SM at the tensor
+// peak), so the mainloop of a 128x128 tile is capped near a third of the peak by operand delivery.  Two variants cut the bytes per MMA:
+//   BN = 256 (one-pass products with N >= 256): A 16 KB + B 32 KB per 512 MMA cycles (96 B/clk at the peak, 1.33x fewer bytes per FLOP);
+//   FUSE (the split-bf16 three-pass scheme): A_hi, A_lo, B_hi, B_lo of a k-block are staged ONCE (64 KB) and the three products
+//   hi*hi, lo*hi, hi*lo issued back to back from that stage (85 B/clk at the peak instead of 128: the unfused kernel streamed the
+//   operands three times).
+template <int BN, int STAGES, bool FUSE>
 __global__ void __launch_bounds__(192, 1)
 tc_gemm_kernel(const __grid_constant__ TcGemmMaps maps, int M, int N, int K, int passes,
                const float* __restrict__ bias, float* __restrict__ C, int ldc, int act, int accumulate,
                float* __restrict__ part, int kb_per_split) {
+  constexpr int B_BYTES = BN * TG_BK * 2;
+  constexpr int NOP = FUSE ? 2 : 1;                 // operand copies per stage (hi [, lo])
+  constexpr int STAGE_A = NOP * TG_A_BYTES, STAGE_B = NOP * B_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
-  uint8_t* sB = smem + TG_STAGES * TG_A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + TG_STAGES * TG_B_BYTES);
-  uint64_t* empty = full + TG_STAGES;
-  uint64_t* tmem_full = empty + TG_STAGES;
+  uint8_t* sB = smem + STAGES * STAGE_A;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * STAGE_B);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TG_BM, n0 = blockIdx.x * TG_BN;
+  const int m0 = blockIdx.y * TG_BM, n0 = blockIdx.x * BN;
   // split-K: blockIdx.z owns k-blocks [kb0, kb0 + kblocks); its raw fp32 tile goes to part[z][M][N] (reduced afterwards)
   const int kb0 = blockIdx.z * kb_per_split;
   const int kblocks = min(kb_per_split, ceil_div(K, TG_BK) - kb0);
-  // pass order: (A0,B0), (A1,B0), (A0,B1)
-  const int total = kblocks * (passes == 1 ? 1 : 3);
+  // unfused pass order: (A0,B0), (A1,B0), (A0,B1)
+  const int total = kblocks * ((FUSE || passes == 1) ? 1 : 3);
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < (passes == 1 ? 1 : 2); ++i) { tma_prefetch_desc(&maps.a[i]); tma_prefetch_desc(&maps.b[i]); }
-    for (int s = 0; s < TG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, TG_BN); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_slot, BN); tmem_relinquish(); }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -57,28 +68,48 @@ tc_gemm_kernel(const __grid_constant__ TcGemmMaps maps, int M, int N, int K, int
   if (warp == 0) {
     if (lane == 0) {
       for (int it = 0; it < total; ++it) {
-        const int s = it % TG_STAGES, ph = (it / TG_STAGES) & 1;
+        const int s = it % STAGES, ph = (it / STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
-        const int p = it / kblocks, kb = kb0 + it - p * kblocks;
-        const CUtensorMap* ma = &maps.a[p == 1 ? 1 : 0];
-        const CUtensorMap* mb = &maps.b[p == 2 ? 1 : 0];
-        mbar_arrive_expect_tx(&full[s], TG_A_BYTES + TG_B_BYTES);
-        tma_load_2d(sA + s * TG_A_BYTES, ma, &full[s], kb * TG_BK, m0);
-        tma_load_2d(sB + s * TG_B_BYTES, mb, &full[s], kb * TG_BK, n0);
+        if (FUSE) {
+          const int kb = kb0 + it;
+          mbar_arrive_expect_tx(&full[s], STAGE_A + STAGE_B);
+          tma_load_2d(sA + s * STAGE_A, &maps.a[0], &full[s], kb * TG_BK, m0);
+          tma_load_2d(sB + s * STAGE_B, &maps.b[0], &full[s], kb * TG_BK, n0);
+          tma_load_2d(sA + s * STAGE_A + TG_A_BYTES, &maps.a[1], &full[s], kb * TG_BK, m0);
+          tma_load_2d(sB + s * STAGE_B + B_BYTES, &maps.b[1], &full[s], kb * TG_BK, n0);
+        } else {
+          const int p = it / kblocks, kb = kb0 + it - p * kblocks;
+          const CUtensorMap* ma = &maps.a[p == 1 ? 1 : 0];
+          const CUtensorMap* mb = &maps.b[p == 2 ? 1 : 0];
+          mbar_arrive_expect_tx(&full[s], STAGE_A + STAGE_B);
+          tma_load_2d(sA + s * STAGE_A, ma, &full[s], kb * TG_BK, m0);
+          tma_load_2d(sB + s * STAGE_B, mb, &full[s], kb * TG_BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16_f32(TG_BM, TG_BN);
+    const uint32_t idesc = make_idesc_bf16_f32(TG_BM, BN);
     for (int it = 0; it < total; ++it) {
-      const int s = it % TG_STAGES, ph = (it / TG_STAGES) & 1;
+      const int s = it % STAGES, ph = (it / STAGES) & 1;
       mbar_wait(&full[s], ph);
       tc_fence_after_sync();
       if (lane == 0) {
-        const uint64_t da = make_smem_desc_sw128(sA + s * TG_A_BYTES);
-        const uint64_t db = make_smem_desc_sw128(sB + s * TG_B_BYTES);
+        const uint64_t da = make_smem_desc_sw128(sA + s * STAGE_A);
+        const uint64_t db = make_smem_desc_sw128(sB + s * STAGE_B);
+        if (FUSE) {
+          const uint64_t dal = make_smem_desc_sw128(sA + s * STAGE_A + TG_A_BYTES);
+          const uint64_t dbl = make_smem_desc_sw128(sB + s * STAGE_B + B_BYTES);
 #pragma unroll
-        for (int k = 0; k < TG_BK / 16; ++k)
-          umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
+          for (int k = 0; k < TG_BK / 16; ++k) {
+            umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
+            umma_bf16(tmem_base, dal + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1);
+            umma_bf16(tmem_base, da + (uint64_t)(k * 2), dbl + (uint64_t)(k * 2), idesc, 1);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < TG_BK / 16; ++k)
+            umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
+        }
         umma_commit(&empty[s]);
         if (it == total - 1) umma_commit(tmem_full);
       }
@@ -91,7 +122,8 @@ tc_gemm_kernel(const __grid_constant__ TcGemmMaps maps, int M, int N, int K, int
     tc_fence_after_sync();
     const int m = m0 + q * 32 + lane;
 #pragma unroll 1
-    for (int c0 = 0; c0 < TG_BN; c0 += 32) {
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= N) break;
       uint32_t v[32];
       tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
@@ -118,7 +150,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmMaps maps, int M, int N, int K, int
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem_base, TG_BN); }
+  if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem_base, BN); }
 }
 
 // sum of the split-K partial tiles + the epilogue of the un-split kernel (deterministic order)
@@ -279,6 +311,11 @@ static int encode_map(CUtensorMap* m, const void* base, int rows, int K, int ld_
   return ZEGGS_OK;
 }
 
+// experiment knob: 0 forces the round-1 kernel shape (128x128 tiles, passes streamed one after the other), -1 = automatic
+static int g_tc_gemm_variant = -1;
+extern "C" int zeggs_debug_set_tc_gemm_variant(int v) { g_tc_gemm_variant = v; return ZEGGS_OK; }
+static int tc_gemm_variant_override() { return g_tc_gemm_variant; }
+
 int tc_gemm_launch(int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, int lda,
                    const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, const float* bias,
                    float* C, int ldc, int act, int accumulate, cudaStream_t stream, float* splitk_ws, size_t splitk_ws_bytes) {
@@ -286,19 +323,30 @@ int tc_gemm_launch(int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bf
   ZCHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "tc_gemm: leading dimensions must be multiples of 8 bf16 (16 B)");
   ZCHECK_ARG(((uintptr_t)A_hi & 15) == 0 && ((uintptr_t)B_hi & 15) == 0, "tc_gemm: operands must be 16-byte aligned");
   const int passes = (A_lo && B_lo) ? 3 : 1;
+  // variant: 0 = 128x128 tiles, 4 stages;  1 = 128x256 tiles (one-pass products, N >= 256);  2 = fused three-pass, 128x128, 3 stages
+  const int forced = tc_gemm_variant_override();
+  int variant = passes == 3 ? 2 : (N >= 256 ? 1 : 0);
+  if (forced == 0) variant = 0;
+  const int BN = variant == 1 ? 256 : 128;
   TcGemmMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc;
   if ((rc = encode_map(&maps.a[0], A_hi, M, K, lda, TG_BM))) return rc;
-  if ((rc = encode_map(&maps.b[0], B_hi, N, K, ldb, TG_BN))) return rc;
+  if ((rc = encode_map(&maps.b[0], B_hi, N, K, ldb, BN))) return rc;
   if (passes == 3) {
     if ((rc = encode_map(&maps.a[1], A_lo, M, K, lda, TG_BM))) return rc;
-    if ((rc = encode_map(&maps.b[1], B_lo, N, K, ldb, TG_BN))) return rc;
+    if ((rc = encode_map(&maps.b[1], B_lo, N, K, ldb, BN))) return rc;
   }
-  const size_t smem = 1024 + TG_STAGES * (TG_A_BYTES + TG_B_BYTES) + (2 * TG_STAGES + 1) * 8 + 16;
+  auto smem_of = [](int bn, int stages, int nop) { return (size_t)1024 + (size_t)stages * nop * (TG_A_BYTES + bn * TG_BK * 2) + (2 * stages + 1) * 8 + 16; };
+  const size_t smem = variant == 1 ? smem_of(256, 4, 1) : variant == 2 ? smem_of(128, 3, 2) : smem_of(128, 4, 1);
   static bool attr_set = false;     // one device per process (one rank per GPU): set once, not on every launch
-  if (!attr_set) { ZCHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
-  dim3 grid(ceil_div(N, TG_BN), ceil_div(M, TG_BM));
+  if (!attr_set) {
+    ZCHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<128, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(128, 4, 1)));
+    ZCHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<256, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(256, 4, 1)));
+    ZCHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<128, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(128, 3, 2)));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(N, BN), ceil_div(M, TG_BM));
   // split-K when the output has too few tiles to fill the 148 SMs and the contraction is long
   const int tiles = (int)(grid.x * grid.y), kblocks = ceil_div(K, TG_BK);
   int splits = 1;
@@ -307,15 +355,19 @@ int tc_gemm_launch(int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bf
     const size_t per = (size_t)M * N * sizeof(float);
     if ((size_t)splits * per > splitk_ws_bytes) splits = (int)(splitk_ws_bytes / per);
   }
-  if (splits <= 1) {
-    tc_gemm_kernel<<<grid, 192, smem, stream>>>(maps, M, N, K, passes, bias, C, ldc, act, accumulate, nullptr, kblocks);
+  auto launch = [&](const float* bias_, int act_, int acc_, float* part, int kbs) {
+    if (variant == 1) tc_gemm_kernel<256, 4, false><<<grid, 192, smem, stream>>>(maps, M, N, K, passes, bias_, C, ldc, act_, acc_, part, kbs);
+    else if (variant == 2) tc_gemm_kernel<128, 3, true><<<grid, 192, smem, stream>>>(maps, M, N, K, passes, bias_, C, ldc, act_, acc_, part, kbs);
+    else tc_gemm_kernel<128, 4, false><<<grid, 192, smem, stream>>>(maps, M, N, K, passes, bias_, C, ldc, act_, acc_, part, kbs);
     count_launch();
+  };
+  if (splits <= 1) {
+    launch(bias, act, accumulate, nullptr, kblocks);
   } else {
     const int kbs = ceil_div(kblocks, splits);
     splits = ceil_div(kblocks, kbs);                      // every z gets at least one k-block
     grid.z = splits;
-    tc_gemm_kernel<<<grid, 192, smem, stream>>>(maps, M, N, K, passes, nullptr, C, ldc, 0, 0, splitk_ws, kbs);
-    count_launch();
+    launch(nullptr, 0, 0, splitk_ws, kbs);
     const size_t total = (size_t)M * N;
     splitk_reduce_kernel<<<(int)std::min<size_t>(1184, (total + 255) / 256), 256, 0, stream>>>(splitk_ws, splits, M, N, bias, C, ldc, act, accumulate);
     count_launch();

@@ -161,8 +161,8 @@ def split_pose(Y, root_pos, root_rot):
             Y[..., o + NJ * 12:o + NJ * 15].reshape(B, T, NJ, 3))
 
 
-def _decoder_args(dec, B, T, dev, tensors, stats, dt, save):
-    """Fill a DecoderFwdArgs; returns (args, keepalive list)."""
+def _decoder_args(dec, B, T, dev, tensors, stats, dt, save, pack_only=False):
+    """Fill a DecoderFwdArgs; returns (args, keepalive list).  pack_only: stop after the weight packs (decoder_prepack)."""
     H, S, Z = dec.hidden_size, dec.speech_encoding_size, dec.style_encoding_size
     l = _lib.lib()
     w = [_f32c(p, dev) for p in dec._weights()]
@@ -207,6 +207,8 @@ def _decoder_args(dec, B, T, dev, tensors, stats, dt, save):
         wtc = WS.get("dec_tc", l.zeggs_decoder_tc_workspace_bytes(H, S, Z), dev)
         a.engine, a.packed_tc, a.workspace_tc = 1, tcc[1].data_ptr(), wtc.data_ptr()
         keep += [tcc[1], wtc]
+    if pack_only:
+        return a, keep, None
     wsb = l.zeggs_decoder_workspace_bytes(B, T, H, S, Z, int(save))
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if save else WS.get("dec_fwd", wsb, dev)
     a.workspace = ws.data_ptr()
@@ -214,6 +216,30 @@ def _decoder_args(dec, B, T, dev, tensors, stats, dt, save):
     a.save_for_backward = int(save)
     keep.append(ws)
     return a, keep, ws
+
+
+def decoder_prepack(dec, B, T, dev, stats, dt, backward=True):
+    """Everything the decoder derives from its WEIGHTS alone -- the engine's packed / bf16 weight images, the folded layer-2 matrix and
+    (backward=True) the transposed images of the BPTT kernel -- issued on the current stream and lane.  The window calls find the caches
+    fresh and skip the work, so a training step can run this next to the encoders' forward instead of in front of the recurrence."""
+    l = _lib.lib()
+    a, keep, _ = _decoder_args(dec, B, T, dev, {}, stats, dt, False, pack_only=True)
+    if backward and a.engine == 1:
+        _pack_bwd_tc(dec, a, dev)
+    return keep
+
+
+def _pack_bwd_tc(dec, a, dev):
+    l = _lib.lib()
+    H, S, Z = a.H, a.S, a.Z
+    ver = weights_key(dec._weights())
+    tcc = dec.__dict__.get("_zeggs_packed_bwd_tc")
+    if tcc is None or tcc[0] != ver or tcc[1].device != dev:
+        ptc = torch.empty(l.zeggs_decoder_packed_bwd_tc_bytes(H, S, Z), dtype=torch.uint8, device=dev)
+        _lib.check(l.zeggs_decoder_pack_weights_bwd_tc(a, ptc.data_ptr(), _lib.stream_ptr()), "zeggs_decoder_pack_weights_bwd_tc")
+        dec.__dict__["_zeggs_packed_bwd_tc"] = (ver, ptc)
+        tcc = dec.__dict__["_zeggs_packed_bwd_tc"]
+    return tcc
 
 
 def decoder_window_forward(dec, root_pos0, root_rot0, pose0, gaze_pos, speech, style, stats, dt, save=False):
@@ -284,12 +310,7 @@ def decoder_window_backward(dec, state, dY, dRp, dRq, grads_out=None, split=Fals
         b.packed_bwd = cache[1].data_ptr()
         hold.append(cache[1])
     else:
-        tcc = dec.__dict__.get("_zeggs_packed_bwd_tc")
-        if tcc is None or tcc[0] != ver or tcc[1].device != dev:
-            ptc = torch.empty(l.zeggs_decoder_packed_bwd_tc_bytes(H, S, Z), dtype=torch.uint8, device=dev)
-            _lib.check(l.zeggs_decoder_pack_weights_bwd_tc(a, ptc.data_ptr(), _lib.stream_ptr()), "zeggs_decoder_pack_weights_bwd_tc")
-            dec.__dict__["_zeggs_packed_bwd_tc"] = (ver, ptc)
-            tcc = dec.__dict__["_zeggs_packed_bwd_tc"]
+        tcc = _pack_bwd_tc(dec, a, dev)
         wtc = WS.get("dec_bwd_tc", l.zeggs_decoder_bwd_tc_workspace_bytes(H, S, Z), dev)
         b.packed_bwd_tc, b.workspace_tc = tcc[1].data_ptr(), wtc.data_ptr()
         hold += [tcc[1], wtc]

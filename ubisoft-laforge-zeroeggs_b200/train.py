@@ -95,10 +95,15 @@ class TrainStep:
         xa = (batch["audio"] - self.audio_mean) / self.audio_std
         cur = torch.cuda.current_stream(self.dev) if self.lanes else None
         s1, s2 = self._lane_streams if self.lanes else (None, None)
+        prep = None
         if self.lanes:
             s1.wait_stream(cur)
             with torch.cuda.stream(s1), ops.lane("speech"):
                 speech, se_state = ops.speech_encoder_fwd(se, xa, ops.speech_encoder_masks(se, xa, None if masks is None else masks.get("speech")))
+            # weight-only preparation of the decoder (bf16 weight images, folded layer-2 matrix, BPTT images) on the second lane
+            s2.wait_stream(cur)
+            with torch.cuda.stream(s2), ops.lane("style"):
+                prep = ops.decoder_prepack(dec, xa.shape[0], xa.shape[1], self.dev, (self.in_mean, self.in_std, self.out_mean, self.out_std), self.dt)
         else:
             speech, se_state = ops.speech_encoder_fwd(se, xa, ops.speech_encoder_masks(se, xa, None if masks is None else masks.get("speech")))
         mu = logvar = st_state = None
@@ -111,6 +116,7 @@ class TrainStep:
             z = batch["style"]
         if self.lanes:
             cur.wait_stream(s1)
+            cur.wait_stream(s2)
         T = speech.shape[1]
         W = [batch[k] for k in POSE_KEYS]
         WY = pack_pose(*W[2:])                                   # ground-truth window, packed once
