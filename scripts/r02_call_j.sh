@@ -1,0 +1,17 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
+mkdir -p gpurun_out
+( time timeout 900 python -m pytest tests -m gpu -q -x -k "gemm or train_step or lanes or full_size" ) > gpurun_out/r02j_pytest.log 2>&1
+( timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --alt 0 --extras 0 ) > gpurun_out/r02j_bench.json 2> gpurun_out/r02j_bench.err
+( ZEGGS_TC_GEMM_VARIANT=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --alt 0 --extras 0 ) > gpurun_out/r02j_bench_v1.json 2> gpurun_out/r02j_bench_v1.err
+( ZEGGS_TC_GEMM_VARIANT=3 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --alt 0 --extras 0 ) > gpurun_out/r02j_bench_v3.json 2> gpurun_out/r02j_bench_v3.err
+grep -E "passed|failed|FAILED|Error" gpurun_out/r02j_pytest.log | tail -20
+python - <<PY
+import json
+for f in ("r02j_bench.json","r02j_bench_v1.json","r02j_bench_v3.json"):
+    try:
+        d=[json.loads(l) for l in open("gpurun_out/"+f) if l.startswith("{")][-1]
+        print(f, d["ms_per_step"], d["kernel_ms_per_step"], d["e2e"]["value"], d["value"], d["config"].get("cuda_graph"))
+    except Exception as e: print(f, "ERR", e)
+PY
+tail -5 gpurun_out/r02j_bench.err

@@ -28,14 +28,17 @@ struct TcGemmMaps {
 //   FUSE (the split-bf16 three-pass scheme): A_hi, A_lo, B_hi, B_lo of a k-block are staged ONCE (64 KB) and the three products
 //   hi*hi, lo*hi, hi*lo issued back to back from that stage (85 B/clk at the peak instead of 128: the unfused kernel streamed the
 //   operands three times).
-template <int BN, int STAGES, bool FUSE>
+//   MT = 2 (256x256 tile per CTA: two 128-row accumulators, all 512 TMEM columns, sharing every B stage): 64 KB per 1024 MMA cycles
+//   (64 B/clk at the peak) for the long-K weight-gradient products.
+template <int BN, int STAGES, bool FUSE, int MT>
 __global__ void __launch_bounds__(192, 1)
 tc_gemm_kernel(const __grid_constant__ TcGemmMaps maps, int M, int N, int K, int passes,
                const float* __restrict__ bias, float* __restrict__ C, int ldc, int act, int accumulate,
                float* __restrict__ part, int kb_per_split) {
   constexpr int B_BYTES = BN * TG_BK * 2;
   constexpr int NOP = FUSE ? 2 : 1;                 // operand copies per stage (hi [, lo])
-  constexpr int STAGE_A = NOP * TG_A_BYTES, STAGE_B = NOP * B_BYTES;
+  constexpr int STAGE_A = NOP * MT * TG_A_BYTES, STAGE_B = NOP * B_BYTES;
+  static_assert(!(FUSE && MT > 1) && BN * MT <= 512, "tile variant");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -46,7 +49,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmMaps maps, int M, int N, int K, int
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TG_BM, n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * (TG_BM * MT), n0 = blockIdx.x * BN;
   // split-K: blockIdx.z owns k-blocks [kb0, kb0 + kblocks); its raw fp32 tile goes to part[z][M][N] (reduced afterwards)
   const int kb0 = blockIdx.z * kb_per_split;
   const int kblocks = min(kb_per_split, ceil_div(K, TG_BK) - kb0);
@@ -59,7 +62,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmMaps maps, int M, int N, int K, int
     mbar_init(tmem_full, 1);
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, BN); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_slot, BN * MT); tmem_relinquish(); }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -107,8 +110,12 @@ tc_gemm_kernel(const __grid_constant__ TcGemmMaps maps, int M, int N, int K, int
           }
         } else {
 #pragma unroll
-          for (int k = 0; k < TG_BK / 16; ++k)
-            umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
+          for (int t = 0; t < MT; ++t) {
+            const uint64_t dat = t == 0 ? da : make_smem_desc_sw128(sA + s * STAGE_A + t * TG_A_BYTES);
+#pragma unroll
+            for (int k = 0; k < TG_BK / 16; ++k)
+              umma_bf16(tmem_base + (uint32_t)(t * BN), dat + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
+          }
         }
         umma_commit(&empty[s]);
         if (it == total - 1) umma_commit(tmem_full);
@@ -120,12 +127,13 @@ tc_gemm_kernel(const __grid_constant__ TcGemmMaps maps, int M, int N, int K, int
     const int q = warp & 3;
     mbar_wait(tmem_full, 0);
     tc_fence_after_sync();
-    const int m = m0 + q * 32 + lane;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= N) break;
+    for (int tc = 0; tc < MT * (BN / 32); ++tc) {
+      const int t = tc / (BN / 32), c0 = (tc - t * (BN / 32)) * 32;
+      const int m = m0 + t * TG_BM + q * 32 + lane;
+      if (n0 + c0 >= N || m0 + t * TG_BM >= M) continue;
       uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * BN + c0), v);
       tmem_ld_wait();
       if (m < M && part) {
         float* prow = part + ((size_t)blockIdx.z * M + m) * N + n0 + c0;
@@ -150,7 +158,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmMaps maps, int M, int N, int K, int
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem_base, BN); }
+  if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem_base, BN * MT); }
 }
 
 // sum of the split-K partial tiles + the epilogue of the un-split kernel (deterministic order)
@@ -323,42 +331,58 @@ int tc_gemm_launch(int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bf
   ZCHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "tc_gemm: leading dimensions must be multiples of 8 bf16 (16 B)");
   ZCHECK_ARG(((uintptr_t)A_hi & 15) == 0 && ((uintptr_t)B_hi & 15) == 0, "tc_gemm: operands must be 16-byte aligned");
   const int passes = (A_lo && B_lo) ? 3 : 1;
-  // variant: 0 = 128x128 tiles, 4 stages;  1 = 128x256 tiles (one-pass products, N >= 256);  2 = fused three-pass, 128x128, 3 stages
+  // variant: 0 = 128x128 tiles, 4 stages;  1 = 128x256 tiles (one-pass products, N >= 256);  2 = fused three-pass, 128x128, 3 stages;
+  // 3 = 256x256 tiles (two accumulators), 3 stages -- experiment only (zeggs_debug_set_tc_gemm_variant(3))
   const int forced = tc_gemm_variant_override();
+  auto plan = [&](int bm, int bn, int* splits_out) {
+    const int tiles = ceil_div(N, bn) * ceil_div(M, bm), kblocks = ceil_div(K, TG_BK);
+    int sp = 1;
+    if (splitk_ws && tiles <= 74 && kblocks >= 8) {
+      sp = std::min(std::max(1, 148 / tiles), kblocks / 2);
+      const size_t per = (size_t)M * N * sizeof(float);
+      if ((size_t)sp * per > splitk_ws_bytes) sp = (int)(splitk_ws_bytes / per);
+      if (sp < 1) sp = 1;
+    }
+    *splits_out = sp;
+    return sp;
+  };
   int variant = passes == 3 ? 2 : (N >= 256 ? 1 : 0);
+  // (variant 3 is never chosen automatically: measured in the train step -- weight-gradient span 2.59 ms vs 2.23 ms with variant 1 next to
+  // the encoders' backward lanes; with only 3 stages of 64 KB the deeper tile does not hide the L2 latency, profiles/r02_tc_gemm_variants.md)
   if (forced == 0) variant = 0;
-  const int BN = variant == 1 ? 256 : 128;
+  else if (forced == 1 && passes == 1 && N >= 256) variant = 1;
+  else if (forced == 3 && passes == 1 && N >= 256 && M >= 256) variant = 3;
+  const int BN = (variant == 1 || variant == 3) ? 256 : 128;
+  const int BMT = variant == 3 ? 256 : 128;
   TcGemmMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc;
-  if ((rc = encode_map(&maps.a[0], A_hi, M, K, lda, TG_BM))) return rc;
+  if ((rc = encode_map(&maps.a[0], A_hi, M, K, lda, BMT))) return rc;
   if ((rc = encode_map(&maps.b[0], B_hi, N, K, ldb, BN))) return rc;
   if (passes == 3) {
-    if ((rc = encode_map(&maps.a[1], A_lo, M, K, lda, TG_BM))) return rc;
+    if ((rc = encode_map(&maps.a[1], A_lo, M, K, lda, BMT))) return rc;
     if ((rc = encode_map(&maps.b[1], B_lo, N, K, ldb, BN))) return rc;
   }
-  auto smem_of = [](int bn, int stages, int nop) { return (size_t)1024 + (size_t)stages * nop * (TG_A_BYTES + bn * TG_BK * 2) + (2 * stages + 1) * 8 + 16; };
-  const size_t smem = variant == 1 ? smem_of(256, 4, 1) : variant == 2 ? smem_of(128, 3, 2) : smem_of(128, 4, 1);
+  auto smem_of = [](int bm, int bn, int stages, int nop) { return (size_t)1024 + (size_t)stages * nop * (bm * TG_BK * 2 + bn * TG_BK * 2) + (2 * stages + 1) * 8 + 16; };
+  const size_t smem = variant == 1 ? smem_of(128, 256, 4, 1) : variant == 2 ? smem_of(128, 128, 3, 2) : variant == 3 ? smem_of(256, 256, 3, 1) : smem_of(128, 128, 4, 1);
   static bool attr_set = false;     // one device per process (one rank per GPU): set once, not on every launch
   if (!attr_set) {
-    ZCHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<128, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(128, 4, 1)));
-    ZCHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<256, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(256, 4, 1)));
-    ZCHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<128, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(128, 3, 2)));
+    ZCHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<128, 4, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(128, 128, 4, 1)));
+    ZCHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<256, 4, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(128, 256, 4, 1)));
+    ZCHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<128, 3, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(128, 128, 3, 2)));
+    ZCHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<256, 3, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(256, 256, 3, 1)));
     attr_set = true;
   }
-  dim3 grid(ceil_div(N, BN), ceil_div(M, TG_BM));
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BMT));
   // split-K when the output has too few tiles to fill the 148 SMs and the contraction is long
-  const int tiles = (int)(grid.x * grid.y), kblocks = ceil_div(K, TG_BK);
+  const int kblocks = ceil_div(K, TG_BK);
   int splits = 1;
-  if (splitk_ws && tiles <= 74 && kblocks >= 8) {
-    splits = std::min(std::max(1, 148 / tiles), kblocks / 2);
-    const size_t per = (size_t)M * N * sizeof(float);
-    if ((size_t)splits * per > splitk_ws_bytes) splits = (int)(splitk_ws_bytes / per);
-  }
+  plan(BMT, BN, &splits);
   auto launch = [&](const float* bias_, int act_, int acc_, float* part, int kbs) {
-    if (variant == 1) tc_gemm_kernel<256, 4, false><<<grid, 192, smem, stream>>>(maps, M, N, K, passes, bias_, C, ldc, act_, acc_, part, kbs);
-    else if (variant == 2) tc_gemm_kernel<128, 3, true><<<grid, 192, smem, stream>>>(maps, M, N, K, passes, bias_, C, ldc, act_, acc_, part, kbs);
-    else tc_gemm_kernel<128, 4, false><<<grid, 192, smem, stream>>>(maps, M, N, K, passes, bias_, C, ldc, act_, acc_, part, kbs);
+    if (variant == 1) tc_gemm_kernel<256, 4, false, 1><<<grid, 192, smem, stream>>>(maps, M, N, K, passes, bias_, C, ldc, act_, acc_, part, kbs);
+    else if (variant == 2) tc_gemm_kernel<128, 3, true, 1><<<grid, 192, smem, stream>>>(maps, M, N, K, passes, bias_, C, ldc, act_, acc_, part, kbs);
+    else if (variant == 3) tc_gemm_kernel<256, 3, false, 2><<<grid, 192, smem, stream>>>(maps, M, N, K, passes, bias_, C, ldc, act_, acc_, part, kbs);
+    else tc_gemm_kernel<128, 4, false, 1><<<grid, 192, smem, stream>>>(maps, M, N, K, passes, bias_, C, ldc, act_, acc_, part, kbs);
     count_launch();
   };
   if (splits <= 1) {
