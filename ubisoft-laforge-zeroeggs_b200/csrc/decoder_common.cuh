@@ -39,6 +39,11 @@ int split_hist_launch(const float* x, long long slot_stride, int S, int R, __nv_
                       float* rowsum = nullptr, int s_begin = 0);
 int transpose_bf16_launch(const __nv_bfloat16* in, int R, int Ncols, size_t ld_in, __nv_bfloat16* out, size_t ld_out, cudaStream_t stream);
 int split_t_launch(const float* x, int rows, int cols, int ld_in, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_out, cudaStream_t stream);
+// convolution-as-GEMM on tcgen05 with the operand produced straight from x (tc_gemm.cu); ZEGGS_CONV_NOT_TAKEN = use the im2col path
+constexpr int ZEGGS_CONV_NOT_TAKEN = -1000;
+int conv_gemm_fwd(const float* x, int B, int T, int C, int k, int pad, int replicate, const float* W, const float* bias, float* y, int N,
+                  int act, cudaStream_t stream);
+int conv_gemm_wgrad(const float* dpre, int N, const float* x, int B, int T, int C, int k, int pad, int replicate, float* dW, cudaStream_t stream);
 int tc_gemm_launch(int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, int lda,
                    const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, const float* bias,
                    float* C, int ldc, int act, int accumulate, cudaStream_t stream, float* splitk_ws = nullptr,

@@ -272,6 +272,30 @@ static int lin_bwd(const float* dpre, const float* x, const float* W, float* dW,
   return 0;
 }
 
+// 1-D convolution (channels-last, 'same' zero or replicate padding) as a GEMM.  Fast path: the bf16 operands are produced straight from
+// x (conv_gemm_*, no im2col matrix in HBM); otherwise im2col into `col` + the generic product.
+static int conv_fwd(const float* x, int B, int T, int C, int k, int pad, int rep, const float* W, const float* b, float* y, int N, int act,
+                    float* col, cudaStream_t s) {
+  const int rc = conv_gemm_fwd(x, B, T, C, k, pad, rep, W, b, y, N, act, s);
+  if (rc != ZEGGS_CONV_NOT_TAKEN) return rc;
+  RC(im2col(x, B, T, C, k, pad, rep, col, s));
+  return lin_fwd(col, W, b, y, B * T, N, C * k, act, s);
+}
+// backward given dpre[(b,t)][N]: dW, db, and (optional) dcol[(b,t)][C*k] = dpre W for col2im
+static int conv_bwd(const float* dpre, const float* x, int B, int T, int C, int k, int pad, int rep, const float* W, float* dW, float* db,
+                    float* dcol, int N, float* col, cudaStream_t s) {
+  const int M = B * T, K = C * k;
+  int rc = conv_gemm_wgrad(dpre, N, x, B, T, C, k, pad, rep, dW, s);
+  if (rc == ZEGGS_CONV_NOT_TAKEN) {
+    RC(im2col(x, B, T, C, k, pad, rep, col, s));
+    rc = gemm_f32_auto(1, N, K, M, dpre, N, col, K, nullptr, dW, K, 0, 0, s);
+  }
+  if (rc) return rc;
+  if (db) RC(colsum(dpre, M, N, db, s));
+  if (dcol) RC(gemm_f32_auto(2, M, K, N, dpre, N, W, K, nullptr, dcol, K, 0, 0, s));
+  return 0;
+}
+
 // ================================================================== SpeechEncoder
 struct SpeechWs { float *h0, *h0d, *col1, *h1, *h1d, *t0, *t1, *dcol, *red; size_t bytes; };
 static SpeechWs speech_ws(void* base, int B, int T, int Cin, int H, int O, int k) {
@@ -297,8 +321,7 @@ extern "C" int zeggs_speech_enc_fwd(const zeggs_speech_enc_args* ap, void* strea
   ScopedTimer tm("encoders_fwd", s);
   RC(lin_fwd(a.x, a.W0, a.b0, w.h0, M, H, Cin, 1, s));                              // conv k=1 + ELU   (:267)
   RC(ew_mul(w.h0d, w.h0, a.mask0, nullptr, 0, (size_t)M * H, s));                   // drop0
-  RC(im2col(w.h0d, B, T, H, k, k / 2, 1, w.col1, s));                               // replicate 'same' padding
-  RC(lin_fwd(w.col1, a.W1, a.b1, w.h1, M, O, H * k, 1, s));                         // conv k=31 + ELU  (:268)
+  RC(conv_fwd(w.h0d, B, T, H, k, k / 2, 1, a.W1, a.b1, w.h1, O, 1, w.col1, s));     // conv k=31, replicate 'same' padding, + ELU  (:268)
   RC(ew_mul(w.h1d, w.h1, a.mask1, nullptr, 0, (size_t)M * O, s));                   // drop1
   RC(lin_fwd(w.h1d, a.W2, a.b2, a.y, M, O, O, 1, s));                               // Linear + ELU     (:270)
   return ZEGGS_OK;
@@ -315,7 +338,7 @@ extern "C" int zeggs_speech_enc_bwd(const zeggs_speech_enc_args* ap, const zeggs
   RC(ew_mul(w.t0, g.dy, nullptr, a.y, 1, (size_t)M * O, s));                        // dpre2 = dy * ELU'(y)
   RC(lin_bwd(w.t0, w.h1d, a.W2, g.dW2, g.db2, w.t1, M, O, O, s));                   // t1 = d h1d
   RC(ew_mul(w.t0, w.t1, a.mask1, w.h1, 1, (size_t)M * O, s));                       // dpre1
-  RC(lin_bwd(w.t0, w.col1, a.W1, g.dW1, g.db1, w.dcol, M, O, H * k, s));            // dcol1
+  RC(conv_bwd(w.t0, w.h0d, B, T, H, k, k / 2, 1, a.W1, g.dW1, g.db1, w.dcol, O, w.col1, s));   // dW1, db1, dcol1
   RC(col2im(w.dcol, B, T, H, k, k / 2, 1, w.t1, s));                                // d h0d
   RC(ew_mul(w.t0, w.t1, a.mask0, w.h0, 1, (size_t)M * H, s));                       // dpre0
   RC(lin_bwd(w.t0, a.x, a.W0, g.dW0, g.db0, nullptr, M, H, Cin, s));
@@ -361,12 +384,10 @@ extern "C" int zeggs_style_enc_fwd(const zeggs_style_enc_args* ap, void* stream_
   ZCHECK_ARG(a.workspace && a.workspace_bytes >= w.bytes, "style_enc: workspace too small");
   ScopedTimer tm("encoders_fwd", s);
   // conv stack (modules.py:359-384): conv k3 zero-pad -> ReLU -> LayerNorm -> Dropout, twice
-  RC(im2col(a.x, B, T, Cin, 3, 1, 0, w.col0, s));
-  RC(lin_fwd(w.col0, a.Wc1, a.bc1, w.c1, M, Hs, Cin * 3, 2, s));
+  RC(conv_fwd(a.x, B, T, Cin, 3, 1, 0, a.Wc1, a.bc1, w.c1, Hs, 2, w.col0, s));
   RC(ln_fwd(w.c1, nullptr, a.ln1_g, a.ln1_b, M, Hs, w.l1, w.xh1, w.rs1, s));
   RC(ew_mul(w.l1d, w.l1, a.mask_c1, nullptr, 0, (size_t)M * Hs, s));
-  RC(im2col(w.l1d, B, T, Hs, 3, 1, 0, w.col1, s));
-  RC(lin_fwd(w.col1, a.Wc2, a.bc2, w.c2, M, E, Hs * 3, 2, s));
+  RC(conv_fwd(w.l1d, B, T, Hs, 3, 1, 0, a.Wc2, a.bc2, w.c2, E, 2, w.col1, s));
   RC(ln_fwd(w.c2, nullptr, a.ln2_g, a.ln2_b, M, E, w.l2, w.xh2, w.rs2, s));
   RC(ew_mul(w.l2d, w.l2, a.mask_c2, nullptr, 0, (size_t)M * E, s));
   ZCHECK_ARG(a.pe != nullptr, "style_enc: positional-encoding table missing");
@@ -383,10 +404,8 @@ extern "C" int zeggs_style_enc_fwd(const zeggs_style_enc_args* ap, void* stream_
   RC(ew_mul(w.aod, w.ao, a.mask_ao, nullptr, 0, (size_t)M * E, s));
   RC(ln_fwd(w.aod, w.x0, a.ln3_g, a.ln3_b, M, E, w.x1, w.xh3, w.rs3, s));                            // :555
   // position-wise conv feed-forward (modules.py:571-603)
-  RC(im2col(w.x1, B, T, E, 3, 1, 0, w.colf, s));
-  RC(lin_fwd(w.colf, a.Wf1, a.bf1, w.f1, M, E, E * 3, 2, s));
-  RC(im2col(w.f1, B, T, E, 3, 1, 0, w.colf2, s));
-  RC(lin_fwd(w.colf2, a.Wf2, a.bf2, w.f2, M, E, E * 3, 0, s));
+  RC(conv_fwd(w.x1, B, T, E, 3, 1, 0, a.Wf1, a.bf1, w.f1, E, 2, w.colf, s));
+  RC(conv_fwd(w.f1, B, T, E, 3, 1, 0, a.Wf2, a.bf2, w.f2, E, 0, w.colf2, s));
   RC(ew_mul(w.f2d, w.f2, a.mask_ff, nullptr, 0, (size_t)M * E, s));
   RC(ln_fwd(w.f2d, w.x1, a.ln4_g, a.ln4_b, M, E, w.x2, w.xh4, w.rs4, s));                            // :603
   meanpool_kernel<<<ceil_div(B * E, 256), 256, 0, s>>>(w.x2, B, T, E, w.pooled); LAUNCH_OK();        // :416-418
@@ -411,10 +430,10 @@ extern "C" int zeggs_style_enc_bwd(const zeggs_style_enc_args* ap, const zeggs_s
   // x2 = LN4(f2d + x1)
   RC(ln_bwd(w.g0, w.xh4, w.rs4, a.ln4_g, M, E, w.g1, g.dln4_g, g.dln4_b, s));                        // g1 = d(f2d + x1)
   RC(ew_mul(w.g0, w.g1, a.mask_ff, nullptr, 0, nE, s));                                              // g0 = d f2 (pre-act, linear)
-  RC(lin_bwd(w.g0, w.colf2, a.Wf2, g.dWf2, g.dbf2, w.gcol, M, E, E * 3, s));
+  RC(conv_bwd(w.g0, w.f1, B, T, E, 3, 1, 0, a.Wf2, g.dWf2, g.dbf2, w.gcol, E, w.colf2, s));
   RC(col2im(w.gcol, B, T, E, 3, 1, 0, w.g0, s));                                                     // g0 = d f1
   RC(ew_mul(w.g0, w.g0, nullptr, w.f1, 2, nE, s));                                                   // ReLU'
-  RC(lin_bwd(w.g0, w.colf, a.Wf1, g.dWf1, g.dbf1, w.gcol, M, E, E * 3, s));
+  RC(conv_bwd(w.g0, w.x1, B, T, E, 3, 1, 0, a.Wf1, g.dWf1, g.dbf1, w.gcol, E, w.colf, s));
   RC(col2im(w.gcol, B, T, E, 3, 1, 0, w.g0, s));                                                     // g0 = d x1 via FF
   RC(ew_add(w.g1, w.g1, w.g0, nE, 0, s));                                                            // g1 = total d x1
   // x1 = LN3(aod + x0)
@@ -439,12 +458,12 @@ extern "C" int zeggs_style_enc_bwd(const zeggs_style_enc_args* ap, const zeggs_s
   RC(ew_mul(w.g0, w.g2, a.mask_c2, nullptr, 0, nE, s));                                              // d l2
   RC(ln_bwd(w.g0, w.xh2, w.rs2, a.ln2_g, M, E, w.g1, g.dln2_g, g.dln2_b, s));                        // g1 = d c2
   RC(ew_mul(w.g1, w.g1, nullptr, w.c2, 2, nE, s));
-  RC(lin_bwd(w.g1, w.col1, a.Wc2, g.dWc2, g.dbc2, w.gcol, M, E, Hs * 3, s));
+  RC(conv_bwd(w.g1, w.l1d, B, T, Hs, 3, 1, 0, a.Wc2, g.dWc2, g.dbc2, w.gcol, E, w.col1, s));
   RC(col2im(w.gcol, B, T, Hs, 3, 1, 0, w.g0, s));                                                    // g0 = d l1d
   RC(ew_mul(w.g0, w.g0, a.mask_c1, nullptr, 0, (size_t)M * Hs, s));
   RC(ln_bwd(w.g0, w.xh1, w.rs1, a.ln1_g, M, Hs, w.g1, g.dln1_g, g.dln1_b, s));                       // g1 = d c1
   RC(ew_mul(w.g1, w.g1, nullptr, w.c1, 2, (size_t)M * Hs, s));
-  RC(lin_bwd(w.g1, w.col0, a.Wc1, g.dWc1, g.dbc1, nullptr, M, Hs, Cin * 3, s));
+  RC(conv_bwd(w.g1, a.x, B, T, Cin, 3, 1, 0, a.Wc1, g.dWc1, g.dbc1, nullptr, Hs, w.col0, s));
   return ZEGGS_OK;
 }
 

@@ -123,37 +123,43 @@ tc_gemm_kernel(const __grid_constant__ TcGemmMaps maps, int M, int N, int K, int
       __syncwarp();
     }
   } else {
-    // epilogue: warp w reads TMEM lanes [32*(w%4), +32)
+    // epilogue: warp w reads TMEM lanes [32*(w%4), +32): tcgen05.ld hands every thread 32 consecutive columns of ITS row; the
+    // 32x32 block goes through a padded shared-memory tile (the pipeline stages are dead once tmem_full fired: every TMA load has
+    // landed and every MMA has read its operands) so that the global accesses are row-contiguous -- one 128-byte line per warp
+    // instruction instead of 32 scattered 4-byte pieces (read-modify-write of C included).
     const int q = warp & 3;
     mbar_wait(tmem_full, 0);
     tc_fence_after_sync();
+    float* tile = reinterpret_cast<float*>(smem) + q * (32 * 33);
 #pragma unroll 1
     for (int tc = 0; tc < MT * (BN / 32); ++tc) {
       const int t = tc / (BN / 32), c0 = (tc - t * (BN / 32)) * 32;
-      const int m = m0 + t * TG_BM + q * 32 + lane;
-      if (n0 + c0 >= N || m0 + t * TG_BM >= M) continue;
+      const int mb = m0 + t * TG_BM + q * 32;                 // first row of this warp's block
+      if (n0 + c0 >= N || mb >= M) continue;
       uint32_t v[32];
       tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * BN + c0), v);
       tmem_ld_wait();
-      if (m < M && part) {
-        float* prow = part + ((size_t)blockIdx.z * M + m) * N + n0 + c0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + c0 + j < N) prow[j] = __uint_as_float(v[j]);
-      } else if (m < M) {
-        float* crow = C + (size_t)m * ldc + n0 + c0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + c0 + j;
-          if (n < N) {
-            float x = __uint_as_float(v[j]);
-            if (bias) x += bias[n];
+      for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(v[j]);
+      __syncwarp();
+      const int n = n0 + c0 + lane;
+      const int rows = min(32, M - mb);
+      if (n < N) {
+        if (part) {
+          float* pcol = part + ((size_t)blockIdx.z * M + mb) * N + n;
+          for (int r = 0; r < rows; ++r) pcol[(size_t)r * N] = tile[r * 33 + lane];
+        } else {
+          const float bv = bias ? bias[n] : 0.f;
+          float* ccol = C + (size_t)mb * ldc + n;
+          for (int r = 0; r < rows; ++r) {
+            float x = tile[r * 33 + lane] + bv;
             if (act == 1) x = elu_f(x); else if (act == 2) x = fmaxf(x, 0.f);
-            if (accumulate) x += crow[j];
-            crow[j] = x;
+            if (accumulate) x += ccol[(size_t)r * ldc];
+            ccol[(size_t)r * ldc] = x;
           }
         }
       }
+      __syncwarp();
     }
   }
   tc_fence_before_sync();
@@ -471,6 +477,117 @@ int gemm_f32_auto(int mode, int M, int N, int K, const float* A, int lda, const 
   p = (char*)(((uintptr_t)p + 255) & ~(uintptr_t)255);
   return tc_gemm_launch(M, N, K, Ah, Al, Kp, Bh, Bl, Kp, bias, C, ldc, act, accumulate, stream, (float*)p,
                         (size_t)(sbase + sbytes - p));
+}
+
+// ------------------------------------------------------------------ convolution operands without a materialised im2col matrix
+// The 1-D convolutions of the encoders are GEMMs over col[(b,t)][c*k + kk] = x[b][t + kk - pad][c].  Writing col in fp32 and splitting
+// it to bf16 afterwards moved the k-fold expanded matrix three times (write fp32, read fp32, write bf16); these producers write the bf16
+// (hi, lo) operand of the GEMM straight from x -- row-major for the forward product, transposed ([c*k+kk][(b,t)]) for the weight gradient.
+__global__ void im2col_split_kernel(const float* __restrict__ x, int B, int T, int C, int k, int pad, int replicate,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ld_out) {
+  const int half = ld_out >> 1, K = C * k;
+  const size_t total = (size_t)B * T * half;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t m = i / half;
+    const int j = 2 * (int)(i - m * half);
+    const int b = (int)(m / T), t = (int)(m - (size_t)b * T);
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = j + e;
+      v[e] = 0.f;
+      if (col < K) {
+        const int c = col / k, kk = col - c * k;
+        int sidx = t + kk - pad;
+        if (replicate) { sidx = sidx < 0 ? 0 : (sidx >= T ? T - 1 : sidx); v[e] = x[((size_t)b * T + sidx) * C + c]; }
+        else if (sidx >= 0 && sidx < T) v[e] = x[((size_t)b * T + sidx) * C + c];
+      }
+    }
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]);
+    __nv_bfloat162 hh; hh.x = h0; hh.y = h1;
+    *reinterpret_cast<__nv_bfloat162*>(hi + m * ld_out + j) = hh;
+    if (lo) {
+      __nv_bfloat162 ll; ll.x = __float2bfloat16_rn(v[0] - __bfloat162float(h0)); ll.y = __float2bfloat16_rn(v[1] - __bfloat162float(h1));
+      *reinterpret_cast<__nv_bfloat162*>(lo + m * ld_out + j) = ll;
+    }
+  }
+}
+// transposed: hi/lo[c*k + kk][m] (ld_out >= B*T, zero padded); grid (ceil(C/32), ceil(ld_out/32), k), block (32, 8)
+__global__ void im2col_split_t_kernel(const float* __restrict__ x, int B, int T, int C, int k, int pad, int replicate,
+                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ld_out) {
+  __shared__ float tile[32][33];
+  const int kk = blockIdx.z, c0 = blockIdx.x * 32, m0 = blockIdx.y * 32, M = B * T;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int m = m0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (m < M && c < C) {
+      const int b = m / T, t = m - b * T;
+      int sidx = t + kk - pad;
+      if (replicate) { sidx = sidx < 0 ? 0 : (sidx >= T ? T - 1 : sidx); v = x[((size_t)b * T + sidx) * C + c]; }
+      else if (sidx >= 0 && sidx < T) v = x[((size_t)b * T + sidx) * C + c];
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, m = m0 + threadIdx.x;
+    if (c < C && m < ld_out) {
+      const float v = tile[threadIdx.x][i];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const size_t o = ((size_t)c * k + kk) * ld_out + m;
+      hi[o] = h;
+      if (lo) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+// y[(b,t)][n] = act(sum_{c,kk} x[b][t+kk-pad][c] W[n][c*k+kk] + bias[n]) on tcgen05; ZEGGS_CONV_NOT_TAKEN when the tensor-core front end
+// does not apply (fp32 SIMT mode, no / too small scratch): the caller then runs im2col + the generic product.
+int conv_gemm_fwd(const float* x, int B, int T, int C, int k, int pad, int replicate, const float* W, const float* bias, float* y, int N,
+                  int act, cudaStream_t stream) {
+  const int M = B * T, K = C * k, Kp = round_up(K, 8);
+  char* const sbase = scratch_base();
+  const size_t sbytes = scratch_bytes();
+  const int gmode = gemm_mode();
+  const bool want_lo = gmode == 1;
+  const size_t need = (size_t)(M + N) * Kp * 2 * (want_lo ? 2 : 1) + 2048;
+  if (gmode == 0 || sbase == nullptr || need > sbytes || (double)M * N * K < 4.0e6) return ZEGGS_CONV_NOT_TAKEN;
+  char* p = sbase;
+  auto take = [&](size_t n) { __nv_bfloat16* r = (__nv_bfloat16*)p; p += ((n * 2 + 255) / 256) * 256; return r; };
+  __nv_bfloat16* Ah = take((size_t)M * Kp); __nv_bfloat16* Bh = take((size_t)N * Kp);
+  __nv_bfloat16* Al = want_lo ? take((size_t)M * Kp) : nullptr; __nv_bfloat16* Bl = want_lo ? take((size_t)N * Kp) : nullptr;
+  if ((size_t)(p - sbase) > sbytes) return ZEGGS_CONV_NOT_TAKEN;
+  im2col_split_kernel<<<1184, 256, 0, stream>>>(x, B, T, C, k, pad, replicate, Ah, Al, Kp);
+  count_launch();
+  split_bf16_kernel<<<592, 256, 0, stream>>>(W, N, K, K, Bh, Bl, Kp);
+  count_launch();
+  ZCHECK_LAUNCH();
+  p = (char*)(((uintptr_t)p + 255) & ~(uintptr_t)255);
+  return tc_gemm_launch(M, N, K, Ah, Al, Kp, Bh, Bl, Kp, bias, y, N, act, 0, stream, (float*)p, (size_t)(sbase + sbytes - p));
+}
+
+// dW[n][c*k+kk] = sum_{(b,t)} dpre[(b,t)][n] x[b][t+kk-pad][c]
+int conv_gemm_wgrad(const float* dpre, int N, const float* x, int B, int T, int C, int k, int pad, int replicate, float* dW, cudaStream_t stream) {
+  const int M = B * T, K = C * k, Mp = round_up(M, 8);
+  char* const sbase = scratch_base();
+  const size_t sbytes = scratch_bytes();
+  const int gmode = gemm_mode();
+  const bool want_lo = gmode == 1 && !fast_wgrad();
+  const size_t need = (size_t)(N + K) * Mp * 2 * (want_lo ? 2 : 1) + 2048;
+  if (gmode == 0 || sbase == nullptr || need > sbytes || (double)M * N * K < 4.0e6) return ZEGGS_CONV_NOT_TAKEN;
+  char* p = sbase;
+  auto take = [&](size_t n) { __nv_bfloat16* r = (__nv_bfloat16*)p; p += ((n * 2 + 255) / 256) * 256; return r; };
+  __nv_bfloat16* Ah = take((size_t)N * Mp); __nv_bfloat16* Bh = take((size_t)K * Mp);
+  __nv_bfloat16* Al = want_lo ? take((size_t)N * Mp) : nullptr; __nv_bfloat16* Bl = want_lo ? take((size_t)K * Mp) : nullptr;
+  if ((size_t)(p - sbase) > sbytes) return ZEGGS_CONV_NOT_TAKEN;
+  const dim3 tb(32, 8);
+  split_bf16_t_kernel<<<dim3(ceil_div(N, 32), ceil_div(Mp, 32)), tb, 0, stream>>>(dpre, M, N, N, Ah, Al, Mp);
+  count_launch();
+  im2col_split_t_kernel<<<dim3(ceil_div(C, 32), ceil_div(Mp, 32), k), tb, 0, stream>>>(x, B, T, C, k, pad, replicate, Bh, Bl, Mp);
+  count_launch();
+  ZCHECK_LAUNCH();
+  p = (char*)(((uintptr_t)p + 255) & ~(uintptr_t)255);
+  return tc_gemm_launch(N, K, M, Ah, Al, Mp, Bh, Bl, Mp, nullptr, dW, K, 0, 0, stream, (float*)p, (size_t)(sbase + sbytes - p));
 }
 
 extern "C" int zeggs_gemm_f32(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* bias,
