@@ -338,6 +338,8 @@ typedef struct {
   const int* ex_n;
 } zeggs_gather_args;
 int zeggs_window_gather(const zeggs_gather_args* a, void* stream);
+/* Input normalisation of train.py:232-234 / 247-249 in one pass: out[r][c] = (x[r][c] - mean[c]) / std[c]  (x, out: [rows][C] fp32). */
+int zeggs_normalize_rows(const float* x, const float* mean, const float* stdv, float* out, long long rows, int C, void* stream);
 
 /* Fused RAdam step over a flat fp32 parameter buffer (optimizers.py:31-99; weight_decay 0,
  * degenerated_to_sgd).  `step` is the 1-based step count; gradients are multiplied by grad_scale first. */

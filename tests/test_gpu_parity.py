@@ -63,6 +63,16 @@ def test_tc_gemm_bf16(dev, M, N, K):
     assert err <= 2e-5 * sc
 
 
+def test_normalize_rows_is_bit_identical_to_the_two_tensor_ops(dev):
+    """zeggs_normalize_rows against (x - mean) / std (train.py:232-234): same fp32 subtract + IEEE divide -> identical bits."""
+    from zeggs_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(3, 37, 1134, generator=g) * 7).to(dev)
+    mean = torch.randn(1134, generator=g).to(dev)
+    std = (torch.rand(1134, generator=g) + 0.05).to(dev)
+    assert torch.equal(ops.normalize_rows(x, mean, std), (x - mean) / std)
+
+
 # ---------------------------------------------------------------------------------------------- mel
 @pytest.mark.parametrize("hop", [200, 160])
 def test_mel_against_reference_golden(dev, golden_dir, hop):

@@ -117,6 +117,7 @@ SYMBOLS = [
     ("zeggs_decoder_step_workspace_bytes", C.c_size_t, [C.c_int] * 4),
     ("zeggs_decoder_step_fwd", C.c_int, [C.POINTER(DecoderStepArgs), C.c_void_p]),
     ("zeggs_window_gather", C.c_int, [C.POINTER(GatherArgs), C.c_void_p]),
+    ("zeggs_normalize_rows", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     ("zeggs_pose_to_bvh_channels", C.c_int, [C.POINTER(PosePostArgs), C.c_void_p]),
     ("zeggs_loudness_workspace_bytes", C.c_size_t, [C.c_int, C.c_int]),
     ("zeggs_loudness_gain", C.c_int, [C.POINTER(LoudnessArgs), C.c_void_p]),

@@ -65,4 +65,24 @@ extern "C" int zeggs_window_gather(const zeggs_gather_args* ap, void* stream) {
   return ZEGGS_OK;
 }
 
+// out[r][c] = (x[r][c] - mean[c]) / std[c]: the reference normalises every network input with two broadcast tensor ops
+// (train.py:232-234, 247-249); one pass instead of two here, same arithmetic (fp32 subtract, then IEEE divide).
+__global__ void normalize_rows_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ stdv,
+                                      float* __restrict__ out, long long rows, int C) {
+  const long long total = rows * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    out[i] = __fdiv_rn(__fsub_rn(x[i], mean[c]), stdv[c]);
+  }
+}
+extern "C" int zeggs_normalize_rows(const float* x, const float* mean, const float* stdv, float* out, long long rows, int C, void* stream) {
+  ZCHECK_ARG(x && mean && stdv && out && rows >= 0 && C >= 1, "normalize_rows: bad arguments");
+  if (rows == 0) return ZEGGS_OK;
+  const long long blocks = (rows * C + 255) / 256;
+  normalize_rows_kernel<<<(unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks), 256, 0, (cudaStream_t)stream>>>(x, mean, stdv, out, rows, C);
+  count_launch();
+  ZCHECK_LAUNCH();
+  return ZEGGS_OK;
+}
+
 }  // namespace zeggs

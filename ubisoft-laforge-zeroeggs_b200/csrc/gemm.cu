@@ -99,26 +99,35 @@ __global__ void __launch_bounds__(256) sgemm_n32_kernel(int M, int N, int K, con
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += 32) {
-    if (MODE == 1) {
-#pragma unroll 4
-      for (int i = tid; i < 32 * 128; i += 256) {
-        const int kk = i >> 7, mm = i & 127, k = k0 + kk;
-        As[kk][mm] = (k < K && m0 + mm < M) ? A[(size_t)k * lda + m0 + mm] : 0.f;
-      }
-    } else {
-#pragma unroll 4
-      for (int i = tid; i < 32 * 128; i += 256) {
-        const int mm = i >> 5, kk = i & 31, k = k0 + kk;
-        As[kk][mm] = (k < K && m0 + mm < M) ? A[(size_t)(m0 + mm) * lda + k] : 0.f;
-      }
+  // register-staged software pipeline: the global loads of chunk c+1 are in flight while chunk c is multiplied out of shared memory
+  float ra[16], rb[4];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int i = tid + u * 256;
+      if (MODE == 1) { const int kk = i >> 7, mm = i & 127, k = k0 + kk; ra[u] = (k < K && m0 + mm < M) ? A[(size_t)k * lda + m0 + mm] : 0.f; }
+      else { const int mm = i >> 5, kk = i & 31, k = k0 + kk; ra[u] = (k < K && m0 + mm < M) ? A[(size_t)(m0 + mm) * lda + k] : 0.f; }
     }
 #pragma unroll
-    for (int i = tid; i < 32 * 32; i += 256) {
-      const int kk = i >> 5, nn = i & 31, k = k0 + kk;
-      Bs[kk][nn] = (k < K && nn < N) ? B[(size_t)k * ldb + nn] : 0.f;
+    for (int u = 0; u < 4; ++u) {
+      const int i = tid + u * 256, kk = i >> 5, nn = i & 31, k = k0 + kk;
+      rb[u] = (k < K && nn < N) ? B[(size_t)k * ldb + nn] : 0.f;
     }
+  };
+  auto sstore = [&]() {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int i = tid + u * 256;
+      if (MODE == 1) As[i >> 7][i & 127] = ra[u]; else As[i & 31][i >> 5] = ra[u];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i = tid + u * 256; Bs[i >> 5][i & 31] = rb[u]; }
+  };
+  gload(0);
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    sstore();
     __syncthreads();
+    if (k0 + 32 < K) gload(k0 + 32);
 #pragma unroll
     for (int kk = 0; kk < 32; ++kk) {
       const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);

@@ -230,17 +230,48 @@ struct TreeTables {           // built on the device from `parents` by loss_tree
   int parents[NJ];
 };
 __global__ void loss_tree_kernel(const int* __restrict__ parents, TreeTables* __restrict__ tt) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  int lvl[NJ];
-  lvl[0] = 0; tt->parents[0] = -1;
-  int maxl = 0;
-  for (int i = 1; i < NJ; ++i) { const int p = parents[i]; tt->parents[i] = p; lvl[i] = lvl[p] + 1; if (lvl[i] > maxl) maxl = lvl[i]; }
-  int n = 0;
-  for (int l = 0; l <= maxl; ++l) { tt->lvl_off[l] = n; for (int i = 0; i < NJ; ++i) if (lvl[i] == l) tt->order[n++] = i; }
-  tt->lvl_off[maxl + 1] = n; tt->nlev = maxl + 1;
-  int m = 0;
-  for (int i = 0; i < NJ; ++i) { tt->child_off[i] = m; for (int c = 1; c < NJ; ++c) if (parents[c] == i) tt->child_idx[m++] = c; }
-  tt->child_off[NJ] = m;
+  // one thread per joint (blockDim >= NJ): level by walking up the parent chain, position inside the level and the child list by one
+  // O(NJ) scan each -- the former single-thread construction (O(NJ^2) dependent steps) cost 50 us on the loss's critical path
+  __shared__ TreeTables st;
+  __shared__ int lvl[NJ], nchild[NJ];
+  if (blockIdx.x != 0) return;
+  const int i = threadIdx.x;
+  if (i < NJ) st.parents[i] = i == 0 ? -1 : parents[i];
+  if (i <= NJ) st.lvl_off[i] = 0;
+  __syncthreads();
+  if (i < NJ) {
+    int l = 0;
+    for (int p = st.parents[i]; p >= 0 && l < NJ; p = st.parents[p]) ++l;
+    lvl[i] = l;
+    int nc = 0;
+    for (int c = 1; c < NJ; ++c) nc += st.parents[c] == i;
+    nchild[i] = nc;
+  }
+  __syncthreads();
+  if (i == 0) {                               // two short prefix sums
+    int maxl = 0;
+    for (int j = 0; j < NJ; ++j) maxl = lvl[j] > maxl ? lvl[j] : maxl;
+    st.nlev = maxl + 1;
+    int n = 0;
+    for (int l = 0; l <= maxl; ++l) { st.lvl_off[l] = n; for (int j = 0; j < NJ; ++j) n += lvl[j] == l; }
+    st.lvl_off[maxl + 1] = n;
+    int m = 0;
+    for (int j = 0; j < NJ; ++j) { st.child_off[j] = m; m += nchild[j]; }
+    st.child_off[NJ] = m;
+  }
+  if (i < NJ) st.child_idx[i] = 0;
+  __syncthreads();
+  if (i < NJ) {
+    int pos = st.lvl_off[lvl[i]];
+    for (int j = 0; j < i; ++j) pos += lvl[j] == lvl[i];
+    st.order[pos] = i;
+    int m = st.child_off[i];
+    for (int c = 1; c < NJ; ++c) if (st.parents[c] == i) st.child_idx[m++] = c;
+  }
+  __syncthreads();
+  const int* src = reinterpret_cast<const int*>(&st);
+  int* dst = reinterpret_cast<int*>(tt);
+  for (int k = threadIdx.x; k < (int)(sizeof(TreeTables) / sizeof(int)); k += blockDim.x) dst[k] = src[k];
 }
 
 constexpr int LW_WARPS = 4;                      // frames per CTA
@@ -697,7 +728,7 @@ extern "C" int zeggs_loss_fwd_bwd(const zeggs_loss_args* ap, void* stream_) {
       ZCHECK_CUDA(cudaFuncSetAttribute(loss_w_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LB_WARPS * 2 * LB_FRAME_FLOATS * sizeof(float))));
       attr = true;
     }
-    loss_tree_kernel<<<1, 32, 0, s>>>(a.parents, w.tt); count_launch();
+    loss_tree_kernel<<<1, 96, 0, s>>>(a.parents, w.tt); count_launch();
     const int nb = ceil_div(BT, LW_WARPS);
     loss_w_fwd_kernel<<<nb, LW_WARPS * 32, LW_WARPS * LW_FWD_FLOATS * sizeof(float), s>>>(wa); count_launch();
     if (a.dY) {

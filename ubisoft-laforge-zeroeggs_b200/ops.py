@@ -150,6 +150,25 @@ def weights_key(params):
     return (_weights_epoch,) + tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)
 
 
+def normalize_rows(x, mean, std):
+    """(x - mean) / std over the last dimension in one pass (zeggs_normalize_rows); same arithmetic as the two torch ops."""
+    if x.device.type != "cuda":
+        raise _lib.ZeggsError("zeggs_b200.ops.normalize_rows runs on CUDA tensors only")
+    x = _f32c(x)
+    Cn = x.shape[-1]
+    try:                                    # statistics broadcast over the channel dimension (the audio std is a scalar)
+        mean = _f32c(mean, x.device).reshape(-1).expand(Cn).contiguous() if mean.numel() in (1, Cn) else None
+        std = _f32c(std, x.device).reshape(-1).expand(Cn).contiguous() if std.numel() in (1, Cn) else None
+    except RuntimeError:
+        mean = std = None
+    if mean is None or std is None:
+        raise _lib.ZeggsError("normalize_rows: mean / std must be scalars or have the size of the last dimension")
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().zeggs_normalize_rows(x.data_ptr(), mean.data_ptr(), std.data_ptr(), out.data_ptr(), x.numel() // Cn, Cn,
+                                               _lib.stream_ptr()), "zeggs_normalize_rows")
+    return out
+
+
 def split_pose(Y, root_pos, root_rot):
     """[B,T,1131] pose vectors -> the reference's 8-tuple (modules.py:153-162, 731-736)."""
     B, T = Y.shape[0], Y.shape[1]

@@ -92,7 +92,7 @@ class TrainStep:
         se, dec, st = self.se, self.dec, self.st
         se.train(train_mode); dec.train(train_mode)
         gv = lambda m: [p.grad for p in m._weights()]
-        xa = (batch["audio"] - self.audio_mean) / self.audio_std
+        xa = ops.normalize_rows(batch["audio"], self.audio_mean, self.audio_std)
         cur = torch.cuda.current_stream(self.dev) if self.lanes else None
         s1, s2 = self._lane_streams if self.lanes else (None, None)
         prep = None
@@ -109,7 +109,7 @@ class TrainStep:
         mu = logvar = st_state = None
         if st is not None:
             st.train(train_mode)
-            xs = (batch["style"] - self.in_mean) / self.in_std
+            xs = ops.normalize_rows(batch["style"], self.in_mean, self.in_std)
             eps_, smasks = ops.style_encoder_prepare(st, xs, eps, None if masks is None else masks.get("style"))
             (z, mu, logvar), st_state = ops.style_encoder_fwd(st, xs, eps_, smasks, 1.0)
         else:
