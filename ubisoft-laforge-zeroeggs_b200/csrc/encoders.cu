@@ -115,11 +115,23 @@ __global__ void colred_kernel(const float* __restrict__ a, const float* __restri
   const int per = (rows + gridDim.y - 1) / gridDim.y;
   const int r_lo = blockIdx.y * per, r_hi = min(rows, r_lo + per);
   float x = 0.f, y = 0.f;
-  if (d < D)
-    for (int r = r_lo + threadIdx.y; r < r_hi; r += 8) {
-      const float v = a[(size_t)r * D + d];
-      if (b) { x += v * b[(size_t)r * D + d]; y += v; } else x += v;
+  if (d < D) {
+    // four independent row streams per thread (fixed order of the final adds): the loads of a stripe are in flight together
+    float xa[4] = {0.f, 0.f, 0.f, 0.f}, ya[4] = {0.f, 0.f, 0.f, 0.f};
+    int r = r_lo + threadIdx.y;
+    for (; r + 24 < r_hi; r += 32) {
+      float v[4], w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { v[u] = a[(size_t)(r + 8 * u) * D + d]; w[u] = b ? b[(size_t)(r + 8 * u) * D + d] : 1.f; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { xa[u] += v[u] * w[u]; ya[u] += v[u]; }
     }
+    for (; r < r_hi; r += 8) {
+      const float v = a[(size_t)r * D + d];
+      xa[0] += b ? v * b[(size_t)r * D + d] : v; ya[0] += v;
+    }
+    x = (xa[0] + xa[1]) + (xa[2] + xa[3]); y = (ya[0] + ya[1]) + (ya[2] + ya[3]);
+  }
   s0[threadIdx.y][threadIdx.x] = x; s1[threadIdx.y][threadIdx.x] = y;
   __syncthreads();
   if (threadIdx.y == 0 && d < D) {

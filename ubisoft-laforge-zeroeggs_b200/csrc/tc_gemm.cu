@@ -151,11 +151,26 @@ tc_gemm_kernel(const __grid_constant__ TcGemmMaps maps, int M, int N, int K, int
         } else {
           const float bv = bias ? bias[n] : 0.f;
           float* ccol = C + (size_t)mb * ldc + n;
-          for (int r = 0; r < rows; ++r) {
-            float x = tile[r * 33 + lane] + bv;
-            if (act == 1) x = elu_f(x); else if (act == 2) x = fmaxf(x, 0.f);
-            if (accumulate) x += ccol[(size_t)r * ldc];
-            ccol[(size_t)r * ldc] = x;
+          if (accumulate) {
+            // read-modify-write: all 32 loads of the block are issued before the first store (a load after a store to the same
+            // array is not hoisted by the compiler, and 32 dependent L2 round trips per block made this epilogue cost 3x the mainloop)
+            float cv[32];
+#pragma unroll
+            for (int r = 0; r < 32; ++r) cv[r] = r < rows ? ccol[(size_t)r * ldc] : 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              if (r < rows) {
+                float x = tile[r * 33 + lane] + bv;
+                if (act == 1) x = elu_f(x); else if (act == 2) x = fmaxf(x, 0.f);
+                ccol[(size_t)r * ldc] = x + cv[r];
+              }
+            }
+          } else {
+            for (int r = 0; r < rows; ++r) {
+              float x = tile[r * 33 + lane] + bv;
+              if (act == 1) x = elu_f(x); else if (act == 2) x = fmaxf(x, 0.f);
+              ccol[(size_t)r * ldc] = x;
+            }
           }
         }
       }
@@ -512,12 +527,13 @@ __global__ void im2col_split_kernel(const float* __restrict__ x, int B, int T, i
     }
   }
 }
-// transposed: hi/lo[c*k + kk][m] (ld_out >= B*T, zero padded); grid (ceil(C/32), ceil(ld_out/32), k), block (32, 8)
+// transposed: hi/lo[c*k + kk][m] (ld_out >= B*T, zero padded); grid (ceil(C/32), ceil(ld_out/128), k), block (32, 8):
+// a block moves 32 channels x 128 rows, so every output row segment is 256 contiguous bytes (the 32 x 32 version wrote 64-byte pieces)
 __global__ void im2col_split_t_kernel(const float* __restrict__ x, int B, int T, int C, int k, int pad, int replicate,
                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ld_out) {
-  __shared__ float tile[32][33];
-  const int kk = blockIdx.z, c0 = blockIdx.x * 32, m0 = blockIdx.y * 32, M = B * T;
-  for (int i = threadIdx.y; i < 32; i += 8) {
+  __shared__ float tile[128][33];
+  const int kk = blockIdx.z, c0 = blockIdx.x * 32, m0 = blockIdx.y * 128, M = B * T;
+  for (int i = threadIdx.y; i < 128; i += 8) {
     const int m = m0 + i, c = c0 + threadIdx.x;
     float v = 0.f;
     if (m < M && c < C) {
@@ -530,13 +546,21 @@ __global__ void im2col_split_t_kernel(const float* __restrict__ x, int B, int T,
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += 8) {
-    const int c = c0 + i, m = m0 + threadIdx.x;
-    if (c < C && m < ld_out) {
-      const float v = tile[threadIdx.x][i];
-      const __nv_bfloat16 h = __float2bfloat16_rn(v);
-      const size_t o = ((size_t)c * k + kk) * ld_out + m;
-      hi[o] = h;
-      if (lo) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+    const int c = c0 + i;
+    if (c >= C) continue;
+    const size_t o = ((size_t)c * k + kk) * ld_out;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {                  // two rows per thread: 4-byte stores, 128 bytes per warp instruction (ld_out % 8 == 0)
+      const int mm = j * 64 + 2 * threadIdx.x, m = m0 + mm;
+      if (m < ld_out) {
+        const float v0 = tile[mm][i], v1 = tile[mm + 1][i];
+        __nv_bfloat162 hh; hh.x = __float2bfloat16_rn(v0); hh.y = __float2bfloat16_rn(v1);
+        *reinterpret_cast<__nv_bfloat162*>(hi + o + m) = hh;
+        if (lo) {
+          __nv_bfloat162 ll; ll.x = __float2bfloat16_rn(v0 - __bfloat162float(hh.x)); ll.y = __float2bfloat16_rn(v1 - __bfloat162float(hh.y));
+          *reinterpret_cast<__nv_bfloat162*>(lo + o + m) = ll;
+        }
+      }
     }
   }
 }
@@ -583,7 +607,7 @@ int conv_gemm_wgrad(const float* dpre, int N, const float* x, int B, int T, int 
   const dim3 tb(32, 8);
   split_bf16_t_kernel<<<dim3(ceil_div(N, 32), ceil_div(Mp, 32)), tb, 0, stream>>>(dpre, M, N, N, Ah, Al, Mp);
   count_launch();
-  im2col_split_t_kernel<<<dim3(ceil_div(C, 32), ceil_div(Mp, 32), k), tb, 0, stream>>>(x, B, T, C, k, pad, replicate, Bh, Bl, Mp);
+  im2col_split_t_kernel<<<dim3(ceil_div(C, 32), ceil_div(Mp, 128), k), tb, 0, stream>>>(x, B, T, C, k, pad, replicate, Bh, Bl, Mp);
   count_launch();
   ZCHECK_LAUNCH();
   p = (char*)(((uintptr_t)p + 255) & ~(uintptr_t)255);
