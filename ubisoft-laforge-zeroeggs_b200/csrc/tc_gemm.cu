@@ -500,30 +500,35 @@ int gemm_f32_auto(int mode, int M, int N, int K, const float* A, int lda, const 
 // (hi, lo) operand of the GEMM straight from x -- row-major for the forward product, transposed ([c*k+kk][(b,t)]) for the weight gradient.
 __global__ void im2col_split_kernel(const float* __restrict__ x, int B, int T, int C, int k, int pad, int replicate,
                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ld_out) {
-  const int half = ld_out >> 1, K = C * k;
-  const size_t total = (size_t)B * T * half;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t m = i / half;
-    const int j = 2 * (int)(i - m * half);
-    const int b = (int)(m / T), t = (int)(m - (size_t)b * T);
-    float v[2];
+  // one output row (b,t) per block iteration, threads over column pairs: 32-bit index arithmetic only (a flat 64-bit index with two
+  // divisions per element pair made the first version issue-bound at 1.4 TB/s)
+  const int half = ld_out >> 1, K = C * k, M = B * T;
+  for (int m = blockIdx.x; m < M; m += gridDim.x) {
+    const int b = m / T, t = m - b * T;
+    const float* xb = x + (size_t)b * T * C;
+    __nv_bfloat16* hrow = hi + (size_t)m * ld_out;
+    __nv_bfloat16* lrow = lo ? lo + (size_t)m * ld_out : nullptr;
+    for (int j2 = threadIdx.x; j2 < half; j2 += blockDim.x) {
+      const int j = 2 * j2;
+      float v[2];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int col = j + e;
-      v[e] = 0.f;
-      if (col < K) {
-        const int c = col / k, kk = col - c * k;
-        int sidx = t + kk - pad;
-        if (replicate) { sidx = sidx < 0 ? 0 : (sidx >= T ? T - 1 : sidx); v[e] = x[((size_t)b * T + sidx) * C + c]; }
-        else if (sidx >= 0 && sidx < T) v[e] = x[((size_t)b * T + sidx) * C + c];
+      for (int e = 0; e < 2; ++e) {
+        const int col = j + e;
+        v[e] = 0.f;
+        if (col < K) {
+          const int c = col / k, kk = col - c * k;
+          int sidx = t + kk - pad;
+          if (replicate) { sidx = sidx < 0 ? 0 : (sidx >= T ? T - 1 : sidx); v[e] = xb[sidx * C + c]; }
+          else if (sidx >= 0 && sidx < T) v[e] = xb[sidx * C + c];
+        }
       }
-    }
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]);
-    __nv_bfloat162 hh; hh.x = h0; hh.y = h1;
-    *reinterpret_cast<__nv_bfloat162*>(hi + m * ld_out + j) = hh;
-    if (lo) {
-      __nv_bfloat162 ll; ll.x = __float2bfloat16_rn(v[0] - __bfloat162float(h0)); ll.y = __float2bfloat16_rn(v[1] - __bfloat162float(h1));
-      *reinterpret_cast<__nv_bfloat162*>(lo + m * ld_out + j) = ll;
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]);
+      __nv_bfloat162 hh; hh.x = h0; hh.y = h1;
+      *reinterpret_cast<__nv_bfloat162*>(hrow + j) = hh;
+      if (lrow) {
+        __nv_bfloat162 ll; ll.x = __float2bfloat16_rn(v[0] - __bfloat162float(h0)); ll.y = __float2bfloat16_rn(v[1] - __bfloat162float(h1));
+        *reinterpret_cast<__nv_bfloat162*>(lrow + j) = ll;
+      }
     }
   }
 }
@@ -581,7 +586,7 @@ int conv_gemm_fwd(const float* x, int B, int T, int C, int k, int pad, int repli
   __nv_bfloat16* Ah = take((size_t)M * Kp); __nv_bfloat16* Bh = take((size_t)N * Kp);
   __nv_bfloat16* Al = want_lo ? take((size_t)M * Kp) : nullptr; __nv_bfloat16* Bl = want_lo ? take((size_t)N * Kp) : nullptr;
   if ((size_t)(p - sbase) > sbytes) return ZEGGS_CONV_NOT_TAKEN;
-  im2col_split_kernel<<<1184, 256, 0, stream>>>(x, B, T, C, k, pad, replicate, Ah, Al, Kp);
+  im2col_split_kernel<<<std::min(M, 148 * 16), 256, 0, stream>>>(x, B, T, C, k, pad, replicate, Ah, Al, Kp);
   count_launch();
   split_bf16_kernel<<<592, 256, 0, stream>>>(W, N, K, K, Bh, Bl, Kp);
   count_launch();

@@ -100,9 +100,16 @@ class TrainStep:
             s1.wait_stream(cur)
             with torch.cuda.stream(s1), ops.lane("speech"):
                 speech, se_state = ops.speech_encoder_fwd(se, xa, ops.speech_encoder_masks(se, xa, None if masks is None else masks.get("speech")))
-            # weight-only preparation of the decoder (bf16 weight images, folded layer-2 matrix, BPTT images) on the second lane
+            # second lane: the StyleEncoder's dropout multipliers / VAE noise first (off the main stream's critical chain; same host order
+            # of the seeded draws as without lanes), then the weight-only preparation of the decoder (bf16 weight images, folded layer-2
+            # matrix, BPTT images)
             s2.wait_stream(cur)
             with torch.cuda.stream(s2), ops.lane("style"):
+                if st is not None:
+                    st.train(train_mode)
+                    pre_style = ops.style_encoder_prepare(st, batch["style"], eps, None if masks is None else masks.get("style"))
+                    ev_style = torch.cuda.Event()
+                    ev_style.record(s2)
                 prep = ops.decoder_prepack(dec, xa.shape[0], xa.shape[1], self.dev, (self.in_mean, self.in_std, self.out_mean, self.out_std), self.dt)
         else:
             speech, se_state = ops.speech_encoder_fwd(se, xa, ops.speech_encoder_masks(se, xa, None if masks is None else masks.get("speech")))
@@ -110,7 +117,11 @@ class TrainStep:
         if st is not None:
             st.train(train_mode)
             xs = ops.normalize_rows(batch["style"], self.in_mean, self.in_std)
-            eps_, smasks = ops.style_encoder_prepare(st, xs, eps, None if masks is None else masks.get("style"))
+            if self.lanes:
+                eps_, smasks = pre_style
+                cur.wait_event(ev_style)
+            else:
+                eps_, smasks = ops.style_encoder_prepare(st, xs, eps, None if masks is None else masks.get("style"))
             (z, mu, logvar), st_state = ops.style_encoder_fwd(st, xs, eps_, smasks, 1.0)
         else:
             z = batch["style"]
