@@ -43,3 +43,23 @@ def test_reference_pickles_unpickle_into_our_classes():
     assert (dec.hidden_size, dec.speech_encoding_size, dec.style_encoding_size) == (1024, 64, 64)
     assert len(dec._weights()) == 18 and len(enc._weights()) == 6 and len(sty._weights()) == 20
     assert sty.encoder.pos_enc.table(5).shape == (5, 128)
+
+
+def test_lane_context_is_scoped_and_nestable():
+    """ops.lane selects which zeggs_ctx (GEMM scratch) the calls issued inside the block travel with: default "main", restored on exit,
+    also when the block raises; nested lanes restore the outer one."""
+    from zeggs_b200 import ops
+    assert ops.current_lane() == "main"
+    with ops.lane("speech"):
+        assert ops.current_lane() == "speech"
+        with ops.lane("style"):
+            assert ops.current_lane() == "style"
+        assert ops.current_lane() == "speech"
+    assert ops.current_lane() == "main"
+    try:
+        with ops.lane("style"):
+            raise RuntimeError("x")
+    except RuntimeError:
+        pass
+    assert ops.current_lane() == "main"
+
